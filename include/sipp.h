@@ -1,0 +1,219 @@
+/*
+ * sipp.h — C ABI of the B200-native scouting-ipp evaluation hot path (libsipp.so).
+ *
+ * This is the drop-in boundary. Every entry point replaces a C++ interface of the reference
+ * (ethz-asl/scouting-ipp; citations are <pkg>/<path>:<line> relative to the reference root).
+ * Plain pointers and sizes only; no torch / Eigen / ROS types. All entry points return an int status
+ * (SIPP_OK == 0, negative = error) and never throw; sipp_last_error() gives the message.
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point launches hand-written sm_100a CUDA
+ * kernels and fails with SIPP_ERR_CUDA when no usable device/driver is present.
+ *
+ * Conventions
+ *   - maps are W x H cells (W = horizontal_units_, H = vertical_units_), host arrays are ROW-MAJOR
+ *     [y * W + x] (the MapData wire layout, advanced_planner_msgs/msg/MapData.msg:1-3 and
+ *     map_server_planexp/src/map_server_planexp.cpp:306-317); the reference's Eigen arrays are
+ *     column-major (row=y, col=x) — only the host adapters care.
+ *   - positions are metres in the map frame, doubles, like Eigen::Vector3d position_W.
+ *   - "_dev" variants take DEVICE pointers and a cudaStream_t (passed as void*) and do not synchronise.
+ */
+#ifndef SIPP_H_
+#define SIPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIPP_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------------------- */
+#define SIPP_OK 0
+#define SIPP_ERR_INVALID_ARG (-1)
+#define SIPP_ERR_CUDA (-2)            /* any CUDA failure incl. "no device": there is no CPU fallback   */
+#define SIPP_ERR_UNSUPPORTED (-3)     /* geometry / parameter combination the kernels do not cover      */
+#define SIPP_ERR_NO_PATH_MASK (-4)    /* path-dependent evaluator used before a plan / mask upload      */
+#define SIPP_ERR_ALLOC (-5)
+
+/* ---- cell state codes: map_server_planexp/include/map_server_planexp/map_server_planexp.h:37-39 ---- */
+#define SIPP_STATE_OCCUPIED 0
+#define SIPP_STATE_FREE 1
+#define SIPP_STATE_UNKNOWN 2
+/* reachability codes: map_server_planexp.h:45-46 */
+#define SIPP_REACHABILITY_UNKNOWN 0
+#define SIPP_REACHABLE 1
+
+/* ---- planner result: planexp_base_planners/include/planexp_base_planners/base_planner.h:39-44 ------ */
+#define SIPP_PLAN_VALID 0
+#define SIPP_PLAN_INVALID 1
+#define SIPP_PLAN_TERMINAL_VALID 2
+#define SIPP_PLAN_TERMINAL_INVALID 3
+
+#define SIPP_MAX_IDS 32
+
+/*
+ * Map + follower-planner description. Mirrors what MapServerPlanExp parses from the map cfg YAML
+ * (map_server_planexp.cpp:73-140) and the PlannerParams it hands to the planner (:181-192,
+ * base_planner.h:13-37).
+ */
+typedef struct sipp_map_desc {
+  int32_t W;                    /* horizontal_units_ (cfg resolution[0])                                */
+  int32_t H;                    /* vertical_units_   (cfg resolution[1])                                */
+  double width;                 /* [m] */
+  double height;                /* [m] */
+  double start_x, start_y;      /* start_location [m] */
+  double goal_x, goal_y;        /* goal_location  [m] */
+  double min_rov_cost;          /* PlannerParams.min_cost  (map_server_planexp.cpp:124-125)             */
+  double max_rov_cost;          /* PlannerParams.max_cost  (:126-127)                                   */
+  double unknown_init_cost;     /* PlannerParams.init_cost (:165-179)                                   */
+  int32_t unknown_id;           /* 3599 */
+  int32_t n_obstacle_ids_mav;   /* ids that make a cell MSR_OCCUPIED in the map state (:252)            */
+  int32_t obstacle_ids_mav[SIPP_MAX_IDS];
+  int32_t n_obstacle_ids_rov;   /* ids whose graph edges the follower planner deletes                   */
+  int32_t obstacle_ids_rov[SIPP_MAX_IDS]; /* (prm_star_planner.cpp:113; the eval binary appends unknown_id, utils.h:272) */
+  int32_t compute_reachability; /* map/compute_reachability (map_planexp.cpp:27)                        */
+  int32_t compute_closest_observed; /* map/compute_closest_observed (map_planexp.cpp:28)                */
+} sipp_map_desc;
+
+/* ---- gain evaluators (following_evaluator `type:` strings) ---------------------------------------- */
+#define SIPP_EVAL_RRT_STAR 0          /* "RRTStarEvaluator"            rrt_star_evaluator.cpp:36-96                 */
+#define SIPP_EVAL_GOAL_DISTANCE 1     /* "GoalDistanceEvaluator"       goal_distance_evaluator.cpp:33-66            */
+#define SIPP_EVAL_EXPAND_REACHABLE 2  /* "ExpandReachableAreaEvaluator" expand_reachable_area_evaluator.cpp:33-67   */
+#define SIPP_EVAL_AVERAGE_VIEW_COST 3 /* "AverageViewCostEvaluator"    average_view_cost_evaluator.cpp:31-61        */
+#define SIPP_EVAL_EXPAND_LOW_COST 4   /* "ExpandLowCostAreaEvaluator"  expand_low_cost_area_evaluator.cpp:33-72     */
+#define SIPP_EVAL_NAIVE 5             /* [upstream] "NaiveEvaluator": gain = number of unknown visible voxels       */
+#define SIPP_EVAL_COUNT_ 6
+
+/*
+ * Evaluator + sensor-model parameters; same keys and defaults as the reference's setupFromParamMap
+ * (rrt_star_evaluator.cpp:22-25, goal_distance_evaluator.cpp:22, expand_reachable_area_evaluator.cpp:22,
+ *  expand_low_cost_area_evaluator.cpp:22, camera_model_planexp.cpp:20) plus the [upstream]
+ *  SimulatedSensorEvaluator bounding volume (cfg/experiments/example.yaml:12-18).
+ */
+typedef struct sipp_eval_params {
+  int32_t evaluator;             /* SIPP_EVAL_*                                               */
+  int32_t half_fov;              /* sensor_model/half_fov, default 10, shipped cfg 32          */
+  double non_path_voxel_gain;    /* RRTStarEvaluator, default 0.0                              */
+  int32_t use_distance_discount; /* RRTStarEvaluator, default false                            */
+  int32_t do_binary_check;       /* RRTStarEvaluator, default false                            */
+  double discount_offset;        /* RRTStarEvaluator, default 0.1                              */
+  double max_gain;               /* GoalDistanceEvaluator, default 100.0                       */
+  double discount_factor;        /* ExpandReachableAreaEvaluator, default 0.1                  */
+  int32_t augment_unknown_with_mean; /* ExpandLowCostAreaEvaluator, default false              */
+  int32_t use_bounding_volume;   /* 0: every on-map voxel passes (the shipped cfgs)            */
+  double bv_x_min, bv_x_max, bv_y_min, bv_y_max; /* inclusive, z is always inside (voxel z = 0)*/
+} sipp_eval_params;
+
+/* counts[] layout written per candidate by sipp_gain_batch (SIPP_COUNTS_PER_CANDIDATE uint32 each). */
+#define SIPP_COUNTS_PER_CANDIDATE 4
+#define SIPP_CNT_VISIBLE 0  /* voxels emitted by the footprint after the bounding-volume filter (centre counted twice) */
+#define SIPP_CNT_UNKNOWN 1  /* of those, state == UNKNOWN                                                               */
+#define SIPP_CNT_AUX 2      /* RRTStar: unknown & on path mask; ExpandReachable: unknown & 3x3-reachable;               */
+                            /* AverageViewCost: observed FREE voxels; others: 0                                         */
+#define SIPP_CNT_AUX2 3     /* AverageViewCost: sum of map cost over observed FREE voxels (integer labels); else 0      */
+
+typedef struct sipp_ctx sipp_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+int sipp_abi_version(void);
+/* Replaces MapServerPlanExp::MapServerPlanExp + PRMStarPlanner::setup (map_server_planexp.cpp:6-218,
+ * prm_star_planner.cpp:11-36,132-156): allocates all map planes on `device`, builds the geometry tables
+ * of the per-pixel grid graph (no explicit edge lists), clears the map. */
+int sipp_create(const sipp_map_desc* desc, int device, sipp_ctx** out);
+void sipp_destroy(sipp_ctx* ctx);
+/* message of the last failing call on this ctx (or of the last failing sipp_create when ctx == NULL) */
+const char* sipp_last_error(const sipp_ctx* ctx);
+/* the stream every host-pointer entry point of this ctx runs on (cudaStream_t) */
+void* sipp_stream(sipp_ctx* ctx);
+
+/* ---- map store (A9/A10) ---------------------------------------------------------------------------- */
+/* MapServerPlanExp::clearMap (map_server_planexp.cpp:461-487) + planner reset to init_cost. */
+int sipp_map_clear(sipp_ctx* ctx);
+/* top-left cell of a rows x cols patch centred on pose (px,py): map_server_planexp.cpp:222-228,340-342. */
+int sipp_patch_origin(const sipp_ctx* ctx, double px, double py, int32_t rows, int32_t cols,
+                      int32_t* x0, int32_t* y0);
+/* MapServerPlanExp::mapDataCallback cell loop + PRMStarPlanner::update_states + reachability /
+ * closest-observed bookkeeping (map_server_planexp.cpp:238-276, prm_star_planner.cpp:104-119).
+ * labels: rows x cols int32 row-major (MapData.data). Off-map cells are skipped. */
+int sipp_map_update_patch(sipp_ctx* ctx, int32_t x0, int32_t y0, int32_t rows, int32_t cols,
+                          const int32_t* labels);
+/* Whole-map ingest: equivalent to ONE mapDataCallback whose patch is the full W x H label image with
+ * top-left (0,0), restricted to the cells where observed[y*W+x] != 0 (observed == NULL: all cells).
+ * This is how planexp_eval_planner feeds a fully known map (planexp_eval_planner.cpp:263-285). */
+int sipp_map_upload_full(sipp_ctx* ctx, const int32_t* labels, const uint8_t* observed);
+/* PRMStarPlanner::update_unknown_cost (prm_star_planner.cpp:121-130). */
+int sipp_update_unknown_cost(sipp_ctx* ctx, double new_cost);
+/* MapServerPlanExp::getMeanCost / getMaxCost (map_server_planexp.h:91-92). */
+int sipp_map_stats(const sipp_ctx* ctx, double* mean_cost, double* max_cost, int64_t* mean_counter);
+/* Debug / test read-back of the per-cell planes (any pointer may be NULL). state: 0/1/2; cost: last
+ * label; reach: 1 iff MSR_REACHABLE; path: current path mask (0/1). All W*H row-major. */
+int sipp_map_download(sipp_ctx* ctx, uint8_t* state, int32_t* cost, uint8_t* reach, uint8_t* path);
+
+/* ---- follower path cost (A11/A12) ------------------------------------------------------------------ */
+/* PRMStarPlanner::plan + MapServerPlanExp::computeCurrentPathEstimate/computePathMap
+ * (prm_star_planner.cpp:38-70, map_server_planexp.cpp:880-926): start-rooted fp64 cost field on the
+ * implicit per-pixel graph (bit-exact fixed point), cost = d[goal] (-1.0 when unreachable), canonical
+ * predecessor path, rasterised path mask swapped in as the current mask, path generation += 1.
+ * path_xy: optional out, up to path_cap points (x,y metres, start -> goal); *path_len = number of path
+ * nodes (may exceed path_cap; only path_cap are written). status: SIPP_PLAN_*. */
+int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap,
+              int32_t* path_len);
+/* the converged field d[] of the last sipp_plan, W*H doubles row-major, +inf = unreachable */
+int sipp_field_download(sipp_ctx* ctx, double* field);
+/* MapServerPlanExp::getCurrentPathMapId (map_server_planexp.h:103) */
+int sipp_path_mask_generation(const sipp_ctx* ctx);
+/* inject a path mask computed elsewhere (tests; MapPlanExp::updatePathMap map_planexp.cpp:240-242) */
+int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask);
+/* relaxation statistics of the last sipp_plan: [0]=global rounds, [1]=tile activations, [2]=tile sweeps */
+int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]);
+
+/* ---- batched footprint gain (A1-A8) ---------------------------------------------------------------- */
+/* Replaces, for n candidates at once, SimulatedSensorEvaluator::computeGain -> getVisibleVoxelsFromTrajectory
+ * -> MapPlanExp::getVoxelArea -> <Evaluator>::computeGainFromVisibleVoxels
+ * (sensor_model_planexp.cpp:18-63, camera_model_planexp.cpp:23-28, map_planexp.cpp:81-101,
+ *  trajectory_evaluator/(all five evaluator sources)).
+ * xy:        n x 2 doubles, view position (last trajectory point + mounting translation).
+ * start_xy:  n x 2 doubles, trajectory[0].position_W of each segment; only read by RRTStarEvaluator in
+ *            binary+discount mode (rrt_star_evaluator.cpp:65), may be NULL otherwise.
+ * gain:      n doubles out.           counts: n x SIPP_COUNTS_PER_CANDIDATE uint32 out (may be NULL).
+ * terminal:  n bytes out, 1 where the reference sets gain_terminal (may be NULL). */
+int sipp_gain_batch(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy,
+                    const double* start_xy, double* gain, uint32_t* counts, uint8_t* terminal);
+int sipp_gain_batch_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy,
+                        const double* d_start_xy, double* d_gain, uint32_t* d_counts,
+                        uint8_t* d_terminal, void* stream);
+
+/* ---- value + selection (A14) ----------------------------------------------------------------------- */
+/* [upstream] GlobalNormalizedGain::computeValue + SubsequentBest::selectNextBest on a parent-index tree.
+ * Node 0 is the root (parent[0] = -1, its gain/cost are forced to 0 like OnlinePlanner does);
+ * parent[i] < i for i > 0. parent == NULL means a flat tree (every node a child of the root).
+ * value[i] = max over the subtree of i of (sum gain root..n)/(sum cost root..n) (0 where cost <= 0).
+ * best_child = index of the root child with the largest value, lowest index on ties (the reference
+ * breaks ties with rand()); -1 when the root has no children. */
+int sipp_value_select(sipp_ctx* ctx, int32_t n, const double* gain, const double* cost,
+                      const int32_t* parent, double* value, int32_t* best_child, double* best_value);
+int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const double* d_cost,
+                          const int32_t* d_parent, double* d_value, int32_t* d_best_child,
+                          double* d_best_value, void* stream);
+
+/* ---- fused evaluation cycle ------------------------------------------------------------------------ */
+/* gain for all n candidates (flat tree, candidate i is node i+1 under a virtual root) + value + argmax
+ * in one call; what the batched root-first updateSegment (mav_active_3d_planning.patch:56) needs.
+ * best_index is a candidate index in [0,n) or -1. */
+int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy,
+               const double* start_xy, const double* cost, double* gain, uint8_t* terminal,
+               double* value, int32_t* best_index, double* best_value);
+/* Device variant; d_best is a 16-byte record {double value; int64 index} (what the multi-GPU gather moves). */
+int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy,
+                   const double* d_start_xy, const double* d_cost, double* d_gain, uint8_t* d_terminal,
+                   double* d_value, void* d_best, void* stream);
+
+/* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
+int64_t sipp_launch_count(const sipp_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIPP_H_ */
