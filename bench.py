@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the scouting-ipp evaluation hot path on B200 (libsipp.so) — see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
+
+One "step" = one pass of the per-cycle evaluation over one candidate batch: footprint gain for every candidate
+(k_gain, TMA-tiled window scan) + value = gain/cost + argmax (k_select); with N > 1 the candidate set is sharded
+(weak scaling: 65536 candidates per GPU, map replicated) and each step ends with the NCCL gather of the
+16-byte best records. Metric: candidate-view evals/s on the 4096^2 map (BASELINE.json). The follower
+cost-to-go / path / mask step runs once per planning cycle; it is timed separately and reported under "cycle".
+
+--impl reference times the reference's own CPU algorithm (the oracle port of the C++ evaluators, faithful
+variant incl. the quadratic erase loop) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scouting-ipp_b200"))
+
+import numpy as np
+
+W = H = 4096
+SEED = 1003
+K_OBS = 1500
+T_PER_GPU = 65536
+HALF_FOV = 32
+NPG = 0.001
+ALG_BYTES_PER_EVAL = 4257   # (2*32+1)^2 one-byte cell records + 16 B pose in + 16 B result out
+WORKLOAD = ("planning-cycle evaluation: %d candidate views per GPU (half_fov %d = 4226 voxels each), RRTStarEvaluator count mode "
+            "(non_path_voxel_gain %g) + GlobalNormalizedGain value + argmax, %dx%d synthetic map (create_artificial_maps.py style, "
+            "seed %d, %d observed footprints, unknown_init_cost max)" % (T_PER_GPU, HALF_FOV, NPG, W, H, SEED, K_OBS))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def build_inputs(n_gpus):
+    from sipp import synth
+    lab = synth.make_labels(W, H, SEED)
+    obs = synth.make_observed(W, H, SEED, K_OBS)
+    xy, cost = synth.make_candidates(W, H, SEED, T_PER_GPU * n_gpus)
+    ids = sorted(set(np.unique(lab).tolist()) - {0})
+    return lab, obs, xy, cost, ids
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU evaluators (oracle port, faithful variant) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    lab, obs, xy, cost, ids = build_inputs(1)
+    desc = orc.make_desc(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), min(ids), max(ids), max(ids))
+    o = orc.Oracle(desc)
+    o.map_upload_full(lab, obs)
+    t0 = time.perf_counter()
+    o.plan()
+    plan_s = time.perf_counter() - t0
+    p = orc.make_params(orc.EVAL_RRT_STAR, half_fov=HALF_FOV, non_path_voxel_gain=NPG)
+    cores = os.cpu_count() or 1
+    # bounded sample per step, sized from a probe so the whole run stays within a couple of minutes
+    probe = 64 * cores
+    t0 = time.perf_counter()
+    o.cycle(p, xy[:probe], cost[:probe], variant=0, threads=cores)
+    rate = probe / (time.perf_counter() - t0)
+    budget_s = 60.0 / max(1, args.steps + args.warmup)
+    sample = int(min(T_PER_GPU, max(probe, rate * budget_s)))
+    for _ in range(args.warmup):
+        o.cycle(p, xy[:sample], cost[:sample], variant=0, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.cycle(p, xy[:sample], cost[:sample], variant=0, threads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "candidate-view evals/sec on 4096^2 cost map", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 counts + f64 gain", "data": "synthetic",
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": "%d of the %d candidates per step, faithful evaluator (voxel vector + quadratic erase loop), %d std::threads; "
+                                   "the reference itself is single-threaded and cannot be built here (ROS/Eigen/Boost/OMPL)" % (sample, T_PER_GPU, cores),
+                         "plan_s": plan_s},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import sipp
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d): launch with torchrun --nproc-per-node %d" % (world, args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lab, obs, xy_all, cost_all, ids = build_inputs(world)
+    desc = sipp.make_desc(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), min(ids), max(ids), max(ids))
+    ctx = sipp.Context(desc, device=local_rank)
+    ctx.map_upload_full(lab, obs)
+    # ---- follower cost-to-go + path + mask: once per planning cycle (replicated per GPU: the wavefront does not shard)
+    ctx.plan()
+    plan_ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        pcost, pstatus, _, plen = ctx.plan()
+        plan_ms.append((time.perf_counter() - t0) * 1e3)
+    pstats = ctx.plan_stats()
+
+    T = T_PER_GPU
+    lo = rank * T
+    xy = np.ascontiguousarray(xy_all[lo:lo + T])
+    cost = np.ascontiguousarray(cost_all[lo:lo + T])
+    params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=HALF_FOV, non_path_voxel_gain=NPG)
+    d_xy = torch.from_numpy(xy).to(dev)
+    d_cost = torch.from_numpy(cost).to(dev)
+    d_gain = torch.empty(T, dtype=torch.float64, device=dev)
+    d_value = torch.empty(T, dtype=torch.float64, device=dev)
+    d_term = torch.empty(T, dtype=torch.uint8, device=dev)
+    d_counts = torch.empty((T, 4), dtype=torch.int32, device=dev)
+    d_best = torch.zeros(2, dtype=torch.int64, device=dev)          # {f64 value bits, i64 index}
+    d_all = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.Stream(device=dev)
+    sh = stream.cuda_stream
+
+    def step():
+        ctx.cycle_dev(params, T, d_xy.data_ptr(), None, d_cost.data_ptr(), d_gain.data_ptr(), d_term.data_ptr(), d_value.data_ptr(),
+                      d_best.data_ptr(), sh)
+        if world > 1:
+            # the only cross-GPU traffic: gather every shard's 16-byte (value, index) record, then argmax on every rank
+            d_best[1] += lo
+            dist.all_gather_into_tensor(d_all, d_best)
+            vals = d_all.view(world, 2)[:, 0].view(torch.float64)
+            j = torch.argmax(vals)          # first maximum = lowest rank = lowest global index
+            return d_all.view(world, 2)[j]
+        return d_best
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.fill_(1)
+            best = step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = ctx.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        wall0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)          # L2 flush between timed iterations (untimed)
+            ev[k][0].record(stream)
+            best = step()
+            ev[k][1].record(stream)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.result()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * T * args.steps / (total_ms * 1e-3)
+    best_host = best.cpu().numpy()
+    best_value = float(best_host[:1].view(np.float64)[0])
+    best_index = int(best_host[1])
+
+    # ---- roofline of the dominant kernel (k_gain alone, CUDA events on its stream, L2 flushed before each launch)
+    peak, peak_src = measured_peaks()
+    gain_ms = []
+    with torch.cuda.stream(stream):
+        for k in range(max(5, args.steps // 2)):
+            flush.fill_(k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.gain_batch_dev(params, T, d_xy.data_ptr(), None, d_gain.data_ptr(), d_counts.data_ptr(), d_term.data_ptr(), sh)
+            e1.record(stream)
+            stream.synchronize()
+            gain_ms.append(e0.elapsed_time(e1))
+    g_ms = float(np.mean(gain_ms))
+    achieved = ALG_BYTES_PER_EVAL * T / (g_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gain_traffic.json")     # written from the committed ncu capture (bytes per launch)
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_gain<MODE_COUNT>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": g_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * T,
+                "note": "the 16 MiB record plane is L2-resident by nature (126 MB L2): frac > 1 of the HBM copy peak is expected; see traffic"}
+
+    # ---- end to end through the host-pointer C ABI (sipp_cycle): pinned host buffers, H2D + D2H inside the timed region
+    h_xy = torch.from_numpy(xy).pin_memory()
+    h_cost = torch.from_numpy(cost).pin_memory()
+    h_gain = torch.empty(T, dtype=torch.float64).pin_memory()
+    h_value = torch.empty(T, dtype=torch.float64).pin_memory()
+    h_term = torch.empty(T, dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        ctx.cycle_host_ptr(params, T, h_xy.data_ptr(), None, h_cost.data_ptr(), h_gain.data_ptr(), h_term.data_ptr(), h_value.data_ptr())
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bi, bv = ctx.cycle_host_ptr(params, T, h_xy.data_ptr(), None, h_cost.data_ptr(), h_gain.data_ptr(), h_term.data_ptr(), h_value.data_ptr())
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e = {"value": world * T * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": T * 24, "d2h_bytes_per_step": T * 17 + 16,
+           "ms_per_step": e2e_s / args.steps * 1e3, "api": "sipp_cycle (host pointers, pinned)"}
+    assert bi + lo == best_index or world > 1, (bi, best_index)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline beside it: the oracle port of the reference evaluators on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        odesc = orc.make_desc(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), min(ids), max(ids), max(ids))
+        o = orc.Oracle(odesc)
+        o.map_upload_full(lab, obs)
+        t0 = time.perf_counter()
+        ocost, ostatus, _, olen = o.plan()
+        oplan_s = time.perf_counter() - t0
+        po = orc.make_params(orc.EVAL_RRT_STAR, half_fov=HALF_FOV, non_path_voxel_gain=NPG)
+        n1 = 256
+        t0 = time.perf_counter()
+        og, ot, ov, oi, obv = o.cycle(po, xy[:n1], cost[:n1], variant=0, threads=1)
+        r1 = n1 / (time.perf_counter() - t0)
+        ns = int(min(T, max(n1, r1 * 12.0)))
+        t0 = time.perf_counter()
+        og, ot, ov, oi, obv = o.cycle(po, xy[:ns], cost[:ns], variant=0, threads=1)
+        b1 = ns / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        o.cycle(po, xy[:ns], cost[:ns], variant=1, threads=1)
+        b2 = ns / (time.perf_counter() - t0)
+        cores = os.cpu_count() or 1
+        nb3 = min(T, ns * cores)
+        t0 = time.perf_counter()
+        o.cycle(po, xy[:nb3], cost[:nb3], variant=1, threads=cores)
+        b3 = nb3 / (time.perf_counter() - t0)
+        # parity spot-check of the timed GPU result against the oracle on the sample (the full check lives in tests/)
+        hg = h_gain.numpy()[:ns]
+        parity = bool(np.allclose(hg, og, rtol=1e-5, atol=0) and (pcost == ocost) and (plen == olen))
+        cpu = {"value": b1, "unit": "evals/s", "cores": 1, "kind": "port",
+               "sample": "first %d of the %d candidates, 1 thread, faithful port of the reference evaluator path (voxel vector + quadratic erase loop)" % (ns, T),
+               "linear_filter_1core": b2, "linear_filter_all_cores": b3, "host_cores": cores,
+               "plan_s": oplan_s, "parity_on_sample": parity}
+
+    line = {
+        "metric": "candidate-view evals/sec on 4096^2 cost map", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 counts + f64 gain", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "candidates_per_gpu": T, "map": "%dx%d" % (W, H), "half_fov": HALF_FOV,
+                   "l2": "flushed between timed steps (256 MiB write, untimed); the 16 MiB record plane is smaller than L2",
+                   "sharding": "candidates sharded, map replicated, NCCL all_gather of one 16-byte record per rank per step" if world > 1 else "single GPU"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "cycle": {"plan_ms": float(np.median(plan_ms)), "plan_cost": pcost, "plan_path_nodes": plen, "plan_stats": pstats,
+                  "eval_ms": total_ms / args.steps, "ms_per_full_cycle": float(np.median(plan_ms)) + total_ms / args.steps,
+                  "note": "plan = fp64 cost-to-go field + canonical path + mask through sipp_plan (host call, wall clock)"},
+        "selected": {"index": best_index, "value": best_value}, "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

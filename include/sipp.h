@@ -191,7 +191,8 @@ int sipp_gain_batch_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n
  * parent[i] < i for i > 0. parent == NULL means a flat tree (every node a child of the root).
  * value[i] = max over the subtree of i of (sum gain root..n)/(sum cost root..n) (0 where cost <= 0).
  * best_child = index of the root child with the largest value, lowest index on ties (the reference
- * breaks ties with rand()); -1 when the root has no children. */
+ * breaks ties with rand()); -1 when the root has no children. Trees deeper than 512 levels are rejected
+ * (SIPP_ERR_UNSUPPORTED; the _dev variant reports it in band as best_child == -2). */
 int sipp_value_select(sipp_ctx* ctx, int32_t n, const double* gain, const double* cost,
                       const int32_t* parent, double* value, int32_t* best_child, double* best_value);
 int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const double* d_cost,

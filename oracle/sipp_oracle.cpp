@@ -751,7 +751,9 @@ int orc_plan(orc_ctx* c, double* cost, int32_t* status, double* path_xy, int32_t
   std::vector<double> pxy;
   const int gx = o.goal_node[0], gy = o.goal_node[1];
   const bool goal_ok = gx >= 0 && gx < o.W && gy >= 0 && gy < o.H && std::isfinite(o.field[(size_t)gy * o.W + gx]);
-  if (goal_ok && planner_backtrack(o)) {
+  const bool walked = goal_ok && planner_backtrack(o);
+  if (goal_ok && !walked) st = SIPP_PLAN_INVALID;   // reachable goal, non-terminating predecessor walk (zero-weight plateau): catch-all of :66-68
+  if (walked) {
     cst = o.field[(size_t)gy * o.W + gx];                             // :63
     bool all_explored = true;                                         // check_termination :183-186
     for (int id : o.last_path) {

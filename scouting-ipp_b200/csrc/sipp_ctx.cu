@@ -1,0 +1,679 @@
+// C ABI of libsipp.so (include/sipp.h): context, host-side sequential bookkeeping, staging and launches.
+// There is no CPU compute path in here: every result comes from the kernels in sipp_{map,gain,field,select}.cu.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "sipp_internal.h"
+
+static thread_local std::string g_create_err;
+
+int sipp_set_err(sipp_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  else g_create_err = buf;
+  return code;
+}
+
+int sipp_debug_sync(sipp_ctx* ctx, cudaStream_t s, const char* what) {
+  static const bool on = getenv("SIPP_DEBUG_SYNC") != nullptr;
+  if (!on) return SIPP_OK;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "[debug sync] %s: %s", what, cudaGetErrorString(e));
+  return SIPP_OK;
+}
+
+namespace {
+
+inline bool in_ids(const int32_t* ids, int n, int v) {
+  for (int i = 0; i < n; ++i)
+    if (ids[i] == v) return true;
+  return false;
+}
+
+template <class T>
+int dev_alloc(sipp_ctx* ctx, T** p, size_t count) {
+  SIPP_CUDA_CHECK(ctx, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return SIPP_OK;
+}
+
+// Index math of MapPlanExp / MapServerPlanExp must be exact for the cell-record planes to be addressable by the
+// voxel index: (int)((k*vs)/mpp) == k, (int)((k*vs)*(1/vs)) == k and likewise for the centre voxel (k+0.5)*vs
+// (map_planexp.cpp:134-144, map_server_planexp.cpp:759,766). True whenever width/W is a power of two (every shipped
+// map: 0.0625); otherwise the reference itself reads neighbouring cells and we refuse instead of diverging silently.
+bool index_math_exact(int W, int H, double width, double height, double vs, double mpp) {
+  const double inv = 1 / vs;
+  const int n = W > H ? W : H;
+  for (int k = 0; k < n; ++k) {
+    const double v = (double)k * vs, c = ((double)k + 0.5) * vs;
+    if ((int)(v / mpp) != k || (int)(v * inv) != k || (int)(c / mpp) != k || (int)(c * inv) != k) return false;
+    if (k < W && !(width > v && width > c)) return false;
+    if (k < H && !(height > v && height > c)) return false;
+  }
+  return true;
+}
+
+// Geometry of the implicit per-pixel graph — PRMStarPlanner::set_derived_params / build_graph
+// (prm_star_planner.cpp:16-36,132-156; node_id2pose / closest_xy prm_star_planner.h:80-81).
+int build_geometry(sipp_ctx* ctx) {
+  const int W = ctx->W, H = ctx->H;
+  const double width = ctx->desc.width, height = ctx->desc.height;
+  ctx->spacing = width / (W + 1);
+  ctx->max_dist = ctx->spacing * std::sqrt(2.0);
+  ctx->off_x = (width - (W + 1) * ctx->spacing) / 2.0;
+  ctx->off_y = (height - (H + 1) * ctx->spacing) / 2.0;
+  ctx->X.resize(W);
+  ctx->Y.resize(H);
+  for (int i = 0; i < W; ++i) ctx->X[i] = ctx->off_x + ctx->spacing * i;
+  for (int j = 0; j < H; ++j) ctx->Y[j] = ctx->off_y + ctx->spacing * j;
+  ctx->start_node[0] = (int)std::round((ctx->desc.start_x - ctx->off_x) / ctx->spacing);
+  ctx->start_node[1] = (int)std::round((ctx->desc.start_y - ctx->off_y) / ctx->spacing);
+  ctx->goal_node[0] = (int)std::round((ctx->desc.goal_x - ctx->off_x) / ctx->spacing);
+  ctx->goal_node[1] = (int)std::round((ctx->desc.goal_y - ctx->off_y) / ctx->spacing);
+
+  // edge-length classes: distinct values of dX*dX (dX = X[i] - X[i+1]) and dY*dY
+  std::vector<uint8_t> xcls(W > 1 ? W - 1 : 1, 0), ycls(H > 1 ? H - 1 : 1, 0);
+  std::vector<double> xs, ys;
+  auto classify = [](const std::vector<double>& P, std::vector<uint8_t>& cls, std::vector<double>& sq) -> bool {
+    std::map<double, int> ids;
+    for (size_t i = 0; i + 1 < P.size(); ++i) {
+      const double d = P[i] - P[i + 1];
+      const double s = d * d;
+      auto it = ids.find(s);
+      if (it == ids.end()) {
+        if (ids.size() >= SIPP_MAX_CLASSES) return false;
+        it = ids.emplace(s, (int)ids.size()).first;
+        sq.push_back(s);
+      }
+      cls[i] = (uint8_t)it->second;
+    }
+    if (sq.empty()) sq.push_back(0.0);
+    return true;
+  };
+  if (!classify(ctx->X, xcls, xs) || !classify(ctx->Y, ycls, ys))
+    return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "more than %d distinct lattice edge lengths per axis", SIPP_MAX_CLASSES);
+  ctx->Kx = (int)xs.size();
+  ctx->Ky = (int)ys.size();
+  const double inf = INFINITY;
+  std::vector<double> hd(ctx->Kx), vd(ctx->Ky), dd((size_t)ctx->Kx * ctx->Ky);
+  // (pose_a - pose_b).norm() = sqrt(dX*dX + dY*dY); an axial edge has dY (or dX) == 0.0 exactly
+  for (int a = 0; a < ctx->Kx; ++a) { const double d = std::sqrt(xs[a] + 0.0 * 0.0); hd[a] = d < ctx->max_dist ? d : inf; }
+  for (int b = 0; b < ctx->Ky; ++b) { const double d = std::sqrt(0.0 * 0.0 + ys[b]); vd[b] = d < ctx->max_dist ? d : inf; }
+  for (int a = 0; a < ctx->Kx; ++a)
+    for (int b = 0; b < ctx->Ky; ++b) {
+      const double d = std::sqrt(xs[a] + ys[b]);
+      dd[(size_t)a * ctx->Ky + b] = d < ctx->max_dist ? d : inf;   // prm_star_planner.cpp:138
+    }
+  if (dev_alloc(ctx, &ctx->d_xcls, xcls.size()) || dev_alloc(ctx, &ctx->d_ycls, ycls.size()) || dev_alloc(ctx, &ctx->d_hdist, hd.size()) ||
+      dev_alloc(ctx, &ctx->d_vdist, vd.size()) || dev_alloc(ctx, &ctx->d_ddist, dd.size()))
+    return SIPP_ERR_CUDA;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpy(ctx->d_xcls, xcls.data(), xcls.size(), cudaMemcpyHostToDevice));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpy(ctx->d_ycls, ycls.data(), ycls.size(), cudaMemcpyHostToDevice));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpy(ctx->d_hdist, hd.data(), hd.size() * 8, cudaMemcpyHostToDevice));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpy(ctx->d_vdist, vd.data(), vd.size() * 8, cudaMemcpyHostToDevice));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpy(ctx->d_ddist, dd.data(), dd.size() * 8, cudaMemcpyHostToDevice));
+  return SIPP_OK;
+}
+
+int host_clear(sipp_ctx* ctx) {
+  ctx->h_state.assign((size_t)ctx->W * ctx->H, SIPP_STATE_UNKNOWN);
+  ctx->mean_cost = 0;
+  ctx->mean_counter = 0;
+  ctx->init_cost = ctx->desc.unknown_init_cost;
+  ctx->path_valid = false;
+  ctx->field_valid = false;
+  ctx->views_dirty = true;
+  SIPP_CUDA_CHECK(ctx, launch_clear_planes(ctx, ctx->stream));
+  return SIPP_OK;
+}
+
+// grows a device buffer (contents are not preserved)
+int ensure_dev(sipp_ctx* ctx, void** p, size_t* cur, size_t need) {
+  if (*cur >= need) return SIPP_OK;
+  if (*p) { cudaStreamSynchronize(ctx->stream); cudaFree(*p); *p = nullptr; *cur = 0; }
+  size_t cap = need + need / 4 + 4096;
+  SIPP_CUDA_CHECK(ctx, cudaMalloc(p, cap));
+  *cur = cap;
+  return SIPP_OK;
+}
+
+struct Stage {   // carve-up of ctx->d_stage for a batch of n candidates
+  double *xy, *start_xy, *cost, *gain, *value;
+  uint32_t* counts;
+  int32_t* parent;
+  uint8_t* terminal;
+};
+size_t stage_bytes(size_t n) { return n * (16 + 16 + 8 + 8 + 8 + 16 + 4 + 1) + 1024; }
+Stage carve(void* base, size_t n) {
+  Stage s;
+  char* p = reinterpret_cast<char*>(base);
+  s.xy = reinterpret_cast<double*>(p); p += 16 * n;
+  s.start_xy = reinterpret_cast<double*>(p); p += 16 * n;
+  s.counts = reinterpret_cast<uint32_t*>(p); p += 16 * n;   // written with 128-bit stores: keep it 16-byte aligned
+  s.cost = reinterpret_cast<double*>(p); p += 8 * n;
+  s.gain = reinterpret_cast<double*>(p); p += 8 * n;
+  s.value = reinterpret_cast<double*>(p); p += 8 * n;
+  s.parent = reinterpret_cast<int32_t*>(p); p += 4 * n;
+  s.terminal = reinterpret_cast<uint8_t*>(p);
+  return s;
+}
+
+// bounding volume -> inclusive index range of the corner voxels k*vs that lie inside [lo, hi]
+void bv_range(int n, double vs, double lo, double hi, int* klo, int* khi) {
+  int a = n, b = -1;
+  for (int k = 0; k < n; ++k) {
+    const double v = (double)k * vs;
+    if (v >= lo && v <= hi) { if (k < a) a = k; if (k > b) b = k; }
+  }
+  *klo = a;
+  *khi = b;
+}
+
+GainGeom make_gain_geom(const sipp_ctx* ctx, const sipp_eval_params* p) {
+  GainGeom g;
+  g.W = ctx->W; g.H = ctx->H;
+  g.vs = ctx->vs;
+  g.inv_vs = 1 / ctx->vs;
+  g.map_width = ctx->desc.width; g.map_height = ctx->desc.height;
+  g.goal_x = ctx->desc.goal_x; g.goal_y = ctx->desc.goal_y;
+  g.mean_cost = ctx->mean_cost;
+  g.bv_kx_lo = 0; g.bv_kx_hi = ctx->W - 1; g.bv_ky_lo = 0; g.bv_ky_hi = ctx->H - 1;
+  if (p->use_bounding_volume) {
+    bv_range(ctx->W, ctx->vs, p->bv_x_min, p->bv_x_max, &g.bv_kx_lo, &g.bv_kx_hi);
+    bv_range(ctx->H, ctx->vs, p->bv_y_min, p->bv_y_max, &g.bv_ky_lo, &g.bv_ky_hi);
+  }
+  return g;
+}
+
+bool same_bv(const sipp_eval_params& a, const sipp_eval_params& b) {
+  if (a.use_bounding_volume != b.use_bounding_volume) return false;
+  if (!a.use_bounding_volume) return true;
+  return a.bv_x_min == b.bv_x_min && a.bv_x_max == b.bv_x_max && a.bv_y_min == b.bv_y_min && a.bv_y_max == b.bv_y_max;
+}
+
+// (re)build the evaluator view planes when the map, the path mask or the bounding volume changed
+int ensure_views(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, cudaStream_t s) {
+  if (!ctx->views_dirty && ctx->view_params_valid && same_bv(ctx->view_params, *p)) return SIPP_OK;
+  SIPP_CUDA_CHECK(ctx, launch_build_views(ctx, g, p->use_bounding_volume != 0, s));
+  if (int rc = sipp_debug_sync(ctx, s, "k_build_views")) return rc;
+  ctx->views_dirty = false;
+  ctx->view_params = *p;
+  ctx->view_params_valid = true;
+  return SIPP_OK;
+}
+
+int check_params(sipp_ctx* ctx, const sipp_eval_params* p) {
+  if (!p) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "params == NULL");
+  if (p->evaluator < 0 || p->evaluator >= SIPP_EVAL_COUNT_) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "unknown evaluator %d", p->evaluator);
+  const bool needs_path = p->evaluator == SIPP_EVAL_RRT_STAR;
+  if (needs_path && !ctx->path_valid)
+    return sipp_set_err(ctx, SIPP_ERR_NO_PATH_MASK, "RRTStarEvaluator needs a path mask: call sipp_plan or sipp_set_path_mask first");
+  return SIPP_OK;
+}
+
+// the sequential part of MapServerPlanExp::mapDataCallback (map_server_planexp.cpp:238-260,276): running mean with its
+// integer division, max cost, state mirror, goal-explored switch. Per-cell planes are updated by k_ingest_patch.
+int host_ingest(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* labels, const uint8_t* observed) {
+  const int W = ctx->W, H = ctx->H;
+  for (size_t i = 0; i < (size_t)rows * cols; ++i)
+    if ((!observed || observed[i]) && (labels[i] < 0 || labels[i] > 65533))
+      return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "label %d outside [0,65533]", labels[i]);
+  const size_t gc = (size_t)ctx->goal_loc[1] * W + ctx->goal_loc[0];
+  const bool goal_inside = ctx->goal_loc[0] >= 0 && ctx->goal_loc[0] < W && ctx->goal_loc[1] >= 0 && ctx->goal_loc[1] < H;
+  const bool pre_goal = goal_inside && ctx->h_state[gc] != SIPP_STATE_UNKNOWN;
+  for (int i = 0; i < rows; ++i) {
+    const int y = y0 + i;
+    if (y < 0 || y >= H) continue;
+    for (int j = 0; j < cols; ++j) {
+      const int x = x0 + j;
+      if (x < 0 || x >= W) continue;
+      if (observed && !observed[(size_t)i * cols + j]) continue;
+      const size_t c = (size_t)y * W + x;
+      const int data_point = labels[(size_t)i * cols + j];
+      if (ctx->h_state[c] == SIPP_STATE_UNKNOWN) {   // :246-248, int / int on the second term
+        ctx->mean_cost = ctx->mean_cost * ((double)ctx->mean_counter / (ctx->mean_counter + 1)) + data_point / (ctx->mean_counter + 1);
+        ++ctx->mean_counter;
+      } else if (ctx->h_state[c] == SIPP_STATE_FREE) {   // :249-251: cost was just overwritten, so this adds 0.0 / n
+        ctx->mean_cost = ctx->mean_cost + (data_point - (double)data_point) / ctx->mean_counter;
+      }
+      ctx->h_state[c] = in_ids(ctx->desc.obstacle_ids_mav, ctx->desc.n_obstacle_ids_mav, data_point) ? SIPP_STATE_OCCUPIED : SIPP_STATE_FREE;
+      if (data_point > ctx->max_cost) ctx->max_cost = data_point;
+    }
+  }
+  const bool post_goal = goal_inside && ctx->h_state[gc] != SIPP_STATE_UNKNOWN;
+  if (post_goal && !pre_goal && ctx->init_cost != ctx->desc.min_rov_cost) ctx->init_cost = ctx->desc.min_rov_cost;   // :276 -> update_unknown_cost
+  return SIPP_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int sipp_abi_version(void) { return SIPP_ABI_VERSION; }
+
+const char* sipp_last_error(const sipp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void* sipp_stream(sipp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int64_t sipp_launch_count(const sipp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void sipp_destroy(sipp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_closest_dist,
+                  ctx->d_recip, ctx->d_field, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
+                  ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_path_nodes, ctx->d_path_xy, ctx->d_plan_out, ctx->d_stage, ctx->d_tree_ws,
+                  ctx->d_best, ctx->d_select_ws};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
+  if (!out) return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "out == NULL");
+  *out = nullptr;
+  if (!d) return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "desc == NULL");
+  if (d->W <= 0 || d->H <= 0 || d->W > 32767 || d->H > 32767 || !(d->width > 0) || !(d->height > 0))
+    return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "bad map size %d x %d (%.3f x %.3f m)", d->W, d->H, d->width, d->height);
+  if (d->n_obstacle_ids_mav < 0 || d->n_obstacle_ids_mav > SIPP_MAX_IDS || d->n_obstacle_ids_rov < 0 || d->n_obstacle_ids_rov > SIPP_MAX_IDS)
+    return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "too many obstacle ids (max %d)", SIPP_MAX_IDS);
+  // map cfg validity as the reference checks it (map_server_planexp.cpp:95-107)
+  if (std::abs(1 - ((d->width / d->W) / (d->height / d->H))) >= 0.01)
+    return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "cells are not square (map_server_planexp.cpp:97)");
+  if (!(d->goal_x >= 0 && d->goal_y >= 0 && d->goal_x < d->width && d->goal_y < d->height && d->start_x >= 0 && d->start_y >= 0 &&
+        d->start_x < d->width && d->start_y < d->height))
+    return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "start / goal outside the map (map_server_planexp.cpp:104-105)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return sipp_set_err(nullptr, SIPP_ERR_CUDA, "no CUDA device (%s); libsipp has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return sipp_set_err(nullptr, SIPP_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, ndev);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return sipp_set_err(nullptr, SIPP_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10) return sipp_set_err(nullptr, SIPP_ERR_CUDA, "device %d is sm_%d%d; libsipp is built for sm_100a only", device, prop.major, prop.minor);
+
+  sipp_ctx* ctx = new sipp_ctx();
+  ctx->desc = *d;
+  ctx->device = device;
+  ctx->launches = 0;
+  ctx->W = d->W;
+  ctx->H = d->H;
+  ctx->mpp = d->width / (unsigned int)d->W;   // m_per_pixel_ map_server_planexp.cpp:116
+  ctx->vs = d->width / (unsigned int)d->W;    // c_voxel_size_ map_planexp.cpp:42
+  ctx->goal_loc[0] = (int)(d->goal_x / ctx->mpp);
+  ctx->goal_loc[1] = (int)(d->goal_y / ctx->mpp);
+  ctx->start_loc[0] = (int)(d->start_x / ctx->mpp);
+  ctx->start_loc[1] = (int)(d->start_y / ctx->mpp);
+  ctx->max_cost = 0.0;
+  ctx->path_generation = 0;
+  ctx->view_params_valid = false;
+  memset(ctx->plan_stats, 0, sizeof(ctx->plan_stats));
+  // zero all device pointers (sipp_ctx has non-trivial members, so no memset of the whole struct)
+  ctx->d_state = ctx->d_path = ctx->d_rec = nullptr;
+  ctx->d_label = ctx->d_pcode = ctx->d_freelab = ctx->d_closest = nullptr;
+  ctx->d_closest_dist = nullptr; ctx->d_recip = nullptr; ctx->d_field = nullptr;
+  ctx->d_xcls = ctx->d_ycls = nullptr; ctx->d_hdist = ctx->d_vdist = ctx->d_ddist = nullptr;
+  ctx->d_tile_flags = nullptr; ctx->d_tile_list = nullptr; ctx->d_relax_ctl = nullptr;
+  ctx->d_path_nodes = nullptr; ctx->d_path_xy = nullptr; ctx->d_plan_out = nullptr;
+  ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; ctx->d_stage = nullptr; ctx->d_stage_bytes = 0;
+  ctx->d_tree_ws = nullptr; ctx->d_tree_ws_bytes = 0; ctx->d_best = nullptr; ctx->d_select_ws = nullptr;
+  ctx->stream = nullptr;
+
+  auto fail = [&](int rc) {
+    g_create_err = ctx->err;
+    sipp_destroy(ctx);
+    return rc;
+  };
+  if (!index_math_exact(ctx->W, ctx->H, d->width, d->height, ctx->vs, ctx->mpp)) {
+    sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "voxel size %.17g makes the reference's position->cell index math inexact; use a power-of-two m_per_pixel", ctx->vs);
+    return fail(SIPP_ERR_UNSUPPORTED);
+  }
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
+
+  ctx->pitch = ((size_t)ctx->W + 127) & ~(size_t)127;
+  ctx->pitch16 = ctx->pitch;
+  const size_t n8 = ctx->pitch * ctx->H;
+  ctx->n_tiles_x = (ctx->W + 31) / 32;
+  ctx->n_tiles_y = (ctx->H + 31) / 32;
+  const size_t ntiles = (size_t)ctx->n_tiles_x * ctx->n_tiles_y;
+  size_t cap = (size_t)16 * (ctx->W + ctx->H);
+  if (cap < (1u << 20)) cap = 1u << 20;
+  if (cap > (size_t)ctx->W * ctx->H) cap = (size_t)ctx->W * ctx->H;
+  ctx->path_cap_nodes = (int)cap;
+  int rc = SIPP_OK;
+  rc |= dev_alloc(ctx, &ctx->d_state, n8);
+  rc |= dev_alloc(ctx, &ctx->d_path, n8);
+  rc |= dev_alloc(ctx, &ctx->d_rec, n8);
+  rc |= dev_alloc(ctx, &ctx->d_label, n8);
+  rc |= dev_alloc(ctx, &ctx->d_pcode, n8);
+  rc |= dev_alloc(ctx, &ctx->d_freelab, n8);
+  rc |= dev_alloc(ctx, &ctx->d_field, (size_t)ctx->W * ctx->H);
+  rc |= dev_alloc(ctx, &ctx->d_tile_flags, 2 * ntiles);
+  rc |= dev_alloc(ctx, &ctx->d_tile_list, ntiles);
+  rc |= dev_alloc(ctx, &ctx->d_relax_ctl, 16);
+  rc |= dev_alloc(ctx, &ctx->d_path_nodes, cap);
+  rc |= dev_alloc(ctx, &ctx->d_path_xy, 2 * cap);
+  rc |= dev_alloc(ctx, &ctx->d_plan_out, 16);
+  rc |= dev_alloc(ctx, &ctx->d_best, 4);
+  if (rc == SIPP_OK) {
+    e = cudaMalloc(&ctx->d_select_ws, select_workspace_bytes());
+    if (e != cudaSuccess) rc = sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    else cudaMemset(ctx->d_select_ws, 0, select_workspace_bytes());
+  }
+  if (rc != SIPP_OK) return fail(SIPP_ERR_CUDA);
+  if ((rc = build_geometry(ctx)) != SIPP_OK) return fail(rc);
+  if ((rc = host_clear(ctx)) != SIPP_OK) return fail(rc);
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "init sync: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
+  *out = ctx;
+  return SIPP_OK;
+}
+
+#define SIPP_ENTER(ctx)                                               \
+  if (!(ctx)) return SIPP_ERR_INVALID_ARG;                            \
+  std::lock_guard<std::mutex> lock__((ctx)->mu);                      \
+  {                                                                   \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);                   \
+    if (e__ != cudaSuccess) return sipp_set_err((ctx), SIPP_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e__)); \
+  }
+
+int sipp_map_clear(sipp_ctx* ctx) {
+  SIPP_ENTER(ctx);
+  // max_cost_ survives clearMap() in the reference (map_server_planexp.cpp:461-487 never touches it)
+  ctx->path_generation = 0;
+  int rc = host_clear(ctx);
+  if (rc != SIPP_OK) return rc;
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return SIPP_OK;
+}
+
+int sipp_patch_origin(const sipp_ctx* ctx, double px, double py, int32_t rows, int32_t cols, int32_t* x0, int32_t* y0) {
+  if (!ctx || !x0 || !y0) return SIPP_ERR_INVALID_ARG;
+  const int ix = (int)(px * (long)ctx->W / ctx->desc.width);     // position2pixelLocation map_server_planexp.cpp:340-342
+  const int iy = (int)(py * (long)ctx->H / ctx->desc.height);
+  *x0 = ix - (int)(cols / 2);                                     // :227-228
+  *y0 = iy - (int)(rows / 2);
+  return SIPP_OK;
+}
+
+static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* labels, const uint8_t* observed) {
+  if (!labels || rows <= 0 || cols <= 0) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad patch %d x %d", rows, cols);
+  int rc = host_ingest(ctx, x0, y0, rows, cols, labels, observed);
+  if (rc != SIPP_OK) return rc;
+  const size_t n = (size_t)rows * cols;
+  const size_t need = n * 4 + (observed ? n : 0) + 256;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
+  int32_t* d_lab = reinterpret_cast<int32_t*>(ctx->d_stage);
+  uint8_t* d_obs = observed ? reinterpret_cast<uint8_t*>(ctx->d_stage) + n * 4 : nullptr;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lab, labels, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (observed) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_obs, observed, n, cudaMemcpyHostToDevice, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, launch_ingest_patch(ctx, x0, y0, rows, cols, d_lab, d_obs, ctx->stream));
+  ctx->views_dirty = true;
+  ctx->field_valid = false;
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return SIPP_OK;
+}
+
+int sipp_map_update_patch(sipp_ctx* ctx, int32_t x0, int32_t y0, int32_t rows, int32_t cols, const int32_t* labels) {
+  SIPP_ENTER(ctx);
+  return ingest_common(ctx, x0, y0, rows, cols, labels, nullptr);
+}
+
+int sipp_map_upload_full(sipp_ctx* ctx, const int32_t* labels, const uint8_t* observed) {
+  SIPP_ENTER(ctx);
+  return ingest_common(ctx, 0, 0, ctx->H, ctx->W, labels, observed);
+}
+
+int sipp_update_unknown_cost(sipp_ctx* ctx, double new_cost) {
+  SIPP_ENTER(ctx);
+  ctx->init_cost = new_cost;   // unexplored cells carry PCODE_UNEXPLORED; their cost is resolved at plan time
+  ctx->field_valid = false;
+  return SIPP_OK;
+}
+
+int sipp_map_stats(const sipp_ctx* ctx, double* mean_cost, double* max_cost, int64_t* mean_counter) {
+  if (!ctx) return SIPP_ERR_INVALID_ARG;
+  if (mean_cost) *mean_cost = ctx->mean_cost;
+  if (max_cost) *max_cost = ctx->max_cost;
+  if (mean_counter) *mean_counter = ctx->mean_counter;
+  return SIPP_OK;
+}
+
+int sipp_map_download(sipp_ctx* ctx, uint8_t* state, int32_t* cost, uint8_t* reach, uint8_t* path) {
+  SIPP_ENTER(ctx);
+  const size_t n = (size_t)ctx->W * ctx->H;
+  int rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, n * 7 + 256);
+  if (rc != SIPP_OK) return rc;
+  char* base = reinterpret_cast<char*>(ctx->d_stage);
+  int32_t* d_cost = reinterpret_cast<int32_t*>(base);
+  uint8_t* d_state = reinterpret_cast<uint8_t*>(base + 4 * n);
+  uint8_t* d_reach = d_state + n;
+  uint8_t* d_path = d_reach + n;
+  SIPP_CUDA_CHECK(ctx, launch_download_planes(ctx, d_state, d_cost, d_reach, d_path, ctx->stream));
+  if (state) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(state, d_state, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cost) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(cost, d_cost, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (reach) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(reach, d_reach, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (path) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(path, d_path, n, cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return SIPP_OK;
+}
+
+int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask) {
+  SIPP_ENTER(ctx);
+  if (!mask) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "mask == NULL");
+  SIPP_CUDA_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_path, ctx->pitch, mask, ctx->W, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->path_valid = true;
+  ctx->views_dirty = true;
+  return SIPP_OK;
+}
+
+int sipp_path_mask_generation(const sipp_ctx* ctx) { return ctx ? ctx->path_generation : -1; }
+
+int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
+  SIPP_ENTER(ctx);
+  int rc = field_plan(ctx, ctx->stream);
+  if (rc != SIPP_OK) return rc;
+  int out[10];
+  int ctl[8];
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->plan_stats[0] = ctl[2];
+  ctx->plan_stats[1] = ctl[3];
+  ctx->plan_stats[2] = ctl[4];
+  ctx->plan_stats[3] = ctl[5];
+  if (ctl[5]) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation hit its round limit without converging");
+  double c;
+  memcpy(&c, &out[8], sizeof(double));
+  const int len = out[0];
+  const bool found = out[2] != 0;
+  // PRMStarPlanner::plan (prm_star_planner.cpp:38-70): cost -1 / TERMINAL_INVALID when the search exhausts the graph.
+  // A reachable goal whose predecessor walk does not terminate (zero-weight plateaus can make the canonical rule cycle;
+  // never the case with the shipped label sets, all traversable labels >= 30) is reported like the reference's
+  // catch-all: INVALID, cost -1, no path.
+  int st = SIPP_PLAN_TERMINAL_INVALID;
+  if (found) st = out[1] ? SIPP_PLAN_TERMINAL_VALID : SIPP_PLAN_VALID;
+  else if (out[4]) st = SIPP_PLAN_INVALID;
+  if (cost) *cost = found ? c : -1.0;
+  if (status) *status = st;
+  if (path_len) *path_len = found ? len : 0;
+  if (path_xy && found && path_cap > 0) {
+    const int m = len < path_cap ? len : path_cap;
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(path_xy, ctx->d_path_xy, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->path_generation += 1;     // path_counter_ map_server_planexp.cpp:896
+  ctx->path_valid = true;
+  ctx->field_valid = true;
+  ctx->views_dirty = true;
+  return SIPP_OK;
+}
+
+int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]) {
+  if (!ctx || !stats) return SIPP_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) stats[i] = ctx->plan_stats[i];
+  return SIPP_OK;
+}
+
+int sipp_field_download(sipp_ctx* ctx, double* field) {
+  SIPP_ENTER(ctx);
+  if (!field) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "field == NULL");
+  if (!ctx->field_valid) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "no field: call sipp_plan first");
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(field, ctx->d_field, (size_t)ctx->W * ctx->H * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return SIPP_OK;
+}
+
+// ---- gain ----------------------------------------------------------------------------------------------
+int sipp_gain_batch_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy,
+                        double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, void* stream) {
+  SIPP_ENTER(ctx);
+  int rc = check_params(ctx, params);
+  if (rc != SIPP_OK) return rc;
+  if (n < 0 || (n > 0 && (!d_xy || !d_gain))) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad batch arguments");
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  const GainGeom g = make_gain_geom(ctx, params);
+  if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
+  return gain_launch(ctx, params, g, n, d_xy, d_start_xy, nullptr, d_gain, d_counts, d_terminal, nullptr, s);
+}
+
+int sipp_gain_batch(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy, double* gain,
+                    uint32_t* counts, uint8_t* terminal) {
+  SIPP_ENTER(ctx);
+  int rc = check_params(ctx, params);
+  if (rc != SIPP_OK) return rc;
+  if (n < 0 || (n > 0 && (!xy || !gain))) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad batch arguments");
+  if (n == 0) return SIPP_OK;
+  cudaStream_t s = ctx->stream;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, stage_bytes(n))) != SIPP_OK) return rc;
+  const Stage st = carve(ctx->d_stage, n);
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.start_xy, start_xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  const GainGeom g = make_gain_geom(ctx, params);
+  if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
+  if ((rc = gain_launch(ctx, params, g, n, st.xy, start_xy ? st.start_xy : nullptr, nullptr, st.gain, counts ? st.counts : nullptr,
+                        terminal ? st.terminal : nullptr, nullptr, s)) != SIPP_OK)
+    return rc;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain, st.gain, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (counts) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, st.counts, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+  if (terminal) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal, st.terminal, (size_t)n, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  return SIPP_OK;
+}
+
+// ---- value + selection -----------------------------------------------------------------------------------
+int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const double* d_cost, const int32_t* d_parent, double* d_value,
+                          int32_t* d_best_child, double* d_best_value, void* stream) {
+  SIPP_ENTER(ctx);
+  if (n < 1 || !d_gain || !d_cost || !d_value) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad value_select arguments");
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  if (d_parent) {
+    int rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, (size_t)n * 16 + 512);
+    if (rc != SIPP_OK) return rc;
+    SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_gain, d_cost, d_parent, d_value, ctx->d_best, ctx->d_tree_ws, s));
+  } else {
+    SIPP_CUDA_CHECK(ctx, launch_value_flat(ctx, n, d_gain, d_cost, d_value, s));
+    // children are nodes 1..n-1: scan value+1, the kernel shifts the index back by one
+    SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n - 1, d_value + 1, 1, ctx->d_best, d_value, s));
+  }
+  // unpack the 16-byte record into the caller's device scalars
+  if (d_best_value) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_best_value, &ctx->d_best->value, 8, cudaMemcpyDeviceToDevice, s));
+  if (d_best_child) {
+    // index is int64 in the record; the low 32 bits (little endian) are the int32 the caller asked for
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_best_child, &ctx->d_best->index, 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return SIPP_OK;
+}
+
+int sipp_value_select(sipp_ctx* ctx, int32_t n, const double* gain, const double* cost, const int32_t* parent, double* value,
+                      int32_t* best_child, double* best_value) {
+  SIPP_ENTER(ctx);
+  if (n < 1 || !gain || !cost) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad value_select arguments");
+  if (parent)
+    for (int i = 1; i < n; ++i)
+      if (parent[i] < 0 || parent[i] >= i) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "parent[%d] = %d violates 0 <= parent[i] < i", i, parent[i]);
+  cudaStream_t s = ctx->stream;
+  int rc;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, stage_bytes(n))) != SIPP_OK) return rc;
+  const Stage st = carve(ctx->d_stage, n);
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.gain, gain, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.cost, cost, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  if (parent) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.parent, parent, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  if (parent) {
+    if ((rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, (size_t)n * 16 + 512)) != SIPP_OK) return rc;
+    SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, st.gain, st.cost, st.parent, st.value, ctx->d_best, ctx->d_tree_ws, s));
+  } else {
+    SIPP_CUDA_CHECK(ctx, launch_value_flat(ctx, n, st.gain, st.cost, st.value, s));
+    if (n > 1) SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n - 1, st.value + 1, 1, ctx->d_best, st.value, s));
+  }
+  BestRec br;
+  br.value = 0.0;
+  br.index = -1;
+  if (parent || n > 1) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(&br, ctx->d_best, sizeof(br), cudaMemcpyDeviceToHost, s));
+  if (value) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value, st.value, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  if (br.index == -2) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "tree deeper than 512 levels");
+  if (best_child) *best_child = (int32_t)br.index;
+  if (best_value) *best_value = br.value;
+  return SIPP_OK;
+}
+
+// ---- fused cycle -----------------------------------------------------------------------------------------
+int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy, const double* d_cost,
+                   double* d_gain, uint8_t* d_terminal, double* d_value, void* d_best, void* stream) {
+  SIPP_ENTER(ctx);
+  int rc = check_params(ctx, params);
+  if (rc != SIPP_OK) return rc;
+  if (n < 1 || !d_xy || !d_cost || !d_gain || !d_value || !d_best) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  const GainGeom g = make_gain_geom(ctx, params);
+  if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
+  if ((rc = gain_launch(ctx, params, g, n, d_xy, d_start_xy, d_cost, d_gain, nullptr, d_terminal, d_value, s)) != SIPP_OK) return rc;
+  SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, d_value, 0, reinterpret_cast<BestRec*>(d_best), nullptr, s));
+  return SIPP_OK;
+}
+
+int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy, const double* cost,
+               double* gain, uint8_t* terminal, double* value, int32_t* best_index, double* best_value) {
+  SIPP_ENTER(ctx);
+  int rc = check_params(ctx, params);
+  if (rc != SIPP_OK) return rc;
+  if (n < 1 || !xy || !cost) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
+  cudaStream_t s = ctx->stream;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, stage_bytes(n))) != SIPP_OK) return rc;
+  const Stage st = carve(ctx->d_stage, n);
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.start_xy, start_xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.cost, cost, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  const GainGeom g = make_gain_geom(ctx, params);
+  if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
+  if ((rc = gain_launch(ctx, params, g, n, st.xy, start_xy ? st.start_xy : nullptr, st.cost, st.gain, nullptr, st.terminal, st.value, s)) != SIPP_OK)
+    return rc;
+  SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, st.value, 0, ctx->d_best, nullptr, s));
+  BestRec br;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(&br, ctx->d_best, sizeof(br), cudaMemcpyDeviceToHost, s));
+  if (gain) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain, st.gain, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (terminal) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal, st.terminal, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (value) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value, st.value, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  if (best_index) *best_index = (int32_t)br.index;
+  if (best_value) *best_value = br.value;
+  return SIPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,540 @@
+// Batched footprint-gain kernels (hot-path rows A1-A8).
+//
+// One warp per candidate view. The candidate's (2h+1)^2 window of the packed one-byte cell records is brought
+// into shared memory by a single TMA tile load (cp.async.bulk.tensor.2d, zero fill outside the map — exactly
+// the reference's "skip off-map voxels", map_planexp.cpp:97), three tiles in flight per warp; lanes then read
+// the tile with 128-bit shared loads, accumulate per-byte-lane SIMD counters and finish with one warp
+// redux. No tensor cores: nothing here is a contraction.
+//
+// Reference semantics (all five evaluators erase the observed voxels, then reduce over the unknown ones):
+//   footprint    MapPlanExp::getVoxelArea                advanced_planner_modules/src/map/map_planexp.cpp:81-101
+//   RRTStar      computeGainFromVisibleVoxels            src/trajectory_evaluator/rrt_star_evaluator.cpp:36-96
+//   GoalDistance                                         src/trajectory_evaluator/goal_distance_evaluator.cpp:33-66
+//   ExpandReach.                                         src/trajectory_evaluator/expand_reachable_area_evaluator.cpp:33-67
+//   AvgViewCost                                          src/trajectory_evaluator/average_view_cost_evaluator.cpp:31-61
+//   ExpandLowCost                                        src/trajectory_evaluator/expand_low_cost_area_evaluator.cpp:33-72
+// The centre cell is emitted twice by the reference (once with centre coordinates, once with corner
+// coordinates); lane 0 adds the duplicate with the reference's own double-precision index math.
+#include <cstdio>
+#include <cstring>
+
+#include "sipp_internal.h"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kStages = 3;
+
+// evaluator "reduction modes"
+enum { MODE_COUNT = 0, MODE_RRT_DISCOUNT = 1, MODE_GOAL_DISTANCE = 2, MODE_AVG_VIEW_COST = 3, MODE_LOW_COST = 4 };
+
+struct GainArgs {
+  GainGeom g;
+  int evaluator;
+  int half_fov;
+  int box_w;          // bytes per tile row of the rec tile (multiple of 16)
+  int box_w16;        // elements per tile row of the uint16 aux tile (multiple of 8)
+  int slot_bytes;     // bytes per pipeline slot (rec tile [+ aux tile]), multiple of 128
+  int aux_off;        // byte offset of the aux tile inside a slot
+  double npg;         // non_path_voxel_gain
+  int use_discount, do_binary;
+  double discount_offset, max_gain, inv_max_gain, discount_factor;
+  int use_bv;
+  double bv_x_min, bv_x_max, bv_y_min, bv_y_max;
+  int n;
+  const double* xy;
+  const double* start_xy;
+  const double* cost;     // optional: value = gain / cost fused in the epilogue (flat tree)
+  double* gain;
+  uint32_t* counts;
+  uint8_t* terminal;
+  double* value;
+  const double* recip;    // ExpandLowCost lookup
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t bytesum(uint32_t v) { return __dp4a(v, 0x01010101u, 0u); }
+// mask with bytes [lo, hi) of a 4-byte word set, 0 <= lo, hi <= 4 after clamping
+__device__ __forceinline__ uint32_t byte_range_mask(int lo, int hi) {
+  lo = max(lo, 0);
+  hi = min(hi, 4);
+  if (hi <= lo) return 0u;
+  return (0xFFFFFFFFu >> (8 * (4 - hi))) & (0xFFFFFFFFu << (8 * lo));
+}
+// same for the two halfwords of a word, 0 <= lo, hi <= 2
+__device__ __forceinline__ uint32_t half_range_mask(int lo, int hi) {
+  lo = max(lo, 0);
+  hi = min(hi, 2);
+  if (hi <= lo) return 0u;
+  return (0xFFFFFFFFu >> (16 * (2 - hi))) & (0xFFFFFFFFu << (16 * lo));
+}
+
+// ---- per-candidate window geometry (the reference's double-precision index math, restated) -------------
+struct Window {
+  int on_map;        // getVoxelCenter returned true (map_planexp.cpp:78,87)
+  int cx, cy;        // centre cell of the window (center_voxel_loc, :89)
+  double vcx, vcy;   // centre voxel coordinates ((loc + 0.5) * vs, :74-76)
+};
+
+__device__ __forceinline__ int trunc_to_int(double v) {
+  // (int) cast of the reference; out-of-range / NaN inputs are UB there, we map them to a far off-map index
+  if (!(v > -1.0e9 && v < 1.0e9)) return -1000000;
+  return (int)v;
+}
+
+__device__ __forceinline__ Window make_window(const GainGeom& g, double px, double py) {
+  Window w;
+  const int lx = trunc_to_int(px * g.inv_vs), ly = trunc_to_int(py * g.inv_vs);   // position32pixelLocation :136-138
+  const double clx = lx + 0.5, cly = ly + 0.5;                                     // :74
+  w.vcx = clx * g.vs;                                                              // pixelLocation2position :142-144
+  w.vcy = cly * g.vs;
+  w.on_map = (0 <= (int)clx) && (0 <= (int)cly) && (g.W > (int)clx) && (g.H > (int)cly) && lx > -1000000 && ly > -1000000;  // isOnMap2 :222-224
+  w.cx = trunc_to_int(w.vcx * g.inv_vs);                                           // :89
+  w.cy = trunc_to_int(w.vcy * g.inv_vs);
+  return w;
+}
+
+// number of window cells (corner voxels) that are on the map and inside the bounding-volume index range
+__device__ __forceinline__ int clipped_extent(int c, int h, int lo, int hi) {
+  const int a = max(c - h, lo), b = min(c + h, hi);
+  return max(b - a + 1, 0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_aux, const GainArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[kWarpsPerCta * kStages];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t slot_base = smem_u32(smem_raw) + (uint32_t)(warp * kStages) * (uint32_t)a.slot_bytes;
+  const uint32_t bar_base = smem_u32(&bars[warp * kStages]);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8u * s, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int wpc = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpc + warp;
+  const int nw = gridDim.x * wpc;
+  const int my_count = gw < a.n ? (a.n - gw + nw - 1) / nw : 0;
+  const int h = a.half_fov;
+  const int side = 2 * h + 1;
+  constexpr bool kNeedRec = (MODE != MODE_LOW_COST);
+  constexpr bool kNeedAux = (MODE == MODE_AVG_VIEW_COST || MODE == MODE_LOW_COST);
+  const uint32_t tx_bytes = (kNeedRec ? (uint32_t)(a.box_w * side) : 0u) + (kNeedAux ? (uint32_t)(a.box_w16 * 2 * side) : 0u);
+
+  auto issue = [&](int k) {
+    if (lane == 0) {
+      const int cand = gw + k * nw;
+      const Window w = make_window(a.g, a.xy[2 * cand], a.xy[2 * cand + 1]);
+      const int s = k % kStages;
+      const uint32_t bar = bar_base + 8u * s;
+      const uint32_t dst = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
+      mbar_expect_tx(bar, tx_bytes);
+      // TMA needs the box start 16-byte aligned in the contiguous dimension: start at the aligned column at or before
+      // the window's first column; the box is wide enough to still cover the window (see gain_launch)
+      if (kNeedRec) tma_load_2d(dst, &tm_rec, bar, (w.cx - h) & ~15, w.cy - h);
+      if (kNeedAux) tma_load_2d(dst + (uint32_t)a.aux_off, &tm_aux, bar, (w.cx - h) & ~7, w.cy - h);
+    }
+  };
+
+  for (int k = 0; k < kStages - 1 && k < my_count; ++k) issue(k);
+
+  for (int k = 0; k < my_count; ++k) {
+    if (k + kStages - 1 < my_count) {
+      __syncwarp();   // every lane is done reading the slot that is about to be refilled
+      issue(k + kStages - 1);
+    }
+    const int cand = gw + k * nw;
+    const int s = k % kStages;
+    const uint32_t tile = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
+    const double px = a.xy[2 * cand], py = a.xy[2 * cand + 1];
+    const Window w = make_window(a.g, px, py);
+    while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)((k / kStages) & 1))) {
+    }
+
+    // ---- window scan -------------------------------------------------------------------------------
+    uint32_t acc_unk = 0, acc_aux = 0;   // per-byte-lane SIMD counters (<= 255 per lane by construction, see host check)
+    uint32_t sum_aux2 = 0;               // AverageViewCost: sum of labels
+    double fsum = 0.0;                   // floating-point modes
+    if (kNeedRec) {
+      const int ncr = a.box_w >> 4;                  // 16-byte chunks per tile row
+      const int total = ncr * side;
+      const int xal = (w.cx - h) & ~15;              // global column of tile column 0
+      const int r0 = (w.cx - h) - xal;               // the window occupies tile columns [r0, r0 + side)
+      for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / ncr, cc = idx - row * ncr;
+        uint4 v = lds128(tile + (uint32_t)idx * 16u);
+        const int lo = r0 - 16 * cc, hi = r0 + side - 16 * cc;   // valid bytes of this chunk: [lo, hi) clipped to [0,16)
+        if (lo > 0 || hi < 16) {                     // only the first and the last one or two chunks of a row
+          v.x &= byte_range_mask(lo, hi);
+          v.y &= byte_range_mask(lo - 4, hi - 4);
+          v.z &= byte_range_mask(lo - 8, hi - 8);
+          v.w &= byte_range_mask(lo - 12, hi - 12);
+        }
+        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+        if (MODE == MODE_COUNT || MODE == MODE_AVG_VIEW_COST) {
+          const uint32_t auxbit = (MODE == MODE_AVG_VIEW_COST) ? REC_OBS_FREE
+                                  : (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE ? REC_UNK_REACH : REC_UNK_PATH);
+          const uint32_t auxmask = auxbit * 0x01010101u;
+          const int auxshift = __ffs(auxbit) - 1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc_unk += wds[q] & 0x01010101u;
+            acc_aux += (wds[q] & auxmask) >> auxshift;
+          }
+        } else {
+          // floating-point modes: walk the bytes of this chunk
+          const int x0 = xal + cc * 16, y = w.cy - h + row;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t wd = wds[q];
+            acc_unk += wd & 0x01010101u;
+            acc_aux += (wd & 0x02020202u) >> 1;
+            const uint32_t sel = (MODE == MODE_RRT_DISCOUNT) ? (wd & 0x02020202u) : (wd & 0x01010101u);
+            if (sel) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                if (sel & (0xFFu << (8 * b))) {
+                  const double vx = (double)(x0 + q * 4 + b) * a.g.vs, vy = (double)y * a.g.vs;   // corner coordinates
+                  const double dx = a.g.goal_x - vx, dy = a.g.goal_y - vy;
+                  const double dist = sqrt(dx * dx + dy * dy);
+                  if (MODE == MODE_RRT_DISCOUNT) fsum += 1.0 / sqrt(dist + a.discount_offset);   // rrt_star_evaluator.cpp:82
+                  else fsum += (dist > a.inv_max_gain) ? 1.0 / dist : a.max_gain;                // goal_distance_evaluator.cpp:55-60
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (kNeedAux) {
+      const uint32_t atile = tile + (uint32_t)a.aux_off;
+      const int ncr = a.box_w16 >> 3;                // 16-byte chunks (8 cells) per aux tile row
+      const int total = ncr * side;
+      const int r0 = (w.cx - h) - ((w.cx - h) & ~7); // the window occupies tile columns [r0, r0 + side)
+      for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / ncr, cc = idx - row * ncr;
+        (void)row;
+        uint4 v = lds128(atile + (uint32_t)idx * 16u);
+        uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+        const int lo = r0 - 8 * cc, hi = r0 + side - 8 * cc;     // valid cells of this chunk: [lo, hi) clipped to [0,8)
+        if (lo > 0 || hi < 8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) wds[q] &= half_range_mask(lo - 2 * q, hi - 2 * q);
+        }
+        if (MODE == MODE_AVG_VIEW_COST) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sum_aux2 += (wds[q] & 0xFFFFu) + (wds[q] >> 16);
+        } else {  // MODE_LOW_COST: entries are 0 (not unknown / off map) or closest_label + 1
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t lo = wds[q] & 0xFFFFu, hi = wds[q] >> 16;
+            if (lo) { acc_unk += 1; fsum += a.recip[lo]; }
+            if (hi) { acc_unk += 1; fsum += a.recip[hi]; }
+          }
+        }
+      }
+    }
+
+    // ---- warp reduction ------------------------------------------------------------------------------
+    uint32_t n_unk = (MODE == MODE_LOW_COST) ? acc_unk : bytesum(acc_unk);
+    uint32_t n_aux = bytesum(acc_aux);
+    n_unk = __reduce_add_sync(0xFFFFFFFFu, n_unk);
+    n_aux = __reduce_add_sync(0xFFFFFFFFu, n_aux);
+    if (MODE == MODE_AVG_VIEW_COST) sum_aux2 = __reduce_add_sync(0xFFFFFFFFu, sum_aux2);
+    if (MODE == MODE_RRT_DISCOUNT || MODE == MODE_GOAL_DISTANCE || MODE == MODE_LOW_COST) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(0xFFFFFFFFu, fsum, off);
+    }
+
+    // ---- centre voxel duplicate + epilogue (lane 0) -------------------------------------------------------
+    if (lane == 0) {
+      uint32_t n_vis = 0;
+      double gain = 0.0;
+      uint32_t terminal = 0;
+      if (!w.on_map) {
+        n_unk = n_aux = sum_aux2 = 0;
+        fsum = 0.0;
+      } else {
+        const GainGeom& g = a.g;
+        n_vis = (uint32_t)(clipped_extent(w.cx, h, max(0, a.use_bv ? g.bv_kx_lo : 0), min(g.W - 1, a.use_bv ? g.bv_kx_hi : g.W - 1)) *
+                           clipped_extent(w.cy, h, max(0, a.use_bv ? g.bv_ky_lo : 0), min(g.H - 1, a.use_bv ? g.bv_ky_hi : g.H - 1)));
+        // centre voxel (centre coordinates): its own bounding-volume and map-server bounds tests, then the per-cell tests
+        const bool c_in_bv = !a.use_bv || (w.vcx >= a.bv_x_min && w.vcx <= a.bv_x_max && w.vcy >= a.bv_y_min && w.vcy <= a.bv_y_max);
+        if (c_in_bv) {
+          n_vis += 1;
+          // getStatusAtLocation bounds test (map_server_planexp.cpp:765). Outside -> MSR_UNKNOWN (:769), cost -1 (:762,:801),
+          // not reachable (:877); the path lookup has no bounds test and lands on the window's centre cell
+          // (map_planexp.cpp:226-229). The window centre cell (tile position (h,h)) is always on the map here.
+          const bool c_in_bounds = 0 <= w.vcx && 0 <= w.vcy && g.map_width > w.vcx && g.map_height > w.vcy;
+          uint32_t crec = 0, caux16 = 0;
+          if (kNeedRec) crec = lds8(tile + (uint32_t)(h * a.box_w + (w.cx - ((w.cx - h) & ~15))));
+          if (kNeedAux) caux16 = lds16(tile + (uint32_t)a.aux_off + 2u * (uint32_t)(h * a.box_w16 + (w.cx - ((w.cx - h) & ~7))));
+          bool c_unk, c_free = false, c_path = false, c_reach = false;
+          if (MODE == MODE_LOW_COST) {
+            c_unk = c_in_bounds ? (caux16 != 0) : true;
+          } else {
+            c_unk = c_in_bounds ? ((crec & REC_RAW_UNK) != 0) : true;
+            c_free = c_in_bounds && (crec & REC_RAW_FREE) != 0;
+            c_path = (crec & REC_PATH_RAW) != 0;
+            c_reach = (crec & REC_REACH_RAW) != 0;
+          }
+          if (c_unk) {
+            n_unk += 1;
+            if (MODE == MODE_COUNT) {
+              if (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) n_aux += c_reach ? 1 : 0;
+              else n_aux += c_path ? 1 : 0;
+            } else if (MODE == MODE_RRT_DISCOUNT) {
+              n_aux += c_path ? 1 : 0;
+              if (c_path) {
+                const double dx = g.goal_x - w.vcx, dy = g.goal_y - w.vcy;
+                fsum += 1.0 / sqrt(sqrt(dx * dx + dy * dy) + a.discount_offset);
+              }
+            } else if (MODE == MODE_GOAL_DISTANCE) {
+              const double dx = g.goal_x - w.vcx, dy = g.goal_y - w.vcy;
+              const double dist = sqrt(dx * dx + dy * dy);
+              fsum += (dist > a.inv_max_gain) ? 1.0 / dist : a.max_gain;
+            } else if (MODE == MODE_LOW_COST) {
+              fsum += c_in_bounds ? a.recip[caux16] : a.recip[1];
+            }
+          } else if (MODE == MODE_AVG_VIEW_COST && c_free) {
+            n_aux += 1;
+            sum_aux2 += caux16;
+          }
+        }
+      }
+      {
+        const GainGeom& g = a.g;
+        // ---- evaluator epilogues
+        if (MODE == MODE_COUNT) {
+          if (a.evaluator == SIPP_EVAL_RRT_STAR) {
+            if (n_unk == 0) terminal = 1;                                             // rrt_star_evaluator.cpp:53-57
+            else if (a.do_binary) {
+              if (n_aux > 0) {
+                if (a.use_discount) {                                                 // :61-68
+                  // single term: round exactly like the reference (no FMA contraction) so the gain is bit-exact
+                  const double dx = g.goal_x - a.start_xy[2 * cand], dy = g.goal_y - a.start_xy[2 * cand + 1];
+                  const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                  gain = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(nrm, a.discount_offset)));
+                } else gain = 1.0;                                                    // :69-75
+              }
+            } else gain = (double)n_aux + (double)(n_unk - n_aux) * a.npg;            // :85-89 (closed form of the running sum)
+          } else if (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) {
+            if (n_unk == 0) terminal = 1;                                             // expand_reachable_area_evaluator.cpp:50-54
+            else gain = (double)n_aux + (double)(n_unk - n_aux) * a.discount_factor;  // :65
+          } else {                                                                    // NaiveEvaluator [upstream]
+            gain = (double)n_unk;
+            n_aux = 0;
+          }
+        } else if (MODE == MODE_RRT_DISCOUNT) {
+          if (n_unk == 0) terminal = 1;
+          else gain = fsum + (double)(n_unk - n_aux) * a.npg;                         // :78-84
+        } else if (MODE == MODE_GOAL_DISTANCE) {
+          gain = fsum;
+          n_aux = 0;
+        } else if (MODE == MODE_AVG_VIEW_COST) {
+          if (n_aux > 0) {                                                            // average_view_cost_evaluator.cpp:54-56
+            const double mean_view_cost = (double)sum_aux2 / (double)n_aux;
+            gain = (double)n_unk * (1.0 / mean_view_cost);
+          } else gain = (double)n_unk * (1.0 / g.mean_cost);                          // :57-59
+        } else if (MODE == MODE_LOW_COST) {
+          gain = fsum;
+        }
+      }
+      a.gain[cand] = gain;
+      if (a.counts) *reinterpret_cast<uint4*>(a.counts + 4 * (size_t)cand) = make_uint4(n_vis, n_unk, n_aux, sum_aux2);
+      if (a.terminal) a.terminal[cand] = (uint8_t)terminal;
+      if (a.value) {
+        // flat tree: GlobalNormalizedGain with a zeroed root: value = gain / cost when cost > 0
+        const double c = 0.0 + a.cost[cand];
+        a.value[cand] = c > 0 ? (0.0 + gain) / c : 0.0;
+      }
+    }
+  }
+}
+
+// ---- host side: tensor maps -----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap(sipp_ctx* ctx, CUtensorMap* out, void* base, int elem_bytes, size_t pitch_bytes, int box_w_elems, int box_h) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->H};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_w_elems, (cuuint32_t)box_h};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) box %dx%d", (int)r, box_w_elems, box_h);
+  return SIPP_OK;
+}
+
+const CUtensorMap* cached_tmap(sipp_ctx* ctx, int half_fov, int kind, int* rc) {
+  for (auto& e : ctx->tma_cache)
+    if (e.half_fov == half_fov && e.kind == kind) return &e.map;
+  sipp_ctx::TmaEntry e;
+  e.half_fov = half_fov;
+  e.kind = kind;
+  const int side = 2 * half_fov + 1;
+  // box width: the window plus up to 15 (7) cells of slack for the 16-byte alignment of the box start
+  if (kind == 0) *rc = make_tmap(ctx, &e.map, ctx->d_rec, 1, ctx->pitch, (side + 15 + 15) & ~15, side);
+  else if (kind == 1) *rc = make_tmap(ctx, &e.map, ctx->d_freelab, 2, ctx->pitch16 * 2, (side + 7 + 7) & ~7, side);
+  else *rc = make_tmap(ctx, &e.map, ctx->d_closest, 2, ctx->pitch16 * 2, (side + 7 + 7) & ~7, side);
+  if (*rc != SIPP_OK) return nullptr;
+  ctx->tma_cache.push_back(e);
+  return &ctx->tma_cache.back().map;
+}
+
+template <int MODE>
+int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_aux, const GainArgs& a, cudaStream_t s) {
+  static int num_sms = 0;
+  if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  // as many warps (each owning kStages tile slots) as fit in 200 KB of shared memory, at most 8
+  int wpc = kWarpsPerCta;
+  while (wpc > 1 && (size_t)wpc * kStages * a.slot_bytes > 200 * 1024) wpc >>= 1;
+  const size_t smem = (size_t)wpc * kStages * a.slot_bytes;
+  if (smem > 227 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %zu bytes of shared memory per CTA", a.half_fov, smem);
+  cudaError_t e = cudaFuncSetAttribute(k_gain<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gain<MODE>, wpc * 32, smem);
+  if (e != cudaSuccess || occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+  const int want = (a.n + wpc - 1) / wpc;
+  const int grid = want < num_sms * occ ? want : num_sms * occ;   // persistent: a multiple of the SM count when saturated
+  k_gain<MODE><<<grid, wpc * 32, smem, s>>>(*tm_rec, *tm_aux, a);
+  ctx->launches += 1;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_gain launch: %s", cudaGetErrorString(e));
+  return sipp_debug_sync(ctx, s, "k_gain");
+}
+
+}  // namespace
+
+int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
+                const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
+                cudaStream_t s) {
+  if (n <= 0) return SIPP_OK;
+  const int h = p->half_fov;
+  if (h < 0 || h > 112) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d outside [0,112] (TMA box limit 256 columns)", h);
+  const int side = 2 * h + 1;
+  GainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.evaluator = p->evaluator;
+  a.half_fov = h;
+  a.box_w = (side + 15 + 15) & ~15;
+  a.box_w16 = (side + 7 + 7) & ~7;
+  a.npg = p->non_path_voxel_gain;
+  a.use_discount = p->use_distance_discount;
+  a.do_binary = p->do_binary_check;
+  a.discount_offset = p->discount_offset;
+  a.max_gain = p->max_gain;
+  a.inv_max_gain = 1.0 / p->max_gain;
+  a.discount_factor = p->discount_factor;
+  a.use_bv = p->use_bounding_volume;
+  a.bv_x_min = p->bv_x_min; a.bv_x_max = p->bv_x_max; a.bv_y_min = p->bv_y_min; a.bv_y_max = p->bv_y_max;
+  a.n = n;
+  a.xy = d_xy;
+  a.start_xy = d_start_xy;
+  a.cost = d_cost;
+  a.gain = d_gain;
+  a.counts = d_counts;
+  a.terminal = d_terminal;
+  a.value = d_cost ? d_value : nullptr;
+  a.recip = ctx->d_recip;
+  // per-byte-lane counters: a lane adds at most 4 words x ceil(chunks/32) times
+  {
+    const int total = (a.box_w >> 4) * side;
+    if (((total + 31) / 32) * 4 > 255) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d overflows the SIMD byte counters", h);
+  }
+  int mode;
+  switch (p->evaluator) {
+    case SIPP_EVAL_RRT_STAR: mode = (p->use_distance_discount && !p->do_binary_check) ? MODE_RRT_DISCOUNT : MODE_COUNT; break;
+    case SIPP_EVAL_EXPAND_REACHABLE:
+    case SIPP_EVAL_NAIVE: mode = MODE_COUNT; break;
+    case SIPP_EVAL_GOAL_DISTANCE: mode = MODE_GOAL_DISTANCE; break;
+    case SIPP_EVAL_AVERAGE_VIEW_COST: mode = MODE_AVG_VIEW_COST; break;
+    case SIPP_EVAL_EXPAND_LOW_COST: mode = MODE_LOW_COST; break;
+    default: return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "unknown evaluator %d", p->evaluator);
+  }
+  if (mode == MODE_COUNT && p->evaluator == SIPP_EVAL_RRT_STAR && p->do_binary_check && p->use_distance_discount && !d_start_xy)
+    return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "RRTStarEvaluator binary+discount mode needs start_xy (trajectory[0])");
+  if (mode == MODE_LOW_COST) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "ExpandLowCostAreaEvaluator is not built yet");
+  const size_t rec_bytes = (size_t)a.box_w * side, aux_bytes = (size_t)a.box_w16 * 2 * side;
+  a.aux_off = (int)((rec_bytes + 127) & ~(size_t)127);
+  const bool need_aux = (mode == MODE_AVG_VIEW_COST);
+  a.slot_bytes = (int)((need_aux ? (a.aux_off + aux_bytes) : rec_bytes) + 127) & ~127;
+  int rc = SIPP_OK;
+  const CUtensorMap* tm_rec = cached_tmap(ctx, h, 0, &rc);
+  if (!tm_rec) return rc;
+  const CUtensorMap* tm_aux = tm_rec;
+  if (need_aux) {
+    tm_aux = cached_tmap(ctx, h, 1, &rc);
+    if (!tm_aux) return rc;
+  }
+  switch (mode) {
+    case MODE_COUNT: return launch_mode<MODE_COUNT>(ctx, tm_rec, tm_aux, a, s);
+    case MODE_RRT_DISCOUNT: return launch_mode<MODE_RRT_DISCOUNT>(ctx, tm_rec, tm_aux, a, s);
+    case MODE_GOAL_DISTANCE: return launch_mode<MODE_GOAL_DISTANCE>(ctx, tm_rec, tm_aux, a, s);
+    case MODE_AVG_VIEW_COST: return launch_mode<MODE_AVG_VIEW_COST>(ctx, tm_rec, tm_aux, a, s);
+  }
+  return SIPP_OK;
+}

@@ -1,0 +1,168 @@
+// Internal (non-ABI) declarations shared by the translation units of libsipp.so.
+#ifndef SIPP_INTERNAL_H_
+#define SIPP_INTERNAL_H_
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <list>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sipp.h"
+
+// ---- packed per-cell gain record (one byte per cell, plane d_rec) ------------------------------------
+// Built by k_build_views from state / path / reachability and the evaluator's bounding volume; off-map
+// cells are never stored — TMA out-of-bounds fill returns 0 for them, which contributes to no count.
+#define REC_UNK 0x01u        // state == UNKNOWN                       (and voxel inside the bounding volume)
+#define REC_UNK_PATH 0x02u   // UNKNOWN and on the current path mask   (")
+#define REC_UNK_REACH 0x04u  // UNKNOWN and a 3x3 neighbour is MSR_REACHABLE (")
+#define REC_OBS_FREE 0x08u   // state == FREE                          (")
+// raw bits (no bounding-volume masking): the duplicated centre voxel has its own coordinates, hence its own
+// bounding-volume / map-bounds tests (done by lane 0 of the gain kernel)
+#define REC_RAW_UNK 0x10u    // state == UNKNOWN
+#define REC_PATH_RAW 0x20u   // path mask bit
+#define REC_REACH_RAW 0x40u  // a 3x3 neighbour is MSR_REACHABLE
+#define REC_RAW_FREE 0x80u   // state == FREE
+
+// planner cell codes (plane d_pcode, uint16): the follower planner's own copy of the map
+// (PRMStarPlanner::map_ / explored_, prm_star_planner.h:52-53)
+#define PCODE_UNEXPLORED 0xFFFFu  // cost = init_cost
+#define PCODE_REMOVED 0xFFFEu     // first observation was an obstacle id: all edges deleted
+
+#define SIPP_MAX_CLASSES 64  // distinct |dX|^2 (or |dY|^2) values of the node lattice (9..14 in practice)
+
+struct FieldGeom {  // device-side view of the implicit per-pixel graph geometry
+  int W, H;
+  int Kx, Ky;              // number of edge-length classes per axis
+  const uint8_t* xcls;     // [W-1] class of the edge between column i and i+1
+  const uint8_t* ycls;     // [H-1]
+  const double* hdist;     // [Kx] axial-x edge length   sqrt(dX^2 + 0)      (+inf when not < max_dist)
+  const double* vdist;     // [Ky] axial-y edge length
+  const double* ddist;     // [Kx*Ky] diagonal edge length sqrt(dX^2 + dY^2)  (+inf when not < max_dist)
+  double init_half_cost;   // init_cost / 2
+  double spacing, off_x, off_y, min_cost;
+  int start_x, start_y, goal_x, goal_y;
+};
+
+struct GainGeom {  // per-candidate index math of MapPlanExp (map_planexp.cpp:72-101,134-144,222-224)
+  int W, H;
+  double vs;          // c_voxel_size_
+  double inv_vs;      // 1 / c_voxel_size_ (the reference multiplies by (1/vs))
+  double map_width, map_height;  // map server bounds test
+  double goal_x, goal_y;
+  double mean_cost;
+  // bounding volume as inclusive cell-index ranges for the corner voxels (k * vs inside [min,max])
+  int bv_kx_lo, bv_kx_hi, bv_ky_lo, bv_ky_hi;
+};
+
+struct BestRec {  // 16-byte record moved by the multi-GPU gather
+  double value;
+  long long index;
+};
+
+struct sipp_ctx {
+  sipp_map_desc desc;
+  int device;
+  cudaStream_t stream;
+  std::mutex mu;
+  std::string err;
+  int64_t launches;
+
+  int W, H;
+  size_t pitch;        // bytes per row of the uint8 planes (multiple of 128)
+  size_t pitch16;      // elements per row of the uint16 planes
+  // host mirrors (bookkeeping that is sequential in the reference)
+  std::vector<uint8_t> h_state;   // map_state_
+  double mean_cost, max_cost;
+  int mean_counter;
+  double init_cost;               // current planner init cost (update_unknown_cost changes it)
+  int start_loc[2], goal_loc[2];
+  double mpp, vs;
+  // planner geometry (host copies)
+  double spacing, max_dist, off_x, off_y;
+  int start_node[2], goal_node[2];
+  std::vector<double> X, Y;
+  // device planes
+  uint8_t* d_state;
+  uint16_t* d_label;     // map_cost_ (last label)
+  uint16_t* d_pcode;     // planner code
+  uint8_t* d_path;       // path mask 0/1
+  uint8_t* d_rec;        // packed gain record (view)
+  uint16_t* d_freelab;   // view: label where state == FREE (inside bv) else 0   (AverageViewCost)
+  uint16_t* d_closest;   // closest observed cost (label) for UNKNOWN cells       (ExpandLowCost)
+  float* d_closest_dist;
+  double* d_recip;       // [65536] 1/label lookup for ExpandLowCost
+  double* d_field;       // W*H doubles
+  // geometry tables on device
+  uint8_t *d_xcls, *d_ycls;
+  double *d_hdist, *d_vdist, *d_ddist;
+  int Kx, Ky;
+  // relax work lists
+  int n_tiles_x, n_tiles_y;
+  uint8_t* d_tile_flags;   // [2][ntiles]
+  int* d_tile_list;        // [ntiles]
+  int* d_relax_ctl;        // small control block (counters, stats)
+  // path
+  int* d_path_nodes;       // reverse order (goal -> start), packed (x<<16 | y)... see sipp_field.cu
+  double* d_path_xy;
+  int path_cap_nodes;
+  int* d_plan_out;         // {len, all_explored, status...}
+  int path_generation;
+  bool path_valid;
+  bool field_valid;
+  int64_t plan_stats[4];
+  // views
+  bool views_dirty;
+  sipp_eval_params view_params;   // bounding volume the views were built for
+  bool view_params_valid;
+  // TMA descriptors cached per half_fov
+  struct TmaEntry { int half_fov; int kind; CUtensorMap map; };
+  std::list<TmaEntry> tma_cache;   // list: handed-out pointers stay valid
+  // staging buffers for the host-pointer entry points
+  void* h_pinned; size_t h_pinned_bytes;
+  void* d_stage; size_t d_stage_bytes;
+  void* d_tree_ws; size_t d_tree_ws_bytes;
+  BestRec* d_best; void* d_select_ws;
+  double* d_plan_cost_dummy;
+};
+
+// error helpers -----------------------------------------------------------------------------------------
+int sipp_set_err(sipp_ctx* ctx, int code, const char* fmt, ...);
+#define SIPP_CUDA_CHECK(ctx, expr)                                                                   \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return sipp_set_err((ctx), SIPP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// SIPP_DEBUG_SYNC=1 in the environment: synchronise after every kernel so an asynchronous fault is attributed to its kernel
+int sipp_debug_sync(sipp_ctx* ctx, cudaStream_t s, const char* what);
+
+// kernel launchers (each returns cudaError_t from the launch) ---------------------------------------------
+// sipp_map.cu
+cudaError_t launch_clear_planes(sipp_ctx* ctx, cudaStream_t s);
+cudaError_t launch_ingest_patch(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* d_labels,
+                                const uint8_t* d_observed, cudaStream_t s);
+cudaError_t launch_unknown_cost_noop(sipp_ctx* ctx, cudaStream_t s);
+cudaError_t launch_build_views(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cudaStream_t s);
+cudaError_t launch_download_planes(sipp_ctx* ctx, uint8_t* d_state_out, int32_t* d_cost_out, uint8_t* d_reach_out,
+                                   uint8_t* d_path_out, cudaStream_t s);
+cudaError_t launch_upload_mask(sipp_ctx* ctx, const uint8_t* d_mask_packed, cudaStream_t s);
+// sipp_gain.cu
+int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy,
+                const double* d_start_xy, const double* d_cost, double* d_gain, uint32_t* d_counts,
+                uint8_t* d_terminal, double* d_value, cudaStream_t s);
+// sipp_select.cu
+cudaError_t launch_select_flat(sipp_ctx* ctx, int n, const double* d_value, long long index_offset, BestRec* d_best, double* d_root_value,
+                               cudaStream_t s);
+cudaError_t launch_value_flat(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, double* d_value, cudaStream_t s);
+cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, const int32_t* d_parent,
+                              double* d_value, BestRec* d_best, void* ws, cudaStream_t s);
+size_t select_workspace_bytes();
+// sipp_field.cu
+int field_plan(sipp_ctx* ctx, cudaStream_t s);
+
+#endif  // SIPP_INTERNAL_H_

@@ -1,0 +1,173 @@
+// Map-store kernels: patch ingest (A10), evaluator view planes, debug read-back.
+//
+// Reference behaviour restated here (cell loop of MapServerPlanExp::mapDataCallback,
+// map_server_planexp/src/map_server_planexp.cpp:238-260, and PRMStarPlanner::update_states,
+// planexp_base_planners/src/prm_star_planner.cpp:104-119). The sequential scalars of that loop
+// (mean_cost_, max_cost_, the goal-explored switch) are kept on the host in sipp_ctx.cu; everything
+// per-cell runs here.
+#include "sipp_internal.h"
+
+namespace {
+
+struct IdList {
+  int n;
+  int ids[SIPP_MAX_IDS];
+};
+
+__device__ __forceinline__ bool in_ids(const IdList& l, int v) {
+  bool hit = false;
+#pragma unroll 4
+  for (int i = 0; i < l.n; ++i) hit |= (l.ids[i] == v);
+  return hit;
+}
+
+// One thread per patch cell. labels: rows x cols int32 row-major (MapData.data); observed: optional mask.
+__global__ void k_ingest_patch(uint8_t* __restrict__ state, uint16_t* __restrict__ label, uint16_t* __restrict__ pcode,
+                               size_t pitch, size_t pitch16, int W, int H, int x0, int y0, int rows, int cols,
+                               const int32_t* __restrict__ labels, const uint8_t* __restrict__ observed, IdList mav,
+                               IdList rov) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)rows * cols) return;
+  const int i = (int)(t / cols), j = (int)(t % cols);
+  const int y = y0 + i, x = x0 + j;
+  if (!(0 <= y && 0 <= x && y < H && x < W)) return;             // map_server_planexp.cpp:240
+  if (observed && !observed[t]) return;
+  const int lab = labels[t];
+  label[(size_t)y * pitch16 + x] = (uint16_t)lab;                  // map_cost_ = label  :242
+  state[(size_t)y * pitch + x] = in_ids(mav, lab) ? SIPP_STATE_OCCUPIED : SIPP_STATE_FREE;  // :252-256
+  uint16_t* pc = pcode + (size_t)y * pitch16 + x;
+  if (*pc == PCODE_UNEXPLORED)                                     // is_new  prm_star_planner.cpp:111
+    *pc = in_ids(rov, lab) ? (uint16_t)PCODE_REMOVED : (uint16_t)lab;   // :112-115
+}
+
+__global__ void k_fill_f32(float* p, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// Builds the evaluator view planes. 16 cells per thread, 128-bit loads/stores.
+//   rec     : packed gain record (REC_* bits)
+//   freelab : label where the cell is observed FREE and inside the bounding volume, else 0
+__global__ void k_build_views(const uint8_t* __restrict__ state, const uint8_t* __restrict__ path,
+                              const uint16_t* __restrict__ label, uint8_t* __restrict__ rec,
+                              uint16_t* __restrict__ freelab, size_t pitch, size_t pitch16, int W, int H, int bv_kx_lo,
+                              int bv_kx_hi, int bv_ky_lo, int bv_ky_hi, int reach_x, int reach_y, int use_reach) {
+  const int chunks_per_row = (int)(pitch / 16);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)chunks_per_row * H) return;
+  const int y = (int)(t / chunks_per_row);
+  const int xc = (int)(t % chunks_per_row) * 16;
+  const uint4 sv = *reinterpret_cast<const uint4*>(state + (size_t)y * pitch + xc);
+  const uint4 pv = *reinterpret_cast<const uint4*>(path + (size_t)y * pitch + xc);
+  const uint4 l0 = *reinterpret_cast<const uint4*>(label + (size_t)y * pitch16 + xc);
+  const uint4 l1 = *reinterpret_cast<const uint4*>(label + (size_t)y * pitch16 + xc + 8);
+  const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+  const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+  const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+  uint32_t rw[4] = {0, 0, 0, 0};
+  uint32_t fw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool row_in_bv = (y >= bv_ky_lo && y <= bv_ky_hi);
+  const bool row_reach = use_reach && (y >= reach_y - 1 && y <= reach_y + 1);
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const int x = xc + b;
+    const uint32_t st = (sw[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
+    const uint32_t pm = (pw[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
+    const uint32_t lb = (lw[b >> 1] >> ((b & 1) * 16)) & 0xFFFFu;
+    const bool inside = x < W;
+    const bool inbv = inside && row_in_bv && x >= bv_kx_lo && x <= bv_kx_hi;
+    const bool r3 = inside && row_reach && (x >= reach_x - 1 && x <= reach_x + 1);
+    const bool unk = inside && st == SIPP_STATE_UNKNOWN;
+    uint32_t r = 0;
+    if (inbv && unk) r |= REC_UNK;
+    if (inbv && unk && pm) r |= REC_UNK_PATH;
+    if (inbv && unk && r3) r |= REC_UNK_REACH;
+    if (inbv && st == SIPP_STATE_FREE) r |= REC_OBS_FREE;
+    if (unk) r |= REC_RAW_UNK;
+    if (inside && st == SIPP_STATE_FREE) r |= REC_RAW_FREE;
+    if (inside && pm) r |= REC_PATH_RAW;
+    if (r3) r |= REC_REACH_RAW;
+    rw[b >> 2] |= r << ((b & 3) * 8);
+    if (inbv && st == SIPP_STATE_FREE) fw[b >> 1] |= lb << ((b & 1) * 16);
+  }
+  *reinterpret_cast<uint4*>(rec + (size_t)y * pitch + xc) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+  *reinterpret_cast<uint4*>(freelab + (size_t)y * pitch16 + xc) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+  *reinterpret_cast<uint4*>(freelab + (size_t)y * pitch16 + xc + 8) = make_uint4(fw[4], fw[5], fw[6], fw[7]);
+}
+
+// debug read-back into compact W*H arrays
+__global__ void k_download(const uint8_t* __restrict__ state, const uint16_t* __restrict__ label,
+                           const uint8_t* __restrict__ path, size_t pitch, size_t pitch16, int W, int H,
+                           uint8_t* __restrict__ o_state, int32_t* __restrict__ o_cost, uint8_t* __restrict__ o_reach,
+                           uint8_t* __restrict__ o_path, int reach_x, int reach_y, int use_reach) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)W * H) return;
+  const int y = (int)(t / W), x = (int)(t % W);
+  if (o_state) o_state[t] = state[(size_t)y * pitch + x];
+  if (o_cost) o_cost[t] = label[(size_t)y * pitch16 + x];
+  if (o_reach) o_reach[t] = (use_reach && x == reach_x && y == reach_y) ? 1 : 0;   // only the start cell is MSR_REACHABLE
+  if (o_path) o_path[t] = path[(size_t)y * pitch + x];
+}
+
+IdList make_ids(const int32_t* ids, int n) {
+  IdList l;
+  l.n = n;
+  for (int i = 0; i < SIPP_MAX_IDS; ++i) l.ids[i] = i < n ? ids[i] : -1;
+  return l;
+}
+
+}  // namespace
+
+cudaError_t launch_clear_planes(sipp_ctx* ctx, cudaStream_t s) {
+  // MapServerPlanExp::clearMap (map_server_planexp.cpp:461-487) + PRMStarPlanner::set_derived_params (:24-27)
+  cudaError_t e;
+  const size_t n8 = ctx->pitch * ctx->H, n16 = ctx->pitch16 * ctx->H;
+  if ((e = cudaMemsetAsync(ctx->d_state, SIPP_STATE_UNKNOWN, n8, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_label, 0, n16 * 2, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_pcode, 0xFF, n16 * 2, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_path, 0, n8, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_rec, 0, n8, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_freelab, 0, n16 * 2, s)) != cudaSuccess) return e;
+  ctx->launches += 6;
+  return cudaSuccess;
+}
+
+cudaError_t launch_ingest_patch(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* d_labels,
+                                const uint8_t* d_observed, cudaStream_t s) {
+  const long long n = (long long)rows * cols;
+  if (n <= 0) return cudaSuccess;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  k_ingest_patch<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->pitch, ctx->pitch16, ctx->W,
+                                            ctx->H, x0, y0, rows, cols, d_labels, d_observed,
+                                            make_ids(ctx->desc.obstacle_ids_mav, ctx->desc.n_obstacle_ids_mav),
+                                            make_ids(ctx->desc.obstacle_ids_rov, ctx->desc.n_obstacle_ids_rov));
+  ctx->launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_views(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cudaStream_t s) {
+  const long long n = (long long)(ctx->pitch / 16) * ctx->H;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  const int klo_x = use_bv ? g.bv_kx_lo : 0, khi_x = use_bv ? g.bv_kx_hi : ctx->W - 1;
+  const int klo_y = use_bv ? g.bv_ky_lo : 0, khi_y = use_bv ? g.bv_ky_hi : ctx->H - 1;
+  k_build_views<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_path, ctx->d_label, ctx->d_rec, ctx->d_freelab,
+                                           ctx->pitch, ctx->pitch16, ctx->W, ctx->H, klo_x, khi_x, klo_y, khi_y,
+                                           ctx->start_loc[0], ctx->start_loc[1], ctx->desc.compute_reachability);
+  ctx->launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_download_planes(sipp_ctx* ctx, uint8_t* o_state, int32_t* o_cost, uint8_t* o_reach, uint8_t* o_path,
+                                   cudaStream_t s) {
+  const long long n = (long long)ctx->W * ctx->H;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  k_download<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_label, ctx->d_path, ctx->pitch, ctx->pitch16, ctx->W, ctx->H,
+                                        o_state, o_cost, o_reach, o_path, ctx->start_loc[0], ctx->start_loc[1],
+                                        ctx->desc.compute_reachability);
+  ctx->launches += 1;
+  return cudaGetLastError();
+}

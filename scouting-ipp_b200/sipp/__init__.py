@@ -1,0 +1,321 @@
+"""ctypes binding of libsipp.so — the B200-native scouting-ipp evaluation hot path.
+
+This module is plumbing for tests and bench.py: it loads the C-ABI shared library declared in include/sipp.h and
+exposes it as `Context`. There is no Python or CPU implementation of any result in here; if the library or a CUDA
+device is missing every compute call raises `SippError`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libsipp.so")
+
+MAX_IDS = 32
+COUNTS_PER_CANDIDATE = 4
+EVAL_RRT_STAR, EVAL_GOAL_DISTANCE, EVAL_EXPAND_REACHABLE, EVAL_AVERAGE_VIEW_COST, EVAL_EXPAND_LOW_COST, EVAL_NAIVE = range(6)
+STATE_OCCUPIED, STATE_FREE, STATE_UNKNOWN = 0, 1, 2
+PLAN_VALID, PLAN_INVALID, PLAN_TERMINAL_VALID, PLAN_TERMINAL_INVALID = 0, 1, 2, 3
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_PATH_MASK, ERR_ALLOC = 0, -1, -2, -3, -4, -5
+
+# every symbol include/sipp.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "sipp_abi_version", "sipp_create", "sipp_destroy", "sipp_last_error", "sipp_stream", "sipp_map_clear",
+    "sipp_patch_origin", "sipp_map_update_patch", "sipp_map_upload_full", "sipp_update_unknown_cost", "sipp_map_stats",
+    "sipp_map_download", "sipp_plan", "sipp_field_download", "sipp_path_mask_generation", "sipp_set_path_mask",
+    "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev",
+    "sipp_cycle", "sipp_cycle_dev", "sipp_launch_count",
+]
+
+
+class MapDesc(C.Structure):  # sipp_map_desc
+    _fields_ = [
+        ("W", C.c_int32), ("H", C.c_int32),
+        ("width", C.c_double), ("height", C.c_double),
+        ("start_x", C.c_double), ("start_y", C.c_double),
+        ("goal_x", C.c_double), ("goal_y", C.c_double),
+        ("min_rov_cost", C.c_double), ("max_rov_cost", C.c_double), ("unknown_init_cost", C.c_double),
+        ("unknown_id", C.c_int32),
+        ("n_obstacle_ids_mav", C.c_int32), ("obstacle_ids_mav", C.c_int32 * MAX_IDS),
+        ("n_obstacle_ids_rov", C.c_int32), ("obstacle_ids_rov", C.c_int32 * MAX_IDS),
+        ("compute_reachability", C.c_int32), ("compute_closest_observed", C.c_int32),
+    ]
+
+
+class EvalParams(C.Structure):  # sipp_eval_params
+    _fields_ = [
+        ("evaluator", C.c_int32), ("half_fov", C.c_int32),
+        ("non_path_voxel_gain", C.c_double),
+        ("use_distance_discount", C.c_int32), ("do_binary_check", C.c_int32),
+        ("discount_offset", C.c_double),
+        ("max_gain", C.c_double),
+        ("discount_factor", C.c_double),
+        ("augment_unknown_with_mean", C.c_int32), ("use_bounding_volume", C.c_int32),
+        ("bv_x_min", C.c_double), ("bv_x_max", C.c_double), ("bv_y_min", C.c_double), ("bv_y_max", C.c_double),
+    ]
+
+
+class SippError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sipp error %d: %s" % (code, msg))
+        self.code = code
+
+
+def make_desc(W, H, width, height, start, goal, min_cost, max_cost, init_cost, obstacle_ids_mav=(0,),
+              obstacle_ids_rov=(0,), unknown_id=3599, compute_reachability=True, compute_closest_observed=False):
+    d = MapDesc()
+    d.W, d.H, d.width, d.height = int(W), int(H), float(width), float(height)
+    d.start_x, d.start_y = float(start[0]), float(start[1])
+    d.goal_x, d.goal_y = float(goal[0]), float(goal[1])
+    d.min_rov_cost, d.max_rov_cost, d.unknown_init_cost = float(min_cost), float(max_cost), float(init_cost)
+    d.unknown_id = int(unknown_id)
+    d.n_obstacle_ids_mav = len(obstacle_ids_mav)
+    for i, v in enumerate(obstacle_ids_mav):
+        d.obstacle_ids_mav[i] = int(v)
+    d.n_obstacle_ids_rov = len(obstacle_ids_rov)
+    for i, v in enumerate(obstacle_ids_rov):
+        d.obstacle_ids_rov[i] = int(v)
+    d.compute_reachability = int(bool(compute_reachability))
+    d.compute_closest_observed = int(bool(compute_closest_observed))
+    return d
+
+
+def make_params(evaluator=EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.0, use_distance_discount=False,
+                do_binary_check=False, discount_offset=0.1, max_gain=100.0, discount_factor=0.1,
+                augment_unknown_with_mean=False, bounding_volume=None):
+    p = EvalParams()
+    p.evaluator, p.half_fov = int(evaluator), int(half_fov)
+    p.non_path_voxel_gain = float(non_path_voxel_gain)
+    p.use_distance_discount, p.do_binary_check = int(bool(use_distance_discount)), int(bool(do_binary_check))
+    p.discount_offset, p.max_gain, p.discount_factor = float(discount_offset), float(max_gain), float(discount_factor)
+    p.augment_unknown_with_mean = int(bool(augment_unknown_with_mean))
+    if bounding_volume is None:
+        p.use_bounding_volume = 0
+    else:
+        p.use_bounding_volume = 1
+        p.bv_x_min, p.bv_x_max, p.bv_y_min, p.bv_y_max = [float(v) for v in bounding_volume]
+    return p
+
+
+def build(force=False, verbose=False):
+    """Compile libsipp.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc"))] + [
+        os.path.join(os.path.dirname(_PKG), "include", "sipp.h")]
+    newest = max(os.path.getmtime(f) for f in srcs if f.endswith((".cu", ".h", ".cuh")))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        out = None if verbose else subprocess.DEVNULL
+        subprocess.check_call(["make", "-C", _PKG, "-j8", "libsipp.so"] + (["-B"] if force else []), stdout=out, stderr=out)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libsipp.so. Raises OSError when it has not been built: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError("libsipp.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i32, f64, i64 = C.c_void_p, C.c_int32, C.c_double, C.c_int64
+        pi32, pf64 = C.POINTER(i32), C.POINTER(f64)
+        L.sipp_abi_version.restype = C.c_int
+        L.sipp_create.argtypes = [C.POINTER(MapDesc), C.c_int, C.POINTER(vp)]
+        L.sipp_destroy.argtypes = [vp]
+        L.sipp_destroy.restype = None
+        L.sipp_last_error.argtypes = [vp]
+        L.sipp_last_error.restype = C.c_char_p
+        L.sipp_stream.argtypes = [vp]
+        L.sipp_stream.restype = vp
+        L.sipp_map_clear.argtypes = [vp]
+        L.sipp_patch_origin.argtypes = [vp, f64, f64, i32, i32, pi32, pi32]
+        L.sipp_map_update_patch.argtypes = [vp, i32, i32, i32, i32, vp]
+        L.sipp_map_upload_full.argtypes = [vp, vp, vp]
+        L.sipp_update_unknown_cost.argtypes = [vp, f64]
+        L.sipp_map_stats.argtypes = [vp, pf64, pf64, C.POINTER(i64)]
+        L.sipp_map_download.argtypes = [vp, vp, vp, vp, vp]
+        L.sipp_plan.argtypes = [vp, pf64, pi32, vp, i32, pi32]
+        L.sipp_field_download.argtypes = [vp, vp]
+        L.sipp_path_mask_generation.argtypes = [vp]
+        L.sipp_set_path_mask.argtypes = [vp, vp]
+        L.sipp_plan_stats.argtypes = [vp, vp]
+        L.sipp_gain_batch.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp]
+        L.sipp_gain_batch_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp]
+        L.sipp_value_select.argtypes = [vp, i32, vp, vp, vp, vp, pi32, pf64]
+        L.sipp_value_select_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.sipp_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, pi32, pf64]
+        L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.sipp_launch_count.argtypes = [vp]
+        L.sipp_launch_count.restype = i64
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One map + follower planner + evaluator state resident on one GPU (sipp_ctx)."""
+
+    def __init__(self, desc, device=0):
+        self.desc = desc
+        self.W, self.H = desc.W, desc.H
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.sipp_create(C.byref(desc), int(device), C.byref(h))
+        if rc != OK:
+            raise SippError(rc, self._L.sipp_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sipp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise SippError(rc, self._L.sipp_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self):
+        return self._L.sipp_stream(self._h)
+
+    def launch_count(self):
+        return int(self._L.sipp_launch_count(self._h))
+
+    # ---- map store
+    def map_clear(self):
+        self._check(self._L.sipp_map_clear(self._h))
+
+    def patch_origin(self, px, py, rows, cols):
+        x0, y0 = C.c_int32(), C.c_int32()
+        self._check(self._L.sipp_patch_origin(self._h, px, py, rows, cols, C.byref(x0), C.byref(y0)))
+        return x0.value, y0.value
+
+    def map_update_patch(self, x0, y0, labels):
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        rows, cols = labels.shape
+        self._check(self._L.sipp_map_update_patch(self._h, int(x0), int(y0), rows, cols, _ptr(labels)))
+
+    def map_upload_full(self, labels, observed=None):
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        assert labels.shape == (self.H, self.W)
+        if observed is not None:
+            observed = np.ascontiguousarray(observed, dtype=np.uint8)
+            assert observed.shape == (self.H, self.W)
+        self._check(self._L.sipp_map_upload_full(self._h, _ptr(labels), _ptr(observed)))
+
+    def update_unknown_cost(self, c):
+        self._check(self._L.sipp_update_unknown_cost(self._h, float(c)))
+
+    def map_stats(self):
+        m, mx, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self._L.sipp_map_stats(self._h, C.byref(m), C.byref(mx), C.byref(n)))
+        return m.value, mx.value, n.value
+
+    def map_download(self):
+        state = np.empty((self.H, self.W), np.uint8)
+        cost = np.empty((self.H, self.W), np.int32)
+        reach = np.empty((self.H, self.W), np.uint8)
+        path = np.empty((self.H, self.W), np.uint8)
+        self._check(self._L.sipp_map_download(self._h, _ptr(state), _ptr(cost), _ptr(reach), _ptr(path)))
+        return state, cost, reach, path
+
+    # ---- follower path cost
+    def plan(self, path_cap=None):
+        cap = path_cap if path_cap is not None else 4 * (self.W + self.H)
+        cost, status, n = C.c_double(), C.c_int32(), C.c_int32()
+        path = np.zeros((cap, 2), np.float64)
+        self._check(self._L.sipp_plan(self._h, C.byref(cost), C.byref(status), _ptr(path), cap, C.byref(n)))
+        return cost.value, status.value, path[: min(n.value, cap)].copy(), n.value
+
+    def plan_stats(self):
+        st = np.zeros(4, np.int64)
+        self._check(self._L.sipp_plan_stats(self._h, _ptr(st)))
+        return dict(rounds=int(st[0]), tile_activations=int(st[1]), tile_sweeps=int(st[2]), aborted=int(st[3]))
+
+    def field_download(self):
+        f = np.empty((self.H, self.W), np.float64)
+        self._check(self._L.sipp_field_download(self._h, _ptr(f)))
+        return f
+
+    def path_mask_generation(self):
+        return self._L.sipp_path_mask_generation(self._h)
+
+    def set_path_mask(self, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert mask.shape == (self.H, self.W)
+        self._check(self._L.sipp_set_path_mask(self._h, _ptr(mask)))
+
+    # ---- gain / value / cycle (host buffers)
+    def gain_batch(self, params, xy, start_xy=None):
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        n = xy.shape[0]
+        if start_xy is not None:
+            start_xy = np.ascontiguousarray(start_xy, dtype=np.float64).reshape(-1, 2)
+        gain = np.zeros(n, np.float64)
+        counts = np.zeros((n, COUNTS_PER_CANDIDATE), np.uint32)
+        terminal = np.zeros(n, np.uint8)
+        self._check(self._L.sipp_gain_batch(self._h, C.byref(params), n, _ptr(xy), _ptr(start_xy), _ptr(gain), _ptr(counts),
+                                            _ptr(terminal)))
+        return gain, counts, terminal
+
+    def value_select(self, gain, cost, parent=None):
+        gain = np.ascontiguousarray(gain, dtype=np.float64)
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        n = gain.shape[0]
+        if parent is not None:
+            parent = np.ascontiguousarray(parent, dtype=np.int32)
+        value = np.zeros(n, np.float64)
+        bc, bv = C.c_int32(), C.c_double()
+        self._check(self._L.sipp_value_select(self._h, n, _ptr(gain), _ptr(cost), _ptr(parent), _ptr(value), C.byref(bc),
+                                              C.byref(bv)))
+        return value, bc.value, bv.value
+
+    def cycle(self, params, xy, cost, start_xy=None):
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        n = xy.shape[0]
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        if start_xy is not None:
+            start_xy = np.ascontiguousarray(start_xy, dtype=np.float64).reshape(-1, 2)
+        gain = np.zeros(n, np.float64)
+        terminal = np.zeros(n, np.uint8)
+        value = np.zeros(n, np.float64)
+        bi, bv = C.c_int32(), C.c_double()
+        self._check(self._L.sipp_cycle(self._h, C.byref(params), n, _ptr(xy), _ptr(start_xy), _ptr(cost), _ptr(gain),
+                                       _ptr(terminal), _ptr(value), C.byref(bi), C.byref(bv)))
+        return gain, terminal, value, bi.value, bv.value
+
+    # ---- raw-pointer variants (device pointers as ints, e.g. torch.Tensor.data_ptr(); stream as int or None)
+    def gain_batch_dev(self, params, n, d_xy, d_start_xy, d_gain, d_counts, d_terminal, stream=None):
+        self._check(self._L.sipp_gain_batch_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_gain),
+                                                _ptr(d_counts), _ptr(d_terminal), _ptr(stream)))
+
+    def cycle_dev(self, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, d_best, stream=None):
+        self._check(self._L.sipp_cycle_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost),
+                                           _ptr(d_gain), _ptr(d_terminal), _ptr(d_value), _ptr(d_best), _ptr(stream)))
+
+    def cycle_host_ptr(self, params, n, xy, start_xy, cost, gain, terminal, value):
+        """sipp_cycle on caller-owned host buffers given as raw addresses (pinned memory for the e2e benchmark)."""
+        bi, bv = C.c_int32(), C.c_double()
+        self._check(self._L.sipp_cycle(self._h, C.byref(params), int(n), _ptr(xy), _ptr(start_xy), _ptr(cost), _ptr(gain),
+                                       _ptr(terminal), _ptr(value), C.byref(bi), C.byref(bv)))
+        return bi.value, bv.value

@@ -1,0 +1,321 @@
+"""GPU parity: libsipp.so (CUDA, through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact for counts, terminal flags, cost fields, paths, masks and selected candidates; floating-point gains
+within 1e-5 relative (north_star tolerance) — exact where the reference's arithmetic is integer valued."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import sipp
+from sipp import synth
+from oracle import oracle as orc
+
+RTOL = 1e-5   # north_star: "within 1e-5 relative for floating-point utilities"
+
+
+def both(desc_kw_fn):
+    return sipp.Context(desc_kw_fn(sipp.make_desc)), orc.Oracle(desc_kw_fn(orc.make_desc))
+
+
+def eval_planner_desc(cfg, mk, **kw):
+    obst = list(cfg["obstacle_ids_rov"]) + [cfg["unknown_id"]]
+    ids = [i for i in cfg["present_ids"] if i not in obst]
+    return mk(cfg["W"], cfg["H"], cfg["width"], cfg["height"], cfg["start"], cfg["goal"], min(ids), max(ids), min(ids),
+              obstacle_ids_mav=cfg["obstacle_ids_mav"], obstacle_ids_rov=obst, unknown_id=cfg["unknown_id"], **kw)
+
+
+def inloop_desc(cfg, mk, init="max", **kw):
+    ids = [i for i in cfg["present_ids"] if i not in cfg["obstacle_ids_rov"]]
+    return mk(cfg["W"], cfg["H"], cfg["width"], cfg["height"], cfg["start"], cfg["goal"], min(ids), max(ids),
+              max(ids) if init == "max" else min(ids), obstacle_ids_mav=cfg["obstacle_ids_mav"],
+              obstacle_ids_rov=cfg["obstacle_ids_rov"], unknown_id=cfg["unknown_id"], **kw)
+
+
+ALL_PARAM_SETS = [
+    dict(evaluator=sipp.EVAL_RRT_STAR, non_path_voxel_gain=0.0),
+    dict(evaluator=sipp.EVAL_RRT_STAR, non_path_voxel_gain=0.001),
+    dict(evaluator=sipp.EVAL_RRT_STAR, do_binary_check=True),
+    dict(evaluator=sipp.EVAL_RRT_STAR, do_binary_check=True, use_distance_discount=True),
+    dict(evaluator=sipp.EVAL_RRT_STAR, use_distance_discount=True, non_path_voxel_gain=0.005),
+    dict(evaluator=sipp.EVAL_GOAL_DISTANCE, max_gain=100.0),
+    dict(evaluator=sipp.EVAL_EXPAND_REACHABLE, discount_factor=0.1),
+    dict(evaluator=sipp.EVAL_EXPAND_REACHABLE, discount_factor=0.0),
+    dict(evaluator=sipp.EVAL_AVERAGE_VIEW_COST),
+    dict(evaluator=sipp.EVAL_NAIVE),
+]
+EXACT_GAIN = lambda kw: (kw["evaluator"] in (sipp.EVAL_NAIVE, sipp.EVAL_EXPAND_REACHABLE)
+                         or (kw["evaluator"] == sipp.EVAL_RRT_STAR and not kw.get("use_distance_discount")
+                             and kw.get("non_path_voxel_gain", 0.0) == 0.0)
+                         or (kw["evaluator"] == sipp.EVAL_RRT_STAR and kw.get("do_binary_check")))
+
+
+def assert_gain_parity(g, o, kw, xy, start_xy=None, half_fov=32, bv=None):
+    pg = sipp.make_params(half_fov=half_fov, bounding_volume=bv, **kw)
+    po = orc.make_params(half_fov=half_fov, bounding_volume=bv, **kw)
+    gg, gc, gt = g.gain_batch(pg, xy, start_xy)
+    og, oc, ot = o.gain_batch(po, xy, start_xy, variant=1, threads=8)
+    assert np.array_equal(gc, oc), "counts differ: %s" % (np.argwhere(gc != oc)[:5],)
+    assert np.array_equal(gt, ot)
+    if EXACT_GAIN(kw):
+        assert np.array_equal(gg, og, equal_nan=True)
+    else:
+        assert np.allclose(gg, og, rtol=RTOL, atol=0.0, equal_nan=True)
+        fin = np.isfinite(og) & (og != 0)
+        if fin.any():
+            assert np.max(np.abs(gg[fin] - og[fin]) / np.abs(og[fin])) < 1e-9   # what we actually achieve
+
+
+# ------------------------------------------------------------------------------------------------------------
+def small_world_pair(observed_cols=(0,)):
+    W = H = 8
+    mk = lambda f: f(W, H, 0.5, 0.5, (0.03, 0.03), (0.4375, 0.4375), 30, 120, 30)
+    g, o = both(mk)
+    labels = np.array([[30 + x + 8 * y for x in range(W)] for y in range(H)], np.int32)
+    obs = np.zeros((H, W), np.uint8)
+    for c in observed_cols:
+        obs[:, c] = 1
+    mask = np.zeros((H, W), np.uint8)
+    mask[3, :] = 1
+    for c in (g, o):
+        c.map_upload_full(labels, obs)
+        c.set_path_mask(mask)
+    return g, o
+
+
+@pytest.mark.parametrize("kw", ALL_PARAM_SETS)
+def test_gain_hand_cases(kw):
+    """SURVEY appendix D positions, incl. clipped corners, off-map centres and the negative-coordinate quirks."""
+    xy = np.array([[0.20, 0.21], [0.01, 0.01], [0.03, 0.20], [0.50, 0.20], [-0.03, 0.20], [-0.07, 0.20], [-0.13, 0.20],
+                   [0.20, -0.07], [0.4999, 0.4999], [0.25, 0.25], [1e9, 0.1], [np.nan, 0.1], [0.1, np.inf]])
+    sxy = xy[::-1].copy()
+    sxy[~np.isfinite(sxy)] = 0.1
+    for cols in ((0,), (0, 1), tuple(range(8))):
+        g, o = small_world_pair(cols)
+        ok = np.isfinite(xy).all(axis=1) & (np.abs(xy) < 1e8).all(axis=1)
+        assert_gain_parity(g, o, kw, xy[ok], sxy[ok], half_fov=1)
+        # non-finite / absurd poses are undefined behaviour in the reference ((int) of NaN); we define them as off-map
+        p = sipp.make_params(half_fov=1, **kw)
+        gg, gc, gt = g.gain_batch(p, xy[~ok], sxy[~ok])
+        assert not gc.any()
+        assert_gain_parity(g, o, kw, xy[ok], sxy[ok], half_fov=1, bv=(0.0, 0.5, 0.0, 0.5))
+        assert_gain_parity(g, o, kw, xy[ok], sxy[ok], half_fov=2, bv=(0.07, 0.3, 0.0, 0.26))
+
+
+@pytest.mark.parametrize("half_fov", [0, 1, 7, 10, 32, 40])
+def test_gain_random_small_map(half_fov):
+    """W, H not multiples of 16, windows larger than the map, every evaluator."""
+    W, H = 100, 70
+    rng = np.random.default_rng(11)
+    mk = lambda f: f(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (5.5, 3.9), 30, 120, 30)
+    g, o = both(mk)
+    for _ in range(5):
+        x0, y0 = (int(v) for v in rng.integers(-10, 90, 2))
+        patch = rng.integers(0, 121, (33, 33)).astype(np.int32)
+        patch[rng.random((33, 33)) < 0.2] = 0
+        g.map_update_patch(x0, y0, patch)
+        o.map_update_patch(x0, y0, patch)
+    cg, sg, pg, ng = g.plan()
+    co, so, po, no = o.plan()
+    assert (cg, sg, ng) == (co, so, no) and np.array_equal(pg, po)
+    xy = rng.uniform(-0.3, W * 0.0625 + 0.3, (257, 2))
+    xy[:, 1] = rng.uniform(-0.3, H * 0.0625 + 0.3, 257)
+    for kw in ALL_PARAM_SETS:
+        assert_gain_parity(g, o, kw, xy, xy[::-1].copy(), half_fov=half_fov)
+
+
+def test_gain_and_cycle_config2_1024(golden):
+    """BASELINE config 2: 4096 candidate poses on a 1024^2 label map, RRTStarEvaluator count mode (npg 0.001 and 0.0)."""
+    W = H = 1024
+    lab, obs, dg = synth.world(W, H, 1002, 100, sipp.make_desc, init_cost="max")
+    _, _, do = synth.world(W, H, 1002, 100, orc.make_desc, init_cost="max")
+    g, o = sipp.Context(dg), orc.Oracle(do)
+    g.map_upload_full(lab, obs)
+    o.map_upload_full(lab, obs)
+    assert g.map_stats() == o.map_stats()
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+    assert np.array_equal(g.field_download(), o.field_download())
+    sg, _, _, pg = g.map_download()
+    so, _, _, po = o.map_download()
+    assert np.array_equal(sg, so) and np.array_equal(pg, po)
+    xy, cost = synth.make_candidates(W, H, 1002, 4096)
+    for kw in ALL_PARAM_SETS:
+        assert_gain_parity(g, o, kw, xy, xy[::-1].copy())
+    for npg in (0.001, 0.0):
+        pgp = sipp.make_params(sipp.EVAL_RRT_STAR, non_path_voxel_gain=npg)
+        pop = orc.make_params(orc.EVAL_RRT_STAR, non_path_voxel_gain=npg)
+        gg, gt, gv, gi, gbv = g.cycle(pgp, xy, cost)
+        og, ot, ov, oi, obv = o.cycle(pop, xy, cost, variant=1, threads=8)
+        assert gi == oi, "selected candidate differs"
+        assert np.array_equal(gt, ot)
+        assert np.allclose(gv, ov, rtol=RTOL, atol=0) and abs(gbv - obv) <= RTOL * abs(obv)
+        if npg == 0.0:
+            assert np.array_equal(gg, og) and np.array_equal(gv, ov) and gbv == obv
+
+
+# ------------------------------------------------------------------------------------------------------------
+GOLDEN_NAMES = ["map_102", "map_110", "map_111", "map_112", "map_113", "map_115", "map_116", "map_122", "map_212", "map_312"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_field_golden_maps(golden, name):
+    """Fully known shipped maps (eval-planner mode): golden cost, bit-exact field, identical path, mask and status."""
+    labels, cfg = golden[name]
+    g = sipp.Context(eval_planner_desc(cfg, sipp.make_desc))
+    o = orc.Oracle(eval_planner_desc(cfg, orc.make_desc))
+    lab = labels.astype(np.int32)
+    g.map_upload_full(lab)
+    o.map_upload_full(lab)
+    cg, sg, pg, ng = g.plan()
+    co, so, po, no = o.plan()
+    if cfg["golden_prm_cost"] < 0:
+        assert cg == -1.0 and sg == sipp.PLAN_TERMINAL_INVALID and ng == 0
+    else:
+        assert float("%.6g" % cg) == cfg["golden_prm_cost"]
+    assert cg == co and sg == so and ng == no
+    assert np.array_equal(pg, po)
+    fg, fo = g.field_download(), o.field_download()
+    assert np.array_equal(fg, fo), "field differs in %d cells" % int((fg != fo).sum())
+    assert np.array_equal(g.map_download()[3], o.map_download()[3])
+    assert g.path_mask_generation() == 1 and o.path_mask_generation() == 1
+
+
+@pytest.mark.parametrize("name,init", [("map_212", "max"), ("map_112", "min"), ("map_116", "max")])
+def test_field_partial_map_in_loop_mode(golden, name, init):
+    """In-loop mode: unknown cells cost init_cost, ROV obstacle ids only, patches arrive one by one; first observation wins
+    in the planner (prm_star_planner.cpp:111) while the map server overwrites (map_server_planexp.cpp:242)."""
+    labels, cfg = golden[name]
+    g = sipp.Context(inloop_desc(cfg, sipp.make_desc, init))
+    o = orc.Oracle(inloop_desc(cfg, orc.make_desc, init))
+    rng = np.random.default_rng(3)
+    lab = labels.astype(np.int32)
+    for k in range(30):
+        px, py = rng.uniform(0, cfg["width"]), rng.uniform(0, cfg["height"])
+        rows = cols = 65
+        x0, y0 = g.patch_origin(px, py, rows, cols)
+        assert (x0, y0) == o.patch_origin(px, py, rows, cols)
+        patch = np.zeros((rows, cols), np.int32)
+        ys, xs = np.clip(np.arange(y0, y0 + rows), 0, cfg["H"] - 1), np.clip(np.arange(x0, x0 + cols), 0, cfg["W"] - 1)
+        patch[:, :] = lab[np.ix_(ys, xs)]
+        if k % 7 == 3:
+            patch = (patch + 5) % 121      # a re-observation with different labels: planner keeps the first, server the last
+        g.map_update_patch(x0, y0, patch)
+        o.map_update_patch(x0, y0, patch)
+        if k % 10 == 9:
+            rg, ro = g.plan(), o.plan()
+            assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+            assert np.array_equal(g.field_download(), o.field_download())
+    assert g.map_stats() == o.map_stats()
+    for a, b in zip(g.map_download(), o.map_download()):
+        assert np.array_equal(a, b)
+    # goal-explored switch (map_server_planexp.cpp:276): observe the goal, init cost drops to min
+    gx, gy = cfg["goal"]
+    x0, y0 = g.patch_origin(gx, gy, 65, 65)
+    ys, xs = np.clip(np.arange(y0, y0 + 65), 0, cfg["H"] - 1), np.clip(np.arange(x0, x0 + 65), 0, cfg["W"] - 1)
+    patch = lab[np.ix_(ys, xs)].copy()
+    g.map_update_patch(x0, y0, patch)
+    o.map_update_patch(x0, y0, patch)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+    assert np.array_equal(g.field_download(), o.field_download())
+    assert g.path_mask_generation() == o.path_mask_generation() == 4
+
+
+def test_field_degenerate_cases():
+    W = H = 64
+    mk = lambda f, s=(0.5, 0.5), t=(3.5, 3.5): f(W, H, 4.0, 4.0, s, t, 30, 120, 30)
+    lab = np.full((H, W), 30, np.int32)
+    # start == goal node
+    g, o = sipp.Context(mk(sipp.make_desc, (1.0, 1.0), (1.01, 1.01))), orc.Oracle(mk(orc.make_desc, (1.0, 1.0), (1.01, 1.01)))
+    for c in (g, o):
+        c.map_upload_full(lab)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] == 0.0 and rg[3] == ro[3] == 1 and rg[1] == ro[1]
+    # start on an obstacle: nothing reachable
+    lab2 = lab.copy()
+    lab2[0:20, 0:20] = 0
+    g, o = both(mk)
+    for c in (g, o):
+        c.map_upload_full(lab2)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] == -1.0 and rg[1] == ro[1] == sipp.PLAN_TERMINAL_INVALID
+    assert np.array_equal(g.field_download(), o.field_download())
+    # a wall with a one-cell gap, zero-cost cells (label 0 is not an obstacle here)
+    mk0 = lambda f: f(W, H, 4.0, 4.0, (0.5, 0.5), (3.5, 3.5), 0, 120, 0, obstacle_ids_mav=(7,), obstacle_ids_rov=(7,))
+    lab3 = np.random.default_rng(1).integers(0, 3, (H, W)).astype(np.int32) * 10
+    lab3[:, 30] = 7
+    lab3[41, 30] = 20
+    g, o = both(mk0)
+    for c in (g, o):
+        c.map_upload_full(lab3)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+    assert np.array_equal(g.field_download(), o.field_download())
+    # the same wall with strictly positive labels: a real path through the gap
+    lab4 = lab3 + 10
+    lab4[:, 30] = 7
+    lab4[41, 30] = 20
+    g, o = both(mk0)
+    for c in (g, o):
+        c.map_upload_full(lab4)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] > 0 and rg[1] == ro[1] and rg[3] == ro[3] > 0 and np.array_equal(rg[2], ro[2])
+    assert np.array_equal(g.field_download(), o.field_download())
+    assert np.array_equal(g.map_download()[3], o.map_download()[3])
+    # untouched map: everything unknown at init cost
+    g, o = both(mk)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] == sipp.PLAN_VALID and np.array_equal(rg[2], ro[2])
+    assert np.array_equal(g.field_download(), o.field_download())
+    g.update_unknown_cost(77.5)
+    o.update_unknown_cost(77.5)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and np.array_equal(g.field_download(), o.field_download())
+
+
+# ------------------------------------------------------------------------------------------------------------
+def test_value_select_flat_and_tree():
+    rng = np.random.default_rng(9)
+    W = H = 64
+    g = sipp.Context(sipp.make_desc(W, H, 4.0, 4.0, (0.5, 0.5), (3.5, 3.5), 30, 120, 30))
+    for n in (1, 2, 3, 33, 1000, 5000):
+        gain = rng.integers(0, 50, n).astype(np.float64) * rng.choice([1.0, 0.001], n)
+        cost = rng.uniform(0.2, 5.0, n)
+        cost[rng.random(n) < 0.05] = 0.0
+        vg, bg, bvg = g.value_select(gain, cost, None)
+        vo, bo, bvo = orc.value_select(gain, cost, None)
+        assert np.array_equal(vg, vo) and bg == bo and (bg < 0 or bvg == bvo)
+        parent = np.zeros(n, np.int32)
+        parent[0] = -1
+        for i in range(1, n):
+            parent[i] = rng.integers(max(0, i - 40), i)
+        vg, bg, bvg = g.value_select(gain, cost, parent)
+        vo, bo, bvo = orc.value_select(gain, cost, parent)
+        assert np.array_equal(vg, vo), np.argwhere(vg != vo)[:5]
+        assert bg == bo and (bg < 0 or bvg == bvo)
+    # a chain deeper than 512 levels is refused, not silently mis-evaluated
+    n = 700
+    with pytest.raises(sipp.SippError) as e:
+        g.value_select(np.ones(n), np.ones(n), np.arange(-1, n - 1, dtype=np.int32))
+    assert e.value.code == sipp.ERR_UNSUPPORTED
+    # ties: lowest index wins
+    gain = np.array([0, 3, 6, 3, 6.0]); cost = np.array([0, 1, 2, 1, 2.0])
+    assert g.value_select(gain, cost)[1] == 1 == orc.value_select(gain, cost)[1]
+
+
+def test_empty_and_error_paths():
+    W = H = 64
+    g = sipp.Context(sipp.make_desc(W, H, 4.0, 4.0, (0.5, 0.5), (3.5, 3.5), 30, 120, 30))
+    p = sipp.make_params(sipp.EVAL_NAIVE, half_fov=3)
+    gg, gc, gt = g.gain_batch(p, np.zeros((0, 2)))
+    assert gg.shape == (0,)
+    with pytest.raises(sipp.SippError) as e:
+        g.gain_batch(sipp.make_params(sipp.EVAL_RRT_STAR), np.zeros((1, 2)))   # no path mask yet
+    assert e.value.code == sipp.ERR_NO_PATH_MASK
+    with pytest.raises(sipp.SippError):
+        g.gain_batch(sipp.make_params(sipp.EVAL_NAIVE, half_fov=200), np.zeros((1, 2)))
+    with pytest.raises(sipp.SippError):
+        sipp.Context(sipp.make_desc(100, 100, 3.3, 3.3, (0.5, 0.5), (2.5, 2.5), 30, 120, 30))   # inexact voxel size
+    with pytest.raises(sipp.SippError):
+        g.map_update_patch(0, 0, np.full((4, 4), 70000, np.int32))
+    assert g.launch_count() > 0
