@@ -22,8 +22,8 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kStages = 3;
+constexpr int kMaxWarpsPerCta = 16;
+constexpr int kStages = 2;
 
 // evaluator "reduction modes"
 enum { MODE_COUNT = 0, MODE_RRT_DISCOUNT = 1, MODE_GOAL_DISTANCE = 2, MODE_AVG_VIEW_COST = 3, MODE_LOW_COST = 4 };
@@ -39,6 +39,7 @@ struct GainArgs {
   double npg;         // non_path_voxel_gain
   int use_discount, do_binary;
   double discount_offset, max_gain, inv_max_gain, discount_factor;
+  double inv_max_gain2_lo, inv_max_gain2_hi;   // (1/max_gain)^2 -+ a safety band: outside it the squared test decides
   int use_bv;
   double bv_x_min, bv_x_max, bv_y_min, bv_y_max;
   int n;
@@ -139,15 +140,25 @@ __device__ __forceinline__ int clipped_extent(int c, int h, int lo, int hi) {
   return max(b - a + 1, 0);
 }
 
+struct WinSlot {   // window parameters of the candidate in flight in one (warp, stage) slot; written by lane 0 at issue time
+  int cx, cy, on_map, pad;
+  double vcx, vcy;
+};
+
+// Lane layout over a tile whose rows are `ncr` 16-byte chunks wide: lane = lrow * ncr + lcc for the first
+// rpi * ncr lanes (rpi = 32 / ncr rows are covered per iteration), the remaining lanes idle. A lane keeps its chunk
+// column for the whole scan, so the column masks of the (unaligned) window are computed once per candidate.
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32)
 k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_aux, const GainArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[kWarpsPerCta * kStages];
+  __shared__ __align__(8) uint64_t bars[kMaxWarpsPerCta * kStages];
+  __shared__ WinSlot wins[kMaxWarpsPerCta * kStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t slot_base = smem_u32(smem_raw) + (uint32_t)(warp * kStages) * (uint32_t)a.slot_bytes;
   const uint32_t bar_base = smem_u32(&bars[warp * kStages]);
+  WinSlot* mywins = &wins[warp * kStages];
 
   if (lane == 0) {
 #pragma unroll
@@ -166,6 +177,19 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   constexpr bool kNeedAux = (MODE == MODE_AVG_VIEW_COST || MODE == MODE_LOW_COST);
   const uint32_t tx_bytes = (kNeedRec ? (uint32_t)(a.box_w * side) : 0u) + (kNeedAux ? (uint32_t)(a.box_w16 * 2 * side) : 0u);
 
+  // lane geometry (fixed for the whole kernel)
+  const int ncr = a.box_w >> 4, rpi = 32 / ncr;
+  const int lrow = lane / ncr, lcc = lane - lrow * ncr;
+  const bool lane_on = lane < rpi * ncr;
+  const int ncr16 = a.box_w16 >> 3, rpi16 = 32 / ncr16;
+  const int lrow16 = lane / ncr16, lcc16 = lane - lrow16 * ncr16;
+  const bool lane_on16 = lane < rpi16 * ncr16;
+  // which record bit feeds counts[AUX]
+  const uint32_t auxbit = (MODE == MODE_AVG_VIEW_COST) ? REC_OBS_FREE
+                          : (MODE == MODE_COUNT && a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) ? REC_UNK_REACH : REC_UNK_PATH;
+  const uint32_t auxmask = auxbit * 0x01010101u;
+  const int auxshift = __ffs(auxbit) - 1;
+
   auto issue = [&](int k) {
     if (lane == 0) {
       const int cand = gw + k * nw;
@@ -173,6 +197,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
       const int s = k % kStages;
       const uint32_t bar = bar_base + 8u * s;
       const uint32_t dst = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
+      mywins[s].cx = w.cx; mywins[s].cy = w.cy; mywins[s].on_map = w.on_map;
+      mywins[s].vcx = w.vcx; mywins[s].vcy = w.vcy;
       mbar_expect_tx(bar, tx_bytes);
       // TMA needs the box start 16-byte aligned in the contiguous dimension: start at the aligned column at or before
       // the window's first column; the box is wide enough to still cover the window (see gain_launch)
@@ -185,106 +211,107 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
 
   for (int k = 0; k < my_count; ++k) {
     if (k + kStages - 1 < my_count) {
-      __syncwarp();   // every lane is done reading the slot that is about to be refilled
+      __syncwarp();   // every lane is done reading the slot (tile + window parameters) that is about to be refilled
       issue(k + kStages - 1);
     }
     const int cand = gw + k * nw;
     const int s = k % kStages;
     const uint32_t tile = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
-    const double px = a.xy[2 * cand], py = a.xy[2 * cand + 1];
-    const Window w = make_window(a.g, px, py);
+    __syncwarp();     // lane 0's window parameters for this slot are visible to the warp
+    const int wcx = mywins[s].cx, wcy = mywins[s].cy;
     while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)((k / kStages) & 1))) {
     }
 
     // ---- window scan -------------------------------------------------------------------------------
-    uint32_t acc_unk = 0, acc_aux = 0;   // per-byte-lane SIMD counters (<= 255 per lane by construction, see host check)
+    uint32_t n_unk = 0, n_aux = 0;       // per-lane totals
     uint32_t sum_aux2 = 0;               // AverageViewCost: sum of labels
     double fsum = 0.0;                   // floating-point modes
-    if (kNeedRec) {
-      const int ncr = a.box_w >> 4;                  // 16-byte chunks per tile row
-      const int total = ncr * side;
-      const int xal = (w.cx - h) & ~15;              // global column of tile column 0
-      const int r0 = (w.cx - h) - xal;               // the window occupies tile columns [r0, r0 + side)
-      for (int idx = lane; idx < total; idx += 32) {
-        const int row = idx / ncr, cc = idx - row * ncr;
-        uint4 v = lds128(tile + (uint32_t)idx * 16u);
-        const int lo = r0 - 16 * cc, hi = r0 + side - 16 * cc;   // valid bytes of this chunk: [lo, hi) clipped to [0,16)
-        if (lo > 0 || hi < 16) {                     // only the first and the last one or two chunks of a row
-          v.x &= byte_range_mask(lo, hi);
-          v.y &= byte_range_mask(lo - 4, hi - 4);
-          v.z &= byte_range_mask(lo - 8, hi - 8);
-          v.w &= byte_range_mask(lo - 12, hi - 12);
-        }
-        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-        if (MODE == MODE_COUNT || MODE == MODE_AVG_VIEW_COST) {
-          const uint32_t auxbit = (MODE == MODE_AVG_VIEW_COST) ? REC_OBS_FREE
-                                  : (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE ? REC_UNK_REACH : REC_UNK_PATH);
-          const uint32_t auxmask = auxbit * 0x01010101u;
-          const int auxshift = __ffs(auxbit) - 1;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc_unk += wds[q] & 0x01010101u;
-            acc_aux += (wds[q] & auxmask) >> auxshift;
+    if (kNeedRec && lane_on) {
+      const int r0 = (wcx - h) & 15;                 // the window occupies tile columns [r0, r0 + side)
+      const int lo = r0 - 16 * lcc, hi = r0 + side - 16 * lcc;   // valid bytes of this lane's chunk: [lo, hi) clipped to [0,16)
+      const uint32_t m0 = byte_range_mask(lo, hi), m1 = byte_range_mask(lo - 4, hi - 4);
+      const uint32_t m2 = byte_range_mask(lo - 8, hi - 8), m3 = byte_range_mask(lo - 12, hi - 12);
+      uint32_t addr = tile + (uint32_t)lane * 16u;
+      const uint32_t step = (uint32_t)(rpi * ncr) * 16u;
+      if (MODE == MODE_COUNT || MODE == MODE_AVG_VIEW_COST) {
+        const uint32_t u0 = m0 & 0x01010101u, u1 = m1 & 0x01010101u, u2 = m2 & 0x01010101u, u3 = m3 & 0x01010101u;
+        const uint32_t a0 = m0 & auxmask, a1 = m1 & auxmask, a2 = m2 & auxmask, a3 = m3 & auxmask;
+        int row = lrow;
+        while (row < side) {
+          // per-byte-lane SIMD counters: at most 60 chunks (<= 240 per byte lane) between flushes
+          uint32_t acc_unk = 0, acc_aux = 0;
+          const int row_end = min(side, row + 60 * rpi);
+#pragma unroll 2
+          for (; row < row_end; row += rpi) {
+            const uint4 v = lds128(addr);
+            addr += step;
+            acc_unk += (v.x & u0) + (v.y & u1);
+            acc_unk += (v.z & u2) + (v.w & u3);
+            const uint32_t t = (v.x & a0) + (v.y & a1) + (v.z & a2) + (v.w & a3);   // bytes <= 4 * auxbit <= 32
+            acc_aux += t >> auxshift;
           }
-        } else {
-          // floating-point modes: walk the bytes of this chunk
-          const int x0 = xal + cc * 16, y = w.cy - h + row;
+          n_unk += bytesum(acc_unk);
+          n_aux += bytesum(acc_aux);
+        }
+      } else {
+        // floating-point modes: walk the selected bytes of each chunk (corner coordinates of the cells)
+        const int x0 = ((wcx - h) & ~15) + lcc * 16;
+        for (int row = lrow; row < side; row += rpi) {
+          uint4 v = lds128(addr);
+          addr += step;
+          const uint32_t wds[4] = {v.x & m0, v.y & m1, v.z & m2, v.w & m3};
+          const double vy = (double)(wcy - h + row) * a.g.vs;
+          const double dy = a.g.goal_y - vy;
+          const double dy2 = dy * dy;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint32_t wd = wds[q];
-            acc_unk += wd & 0x01010101u;
-            acc_aux += (wd & 0x02020202u) >> 1;
-            const uint32_t sel = (MODE == MODE_RRT_DISCOUNT) ? (wd & 0x02020202u) : (wd & 0x01010101u);
-            if (sel) {
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                if (sel & (0xFFu << (8 * b))) {
-                  const double vx = (double)(x0 + q * 4 + b) * a.g.vs, vy = (double)y * a.g.vs;   // corner coordinates
-                  const double dx = a.g.goal_x - vx, dy = a.g.goal_y - vy;
-                  const double dist = sqrt(dx * dx + dy * dy);
-                  if (MODE == MODE_RRT_DISCOUNT) fsum += 1.0 / sqrt(dist + a.discount_offset);   // rrt_star_evaluator.cpp:82
-                  else fsum += (dist > a.inv_max_gain) ? 1.0 / dist : a.max_gain;                // goal_distance_evaluator.cpp:55-60
-                }
-              }
+            const uint32_t wd = wds[q];
+            n_unk += __popc(wd & 0x01010101u);
+            n_aux += __popc(wd & 0x02020202u);
+            uint32_t sel = (MODE == MODE_RRT_DISCOUNT) ? (wd & 0x02020202u) : (wd & 0x01010101u);
+            while (sel) {
+              const int b = (__ffs(sel) - 1) >> 3;
+              sel &= sel - 1;
+              const double vx = (double)(x0 + q * 4 + b) * a.g.vs;
+              const double dx = a.g.goal_x - vx;
+              const double d2 = dx * dx + dy2;
+              if (MODE == MODE_RRT_DISCOUNT) fsum += rsqrt(sqrt(d2) + a.discount_offset);                 // rrt_star_evaluator.cpp:82
+              else fsum += (d2 > a.inv_max_gain2_hi) ? rsqrt(d2)                                           // goal_distance_evaluator.cpp:55-60
+                           : ((d2 < a.inv_max_gain2_lo) ? a.max_gain : ((sqrt(d2) > a.inv_max_gain) ? 1.0 / sqrt(d2) : a.max_gain));
             }
           }
         }
       }
     }
-    if (kNeedAux) {
+    if (kNeedAux && lane_on16) {
       const uint32_t atile = tile + (uint32_t)a.aux_off;
-      const int ncr = a.box_w16 >> 3;                // 16-byte chunks (8 cells) per aux tile row
-      const int total = ncr * side;
-      const int r0 = (w.cx - h) - ((w.cx - h) & ~7); // the window occupies tile columns [r0, r0 + side)
-      for (int idx = lane; idx < total; idx += 32) {
-        const int row = idx / ncr, cc = idx - row * ncr;
-        (void)row;
-        uint4 v = lds128(atile + (uint32_t)idx * 16u);
-        uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-        const int lo = r0 - 8 * cc, hi = r0 + side - 8 * cc;     // valid cells of this chunk: [lo, hi) clipped to [0,8)
-        if (lo > 0 || hi < 8) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) wds[q] &= half_range_mask(lo - 2 * q, hi - 2 * q);
-        }
+      const int r0 = (wcx - h) & 7;                  // the window occupies tile columns [r0, r0 + side)
+      const int lo = r0 - 8 * lcc16, hi = r0 + side - 8 * lcc16;   // valid cells of this lane's chunk: [lo, hi) clipped to [0,8)
+      const uint32_t m0 = half_range_mask(lo, hi), m1 = half_range_mask(lo - 2, hi - 2);
+      const uint32_t m2 = half_range_mask(lo - 4, hi - 4), m3 = half_range_mask(lo - 6, hi - 6);
+      uint32_t addr = atile + (uint32_t)lane * 16u;
+      const uint32_t step = (uint32_t)(rpi16 * ncr16) * 16u;
+      for (int row = lrow16; row < side; row += rpi16) {
+        const uint4 v = lds128(addr);
+        addr += step;
+        const uint32_t wds[4] = {v.x & m0, v.y & m1, v.z & m2, v.w & m3};
         if (MODE == MODE_AVG_VIEW_COST) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) sum_aux2 += (wds[q] & 0xFFFFu) + (wds[q] >> 16);
         } else {  // MODE_LOW_COST: entries are 0 (not unknown / off map) or closest_label + 1
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t lo = wds[q] & 0xFFFFu, hi = wds[q] >> 16;
-            if (lo) { acc_unk += 1; fsum += a.recip[lo]; }
-            if (hi) { acc_unk += 1; fsum += a.recip[hi]; }
+            const uint32_t l0 = wds[q] & 0xFFFFu, l1 = wds[q] >> 16;
+            if (l0) { n_unk += 1; fsum += a.recip[l0]; }
+            if (l1) { n_unk += 1; fsum += a.recip[l1]; }
           }
         }
       }
     }
 
     // ---- warp reduction ------------------------------------------------------------------------------
-    uint32_t n_unk = (MODE == MODE_LOW_COST) ? acc_unk : bytesum(acc_unk);
-    uint32_t n_aux = bytesum(acc_aux);
     n_unk = __reduce_add_sync(0xFFFFFFFFu, n_unk);
-    n_aux = __reduce_add_sync(0xFFFFFFFFu, n_aux);
+    if (MODE != MODE_GOAL_DISTANCE && MODE != MODE_LOW_COST) n_aux = __reduce_add_sync(0xFFFFFFFFu, n_aux);
     if (MODE == MODE_AVG_VIEW_COST) sum_aux2 = __reduce_add_sync(0xFFFFFFFFu, sum_aux2);
     if (MODE == MODE_RRT_DISCOUNT || MODE == MODE_GOAL_DISTANCE || MODE == MODE_LOW_COST) {
 #pragma unroll
@@ -293,6 +320,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
 
     // ---- centre voxel duplicate + epilogue (lane 0) -------------------------------------------------------
     if (lane == 0) {
+      Window w;
+      w.cx = wcx; w.cy = wcy; w.on_map = mywins[s].on_map; w.vcx = mywins[s].vcx; w.vcy = mywins[s].vcy;
       uint32_t n_vis = 0;
       double gain = 0.0;
       uint32_t terminal = 0;
@@ -448,7 +477,7 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
   static int num_sms = 0;
   if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
   // as many warps (each owning kStages tile slots) as fit in 200 KB of shared memory, at most 8
-  int wpc = kWarpsPerCta;
+  int wpc = kMaxWarpsPerCta;
   while (wpc > 1 && (size_t)wpc * kStages * a.slot_bytes > 200 * 1024) wpc >>= 1;
   const size_t smem = (size_t)wpc * kStages * a.slot_bytes;
   if (smem > 227 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %zu bytes of shared memory per CTA", a.half_fov, smem);
@@ -488,6 +517,8 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.discount_offset = p->discount_offset;
   a.max_gain = p->max_gain;
   a.inv_max_gain = 1.0 / p->max_gain;
+  a.inv_max_gain2_lo = a.inv_max_gain * a.inv_max_gain * (1.0 - 1e-9);
+  a.inv_max_gain2_hi = a.inv_max_gain * a.inv_max_gain * (1.0 + 1e-9);
   a.discount_factor = p->discount_factor;
   a.use_bv = p->use_bounding_volume;
   a.bv_x_min = p->bv_x_min; a.bv_x_max = p->bv_x_max; a.bv_y_min = p->bv_y_min; a.bv_y_max = p->bv_y_max;
@@ -500,11 +531,6 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.terminal = d_terminal;
   a.value = d_cost ? d_value : nullptr;
   a.recip = ctx->d_recip;
-  // per-byte-lane counters: a lane adds at most 4 words x ceil(chunks/32) times
-  {
-    const int total = (a.box_w >> 4) * side;
-    if (((total + 31) / 32) * 4 > 255) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d overflows the SIMD byte counters", h);
-  }
   int mode;
   switch (p->evaluator) {
     case SIPP_EVAL_RRT_STAR: mode = (p->use_distance_discount && !p->do_binary_check) ? MODE_RRT_DISCOUNT : MODE_COUNT; break;
