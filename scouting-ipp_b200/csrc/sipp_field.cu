@@ -30,7 +30,6 @@ namespace {
 
 constexpr int TS = 32;        // tile edge (cells)
 constexpr int TP = TS + 2;    // with a one-cell halo
-constexpr int kRelaxThreads = 256;
 constexpr int kMaxDd = 1024;  // diagonal class table entries kept in shared memory
 
 struct RelaxArgs {
@@ -60,49 +59,98 @@ __device__ __forceinline__ double half_cost(uint32_t code, double init_half) {
   return 0.5 * (double)code;
 }
 
-// one relaxation of cell (lx,ly) (tile-local coordinates incl. halo) against its 8 neighbours
-__device__ __forceinline__ double relax_cell(const volatile double (*sd)[TP], const double (*shc)[TP], const double (*sq)[TP],
-                                             const double* s_hd, const double* s_vd, int lx, int ly, double hc0) {
-  double best = sd[ly][lx];
-#define RELAX(nx, ny, dist)                                                              \
-  {                                                                                      \
-    const double cand = __dadd_rn(sd[ny][nx], __dmul_rn((dist), __dadd_rn(hc0, shc[ny][nx]))); \
-    if (cand < best) best = cand;                                                        \
-  }
-  RELAX(lx - 1, ly, s_hd[lx - 1]);
-  RELAX(lx + 1, ly, s_hd[lx]);
-  RELAX(lx, ly - 1, s_vd[ly - 1]);
-  RELAX(lx, ly + 1, s_vd[ly]);
-  RELAX(lx - 1, ly - 1, sq[ly - 1][lx - 1]);
-  RELAX(lx + 1, ly - 1, sq[ly - 1][lx]);
-  RELAX(lx - 1, ly + 1, sq[ly][lx - 1]);
-  RELAX(lx + 1, ly + 1, sq[ly][lx]);
-#undef RELAX
-  return best;
+// ---- tile solver: one WARP per 32x32 tile, Gauss-Seidel row sweeps ------------------------------------------
+// A warp owns a tile for one activation. Lane x owns interior column x. A sweep walks the rows top->bottom (or
+// bottom->top): row r is relaxed against the already final row r-1 (N, NW, NE) and then against itself (W, E) with a
+// warp-shuffle fixed-point loop, so information crosses the whole tile in one sweep in the sweep direction and along
+// rows. Sweeps alternate direction until one of them changes nothing: at that point every cell satisfies all eight
+// inequalities d[v] <= d[u] + w(u,v), i.e. the tile is at its local fixed point. No block barriers.
+constexpr int kRelaxWarps = 8;
+
+struct TileSmem {
+  double d[TP][TP];      // tentative costs incl. one-cell halo
+  double hc[TP][TP];     // half costs incl. halo (+inf: removed node / off map)
+  double vd[TP];         // vd[r]: length of the vertical edge between local rows r and r+1
+  int yc[TP];            // its class (for the diagonal table), -1 off map
+};
+
+__device__ __forceinline__ double relax1(double best, double dn, double dist, double hc0, double hcn) {
+  const double cand = __dadd_rn(dn, __dmul_rn(dist, __dadd_rn(hc0, hcn)));
+  return cand < best ? cand : best;
 }
 
-__global__ void __launch_bounds__(kRelaxThreads)
+// One sweep over the interior rows. DIR = +1: rows 1..32 using row r-1; DIR = -1: rows 32..1 using row r+1.
+// Returns (warp-uniform) whether any cell was lowered; `mask` collects which tile borders changed.
+template <int DIR>
+__device__ __forceinline__ bool sweep_rows(TileSmem& t, const double* ddp, int Ky, int lane, int xcl, int xcr, double hdl, double hdr,
+                                           int& mask) {
+  const int lx = lane + 1;
+  bool chg = false;
+  for (int i = 0; i < TS; ++i) {
+    const int r = (DIR > 0) ? (1 + i) : (TS - i);
+    const int pr = r - DIR;                       // the row this sweep has just finished (or the halo row)
+    const int er = (DIR > 0) ? pr : r;            // vertical / diagonal edges between rows er and er+1
+    const double hc0 = t.hc[r][lx];
+    double d = t.d[r][lx];
+    const double d0 = d;
+    const double hl = t.d[r][0], hr = t.d[r][TP - 1];      // left / right halo of this row (constant during the activation)
+    const double hcl = t.hc[r][lx - 1], hcr = t.hc[r][lx + 1];
+    if (hc0 < CUDART_INF) {
+      const int yc = t.yc[er];
+      const double vdist = t.vd[er];
+      const double ddl = (yc >= 0 && xcl >= 0) ? ddp[xcl * Ky + yc] : CUDART_INF;   // quad left of this column
+      const double ddr = (yc >= 0 && xcr >= 0) ? ddp[xcr * Ky + yc] : CUDART_INF;   // quad right of this column
+      d = relax1(d, t.d[pr][lx], vdist, hc0, t.hc[pr][lx]);
+      d = relax1(d, t.d[pr][lx - 1], ddl, hc0, t.hc[pr][lx - 1]);
+      d = relax1(d, t.d[pr][lx + 1], ddr, hc0, t.hc[pr][lx + 1]);
+    }
+    // in-row fixed point (W / E neighbours) with shuffles
+    const double wl = __dmul_rn(hdl, __dadd_rn(hc0, hcl)), wr = __dmul_rn(hdr, __dadd_rn(hc0, hcr));
+    bool again;
+    do {
+      double dl = __shfl_up_sync(0xFFFFFFFFu, d, 1), dr = __shfl_down_sync(0xFFFFFFFFu, d, 1);
+      if (lane == 0) dl = hl;
+      if (lane == 31) dr = hr;
+      double nd = d;
+      if (hc0 < CUDART_INF) {
+        const double cl = __dadd_rn(dl, wl), cr = __dadd_rn(dr, wr);
+        if (cl < nd) nd = cl;
+        if (cr < nd) nd = cr;
+      }
+      again = nd < d;
+      d = nd;
+    } while (__any_sync(0xFFFFFFFFu, again));
+    if (d < d0) {
+      chg = true;
+      t.d[r][lx] = d;
+      if (r == 1) mask |= 1;
+      if (r == TS) mask |= 2;
+      if (lane == 0) mask |= 4;
+      if (lane == 31) mask |= 8;
+    }
+    __syncwarp();                                  // row r is final and visible before the next row reads it
+  }
+  return __any_sync(0xFFFFFFFFu, chg);
+}
+
+__global__ void __launch_bounds__(kRelaxWarps * 32)
 k_relax(const RelaxArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sd_[TP][TP];
-  __shared__ double shc[TP][TP];
-  __shared__ double sq[TP][TP];      // sq[y][x]: diagonal length of the quad whose top-left cell is (x,y)
-  __shared__ double s_hd[TP], s_vd[TP];
-  __shared__ int s_xc[TP], s_yc[TP];
+  extern __shared__ __align__(16) uint8_t relax_smem[];
   __shared__ double s_dd[kMaxDd];
-  __shared__ int s_mask;
-  volatile double (*sd)[TP] = sd_;
 
   const FieldGeom& g = a.g;
   const int ntiles = a.ntx * a.nty;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = kRelaxThreads / 32;
+  const int nwarps = kRelaxWarps;
+  TileSmem& t = reinterpret_cast<TileSmem*>(relax_smem)[warp];
   const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
   if (dd_in_smem)
     for (int i = threadIdx.x; i < g.Kx * g.Ky; i += blockDim.x) s_dd[i] = g.ddist[i];
   const double* ddp = dd_in_smem ? s_dd : g.ddist;
   __syncthreads();
 
+  const int gwarp = blockIdx.x * nwarps + warp, total_warps = gridDim.x * nwarps;
   int sweeps_local = 0, act_local = 0;
   int round = 0;
   for (;; ++round) {
@@ -110,16 +158,16 @@ k_relax(const RelaxArgs a) {
     uint8_t* flags_cur = a.flags + (size_t)par * ntiles;
     uint8_t* flags_next = a.flags + (size_t)(par ^ 1) * ntiles;
     // ---- (1) frontier compaction with warp ballots
-    for (int base = (blockIdx.x * nwarps + warp) * 32; base < ntiles; base += gridDim.x * nwarps * 32) {
-      const int t = base + lane;
-      const int f = t < ntiles ? flags_cur[t] : 0;
-      if (f) flags_cur[t] = 0;
+    for (int base = gwarp * 32; base < ntiles; base += total_warps * 32) {
+      const int ti = base + lane;
+      const int f = ti < ntiles ? flags_cur[ti] : 0;
+      if (f) flags_cur[ti] = 0;
       const unsigned ballot = __ballot_sync(0xFFFFFFFFu, f);
       if (ballot) {
         int pos = 0;
         if (lane == 0) pos = atomicAdd(&a.ctl[par], __popc(ballot));
         pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        if (f) a.list[pos + __popc(ballot & ((1u << lane) - 1u))] = t;
+        if (f) a.list[pos + __popc(ballot & ((1u << lane) - 1u))] = ti;
       }
     }
     grid.sync();
@@ -130,105 +178,123 @@ k_relax(const RelaxArgs a) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl[par ^ 1] = 0;   // next round's counter; nobody touches it before the next barrier
 
-    // ---- (2) relax the active tiles
-    for (int li = blockIdx.x; li < count; li += gridDim.x) {
-      const int t = a.list[li];
-      const int tx = t % a.ntx, ty = t / a.ntx;
+    // ---- (2) relax the active tiles, one warp each. Warps of one CTA take list entries gridDim apart so that a short
+    //      list spreads over all SMs first.
+    for (int li = warp * gridDim.x + blockIdx.x; li < count; li += total_warps) {
+      const int ti = a.list[li];
+      const int tx = ti % a.ntx, ty = ti / a.ntx;
       const int x0 = tx * TS, y0 = ty * TS;
-      if (threadIdx.x == 0) s_mask = 0;
-      for (int idx = threadIdx.x; idx < TP * TP; idx += blockDim.x) {
-        const int lx = idx % TP, ly = idx / TP;
-        const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
-        const bool inb = gx >= 0 && gx < g.W && gy >= 0 && gy < g.H;
-        sd[ly][lx] = inb ? ld_relaxed(a.field + (size_t)gy * g.W + gx) : CUDART_INF;
-        shc[ly][lx] = inb ? half_cost(a.pcode[(size_t)gy * a.pitch16 + gx], g.init_half_cost) : CUDART_INF;
-      }
-      if (threadIdx.x < TP) {
-        const int c = threadIdx.x;
-        const int gx = x0 - 1 + c;   // edge between global column gx and gx+1
-        const bool ok = gx >= 0 && gx + 1 < g.W;
-        const int cls = ok ? g.xcls[gx] : -1;
-        s_xc[c] = cls;
-        s_hd[c] = ok ? g.hdist[cls] : CUDART_INF;
-      } else if (threadIdx.x >= 64 && threadIdx.x < 64 + TP) {
-        const int r = threadIdx.x - 64;
-        const int gy = y0 - 1 + r;
-        const bool ok = gy >= 0 && gy + 1 < g.H;
-        const int cls = ok ? g.ycls[gy] : -1;
-        s_yc[r] = cls;
-        s_vd[r] = ok ? g.vdist[cls] : CUDART_INF;
-      }
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < TP * TP; idx += blockDim.x) {
-        const int lx = idx % TP, ly = idx / TP;
-        const int xc = s_xc[lx], yc = s_yc[ly];
-        sq[ly][lx] = (xc >= 0 && yc >= 0) ? ddp[xc * g.Ky + yc] : CUDART_INF;
-      }
-      __syncthreads();
-
-      // chaotic in-place sweeps to the tile-local fixed point; thread owns column ix, rows iy0 + 8k
-      const int ix = threadIdx.x & 31, iy0 = threadIdx.x >> 5;
-      int mask = 0;
-      bool any = false;
-      int changed;
-      do {
-        changed = 0;
+      // load the tile + halo. Loads are issued in batches (plain L2-coherent ld.global.cg: other CTAs write the field during
+      // this kernel, so L1 is bypassed; an aligned 8-byte load cannot tear) so that their latencies overlap.
+      {
+        const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
+        const bool colin = gx < g.W;
+#pragma unroll 1
+        for (int lyb = 0; lyb < TP; lyb += 17) {
+          double dv[17];
+          uint32_t cv[17];
 #pragma unroll
-        for (int k = 0; k < TS / 8; ++k) {
-          const int iy = iy0 + 8 * k;
-          const int lx = ix + 1, ly = iy + 1;
-          const double hc0 = shc[ly][lx];
-          if (hc0 == CUDART_INF) continue;     // removed node: no edges
-          const double cur = sd[ly][lx];
-          const double best = relax_cell(sd, shc, sq, s_hd, s_vd, lx, ly, hc0);
-          if (best < cur) {
-            sd[ly][lx] = best;
-            changed = 1;
-            if (iy == 0) mask |= 1;            // N
-            if (iy == TS - 1) mask |= 2;       // S
-            if (ix == 0) mask |= 4;            // W
-            if (ix == TS - 1) mask |= 8;       // E
+          for (int j = 0; j < 17; ++j) {
+            const int gy = y0 - 1 + lyb + j;
+            const bool inb = colin && gy >= 0 && gy < g.H;
+            dv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + gx) : CUDART_INF;
+            cv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + gx] : (uint32_t)PCODE_REMOVED;
+          }
+#pragma unroll
+          for (int j = 0; j < 17; ++j) {
+            t.d[lyb + j][lane + 1] = dv[j];
+            t.hc[lyb + j][lane + 1] = half_cost(cv[j], g.init_half_cost);
           }
         }
-        any |= (changed != 0);
+        // the two halo columns: 68 entries over the warp
+        double hv[3];
+        uint32_t hcv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int e = lane + 32 * j;
+          const int ly = e >> 1, side_r = e & 1;
+          const int hx = side_r ? x0 + TS : x0 - 1, gy = y0 - 1 + ly;
+          const bool inb = e < 2 * TP && hx >= 0 && hx < g.W && gy >= 0 && gy < g.H;
+          hv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + hx) : CUDART_INF;
+          hcv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + hx] : (uint32_t)PCODE_REMOVED;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int e = lane + 32 * j;
+          if (e < 2 * TP) {
+            const int ly = e >> 1, lxh = (e & 1) ? TP - 1 : 0;
+            t.d[ly][lxh] = hv[j];
+            t.hc[ly][lxh] = half_cost(hcv[j], g.init_half_cost);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = lane + 32 * k;
+        if (r < TP) {
+          const int gy = y0 - 1 + r;               // edge between global rows gy and gy+1
+          const bool ok = gy >= 0 && gy + 1 < g.H;
+          const int cls = ok ? g.ycls[gy] : -1;
+          t.yc[r] = cls;
+          t.vd[r] = ok ? g.vdist[cls] : CUDART_INF;
+        }
+      }
+      // this lane's column: classes / lengths of the horizontal edges to its left and right
+      const int gxl = x0 + lane - 1, gxr = x0 + lane;       // edges (gxl, gxl+1) and (gxr, gxr+1)
+      const int xcl = (gxl >= 0 && gxl + 1 < g.W) ? g.xcls[gxl] : -1;
+      const int xcr = (gxr >= 0 && gxr + 1 < g.W) ? g.xcls[gxr] : -1;
+      const double hdl = xcl >= 0 ? g.hdist[xcl] : CUDART_INF, hdr = xcr >= 0 ? g.hdist[xcr] : CUDART_INF;
+      __syncwarp();
+
+      int mask = 0;
+      bool any = false;
+      for (;;) {
+        const bool c1 = sweep_rows<+1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
         ++sweeps_local;
-        changed = __syncthreads_or(changed);
-      } while (changed);
+        any |= c1;
+        const bool c2 = sweep_rows<-1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
+        ++sweeps_local;
+        any |= c2;
+        if (!c2) break;                            // the last sweep changed nothing and its opposite was completed before it
+        // the upward sweep changed something: a downward sweep that changes nothing would also prove the fixed point
+        const bool c3 = sweep_rows<+1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
+        ++sweeps_local;
+        if (!c3) break;
+        const bool c4 = sweep_rows<-1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
+        ++sweeps_local;
+        if (!c4) break;
+      }
       ++act_local;
 
-      // write back what this thread lowered (its own cells only), then publish
       if (any) {
-#pragma unroll
-        for (int k = 0; k < TS / 8; ++k) {
-          const int iy = iy0 + 8 * k;
-          const int gx = x0 + ix, gy = y0 + iy;
-          if (gx < g.W && gy < g.H) st_relaxed(a.field + (size_t)gy * g.W + gx, sd[iy + 1][ix + 1]);
+        for (int r = 1; r <= TS; ++r) {
+          const int gx = x0 + lane, gy = y0 + r - 1;
+          if (gx < g.W && gy < g.H) st_relaxed(a.field + (size_t)gy * g.W + gx, t.d[r][lane + 1]);
         }
         __threadfence();
       }
-      if (mask) atomicOr(&s_mask, mask);
-      __syncthreads();
-      if (threadIdx.x < 8) {
-        // neighbours: N S W E NW NE SW SE. A corner cell sits on two edges, so "N and W changed" may over-activate the
-        // NW tile when different cells set the two bits — harmless (an activation with nothing to do converges in one sweep).
-        const int m = s_mask;
-        const int k = threadIdx.x;
+      // neighbours: N S W E NW NE SW SE (a corner cell sets two edge bits; "both bits set" may over-activate a diagonal tile —
+      // harmless, an activation with nothing to do costs two sweeps)
+      int m = mask;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xFFFFFFFFu, m, off);
+      if (lane < 8 && m) {
         const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
         const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
         const int need[8] = {1, 2, 4, 8, 1 | 4, 1 | 8, 2 | 4, 2 | 8};
-        const bool on = (k < 4) ? ((m & need[k]) != 0) : ((m & need[k]) == need[k]);
-        const int ntx_ = tx + ddx[k], nty_ = ty + ddy[k];
+        const bool on = (lane < 4) ? ((m & need[lane]) != 0) : ((m & need[lane]) == need[lane]);
+        const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
         if (on && ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) flags_next[nty_ * a.ntx + ntx_] = 1;
       }
-      __syncthreads();
+      __syncwarp();
     }
     grid.sync();
   }
   // statistics
-  if (lane == 0 && warp == 0) {
+  if (lane == 0) {
     atomicAdd(&a.ctl[3], act_local);
     atomicAdd(&a.ctl[4], sweeps_local);
-    if (blockIdx.x == 0) a.ctl[2] = round;
+    if (blockIdx.x == 0 && warp == 0) a.ctl[2] = round;
   }
 }
 
@@ -421,7 +487,8 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   static int num_sms = 0, occ = 0;
   if (!num_sms) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxThreads, 0));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
+    SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem)));
     if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
   }
   RelaxArgs ra;
@@ -435,9 +502,8 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   ra.ctl = ctx->d_relax_ctl;
   ra.max_rounds = 8 * ntiles + 1024;
   int grid = num_sms * occ;
-  if (grid > ntiles) grid = ntiles < 1 ? 1 : ntiles;
   void* kargs[] = {(void*)&ra};
-  SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxThreads), kargs, 0, s));
+  SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxWarps * 32), kargs, kRelaxWarps * sizeof(TileSmem), s));
   ctx->launches += 1;
 
   PathArgs pa;
