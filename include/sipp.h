@@ -166,7 +166,7 @@ int sipp_field_download(sipp_ctx* ctx, double* field);
 int sipp_path_mask_generation(const sipp_ctx* ctx);
 /* inject a path mask computed elsewhere (tests; MapPlanExp::updatePathMap map_planexp.cpp:240-242) */
 int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask);
-/* relaxation statistics of the last sipp_plan: [0]=global rounds, [1]=tile activations, [2]=tile sweeps */
+/* relaxation statistics of the last sipp_plan: [0]=tile queue pushes, [1]=tile activations, [2]=tile sweeps, [3]=aborted */
 int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]);
 
 /* ---- batched footprint gain (A1-A8) ---------------------------------------------------------------- */

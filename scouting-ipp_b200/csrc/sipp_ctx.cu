@@ -362,8 +362,8 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   rc |= dev_alloc(ctx, &ctx->d_pcode, n8);
   rc |= dev_alloc(ctx, &ctx->d_freelab, n8);
   rc |= dev_alloc(ctx, &ctx->d_field, (size_t)ctx->W * ctx->H);
-  rc |= dev_alloc(ctx, &ctx->d_tile_flags, 2 * ntiles);
-  rc |= dev_alloc(ctx, &ctx->d_tile_list, ntiles);
+  rc |= dev_alloc(ctx, &ctx->d_tile_flags, ntiles);
+  rc |= dev_alloc(ctx, &ctx->d_tile_list, ntiles > 16384 ? ntiles : (size_t)16384);   // ring queue: >= tiles and >= resident warps
   rc |= dev_alloc(ctx, &ctx->d_relax_ctl, 16);
   rc |= dev_alloc(ctx, &ctx->d_path_nodes, cap);
   rc |= dev_alloc(ctx, &ctx->d_path_xy, 2 * cap);
@@ -489,15 +489,15 @@ int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int
   int rc = field_plan(ctx, ctx->stream);
   if (rc != SIPP_OK) return rc;
   int out[10];
-  int ctl[8];
+  int ctl[8];   // CTL_* of sipp_field.cu: head, tail, pending, activations, sweeps, abort, pushes
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->plan_stats[0] = ctl[2];
+  ctx->plan_stats[0] = ctl[6];
   ctx->plan_stats[1] = ctl[3];
   ctx->plan_stats[2] = ctl[4];
   ctx->plan_stats[3] = ctl[5];
-  if (ctl[5]) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation hit its round limit without converging");
+  if (ctl[5]) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation aborted by its watchdog (work queue starved)");
   double c;
   memcpy(&c, &out[8], sizeof(double));
   const int len = out[0];

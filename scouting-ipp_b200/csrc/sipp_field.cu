@@ -13,9 +13,9 @@
 // on the relaxation order (rounding is monotone), so a chaotic tile-parallel relaxation reproduces the bits a
 // sequential Dijkstra / A* leaves in d[goal]; all adds and multiplies use _rn intrinsics so nothing is fused.
 //
-// Relaxation = block-asynchronous Bellman-Ford on 32x32 tiles: a persistent cooperative kernel keeps a
-// ballot-compacted list of active tiles; a CTA iterates its tile in shared memory to a local fixed point, writes
-// it back and activates the neighbours whose halo it changed; rounds are separated by grid barriers.
+// Relaxation = asynchronous tile-level label correcting on 32x32 tiles: persistent warps pull active tiles from a ring
+// queue, a warp iterates its tile in shared memory to the tile-local fixed point with Gauss-Seidel row sweeps, merges
+// the result with atomicMin and queues the neighbours whose halo it lowered. No grid barriers (see k_relax).
 #include <cooperative_groups.h>
 #include <math_constants.h>
 
@@ -38,11 +38,14 @@ struct RelaxArgs {
   const uint16_t* pcode;    // [H][pitch16]
   size_t pitch16;
   int ntx, nty;
-  uint8_t* flags;           // [2][ntiles]
-  int* list;                // [ntiles]
-  int* ctl;                 // [0],[1] list counts by round parity, [2] rounds, [3] activations, [4] sweeps, [5] aborted
-  int max_rounds;
+  int* flags;               // [ntiles] 1 = tile is in the work queue
+  int* queue;               // [cap] ring buffer of tile ids, -1 = empty slot
+  int cap;
+  int* ctl;                 // see CTL_* below
+  int spin_limit;           // watchdog: a warp that polls an empty queue this many times aborts the kernel
 };
+enum { CTL_HEAD = 0, CTL_TAIL = 1, CTL_PENDING = 2, CTL_ACTIVATIONS = 3, CTL_SWEEPS = 4, CTL_ABORT = 5, CTL_PUSHES = 6 };
+
 
 __device__ __forceinline__ double ld_relaxed(const double* p) {
   double v;
@@ -51,6 +54,15 @@ __device__ __forceinline__ double ld_relaxed(const double* p) {
 }
 __device__ __forceinline__ void st_relaxed(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ int ld_volatile_i32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_i32(int* p, int v) {
+  asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ double half_cost(uint32_t code, double init_half) {
@@ -83,7 +95,7 @@ __device__ __forceinline__ double relax1(double best, double dn, double dist, do
 // Returns (warp-uniform) whether any cell was lowered; `mask` collects which tile borders changed.
 template <int DIR>
 __device__ __forceinline__ bool sweep_rows(TileSmem& t, const double* ddp, int Ky, int lane, int xcl, int xcr, double hdl, double hdr,
-                                           int& mask) {
+                                           int& mask, uint32_t& rows_changed) {
   const int lx = lane + 1;
   bool chg = false;
   for (int i = 0; i < TS; ++i) {
@@ -122,6 +134,7 @@ __device__ __forceinline__ bool sweep_rows(TileSmem& t, const double* ddp, int K
     } while (__any_sync(0xFFFFFFFFu, again));
     if (d < d0) {
       chg = true;
+      rows_changed |= 1u << (r - 1);
       t.d[r][lx] = d;
       if (r == 1) mask |= 1;
       if (r == TS) mask |= 2;
@@ -133,16 +146,20 @@ __device__ __forceinline__ bool sweep_rows(TileSmem& t, const double* ddp, int K
   return __any_sync(0xFFFFFFFFu, chg);
 }
 
+// Persistent, barrier-free worker kernel. Warps pull tile ids from a global ring queue, solve the tile to its local
+// fixed point and push the neighbours whose halo they lowered. Why this is still exact: (1) every value ever written is the
+// rounded length of a real path (an upper bound of the fixed point) and is merged with atomicMin on the bit pattern (for
+// non-negative doubles the integer order is the numeric order), so the field only ever decreases, even if two warps work
+// on the same tile at once; (2) a tile is re-queued whenever a neighbour lowers its halo after the tile last cleared its
+// "queued" flag, and the flag is cleared BEFORE the halo is loaded, so no update can be missed; (3) the kernel ends when
+// the number of queued + in-flight tiles drops to zero, i.e. at a global fixed point, which is unique.
 __global__ void __launch_bounds__(kRelaxWarps * 32)
 k_relax(const RelaxArgs a) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) uint8_t relax_smem[];
   __shared__ double s_dd[kMaxDd];
 
   const FieldGeom& g = a.g;
-  const int ntiles = a.ntx * a.nty;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = kRelaxWarps;
   TileSmem& t = reinterpret_cast<TileSmem*>(relax_smem)[warp];
   const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
   if (dd_in_smem)
@@ -150,165 +167,182 @@ k_relax(const RelaxArgs a) {
   const double* ddp = dd_in_smem ? s_dd : g.ddist;
   __syncthreads();
 
-  const int gwarp = blockIdx.x * nwarps + warp, total_warps = gridDim.x * nwarps;
-  int sweeps_local = 0, act_local = 0;
-  int round = 0;
-  for (;; ++round) {
-    const int par = round & 1;
-    uint8_t* flags_cur = a.flags + (size_t)par * ntiles;
-    uint8_t* flags_next = a.flags + (size_t)(par ^ 1) * ntiles;
-    // ---- (1) frontier compaction with warp ballots
-    for (int base = gwarp * 32; base < ntiles; base += total_warps * 32) {
-      const int ti = base + lane;
-      const int f = ti < ntiles ? flags_cur[ti] : 0;
-      if (f) flags_cur[ti] = 0;
-      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, f);
-      if (ballot) {
-        int pos = 0;
-        if (lane == 0) pos = atomicAdd(&a.ctl[par], __popc(ballot));
-        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        if (f) a.list[pos + __popc(ballot & ((1u << lane) - 1u))] = ti;
-      }
-    }
-    grid.sync();
-    const int count = *reinterpret_cast<volatile int*>(&a.ctl[par]);
-    if (count == 0 || round >= a.max_rounds) {
-      if (count != 0 && blockIdx.x == 0 && threadIdx.x == 0) a.ctl[5] = 1;
-      break;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl[par ^ 1] = 0;   // next round's counter; nobody touches it before the next barrier
-
-    // ---- (2) relax the active tiles, one warp each. Warps of one CTA take list entries gridDim apart so that a short
-    //      list spreads over all SMs first.
-    for (int li = warp * gridDim.x + blockIdx.x; li < count; li += total_warps) {
-      const int ti = a.list[li];
-      const int tx = ti % a.ntx, ty = ti / a.ntx;
-      const int x0 = tx * TS, y0 = ty * TS;
-      // load the tile + halo. Loads are issued in batches (plain L2-coherent ld.global.cg: other CTAs write the field during
-      // this kernel, so L1 is bypassed; an aligned 8-byte load cannot tear) so that their latencies overlap.
-      {
-        const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
-        const bool colin = gx < g.W;
-#pragma unroll 1
-        for (int lyb = 0; lyb < TP; lyb += 17) {
-          double dv[17];
-          uint32_t cv[17];
-#pragma unroll
-          for (int j = 0; j < 17; ++j) {
-            const int gy = y0 - 1 + lyb + j;
-            const bool inb = colin && gy >= 0 && gy < g.H;
-            dv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + gx) : CUDART_INF;
-            cv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + gx] : (uint32_t)PCODE_REMOVED;
-          }
-#pragma unroll
-          for (int j = 0; j < 17; ++j) {
-            t.d[lyb + j][lane + 1] = dv[j];
-            t.hc[lyb + j][lane + 1] = half_cost(cv[j], g.init_half_cost);
-          }
-        }
-        // the two halo columns: 68 entries over the warp
-        double hv[3];
-        uint32_t hcv[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int e = lane + 32 * j;
-          const int ly = e >> 1, side_r = e & 1;
-          const int hx = side_r ? x0 + TS : x0 - 1, gy = y0 - 1 + ly;
-          const bool inb = e < 2 * TP && hx >= 0 && hx < g.W && gy >= 0 && gy < g.H;
-          hv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + hx) : CUDART_INF;
-          hcv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + hx] : (uint32_t)PCODE_REMOVED;
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int e = lane + 32 * j;
-          if (e < 2 * TP) {
-            const int ly = e >> 1, lxh = (e & 1) ? TP - 1 : 0;
-            t.d[ly][lxh] = hv[j];
-            t.hc[ly][lxh] = half_cost(hcv[j], g.init_half_cost);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int r = lane + 32 * k;
-        if (r < TP) {
-          const int gy = y0 - 1 + r;               // edge between global rows gy and gy+1
-          const bool ok = gy >= 0 && gy + 1 < g.H;
-          const int cls = ok ? g.ycls[gy] : -1;
-          t.yc[r] = cls;
-          t.vd[r] = ok ? g.vdist[cls] : CUDART_INF;
-        }
-      }
-      // this lane's column: classes / lengths of the horizontal edges to its left and right
-      const int gxl = x0 + lane - 1, gxr = x0 + lane;       // edges (gxl, gxl+1) and (gxr, gxr+1)
-      const int xcl = (gxl >= 0 && gxl + 1 < g.W) ? g.xcls[gxl] : -1;
-      const int xcr = (gxr >= 0 && gxr + 1 < g.W) ? g.xcls[gxr] : -1;
-      const double hdl = xcl >= 0 ? g.hdist[xcl] : CUDART_INF, hdr = xcr >= 0 ? g.hdist[xcr] : CUDART_INF;
-      __syncwarp();
-
-      int mask = 0;
-      bool any = false;
+  int sweeps_local = 0, act_local = 0, push_local = 0;
+  for (;;) {
+    // ---- pop: take a ticket, wait for its slot to be filled (or for global termination)
+    int ti = -2;
+    if (lane == 0) {
+      const unsigned ticket = (unsigned)atomicAdd(&a.ctl[CTL_HEAD], 1);
+      int* slot = a.queue + (ticket % (unsigned)a.cap);
+      int spins = 0;
       for (;;) {
-        const bool c1 = sweep_rows<+1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
-        ++sweeps_local;
-        any |= c1;
-        const bool c2 = sweep_rows<-1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
-        ++sweeps_local;
-        any |= c2;
-        if (!c2) break;                            // the last sweep changed nothing and its opposite was completed before it
-        // the upward sweep changed something: a downward sweep that changes nothing would also prove the fixed point
-        const bool c3 = sweep_rows<+1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
-        ++sweeps_local;
-        if (!c3) break;
-        const bool c4 = sweep_rows<-1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask);
-        ++sweeps_local;
-        if (!c4) break;
-      }
-      ++act_local;
-
-      if (any) {
-        for (int r = 1; r <= TS; ++r) {
-          const int gx = x0 + lane, gy = y0 + r - 1;
-          if (gx < g.W && gy < g.H) st_relaxed(a.field + (size_t)gy * g.W + gx, t.d[r][lane + 1]);
+        const int v = ld_volatile_i32(slot);
+        if (v >= 0) {
+          st_volatile_i32(slot, -1);
+          ti = v;
+          break;
         }
+        if (ld_volatile_i32(&a.ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) break;
+        if (++spins > a.spin_limit) {
+          atomicExch(&a.ctl[CTL_ABORT], 1);
+          break;
+        }
+        __nanosleep(64);
+      }
+      if (ti >= 0) {
+        __threadfence();
+        atomicExch(&a.flags[ti], 0);   // from here on a neighbour that lowers our halo re-queues this tile
         __threadfence();
       }
-      // neighbours: N S W E NW NE SW SE (a corner cell sets two edge bits; "both bits set" may over-activate a diagonal tile —
-      // harmless, an activation with nothing to do costs two sweeps)
-      int m = mask;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xFFFFFFFFu, m, off);
-      if (lane < 8 && m) {
-        const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-        const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-        const int need[8] = {1, 2, 4, 8, 1 | 4, 1 | 8, 2 | 4, 2 | 8};
-        const bool on = (lane < 4) ? ((m & need[lane]) != 0) : ((m & need[lane]) == need[lane]);
-        const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
-        if (on && ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) flags_next[nty_ * a.ntx + ntx_] = 1;
-      }
-      __syncwarp();
     }
-    grid.sync();
+    ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+    if (ti < 0) break;
+
+    const int tx = ti % a.ntx, ty = ti / a.ntx;
+    const int x0 = tx * TS, y0 = ty * TS;
+    // load the tile + halo. Loads are issued in batches (plain L2-coherent ld.global.cg: other warps update the field with
+    // L2 atomics during this kernel, so L1 is bypassed; an aligned 8-byte load cannot tear) so that their latencies overlap.
+    {
+      const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
+      const bool colin = gx < g.W;
+#pragma unroll 1
+      for (int lyb = 0; lyb < TP; lyb += 17) {
+        double dv[17];
+        uint32_t cv[17];
+#pragma unroll
+        for (int j = 0; j < 17; ++j) {
+          const int gy = y0 - 1 + lyb + j;
+          const bool inb = colin && gy >= 0 && gy < g.H;
+          dv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + gx) : CUDART_INF;
+          cv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + gx] : (uint32_t)PCODE_REMOVED;
+        }
+#pragma unroll
+        for (int j = 0; j < 17; ++j) {
+          t.d[lyb + j][lane + 1] = dv[j];
+          t.hc[lyb + j][lane + 1] = half_cost(cv[j], g.init_half_cost);
+        }
+      }
+      // the two halo columns: 68 entries over the warp
+      double hv[3];
+      uint32_t hcv[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int e = lane + 32 * j;
+        const int ly = e >> 1, side_r = e & 1;
+        const int hx = side_r ? x0 + TS : x0 - 1, gy = y0 - 1 + ly;
+        const bool inb = e < 2 * TP && hx >= 0 && hx < g.W && gy >= 0 && gy < g.H;
+        hv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + hx) : CUDART_INF;
+        hcv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + hx] : (uint32_t)PCODE_REMOVED;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int e = lane + 32 * j;
+        if (e < 2 * TP) {
+          const int ly = e >> 1, lxh = (e & 1) ? TP - 1 : 0;
+          t.d[ly][lxh] = hv[j];
+          t.hc[ly][lxh] = half_cost(hcv[j], g.init_half_cost);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = lane + 32 * k;
+      if (r < TP) {
+        const int gy = y0 - 1 + r;               // edge between global rows gy and gy+1
+        const bool ok = gy >= 0 && gy + 1 < g.H;
+        const int cls = ok ? g.ycls[gy] : -1;
+        t.yc[r] = cls;
+        t.vd[r] = ok ? g.vdist[cls] : CUDART_INF;
+      }
+    }
+    // this lane's column: classes / lengths of the horizontal edges to its left and right
+    const int gxl = x0 + lane - 1, gxr = x0 + lane;       // edges (gxl, gxl+1) and (gxr, gxr+1)
+    const int xcl = (gxl >= 0 && gxl + 1 < g.W) ? g.xcls[gxl] : -1;
+    const int xcr = (gxr >= 0 && gxr + 1 < g.W) ? g.xcls[gxr] : -1;
+    const double hdl = xcl >= 0 ? g.hdist[xcl] : CUDART_INF, hdr = xcr >= 0 ? g.hdist[xcr] : CUDART_INF;
+    __syncwarp();
+
+    // alternate downward / upward sweeps until one of them changes nothing (its opposite was completed right before it)
+    int mask = 0;
+    uint32_t rows_changed = 0;
+    for (int it = 0;; ++it) {
+      const bool c = (it & 1) ? sweep_rows<-1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask, rows_changed)
+                              : sweep_rows<+1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask, rows_changed);
+      ++sweeps_local;
+      if (!c && it >= 1) break;
+    }
+    ++act_local;
+
+    // merge what this lane lowered (monotone: atomicMin on the bit pattern of non-negative doubles)
+    {
+      const int gx = x0 + lane;
+      uint32_t rc = rows_changed;
+      while (rc) {
+        const int r = __ffs(rc) - 1;
+        rc &= rc - 1;
+        const int gy = y0 + r;
+        if (gx < g.W && gy < g.H)
+          atomicMin(reinterpret_cast<unsigned long long*>(a.field + (size_t)gy * g.W + gx),
+                    (unsigned long long)__double_as_longlong(t.d[r + 1][lane + 1]));
+      }
+    }
+    int m = mask;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xFFFFFFFFu, m, off);
+    __threadfence();      // our field updates are visible before any neighbour can be told to look at them
+    __syncwarp();
+    // neighbours: N S W E NW NE SW SE (a corner cell sets two edge bits; "both bits set" may over-activate a diagonal tile —
+    // harmless, an activation with nothing to do costs two sweeps)
+    if (lane < 8 && m) {
+      const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+      const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+      const int need[8] = {1, 2, 4, 8, 1 | 4, 1 | 8, 2 | 4, 2 | 8};
+      const bool on = (lane < 4) ? ((m & need[lane]) != 0) : ((m & need[lane]) == need[lane]);
+      const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
+      if (on && ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
+        const int nt = nty_ * a.ntx + ntx_;
+        if (atomicExch(&a.flags[nt], 1) == 0) {
+          atomicAdd(&a.ctl[CTL_PENDING], 1);
+          const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
+          int* slot = a.queue + (pos % (unsigned)a.cap);
+          int spins = 0;
+          while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);   // never expected: cap >= number of tiles
+          __threadfence();
+          st_volatile_i32(slot, nt);
+          ++push_local;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicSub(&a.ctl[CTL_PENDING], 1);   // after our pushes were counted: pending reaches 0 only at the global fixed point
+    }
   }
   // statistics
+  atomicAdd(&a.ctl[CTL_PUSHES], push_local);
   if (lane == 0) {
-    atomicAdd(&a.ctl[3], act_local);
-    atomicAdd(&a.ctl[4], sweeps_local);
-    if (blockIdx.x == 0 && warp == 0) a.ctl[2] = round;
+    atomicAdd(&a.ctl[CTL_ACTIVATIONS], act_local);
+    atomicAdd(&a.ctl[CTL_SWEEPS], sweeps_local);
   }
 }
 
-__global__ void k_field_init(double* field, size_t n, int W, int sx, int sy, int H, uint8_t* flags, int ntiles2, int ntx, int* ctl) {
+__global__ void k_field_init(double* field, size_t n, int* flags, int* queue, int ntiles, int qcap, int* ctl) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t k = i; k < n; k += stride) field[k] = CUDART_INF;
-  for (size_t k = i; k < (size_t)ntiles2; k += stride) flags[k] = 0;
-  if (i < 8) ctl[i] = 0;
+  for (size_t k = i; k < (size_t)ntiles; k += stride) flags[k] = 0;
+  for (size_t k = i; k < (size_t)qcap; k += stride) queue[k] = -1;
+  if (i < 16) ctl[i] = 0;
 }
-__global__ void k_field_seed(double* field, int W, int H, int sx, int sy, uint8_t* flags, int ntx) {
+__global__ void k_field_seed(double* field, int W, int H, int sx, int sy, int* flags, int* queue, int ntx, int* ctl) {
   if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
     field[(size_t)sy * W + sx] = 0.0;
-    flags[(sy / TS) * ntx + (sx / TS)] = 1;
+    const int t = (sy / TS) * ntx + (sx / TS);
+    flags[t] = 1;
+    queue[0] = t;
+    ctl[CTL_TAIL] = 1;
+    ctl[CTL_PENDING] = 1;
   }
 }
 
@@ -478,9 +512,11 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   const FieldGeom g = make_geom(ctx);
   const size_t ncell = (size_t)ctx->W * ctx->H;
   const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
-  k_field_init<<<592, 256, 0, s>>>(ctx->d_field, ncell, ctx->W, g.start_x, g.start_y, ctx->H, ctx->d_tile_flags, 2 * ntiles,
-                                   ctx->n_tiles_x, ctx->d_relax_ctl);
-  k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->n_tiles_x);
+  // ring capacity: every tile can be queued at most once, and every waiting warp must own a distinct slot (ticket % cap)
+  const int qcap = ntiles > 16384 ? ntiles : 16384;
+  k_field_init<<<592, 256, 0, s>>>(ctx->d_field, ncell, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
+  k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->n_tiles_x,
+                               ctx->d_relax_ctl);
   ctx->launches += 2;
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
 
@@ -498,10 +534,12 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   ra.pitch16 = ctx->pitch16;
   ra.ntx = ctx->n_tiles_x; ra.nty = ctx->n_tiles_y;
   ra.flags = ctx->d_tile_flags;
-  ra.list = ctx->d_tile_list;
+  ra.queue = ctx->d_tile_list;
+  ra.cap = qcap;
   ra.ctl = ctx->d_relax_ctl;
-  ra.max_rounds = 8 * ntiles + 1024;
+  ra.spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
   int grid = num_sms * occ;
+  if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
   void* kargs[] = {(void*)&ra};
   SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxWarps * 32), kargs, kRelaxWarps * sizeof(TileSmem), s));
   ctx->launches += 1;

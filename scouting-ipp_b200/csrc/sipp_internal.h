@@ -102,8 +102,8 @@ struct sipp_ctx {
   int Kx, Ky;
   // relax work lists
   int n_tiles_x, n_tiles_y;
-  uint8_t* d_tile_flags;   // [2][ntiles]
-  int* d_tile_list;        // [ntiles]
+  int* d_tile_flags;       // [ntiles] tile is queued
+  int* d_tile_list;        // [ntiles] ring queue of tile ids
   int* d_relax_ctl;        // small control block (counters, stats)
   // path
   int* d_path_nodes;       // reverse order (goal -> start), packed (x<<16 | y)... see sipp_field.cu

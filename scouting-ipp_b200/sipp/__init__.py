@@ -250,7 +250,7 @@ class Context:
     def plan_stats(self):
         st = np.zeros(4, np.int64)
         self._check(self._L.sipp_plan_stats(self._h, _ptr(st)))
-        return dict(rounds=int(st[0]), tile_activations=int(st[1]), tile_sweeps=int(st[2]), aborted=int(st[3]))
+        return dict(pushes=int(st[0]), tile_activations=int(st[1]), tile_sweeps=int(st[2]), aborted=int(st[3]))
 
     def field_download(self):
         f = np.empty((self.H, self.W), np.float64)
