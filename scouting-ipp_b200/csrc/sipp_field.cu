@@ -146,6 +146,53 @@ __device__ __forceinline__ bool sweep_rows(TileSmem& t, const double* ddp, int K
   return __any_sync(0xFFFFFFFFu, chg);
 }
 
+// Loads d and the half costs of the 34x34 window whose interior starts at (x0, y0) into shared memory. Loads are issued in
+// batches (plain L2-coherent ld.global.cg: other warps update the field with L2 atomics while k_relax runs, so L1 is
+// bypassed; an aligned 8-byte load cannot tear) so that their latencies overlap instead of serialising on the stores.
+__device__ __forceinline__ void load_tile(TileSmem& t, const FieldGeom& g, const double* field, const uint16_t* pcode, size_t pitch16,
+                                          int x0, int y0, int lane) {
+  const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
+  const bool colin = gx >= 0 && gx < g.W;
+#pragma unroll 1
+  for (int lyb = 0; lyb < TP; lyb += 17) {
+    double dv[17];
+    uint32_t cv[17];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      const int gy = y0 - 1 + lyb + j;
+      const bool inb = colin && gy >= 0 && gy < g.H;
+      dv[j] = inb ? __ldcg(field + (size_t)gy * g.W + gx) : CUDART_INF;
+      cv[j] = inb ? (uint32_t)pcode[(size_t)gy * pitch16 + gx] : (uint32_t)PCODE_REMOVED;
+    }
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      t.d[lyb + j][lane + 1] = dv[j];
+      t.hc[lyb + j][lane + 1] = half_cost(cv[j], g.init_half_cost);
+    }
+  }
+  // the two halo columns: 68 entries over the warp
+  double hv[3];
+  uint32_t hcv[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int e = lane + 32 * j;
+    const int ly = e >> 1, side_r = e & 1;
+    const int hx = side_r ? x0 + TS : x0 - 1, gy = y0 - 1 + ly;
+    const bool inb = e < 2 * TP && hx >= 0 && hx < g.W && gy >= 0 && gy < g.H;
+    hv[j] = inb ? __ldcg(field + (size_t)gy * g.W + hx) : CUDART_INF;
+    hcv[j] = inb ? (uint32_t)pcode[(size_t)gy * pitch16 + hx] : (uint32_t)PCODE_REMOVED;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int e = lane + 32 * j;
+    if (e < 2 * TP) {
+      const int ly = e >> 1, lxh = (e & 1) ? TP - 1 : 0;
+      t.d[ly][lxh] = hv[j];
+      t.hc[ly][lxh] = half_cost(hcv[j], g.init_half_cost);
+    }
+  }
+}
+
 // Persistent, barrier-free worker kernel. Warps pull tile ids from a global ring queue, solve the tile to its local
 // fixed point and push the neighbours whose halo they lowered. Why this is still exact: (1) every value ever written is the
 // rounded length of a real path (an upper bound of the fixed point) and is merged with atomicMin on the bit pattern (for
@@ -200,50 +247,7 @@ k_relax(const RelaxArgs a) {
 
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
-    // load the tile + halo. Loads are issued in batches (plain L2-coherent ld.global.cg: other warps update the field with
-    // L2 atomics during this kernel, so L1 is bypassed; an aligned 8-byte load cannot tear) so that their latencies overlap.
-    {
-      const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
-      const bool colin = gx < g.W;
-#pragma unroll 1
-      for (int lyb = 0; lyb < TP; lyb += 17) {
-        double dv[17];
-        uint32_t cv[17];
-#pragma unroll
-        for (int j = 0; j < 17; ++j) {
-          const int gy = y0 - 1 + lyb + j;
-          const bool inb = colin && gy >= 0 && gy < g.H;
-          dv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + gx) : CUDART_INF;
-          cv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + gx] : (uint32_t)PCODE_REMOVED;
-        }
-#pragma unroll
-        for (int j = 0; j < 17; ++j) {
-          t.d[lyb + j][lane + 1] = dv[j];
-          t.hc[lyb + j][lane + 1] = half_cost(cv[j], g.init_half_cost);
-        }
-      }
-      // the two halo columns: 68 entries over the warp
-      double hv[3];
-      uint32_t hcv[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int e = lane + 32 * j;
-        const int ly = e >> 1, side_r = e & 1;
-        const int hx = side_r ? x0 + TS : x0 - 1, gy = y0 - 1 + ly;
-        const bool inb = e < 2 * TP && hx >= 0 && hx < g.W && gy >= 0 && gy < g.H;
-        hv[j] = inb ? __ldcg(a.field + (size_t)gy * g.W + hx) : CUDART_INF;
-        hcv[j] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + hx] : (uint32_t)PCODE_REMOVED;
-      }
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int e = lane + 32 * j;
-        if (e < 2 * TP) {
-          const int ly = e >> 1, lxh = (e & 1) ? TP - 1 : 0;
-          t.d[ly][lxh] = hv[j];
-          t.hc[ly][lxh] = half_cost(hcv[j], g.init_half_cost);
-        }
-      }
-    }
+    load_tile(t, g, a.field, a.pcode, a.pitch16, x0, y0, lane);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int r = lane + 32 * k;
@@ -365,7 +369,13 @@ __device__ __forceinline__ double edge_len(const FieldGeom& g, int ax, int ay, i
   return g.ddist[g.xcls[mx] * g.Ky + g.ycls[my]];
 }
 
-__global__ void k_backtrack(const PathArgs a) {
+// One warp. The walk runs inside a 32x32 window (plus halo) of d and half costs held in shared memory, centred on the
+// current node and re-loaded whenever the walk reaches the window's border; lanes 0..7 evaluate the 8 neighbours.
+__global__ void __launch_bounds__(32)
+k_backtrack(const PathArgs a) {
+  __shared__ TileSmem t;
+  __shared__ int s_xc[TP];
+  __shared__ double s_hd[TP];
   const FieldGeom& g = a.g;
   const int lane = threadIdx.x;
   int x = g.goal_x, y = g.goal_y;
@@ -375,51 +385,75 @@ __global__ void k_backtrack(const PathArgs a) {
     if (lane == 0) { a.out[0] = 0; a.out[1] = 0; a.out[2] = 0; a.out[3] = 0; a.out[4] = 0; *a.cost_out = -1.0; }
     return;
   }
-  const int NDX[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  const int NDX[8] = {-1, -1, -1, 0, 0, 1, 1, 1};   // ascending node id = x*H + y
   const int NDY[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  const int ndx = NDX[lane & 7], ndy = NDY[lane & 7];
   int len = 0;
   if (lane == 0) a.nodes[0] = (x << 16) | y;
   len = 1;
   bool fail = false;
-  while (!(x == g.start_x && y == g.start_y)) {
-    const double dv = a.field[(size_t)y * g.W + x];
-    const double hcv = half_cost(a.pcode[(size_t)y * a.pitch16 + x], g.init_half_cost);
-    bool ok = false;
-    double f = CUDART_INF;
-    if (lane < 8) {
-      const int ux = x + NDX[lane], uy = y + NDY[lane];
-      if (ux >= 0 && ux < g.W && uy >= 0 && uy < g.H) {
-        const double dist = edge_len(g, ux, uy, x, y);
-        const double hcu = half_cost(a.pcode[(size_t)uy * a.pitch16 + ux], g.init_half_cost);
+  while (!fail && !(x == g.start_x && y == g.start_y)) {
+    // ---- (re)load a window whose interior [x0, x0+32) x [y0, y0+32) has the current node at its centre
+    const int x0 = x - TS / 2, y0 = y - TS / 2;
+    load_tile(t, g, a.field, a.pcode, a.pitch16, x0, y0, lane);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int e = lane + 32 * k;
+      if (e < TP) {
+        const int gy = y0 - 1 + e, gx = x0 - 1 + e;     // edges (gy, gy+1) and (gx, gx+1)
+        const bool oky = gy >= 0 && gy + 1 < g.H, okx = gx >= 0 && gx + 1 < g.W;
+        const int cy = oky ? g.ycls[gy] : -1, cx = okx ? g.xcls[gx] : -1;
+        t.yc[e] = cy;
+        t.vd[e] = oky ? g.vdist[cy] : CUDART_INF;
+        s_xc[e] = cx;
+        s_hd[e] = okx ? g.hdist[cx] : CUDART_INF;
+      }
+    }
+    __syncwarp();
+    // ---- walk while the node stays in the interior
+    int lx = x - x0 + 1, ly = y - y0 + 1;            // window coordinates incl. halo offset
+    while (lx >= 1 && lx <= TS && ly >= 1 && ly <= TS && !(x == g.start_x && y == g.start_y)) {
+      const double dv = t.d[ly][lx];
+      const double hcv = t.hc[ly][lx];
+      bool ok = false;
+      double f = CUDART_INF;
+      if (lane < 8) {
+        const int ux = lx + ndx, uy = ly + ndy;
+        const int ex = min(lx, ux), ey = min(ly, uy);  // local edge indices (edge e joins local e and e+1)
+        double dist;
+        if (ndy == 0) dist = s_hd[ex];
+        else if (ndx == 0) dist = t.vd[ey];
+        else dist = (s_xc[ex] >= 0 && t.yc[ey] >= 0) ? g.ddist[s_xc[ex] * g.Ky + t.yc[ey]] : CUDART_INF;
+        const double hcu = t.hc[uy][ux];
         if (dist < CUDART_INF && hcu < CUDART_INF && hcv < CUDART_INF) {
-          const double du = a.field[(size_t)uy * g.W + ux];
+          const double du = t.d[uy][ux];
           const double w = __dmul_rn(dist, __dadd_rn(hcu, hcv));
           if (__dadd_rn(du, w) == dv) {
             ok = true;
-            const int gx = g.goal_x - ux, gy = g.goal_y - uy;
+            const int gx = g.goal_x - (x + ndx), gy = g.goal_y - (y + ndy);
             const double hh = __dmul_rn(__dmul_rn(__dsqrt_rn((double)(gx * gx + gy * gy)), g.min_cost), g.spacing);   // prm_star_planner.h:108-112
             f = __dadd_rn(du, hh);
           }
         }
       }
-    }
-    // min f, lowest lane on ties
-    int best_lane = ok ? lane : 99;
-    double best_f = f;
+      // smallest f, lowest neighbour id on ties
+      int best_lane = ok ? lane : 99;
+      double best_f = f;
 #pragma unroll
-    for (int off = 4; off > 0; off >>= 1) {
-      const double of = __shfl_xor_sync(0xFFFFFFFFu, best_f, off);
-      const int ol = __shfl_xor_sync(0xFFFFFFFFu, best_lane, off);
-      const bool take = (ol != 99) && (best_lane == 99 || of < best_f || (of == best_f && ol < best_lane));
-      if (take) { best_f = of; best_lane = ol; }
+      for (int off = 4; off > 0; off >>= 1) {
+        const double of = __shfl_xor_sync(0xFFFFFFFFu, best_f, off);
+        const int ol = __shfl_xor_sync(0xFFFFFFFFu, best_lane, off);
+        const bool take = (ol != 99) && (best_lane == 99 || of < best_f || (of == best_f && ol < best_lane));
+        if (take) { best_f = of; best_lane = ol; }
+      }
+      best_lane = __shfl_sync(0xFFFFFFFFu, best_lane, 0);
+      if (best_lane == 99 || len >= a.cap) { fail = true; break; }
+      x += NDX[best_lane]; y += NDY[best_lane];
+      lx += NDX[best_lane]; ly += NDY[best_lane];
+      if (lane == 0) a.nodes[len] = (x << 16) | y;
+      ++len;
     }
-    best_lane = __shfl_sync(0xFFFFFFFFu, best_lane, 0);
-    if (best_lane == 99) { fail = true; break; }
-    x += NDX[best_lane];
-    y += NDY[best_lane];
-    if (len >= a.cap) { fail = true; break; }
-    if (lane == 0) a.nodes[len] = (x << 16) | y;
-    ++len;
+    __syncwarp();
   }
   if (lane == 0) {
     a.out[0] = fail ? 0 : len;
