@@ -416,7 +416,7 @@ k_backtrack(const PathArgs a) {
       const double dv = t.d[ly][lx];
       const double hcv = t.hc[ly][lx];
       bool ok = false;
-      double f = CUDART_INF;
+      double du = CUDART_INF;
       if (lane < 8) {
         const int ux = lx + ndx, uy = ly + ndy;
         const int ex = min(lx, ux), ey = min(ly, uy);  // local edge indices (edge e joins local e and e+1)
@@ -426,27 +426,34 @@ k_backtrack(const PathArgs a) {
         else dist = (s_xc[ex] >= 0 && t.yc[ey] >= 0) ? g.ddist[s_xc[ex] * g.Ky + t.yc[ey]] : CUDART_INF;
         const double hcu = t.hc[uy][ux];
         if (dist < CUDART_INF && hcu < CUDART_INF && hcv < CUDART_INF) {
-          const double du = t.d[uy][ux];
-          const double w = __dmul_rn(dist, __dadd_rn(hcu, hcv));
-          if (__dadd_rn(du, w) == dv) {
-            ok = true;
-            const int gx = g.goal_x - (x + ndx), gy = g.goal_y - (y + ndy);
-            const double hh = __dmul_rn(__dmul_rn(__dsqrt_rn((double)(gx * gx + gy * gy)), g.min_cost), g.spacing);   // prm_star_planner.h:108-112
-            f = __dadd_rn(du, hh);
-          }
+          du = t.d[uy][ux];
+          ok = __dadd_rn(du, __dmul_rn(dist, __dadd_rn(hcu, hcv))) == dv;
         }
       }
-      // smallest f, lowest neighbour id on ties
-      int best_lane = ok ? lane : 99;
-      double best_f = f;
+      // tied predecessors: smallest f = d[u] + h(u), lowest neighbour id among equal f. Most nodes have a single
+      // predecessor, so the heuristic (a double sqrt) is only evaluated when there is a tie to break.
+      const unsigned okmask = __ballot_sync(0xFFFFFFFFu, ok);
+      int best_lane = 99;
+      if (okmask && (okmask & (okmask - 1)) == 0) {
+        best_lane = __ffs(okmask) - 1;
+      } else if (okmask) {
+        double f = CUDART_INF;
+        if (ok) {
+          const int gx = g.goal_x - (x + ndx), gy = g.goal_y - (y + ndy);
+          const double hh = __dmul_rn(__dmul_rn(__dsqrt_rn((double)(gx * gx + gy * gy)), g.min_cost), g.spacing);   // prm_star_planner.h:108-112
+          f = __dadd_rn(du, hh);
+        }
+        best_lane = ok ? lane : 99;
+        double best_f = f;
 #pragma unroll
-      for (int off = 4; off > 0; off >>= 1) {
-        const double of = __shfl_xor_sync(0xFFFFFFFFu, best_f, off);
-        const int ol = __shfl_xor_sync(0xFFFFFFFFu, best_lane, off);
-        const bool take = (ol != 99) && (best_lane == 99 || of < best_f || (of == best_f && ol < best_lane));
-        if (take) { best_f = of; best_lane = ol; }
+        for (int off = 4; off > 0; off >>= 1) {
+          const double of = __shfl_xor_sync(0xFFFFFFFFu, best_f, off);
+          const int ol = __shfl_xor_sync(0xFFFFFFFFu, best_lane, off);
+          const bool take = (ol != 99) && (best_lane == 99 || of < best_f || (of == best_f && ol < best_lane));
+          if (take) { best_f = of; best_lane = ol; }
+        }
+        best_lane = __shfl_sync(0xFFFFFFFFu, best_lane, 0);
       }
-      best_lane = __shfl_sync(0xFFFFFFFFu, best_lane, 0);
       if (best_lane == 99 || len >= a.cap) { fail = true; break; }
       x += NDX[best_lane]; y += NDY[best_lane];
       lx += NDX[best_lane]; ly += NDY[best_lane];
