@@ -195,16 +195,15 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     sh = stream.cuda_stream
 
+    from sipp import shard
+
     def step():
         ctx.cycle_dev(params, T, d_xy.data_ptr(), None, d_cost.data_ptr(), d_gain.data_ptr(), d_term.data_ptr(), d_value.data_ptr(),
                       d_best.data_ptr(), sh)
         if world > 1:
-            # the only cross-GPU traffic: gather every shard's 16-byte (value, index) record, then argmax on every rank
+            # the only cross-GPU traffic: gather every shard's 16-byte (value, index) record, then the same argmax on every rank
             d_best[1] += lo
-            dist.all_gather_into_tensor(d_all, d_best)
-            vals = d_all.view(world, 2)[:, 0].view(torch.float64)
-            j = torch.argmax(vals)          # first maximum = lowest rank = lowest global index
-            return d_all.view(world, 2)[j]
+            return shard.gather_best(d_best, world, out=d_all)
         return d_best
 
     with torch.cuda.stream(stream):
