@@ -106,6 +106,21 @@ typedef struct sipp_eval_params {
   double bv_x_min, bv_x_max, bv_y_min, bv_y_max; /* inclusive, z is always inside (voxel z = 0)*/
 } sipp_eval_params;
 
+/* ---- evaluator-updater policy (A13): which tree nodes are re-scored in a cycle ------------------------------------- */
+#define SIPP_UPD_RRT_STAR 0     /* "RRTStarUpdater"  advanced_planner_modules/src/evaluator_updater/rrt_star_updater.cpp:19-42 */
+#define SIPP_UPD_CONSTRAINED 1  /* [upstream] "ConstrainedUpdater" (cfg/planners/example_config.yaml:109-117)               */
+#define SIPP_UPD_DIRECT 2       /* the following updater IS the evaluator_updater (cfg/evaluators/expand_reachable_area.yaml:23-27) */
+#define SIPP_FOLLOW_UPDATE_ALL 0              /* [upstream] "UpdateAll"                                                  */
+#define SIPP_FOLLOW_UPDATE_ALL_NON_TERMINAL 1 /* "UpdateAllNonTerminal"  src/evaluator_updater/update_all_non_terminal.cpp:16-27 */
+typedef struct sipp_updater_params {
+  int32_t updater;        /* SIPP_UPD_*                                   */
+  int32_t following;      /* SIPP_FOLLOW_*                                */
+  double minimum_gain;    /* default -1e9 (rrt_star_updater.cpp:45)       */
+  double update_range;    /* default  1e9 (:46)                           */
+  int32_t update_gain, update_cost, update_value;   /* following updater flags, default true */
+  int32_t pad_;
+} sipp_updater_params;
+
 /* counts[] layout written per candidate by sipp_gain_batch (SIPP_COUNTS_PER_CANDIDATE uint32 each). */
 #define SIPP_COUNTS_PER_CANDIDATE 4
 #define SIPP_CNT_VISIBLE 0  /* voxels emitted by the footprint after the bounding-volume filter (centre counted twice) */
@@ -198,6 +213,12 @@ int sipp_value_select(sipp_ctx* ctx, int32_t n, const double* gain, const double
 int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const double* d_cost,
                           const int32_t* d_parent, double* d_value, int32_t* d_best_child,
                           double* d_best_value, void* stream);
+
+/* Values as the reference's pre-order re-evaluation pass leaves them ([upstream] OnlinePlanner::updateEvaluatorStep calls
+ * updateSegment -> computeValue node by node, parents first): value[i] is computed with this cycle's gains (gain_new) on the
+ * root..i chain and LAST cycle's gains (gain_old) on i's descendants. Same tree conventions as sipp_value_select. */
+int sipp_value_preorder(sipp_ctx* ctx, int32_t n, const double* gain_new, const double* gain_old, const double* cost,
+                        const int32_t* parent, double* value);
 
 /* ---- fused evaluation cycle ------------------------------------------------------------------------ */
 /* gain for all n candidates (flat tree, candidate i is node i+1 under a virtual root) + value + argmax

@@ -848,6 +848,60 @@ int orc_value_select(int32_t n, const double* gain_in, const double* cost_in, co
   return 0;
 }
 
+// Literal emulation of one tree re-evaluation pass of the reference: [upstream] OnlinePlanner::updateEvaluatorStep visits the
+// tree in pre-order and calls trajectory_evaluator_->updateSegment(node) -> evaluator_updater chain:
+//   RRTStarUpdater::updateSegment            advanced_planner_modules/src/evaluator_updater/rrt_star_updater.cpp:19-42
+//   [upstream] ConstrainedUpdater::updateSegment (same predicate without the terminal / path-changed terms)
+//   [upstream] UpdateAll::updateSegment / UpdateAllNonTerminal::updateSegment  (update_all_non_terminal.cpp:16-27)
+// Nodes are given in pre-order (parent[i] < i, children in index order), node 0 is the root (never updated).
+// gain / value / terminal are in-out; computeValue sees whatever gains the array holds at that moment.
+int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
+                    const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                    const double* cur_xy, int path_changed, int variant) {
+  Oracle& o = c->o;
+  std::vector<std::vector<int>> children(n);
+  for (int i = 1; i < n; ++i) children[parent[i]].push_back(i);
+  std::vector<double> g(gain, gain + n), cst(cost, cost + n);
+  g[0] = 0.0; cst[0] = 0.0;
+  const bool setsTerminal = p->evaluator == SIPP_EVAL_RRT_STAR || p->evaluator == SIPP_EVAL_EXPAND_REACHABLE;
+  auto compute_gain = [&](int i) {
+    double gi; uint8_t ti;
+    eval_one(o, *p, end_xy[2 * i], end_xy[2 * i + 1], start_xy ? start_xy + 2 * i : end_xy + 2 * i, variant == 0, &gi, nullptr, &ti);
+    g[i] = gi;
+    if (setsTerminal && ti) terminal[i] = 1;      // the evaluators only ever set gain_terminal, never clear it
+  };
+  auto compute_value = [&](int i) {
+    double gs = 0.0, cs = 0.0;
+    for (int cur = parent[i]; cur >= 0; cur = (cur == 0) ? -1 : parent[cur]) { gs += g[cur]; cs += cst[cur]; }
+    value[i] = find_best(children, g.data(), cst.data(), i, gs, cs);
+  };
+  auto following = [&](int i) {
+    if (u->following == SIPP_FOLLOW_UPDATE_ALL) {
+      if (u->update_gain) compute_gain(i);
+      if (u->update_value) compute_value(i);
+    } else {
+      if (u->update_gain && !terminal[i]) compute_gain(i);
+      if (u->update_value && !(terminal[i] && !u->update_cost)) compute_value(i);
+    }
+  };
+  for (int i = 1; i < n; ++i) {     // pre-order; the root segment cannot be updated (rrt_star_updater.cpp:21)
+    const double dx = cur_xy[0] - end_xy[2 * i], dy = cur_xy[1] - end_xy[2 * i + 1];
+    const double dist = std::sqrt(dx * dx + dy * dy + 0.0 * 0.0);
+    if (u->updater == SIPP_UPD_RRT_STAR) {
+      if (terminal[i]) continue;
+      if (g[i] > u->minimum_gain || path_changed)
+        if (dist <= u->update_range || path_changed) following(i);
+    } else if (u->updater == SIPP_UPD_CONSTRAINED) {
+      if (g[i] > u->minimum_gain)
+        if (dist <= u->update_range) following(i);
+    } else {
+      following(i);                 // cfg/evaluators/expand_reachable_area.yaml:23-27: no gating updater in front
+    }
+  }
+  for (int i = 1; i < n; ++i) gain[i] = g[i];
+  return 0;
+}
+
 // flat-tree cycle: candidate i is node i+1 under a virtual root.
 int orc_cycle(orc_ctx* c, const sipp_eval_params* p, int32_t n, const double* xy, const double* start_xy, const double* cost,
               double* gain, uint8_t* terminal, double* value, int32_t* best_index, double* best_value, int variant, int threads) {

@@ -585,7 +585,7 @@ int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const 
   if (d_parent) {
     int rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, (size_t)n * 16 + 512);
     if (rc != SIPP_OK) return rc;
-    SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_gain, d_cost, d_parent, d_value, ctx->d_best, ctx->d_tree_ws, s));
+    SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_gain, nullptr, d_cost, d_parent, d_value, ctx->d_best, ctx->d_tree_ws, s));
   } else {
     SIPP_CUDA_CHECK(ctx, launch_value_flat(ctx, n, d_gain, d_cost, d_value, s));
     // children are nodes 1..n-1: scan value+1, the kernel shifts the index back by one
@@ -616,7 +616,7 @@ int sipp_value_select(sipp_ctx* ctx, int32_t n, const double* gain, const double
   if (parent) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.parent, parent, (size_t)n * 4, cudaMemcpyHostToDevice, s));
   if (parent) {
     if ((rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, (size_t)n * 16 + 512)) != SIPP_OK) return rc;
-    SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, st.gain, st.cost, st.parent, st.value, ctx->d_best, ctx->d_tree_ws, s));
+    SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, st.gain, nullptr, st.cost, st.parent, st.value, ctx->d_best, ctx->d_tree_ws, s));
   } else {
     SIPP_CUDA_CHECK(ctx, launch_value_flat(ctx, n, st.gain, st.cost, st.value, s));
     if (n > 1) SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n - 1, st.value + 1, 1, ctx->d_best, st.value, s));
@@ -630,6 +630,33 @@ int sipp_value_select(sipp_ctx* ctx, int32_t n, const double* gain, const double
   if (br.index == -2) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "tree deeper than 512 levels");
   if (best_child) *best_child = (int32_t)br.index;
   if (best_value) *best_value = br.value;
+  return SIPP_OK;
+}
+
+int sipp_value_preorder(sipp_ctx* ctx, int32_t n, const double* gain_new, const double* gain_old, const double* cost, const int32_t* parent,
+                        double* value) {
+  SIPP_ENTER(ctx);
+  if (n < 1 || !gain_new || !gain_old || !cost || !parent || !value) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad value_preorder arguments");
+  for (int i = 1; i < n; ++i)
+    if (parent[i] < 0 || parent[i] >= i) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "parent[%d] = %d violates 0 <= parent[i] < i", i, parent[i]);
+  cudaStream_t s = ctx->stream;
+  int rc;
+  // stage: gain_new | gain_old | cost | value (doubles) | parent (int32)
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, (size_t)n * 36 + 256)) != SIPP_OK) return rc;
+  double* d_new = reinterpret_cast<double*>(ctx->d_stage);
+  double *d_old = d_new + n, *d_cost = d_old + n, *d_value = d_cost + n;
+  int32_t* d_parent = reinterpret_cast<int32_t*>(d_value + n);
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_new, gain_new, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_old, gain_old, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cost, cost, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_parent, parent, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  if ((rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, (size_t)n * 16 + 512)) != SIPP_OK) return rc;
+  SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_new, d_old, d_cost, d_parent, d_value, ctx->d_best, ctx->d_tree_ws, s));
+  BestRec br;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(&br, ctx->d_best, sizeof(br), cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value, d_value, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  if (br.index == -2) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "tree deeper than 512 levels");
   return SIPP_OK;
 }
 

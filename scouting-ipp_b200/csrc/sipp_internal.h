@@ -159,8 +159,8 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
 cudaError_t launch_select_flat(sipp_ctx* ctx, int n, const double* d_value, long long index_offset, BestRec* d_best, double* d_root_value,
                                cudaStream_t s);
 cudaError_t launch_value_flat(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, double* d_value, cudaStream_t s);
-cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, const int32_t* d_parent,
-                              double* d_value, BestRec* d_best, void* ws, cudaStream_t s);
+cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_gain_below, const double* d_cost,
+                              const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s);
 size_t select_workspace_bytes();
 // sipp_field.cu
 int field_plan(sipp_ctx* ctx, cudaStream_t s);

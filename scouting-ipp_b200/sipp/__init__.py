@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "sipp_abi_version", "sipp_create", "sipp_destroy", "sipp_last_error", "sipp_stream", "sipp_map_clear",
     "sipp_patch_origin", "sipp_map_update_patch", "sipp_map_upload_full", "sipp_update_unknown_cost", "sipp_map_stats",
     "sipp_map_download", "sipp_plan", "sipp_field_download", "sipp_path_mask_generation", "sipp_set_path_mask",
-    "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev",
+    "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
     "sipp_cycle", "sipp_cycle_dev", "sipp_launch_count",
 ]
 
@@ -146,6 +146,7 @@ def lib():
         L.sipp_gain_batch_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp]
         L.sipp_value_select.argtypes = [vp, i32, vp, vp, vp, vp, pi32, pf64]
         L.sipp_value_select_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.sipp_value_preorder.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.sipp_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, pi32, pf64]
         L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.sipp_launch_count.argtypes = [vp]
@@ -289,6 +290,16 @@ class Context:
         self._check(self._L.sipp_value_select(self._h, n, _ptr(gain), _ptr(cost), _ptr(parent), _ptr(value), C.byref(bc),
                                               C.byref(bv)))
         return value, bc.value, bv.value
+
+    def value_preorder(self, gain_new, gain_old, cost, parent):
+        gain_new = np.ascontiguousarray(gain_new, dtype=np.float64)
+        gain_old = np.ascontiguousarray(gain_old, dtype=np.float64)
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        value = np.zeros(gain_new.shape[0], np.float64)
+        self._check(self._L.sipp_value_preorder(self._h, gain_new.shape[0], _ptr(gain_new), _ptr(gain_old), _ptr(cost), _ptr(parent),
+                                                _ptr(value)))
+        return value
 
     def cycle(self, params, xy, cost, start_xy=None):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

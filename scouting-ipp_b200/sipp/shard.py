@@ -30,15 +30,13 @@ def gather_best(local_rec, world, group=None, out=None):
         out = torch.empty(2 * world, dtype=torch.int64, device=local_rec.device)
     dist.all_gather_into_tensor(out, local_rec, group=group)
     recs = out.view(world, 2)
-    vals = recs[:, 0].view(torch.float64).clone()
+    vals = recs[:, 0].view(torch.float64)
     idx = recs[:, 1]
     valid = (idx >= 0) & ~torch.isnan(vals)
-    if not bool(valid.any()):
-        # no comparable value anywhere: the sequential scan keeps its first element
-        first = torch.nonzero(idx >= 0)
-        return recs[int(first[0])] if first.numel() else recs[0]
     vals = torch.where(valid, vals, torch.full_like(vals, float("-inf")))
     best = vals.max()
+    # lowest global index among the ranks holding the maximum; with no comparable value anywhere every entry ties at
+    # int64 max and rank 0's record is returned (the sequential scan keeps its first element). No host synchronisation.
     cand = torch.where(valid & (vals == best), idx, torch.full_like(idx, torch.iinfo(torch.int64).max))
-    j = int(torch.argmin(cand))
-    return recs[j]
+    j = torch.argmin(cand)
+    return recs.index_select(0, j.view(1)).view(2)
