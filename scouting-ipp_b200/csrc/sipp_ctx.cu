@@ -309,6 +309,8 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   ctx->desc = *d;
   ctx->device = device;
   ctx->launches = 0;
+  ctx->gain_warps = getenv("SIPP_GAIN_WARPS") ? atoi(getenv("SIPP_GAIN_WARPS")) : 0;
+  ctx->gain_stages = getenv("SIPP_GAIN_STAGES") ? atoi(getenv("SIPP_GAIN_STAGES")) : 0;
   ctx->W = d->W;
   ctx->H = d->H;
   ctx->mpp = d->width / (unsigned int)d->W;   // m_per_pixel_ map_server_planexp.cpp:116

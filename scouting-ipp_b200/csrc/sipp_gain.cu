@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int kMaxWarpsPerCta = 16;
-constexpr int kStages = 2;
+constexpr int kMaxStages = 8;       // tile slots per warp (runtime choice, GainArgs::stages)
 
 // evaluator "reduction modes"
 enum { MODE_COUNT = 0, MODE_RRT_DISCOUNT = 1, MODE_GOAL_DISTANCE = 2, MODE_AVG_VIEW_COST = 3, MODE_LOW_COST = 4 };
@@ -35,6 +35,7 @@ struct GainArgs {
   int box_w;          // bytes per tile row of the rec tile (multiple of 16)
   int box_w16;        // elements per tile row of the uint16 aux tile (multiple of 8)
   int slot_bytes;     // bytes per pipeline slot (rec tile [+ aux tile]), multiple of 128
+  int stages;         // tile slots per warp: stages - 1 TMA loads in flight while one tile is scanned
   int aux_off;        // byte offset of the aux tile inside a slot
   double npg;         // non_path_voxel_gain
   int use_discount, do_binary;
@@ -140,11 +141,13 @@ __device__ __forceinline__ int clipped_extent(int c, int h, int lo, int hi) {
   return max(b - a + 1, 0);
 }
 
-struct WinSlot {   // window parameters of the candidate in flight in one (warp, stage) slot; written by lane 0 at issue time
-  int cx, cy, on_map, pad;
-  double vcx, vcy;
-};
-
+// Work split: warp gw owns the CONTIGUOUS candidate range [gw*n/nw, (gw+1)*n/nw) and walks it in batches of up to 32.
+// Per batch, lane j does the per-candidate scalar work of candidate j — the reference's double-precision index math before
+// the scan, the duplicated centre voxel and the evaluator epilogue after it — so that work runs 32-wide instead of serially
+// on lane 0, and pose loads / result stores are coalesced. Between the two, the warp scans the batch's tiles one after the
+// other; lane j issues the TMA load of its own candidate `stages - 1` scans ahead (the next batch's windows are computed one
+// batch early so the pipeline never drains).
+//
 // Lane layout over a tile whose rows are `ncr` 16-byte chunks wide: lane = lrow * ncr + lcc for the first
 // rpi * ncr lanes (rpi = 32 / ncr rows are covered per iteration), the remaining lanes idle. A lane keeps its chunk
 // column for the whole scan, so the column masks of the (unaligned) window are computed once per candidate.
@@ -152,16 +155,15 @@ template <int MODE>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32)
 k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_aux, const GainArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[kMaxWarpsPerCta * kStages];
-  __shared__ WinSlot wins[kMaxWarpsPerCta * kStages];
+  __shared__ __align__(8) uint64_t bars[kMaxWarpsPerCta * kMaxStages];
+  __shared__ uint4 mask_tbl[16 * 16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kStages = a.stages;
   const uint32_t slot_base = smem_u32(smem_raw) + (uint32_t)(warp * kStages) * (uint32_t)a.slot_bytes;
   const uint32_t bar_base = smem_u32(&bars[warp * kStages]);
-  WinSlot* mywins = &wins[warp * kStages];
 
   if (lane == 0) {
-#pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8u * s, 1);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,11 +172,13 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   const int wpc = blockDim.x >> 5;
   const int gw = blockIdx.x * wpc + warp;
   const int nw = gridDim.x * wpc;
-  const int my_count = gw < a.n ? (a.n - gw + nw - 1) / nw : 0;
+  const int c0 = (int)(((long long)gw * a.n) / nw), c1 = (int)(((long long)(gw + 1) * a.n) / nw);
+  const int total = c1 - c0;
   const int h = a.half_fov;
   const int side = 2 * h + 1;
   constexpr bool kNeedRec = (MODE != MODE_LOW_COST);
   constexpr bool kNeedAux = (MODE == MODE_AVG_VIEW_COST || MODE == MODE_LOW_COST);
+  constexpr bool kFloat = (MODE == MODE_RRT_DISCOUNT || MODE == MODE_GOAL_DISTANCE || MODE == MODE_LOW_COST);
   const uint32_t tx_bytes = (kNeedRec ? (uint32_t)(a.box_w * side) : 0u) + (kNeedAux ? (uint32_t)(a.box_w16 * 2 * side) : 0u);
 
   // lane geometry (fixed for the whole kernel)
@@ -189,147 +193,186 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
                           : (MODE == MODE_COUNT && a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) ? REC_UNK_REACH : REC_UNK_PATH;
   const uint32_t auxmask = auxbit * 0x01010101u;
   const int auxshift = __ffs(auxbit) - 1;
+  // per-byte-lane SIMD counters take 4 * auxbit per iteration at most: iterations between flushes
+  const int flush_iters = 255 / (4 * (int)auxbit);
+  const int my_iters = (lane_on && lrow < side) ? (side - lrow + rpi - 1) / rpi : 0;
+  // column masks of the unaligned window, tabulated once per CTA: entry [r0 * ncr + chunk] holds the four byte masks of
+  // 16-byte chunk `chunk` when the window starts at byte r0 of the tile row (r0 = (cx - h) & 15)
+  for (int e = threadIdx.x; e < 16 * ncr; e += blockDim.x) {
+    const int r0 = e / ncr, cc = e - r0 * ncr;
+    const int lo = r0 - 16 * cc, hi = r0 + side - 16 * cc;   // valid bytes of the chunk: [lo, hi) clipped to [0,16)
+    mask_tbl[e] = make_uint4(byte_range_mask(lo, hi), byte_range_mask(lo - 4, hi - 4), byte_range_mask(lo - 8, hi - 8),
+                             byte_range_mask(lo - 12, hi - 12));
+  }
+  __syncthreads();
 
-  auto issue = [&](int k) {
-    if (lane == 0) {
-      const int cand = gw + k * nw;
-      const Window w = make_window(a.g, a.xy[2 * cand], a.xy[2 * cand + 1]);
-      const int s = k % kStages;
-      const uint32_t bar = bar_base + 8u * s;
-      const uint32_t dst = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
-      mywins[s].cx = w.cx; mywins[s].cy = w.cy; mywins[s].on_map = w.on_map;
-      mywins[s].vcx = w.vcx; mywins[s].vcy = w.vcy;
-      mbar_expect_tx(bar, tx_bytes);
-      // TMA needs the box start 16-byte aligned in the contiguous dimension: start at the aligned column at or before
-      // the window's first column; the box is wide enough to still cover the window (see gain_launch)
-      if (kNeedRec) tma_load_2d(dst, &tm_rec, bar, (w.cx - h) & ~15, w.cy - h);
-      if (kNeedAux) tma_load_2d(dst + (uint32_t)a.aux_off, &tm_aux, bar, (w.cx - h) & ~7, w.cy - h);
+  // ---- per-batch lane state: the window of candidate (batch base + lane)
+  Window cur, nxt;
+  auto load_window = [&](int idx) {   // idx = index inside this warp's range
+    Window w;
+    w.on_map = 0; w.cx = w.cy = -1000000; w.vcx = w.vcy = 0.0;
+    if (idx < total) {
+      const double2 p = *reinterpret_cast<const double2*>(a.xy + 2 * (size_t)(c0 + idx));
+      w = make_window(a.g, p.x, p.y);
     }
+    return w;
+  };
+  auto issue = [&](const Window& w, int s) {   // executed by the one lane that owns the candidate
+    const uint32_t bar = bar_base + 8u * s;
+    const uint32_t dst = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
+    mbar_expect_tx(bar, tx_bytes);
+    // TMA needs the box start 16-byte aligned in the contiguous dimension: start at the aligned column at or before
+    // the window's first column; the box is wide enough to still cover the window (see gain_launch)
+    if (kNeedRec) tma_load_2d(dst, &tm_rec, bar, (w.cx - h) & ~15, w.cy - h);
+    if (kNeedAux) tma_load_2d(dst + (uint32_t)a.aux_off, &tm_aux, bar, (w.cx - h) & ~7, w.cy - h);
   };
 
-  for (int k = 0; k < kStages - 1 && k < my_count; ++k) issue(k);
+  if (total <= 0) return;
+  cur = load_window(lane);
+  for (int k = 0; k < kStages - 1 && k < total; ++k)
+    if (lane == k) issue(cur, k);   // kStages - 1 <= 7 < 32: all inside the first batch
 
-  for (int k = 0; k < my_count; ++k) {
-    if (k + kStages - 1 < my_count) {
-      __syncwarp();   // every lane is done reading the slot (tile + window parameters) that is about to be refilled
-      issue(k + kStages - 1);
-    }
-    const int cand = gw + k * nw;
-    const int s = k % kStages;
-    const uint32_t tile = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
-    __syncwarp();     // lane 0's window parameters for this slot are visible to the warp
-    const int wcx = mywins[s].cx, wcy = mywins[s].cy;
-    while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)((k / kStages) & 1))) {
-    }
+  int s = 0, s_issue = kStages - 1;   // slot being scanned / slot refilled next (the one scanned in the previous iteration)
+  uint32_t parity = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int nb = min(32, total - base);
+    nxt = load_window(base + 32 + lane);
+    // per-candidate scan results, parked in the lane that owns the candidate
+    uint32_t my_unk = 0, my_aux = 0, my_sum2 = 0, my_crec = 0, my_caux16 = 0;
+    double my_fsum = 0.0;
 
-    // ---- window scan -------------------------------------------------------------------------------
-    uint32_t n_unk = 0, n_aux = 0;       // per-lane totals
-    uint32_t sum_aux2 = 0;               // AverageViewCost: sum of labels
-    double fsum = 0.0;                   // floating-point modes
-    if (kNeedRec && lane_on) {
-      const int r0 = (wcx - h) & 15;                 // the window occupies tile columns [r0, r0 + side)
-      const int lo = r0 - 16 * lcc, hi = r0 + side - 16 * lcc;   // valid bytes of this lane's chunk: [lo, hi) clipped to [0,16)
-      const uint32_t m0 = byte_range_mask(lo, hi), m1 = byte_range_mask(lo - 4, hi - 4);
-      const uint32_t m2 = byte_range_mask(lo - 8, hi - 8), m3 = byte_range_mask(lo - 12, hi - 12);
-      uint32_t addr = tile + (uint32_t)lane * 16u;
-      const uint32_t step = (uint32_t)(rpi * ncr) * 16u;
-      if (MODE == MODE_COUNT || MODE == MODE_AVG_VIEW_COST) {
-        const uint32_t u0 = m0 & 0x01010101u, u1 = m1 & 0x01010101u, u2 = m2 & 0x01010101u, u3 = m3 & 0x01010101u;
-        const uint32_t a0 = m0 & auxmask, a1 = m1 & auxmask, a2 = m2 & auxmask, a3 = m3 & auxmask;
-        int row = lrow;
-        while (row < side) {
-          // per-byte-lane SIMD counters: at most 60 chunks (<= 240 per byte lane) between flushes
-          uint32_t acc_unk = 0, acc_aux = 0;
-          const int row_end = min(side, row + 60 * rpi);
-#pragma unroll 2
-          for (; row < row_end; row += rpi) {
-            const uint4 v = lds128(addr);
-            addr += step;
-            acc_unk += (v.x & u0) + (v.y & u1);
-            acc_unk += (v.z & u2) + (v.w & u3);
-            const uint32_t t = (v.x & a0) + (v.y & a1) + (v.z & a2) + (v.w & a3);   // bytes <= 4 * auxbit <= 32
-            acc_aux += t >> auxshift;
+    for (int j = 0; j < nb; ++j) {
+      const int ahead = j + kStages - 1;
+      if (base + ahead < total) {
+        __syncwarp();   // every lane is done reading the slot that is about to be refilled
+        if (ahead < 32) { if (lane == ahead) issue(cur, s_issue); }
+        else            { if (lane == ahead - 32) issue(nxt, s_issue); }
+      }
+      const uint32_t tile = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
+      const int wcx = __shfl_sync(0xFFFFFFFFu, cur.cx, j), wcy = __shfl_sync(0xFFFFFFFFu, cur.cy, j);
+      while (!mbar_try_wait(bar_base + 8u * s, parity)) {
+      }
+
+      // ---- window scan -------------------------------------------------------------------------------
+      uint32_t n_unk = 0, n_aux = 0;       // per-lane totals
+      uint32_t sum_aux2 = 0;               // AverageViewCost: sum of labels
+      double fsum = 0.0;                   // floating-point modes
+      if (kNeedRec && lane_on) {
+        const int r0 = (wcx - h) & 15;                 // the window occupies tile columns [r0, r0 + side)
+        const uint4 m = mask_tbl[r0 * ncr + lcc];      // byte masks of this lane's 16-byte chunk column for that offset
+        const uint32_t m0 = m.x, m1 = m.y, m2 = m.z, m3 = m.w;
+        uint32_t addr = tile + (uint32_t)lane * 16u;
+        const uint32_t step = (uint32_t)(rpi * ncr) * 16u;
+        if (MODE == MODE_COUNT || MODE == MODE_AVG_VIEW_COST) {
+          const uint32_t u0 = m0 & 0x01010101u, u1 = m1 & 0x01010101u, u2 = m2 & 0x01010101u, u3 = m3 & 0x01010101u;
+          const uint32_t a0 = m0 & auxmask, a1 = m1 & auxmask, a2 = m2 & auxmask, a3 = m3 & auxmask;
+          int left = my_iters;                           // rows lrow, lrow + rpi, ... < side (fixed per lane)
+          while (left > 0) {
+            // per-byte-lane SIMD counters, flushed before a byte lane can overflow
+            uint32_t acc_unk = 0, acc_aux = 0;
+            const int todo = min(left, flush_iters);
+            left -= todo;
+#pragma unroll 4
+            for (int it = 0; it < todo; ++it) {
+              const uint4 v = lds128(addr);
+              addr += step;
+              acc_unk += (v.x & u0) + (v.y & u1);
+              acc_unk += (v.z & u2) + (v.w & u3);
+              acc_aux += (v.x & a0) + (v.y & a1);
+              acc_aux += (v.z & a2) + (v.w & a3);
+            }
+            n_unk += bytesum(acc_unk);
+            n_aux += bytesum(acc_aux >> auxshift);    // every byte is a multiple of auxbit: the shift cannot mix byte lanes
           }
-          n_unk += bytesum(acc_unk);
-          n_aux += bytesum(acc_aux);
-        }
-      } else {
-        // floating-point modes: walk the selected bytes of each chunk (corner coordinates of the cells)
-        const int x0 = ((wcx - h) & ~15) + lcc * 16;
-        for (int row = lrow; row < side; row += rpi) {
-          uint4 v = lds128(addr);
-          addr += step;
-          const uint32_t wds[4] = {v.x & m0, v.y & m1, v.z & m2, v.w & m3};
-          const double vy = (double)(wcy - h + row) * a.g.vs;
-          const double dy = a.g.goal_y - vy;
-          const double dy2 = dy * dy;
+        } else {
+          // floating-point modes: walk the selected bytes of each chunk (corner coordinates of the cells)
+          const int x0 = ((wcx - h) & ~15) + lcc * 16;
+          for (int row = lrow; row < side; row += rpi) {
+            uint4 v = lds128(addr);
+            addr += step;
+            const uint32_t wds[4] = {v.x & m0, v.y & m1, v.z & m2, v.w & m3};
+            const double vy = (double)(wcy - h + row) * a.g.vs;
+            const double dy = a.g.goal_y - vy;
+            const double dy2 = dy * dy;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t wd = wds[q];
-            n_unk += __popc(wd & 0x01010101u);
-            n_aux += __popc(wd & 0x02020202u);
-            uint32_t sel = (MODE == MODE_RRT_DISCOUNT) ? (wd & 0x02020202u) : (wd & 0x01010101u);
-            while (sel) {
-              const int b = (__ffs(sel) - 1) >> 3;
-              sel &= sel - 1;
-              const double vx = (double)(x0 + q * 4 + b) * a.g.vs;
-              const double dx = a.g.goal_x - vx;
-              const double d2 = dx * dx + dy2;
-              if (MODE == MODE_RRT_DISCOUNT) fsum += rsqrt(sqrt(d2) + a.discount_offset);                 // rrt_star_evaluator.cpp:82
-              else fsum += (d2 > a.inv_max_gain2_hi) ? rsqrt(d2)                                           // goal_distance_evaluator.cpp:55-60
-                           : ((d2 < a.inv_max_gain2_lo) ? a.max_gain : ((sqrt(d2) > a.inv_max_gain) ? 1.0 / sqrt(d2) : a.max_gain));
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t wd = wds[q];
+              n_unk += __popc(wd & 0x01010101u);
+              n_aux += __popc(wd & 0x02020202u);
+              uint32_t sel = (MODE == MODE_RRT_DISCOUNT) ? (wd & 0x02020202u) : (wd & 0x01010101u);
+              while (sel) {
+                const int b = (__ffs(sel) - 1) >> 3;
+                sel &= sel - 1;
+                const double vx = (double)(x0 + q * 4 + b) * a.g.vs;
+                const double dx = a.g.goal_x - vx;
+                const double d2 = dx * dx + dy2;
+                if (MODE == MODE_RRT_DISCOUNT) fsum += rsqrt(sqrt(d2) + a.discount_offset);                 // rrt_star_evaluator.cpp:82
+                else fsum += (d2 > a.inv_max_gain2_hi) ? rsqrt(d2)                                           // goal_distance_evaluator.cpp:55-60
+                             : ((d2 < a.inv_max_gain2_lo) ? a.max_gain : ((sqrt(d2) > a.inv_max_gain) ? 1.0 / sqrt(d2) : a.max_gain));
+              }
             }
           }
         }
       }
-    }
-    if (kNeedAux && lane_on16) {
-      const uint32_t atile = tile + (uint32_t)a.aux_off;
-      const int r0 = (wcx - h) & 7;                  // the window occupies tile columns [r0, r0 + side)
-      const int lo = r0 - 8 * lcc16, hi = r0 + side - 8 * lcc16;   // valid cells of this lane's chunk: [lo, hi) clipped to [0,8)
-      const uint32_t m0 = half_range_mask(lo, hi), m1 = half_range_mask(lo - 2, hi - 2);
-      const uint32_t m2 = half_range_mask(lo - 4, hi - 4), m3 = half_range_mask(lo - 6, hi - 6);
-      uint32_t addr = atile + (uint32_t)lane * 16u;
-      const uint32_t step = (uint32_t)(rpi16 * ncr16) * 16u;
-      for (int row = lrow16; row < side; row += rpi16) {
-        const uint4 v = lds128(addr);
-        addr += step;
-        const uint32_t wds[4] = {v.x & m0, v.y & m1, v.z & m2, v.w & m3};
-        if (MODE == MODE_AVG_VIEW_COST) {
+      if (kNeedAux && lane_on16) {
+        const uint32_t atile = tile + (uint32_t)a.aux_off;
+        const int r0 = (wcx - h) & 7;                  // the window occupies tile columns [r0, r0 + side)
+        const int lo = r0 - 8 * lcc16, hi = r0 + side - 8 * lcc16;   // valid cells of this lane's chunk: [lo, hi) clipped to [0,8)
+        const uint32_t m0 = half_range_mask(lo, hi), m1 = half_range_mask(lo - 2, hi - 2);
+        const uint32_t m2 = half_range_mask(lo - 4, hi - 4), m3 = half_range_mask(lo - 6, hi - 6);
+        uint32_t addr = atile + (uint32_t)lane * 16u;
+        const uint32_t step = (uint32_t)(rpi16 * ncr16) * 16u;
+        for (int row = lrow16; row < side; row += rpi16) {
+          const uint4 v = lds128(addr);
+          addr += step;
+          const uint32_t wds[4] = {v.x & m0, v.y & m1, v.z & m2, v.w & m3};
+          if (MODE == MODE_AVG_VIEW_COST) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) sum_aux2 += (wds[q] & 0xFFFFu) + (wds[q] >> 16);
-        } else {  // MODE_LOW_COST: entries are 0 (not unknown / off map) or closest_label + 1
+            for (int q = 0; q < 4; ++q) sum_aux2 += (wds[q] & 0xFFFFu) + (wds[q] >> 16);
+          } else {  // MODE_LOW_COST: entries are 0 (not unknown / off map / outside the bounding volume) or closest_label + 2
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t l0 = wds[q] & 0xFFFFu, l1 = wds[q] >> 16;
-            if (l0) { n_unk += 1; fsum += a.recip[l0]; }
-            if (l1) { n_unk += 1; fsum += a.recip[l1]; }
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t l0 = wds[q] & 0xFFFFu, l1 = wds[q] >> 16;
+              if (l0) { n_unk += 1; fsum += a.recip[l0]; }
+              if (l1) { n_unk += 1; fsum += a.recip[l1]; }
+            }
           }
         }
       }
-    }
 
-    // ---- warp reduction ------------------------------------------------------------------------------
-    n_unk = __reduce_add_sync(0xFFFFFFFFu, n_unk);
-    if (MODE != MODE_GOAL_DISTANCE && MODE != MODE_LOW_COST) n_aux = __reduce_add_sync(0xFFFFFFFFu, n_aux);
-    if (MODE == MODE_AVG_VIEW_COST) sum_aux2 = __reduce_add_sync(0xFFFFFFFFu, sum_aux2);
-    if (MODE == MODE_RRT_DISCOUNT || MODE == MODE_GOAL_DISTANCE || MODE == MODE_LOW_COST) {
+      // ---- warp reduction + the centre cell of the tile (for the duplicated centre voxel) -------------------
+      n_unk = __reduce_add_sync(0xFFFFFFFFu, n_unk);
+      if (MODE != MODE_GOAL_DISTANCE && MODE != MODE_LOW_COST) n_aux = __reduce_add_sync(0xFFFFFFFFu, n_aux);
+      if (MODE == MODE_AVG_VIEW_COST) sum_aux2 = __reduce_add_sync(0xFFFFFFFFu, sum_aux2);
+      if (kFloat) {
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(0xFFFFFFFFu, fsum, off);
+        for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(0xFFFFFFFFu, fsum, off);
+      }
+      if (lane == j) {
+        my_unk = n_unk; my_aux = n_aux; my_sum2 = sum_aux2;
+        if (kFloat) my_fsum = fsum;
+        // the window centre cell sits at tile position (h, cx - aligned box start); only meaningful for on-map candidates
+        if (kNeedRec) my_crec = lds8(tile + (uint32_t)(h * a.box_w + (wcx - ((wcx - h) & ~15))));
+        if (kNeedAux) my_caux16 = lds16(tile + (uint32_t)a.aux_off + 2u * (uint32_t)(h * a.box_w16 + (wcx - ((wcx - h) & ~7))));
+      }
+      s_issue = s;
+      if (++s == kStages) { s = 0; parity ^= 1u; }
     }
 
-    // ---- centre voxel duplicate + epilogue (lane 0) -------------------------------------------------------
-    if (lane == 0) {
-      Window w;
-      w.cx = wcx; w.cy = wcy; w.on_map = mywins[s].on_map; w.vcx = mywins[s].vcx; w.vcy = mywins[s].vcy;
+    // ---- centre voxel duplicate + evaluator epilogue: lane j finishes candidate base + j ------------------------
+    if (lane < nb) {
+      const int cand = c0 + base + lane;
+      const Window& w = cur;
+      uint32_t n_unk = my_unk, n_aux = my_aux, sum_aux2 = my_sum2;
+      double fsum = my_fsum;
       uint32_t n_vis = 0;
       double gain = 0.0;
       uint32_t terminal = 0;
+      const GainGeom& g = a.g;
       if (!w.on_map) {
         n_unk = n_aux = sum_aux2 = 0;
         fsum = 0.0;
       } else {
-        const GainGeom& g = a.g;
         n_vis = (uint32_t)(clipped_extent(w.cx, h, max(0, a.use_bv ? g.bv_kx_lo : 0), min(g.W - 1, a.use_bv ? g.bv_kx_hi : g.W - 1)) *
                            clipped_extent(w.cy, h, max(0, a.use_bv ? g.bv_ky_lo : 0), min(g.H - 1, a.use_bv ? g.bv_ky_hi : g.H - 1)));
         // centre voxel (centre coordinates): its own bounding-volume and map-server bounds tests, then the per-cell tests
@@ -340,12 +383,10 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           // not reachable (:877); the path lookup has no bounds test and lands on the window's centre cell
           // (map_planexp.cpp:226-229). The window centre cell (tile position (h,h)) is always on the map here.
           const bool c_in_bounds = 0 <= w.vcx && 0 <= w.vcy && g.map_width > w.vcx && g.map_height > w.vcy;
-          uint32_t crec = 0, caux16 = 0;
-          if (kNeedRec) crec = lds8(tile + (uint32_t)(h * a.box_w + (w.cx - ((w.cx - h) & ~15))));
-          if (kNeedAux) caux16 = lds16(tile + (uint32_t)a.aux_off + 2u * (uint32_t)(h * a.box_w16 + (w.cx - ((w.cx - h) & ~7))));
+          const uint32_t crec = my_crec, caux16 = my_caux16;
           bool c_unk, c_free = false, c_path = false, c_reach = false;
           if (MODE == MODE_LOW_COST) {
-            c_unk = c_in_bounds ? (caux16 != 0) : true;
+            c_unk = c_in_bounds ? ((caux16 & 0x8000u) != 0) : true;
           } else {
             c_unk = c_in_bounds ? ((crec & REC_RAW_UNK) != 0) : true;
             c_free = c_in_bounds && (crec & REC_RAW_FREE) != 0;
@@ -368,7 +409,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
               const double dist = sqrt(dx * dx + dy * dy);
               fsum += (dist > a.inv_max_gain) ? 1.0 / dist : a.max_gain;
             } else if (MODE == MODE_LOW_COST) {
-              fsum += c_in_bounds ? a.recip[caux16] : a.recip[1];
+              fsum += a.recip[c_in_bounds ? (caux16 & 0x7FFFu) : 0u];
             }
           } else if (MODE == MODE_AVG_VIEW_COST && c_free) {
             n_aux += 1;
@@ -376,43 +417,40 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           }
         }
       }
-      {
-        const GainGeom& g = a.g;
-        // ---- evaluator epilogues
-        if (MODE == MODE_COUNT) {
-          if (a.evaluator == SIPP_EVAL_RRT_STAR) {
-            if (n_unk == 0) terminal = 1;                                             // rrt_star_evaluator.cpp:53-57
-            else if (a.do_binary) {
-              if (n_aux > 0) {
-                if (a.use_discount) {                                                 // :61-68
-                  // single term: round exactly like the reference (no FMA contraction) so the gain is bit-exact
-                  const double dx = g.goal_x - a.start_xy[2 * cand], dy = g.goal_y - a.start_xy[2 * cand + 1];
-                  const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                  gain = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(nrm, a.discount_offset)));
-                } else gain = 1.0;                                                    // :69-75
-              }
-            } else gain = (double)n_aux + (double)(n_unk - n_aux) * a.npg;            // :85-89 (closed form of the running sum)
-          } else if (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) {
-            if (n_unk == 0) terminal = 1;                                             // expand_reachable_area_evaluator.cpp:50-54
-            else gain = (double)n_aux + (double)(n_unk - n_aux) * a.discount_factor;  // :65
-          } else {                                                                    // NaiveEvaluator [upstream]
-            gain = (double)n_unk;
-            n_aux = 0;
-          }
-        } else if (MODE == MODE_RRT_DISCOUNT) {
-          if (n_unk == 0) terminal = 1;
-          else gain = fsum + (double)(n_unk - n_aux) * a.npg;                         // :78-84
-        } else if (MODE == MODE_GOAL_DISTANCE) {
-          gain = fsum;
+      // ---- evaluator epilogues
+      if (MODE == MODE_COUNT) {
+        if (a.evaluator == SIPP_EVAL_RRT_STAR) {
+          if (n_unk == 0) terminal = 1;                                             // rrt_star_evaluator.cpp:53-57
+          else if (a.do_binary) {
+            if (n_aux > 0) {
+              if (a.use_discount) {                                                 // :61-68
+                // single term: round exactly like the reference (no FMA contraction) so the gain is bit-exact
+                const double dx = g.goal_x - a.start_xy[2 * cand], dy = g.goal_y - a.start_xy[2 * cand + 1];
+                const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                gain = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(nrm, a.discount_offset)));
+              } else gain = 1.0;                                                    // :69-75
+            }
+          } else gain = (double)n_aux + (double)(n_unk - n_aux) * a.npg;            // :85-89 (closed form of the running sum)
+        } else if (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) {
+          if (n_unk == 0) terminal = 1;                                             // expand_reachable_area_evaluator.cpp:50-54
+          else gain = (double)n_aux + (double)(n_unk - n_aux) * a.discount_factor;  // :65
+        } else {                                                                    // NaiveEvaluator [upstream]
+          gain = (double)n_unk;
           n_aux = 0;
-        } else if (MODE == MODE_AVG_VIEW_COST) {
-          if (n_aux > 0) {                                                            // average_view_cost_evaluator.cpp:54-56
-            const double mean_view_cost = (double)sum_aux2 / (double)n_aux;
-            gain = (double)n_unk * (1.0 / mean_view_cost);
-          } else gain = (double)n_unk * (1.0 / g.mean_cost);                          // :57-59
-        } else if (MODE == MODE_LOW_COST) {
-          gain = fsum;
         }
+      } else if (MODE == MODE_RRT_DISCOUNT) {
+        if (n_unk == 0) terminal = 1;
+        else gain = fsum + (double)(n_unk - n_aux) * a.npg;                         // :78-84
+      } else if (MODE == MODE_GOAL_DISTANCE) {
+        gain = fsum;
+        n_aux = 0;
+      } else if (MODE == MODE_AVG_VIEW_COST) {
+        if (n_aux > 0) {                                                            // average_view_cost_evaluator.cpp:54-56
+          const double mean_view_cost = (double)sum_aux2 / (double)n_aux;
+          gain = (double)n_unk * (1.0 / mean_view_cost);
+        } else gain = (double)n_unk * (1.0 / g.mean_cost);                          // :57-59
+      } else if (MODE == MODE_LOW_COST) {
+        gain = fsum;
       }
       a.gain[cand] = gain;
       if (a.counts) *reinterpret_cast<uint4*>(a.counts + 4 * (size_t)cand) = make_uint4(n_vis, n_unk, n_aux, sum_aux2);
@@ -423,6 +461,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
         a.value[cand] = c > 0 ? (0.0 + gain) / c : 0.0;
       }
     }
+    cur = nxt;
   }
 }
 
@@ -476,9 +515,10 @@ template <int MODE>
 int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_aux, const GainArgs& a, cudaStream_t s) {
   static int num_sms = 0;
   if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  // as many warps (each owning kStages tile slots) as fit in 200 KB of shared memory, at most 8
-  int wpc = kMaxWarpsPerCta;
-  while (wpc > 1 && (size_t)wpc * kStages * a.slot_bytes > 200 * 1024) wpc >>= 1;
+  // warps per CTA x tile slots per warp: as many slots as fit in ~220 KB of shared memory
+  const int kStages = a.stages;
+  int wpc = ctx->gain_warps > 0 ? ctx->gain_warps : kMaxWarpsPerCta;
+  while (wpc > 1 && (size_t)wpc * kStages * a.slot_bytes > 220 * 1024) --wpc;
   const size_t smem = (size_t)wpc * kStages * a.slot_bytes;
   if (smem > 227 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %zu bytes of shared memory per CTA", a.half_fov, smem);
   cudaError_t e = cudaFuncSetAttribute(k_gain<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -548,6 +588,9 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.aux_off = (int)((rec_bytes + 127) & ~(size_t)127);
   const bool need_aux = (mode == MODE_AVG_VIEW_COST);
   a.slot_bytes = (int)((need_aux ? (a.aux_off + aux_bytes) : rec_bytes) + 127) & ~127;
+  a.stages = ctx->gain_stages > 0 ? ctx->gain_stages : 2;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  while (a.stages > 2 && (size_t)a.stages * a.slot_bytes > 220 * 1024) --a.stages;
   int rc = SIPP_OK;
   const CUtensorMap* tm_rec = cached_tmap(ctx, h, 0, &rc);
   if (!tm_rec) return rc;

@@ -70,6 +70,7 @@ struct sipp_ctx {
   std::mutex mu;
   std::string err;
   int64_t launches;
+  int gain_warps, gain_stages;   // k_gain pipeline shape (0 = default); tuning knobs SIPP_GAIN_WARPS / SIPP_GAIN_STAGES
 
   int W, H;
   size_t pitch;        // bytes per row of the uint8 planes (multiple of 128)
