@@ -20,6 +20,8 @@
 #include <math_constants.h>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sipp_internal.h"
@@ -215,6 +217,13 @@ k_relax(const RelaxArgs a) {
   __syncthreads();
 
   int sweeps_local = 0, act_local = 0, push_local = 0;
+#ifdef SIPP_RELAX_PROFILE
+  long long tp[6] = {0, 0, 0, 0, 0, 0};
+  long long tk = clock64();
+#define SIPP_TICK(i) { const long long now_ = clock64(); tp[i] += now_ - tk; tk = now_; }
+#else
+#define SIPP_TICK(i)
+#endif
   for (;;) {
     // ---- pop: take a ticket, wait for its slot to be filled (or for global termination)
     int ti = -2;
@@ -244,6 +253,7 @@ k_relax(const RelaxArgs a) {
     }
     ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
     if (ti < 0) break;
+    SIPP_TICK(0)
 
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
@@ -266,6 +276,7 @@ k_relax(const RelaxArgs a) {
     const double hdl = xcl >= 0 ? g.hdist[xcl] : CUDART_INF, hdr = xcr >= 0 ? g.hdist[xcr] : CUDART_INF;
     __syncwarp();
 
+    SIPP_TICK(1)
     // alternate downward / upward sweeps until one of them changes nothing (its opposite was completed right before it)
     int mask = 0;
     uint32_t rows_changed = 0;
@@ -276,6 +287,7 @@ k_relax(const RelaxArgs a) {
       if (!c && it >= 1) break;
     }
     ++act_local;
+    SIPP_TICK(2)
 
     // merge what this lane lowered (monotone: atomicMin on the bit pattern of non-negative doubles)
     {
@@ -290,20 +302,80 @@ k_relax(const RelaxArgs a) {
                     (unsigned long long)__double_as_longlong(t.d[r + 1][lane + 1]));
       }
     }
-    int m = mask;
+    // ---- relax ACROSS the tile border: every halo cell n (it belongs to a neighbour tile) against its up to three
+    // neighbours c on our side, cand = d[c] + w(c,n) — bit for bit what the neighbour tile would compute from its own halo.
+    // A neighbour is queued only if one of its cells was actually lowered (the atomicMin returned a larger value), so a tile
+    // is not re-activated by the echo of the values it produced itself. Lane l handles column l+1 of the top / bottom halo
+    // rows and row l+1 of the left / right halo columns; lanes 0..3 the four corners.
+    // Done on EVERY activation, changed border or not: a border cell of ours may have been lowered by a neighbour's push since
+    // we last ran, and only we can carry that value on across our other borders.
+    int m = 0;   // bit k: neighbour k (N S W E NW NE SW SE) received a lower value
+    {
+      const int lx = lane + 1;
+      const double hdl0 = __shfl_sync(0xFFFFFFFFu, hdl, 0), hdr31 = __shfl_sync(0xFFFFFFFFu, hdr, 31);
+      const int xcl0 = __shfl_sync(0xFFFFFFFFu, xcl, 0), xcr31 = __shfl_sync(0xFFFFFFFFu, xcr, 31);
+      auto dd = [&](int xc, int yc) { return (xc >= 0 && yc >= 0) ? ddp[xc * g.Ky + yc] : CUDART_INF; };
+      auto push_min = [&](int hy, int hx, double cand) -> bool {   // (hy,hx): halo cell in tile coordinates
+        if (!(cand < t.d[hy][hx])) return false;                   // cannot beat the value we loaded, let alone the current one
+        const int gx = x0 - 1 + hx, gy = y0 - 1 + hy;              // on the map: hc of an off-map halo cell is +inf -> cand = +inf
+        const unsigned long long nb = (unsigned long long)__double_as_longlong(cand);
+        return atomicMin(reinterpret_cast<unsigned long long*>(a.field + (size_t)gy * g.W + gx), nb) > nb;
+      };
+      // top halo row (tile row 0) from interior row 1; bottom halo row (TP-1) from interior row TS
+#pragma unroll
+      for (int sgn = 0; sgn < 2; ++sgn) {
+        const int hy = sgn ? TP - 1 : 0, iy = sgn ? TS : 1, er = sgn ? TS : 0;   // edges between tile rows er and er+1
+        {
+          const double hcn = t.hc[hy][lx];
+          double cand = CUDART_INF;
+          if (hcn < CUDART_INF) {
+            cand = relax1(cand, t.d[iy][lx], t.vd[er], hcn, t.hc[iy][lx]);
+            if (lx > 1) cand = relax1(cand, t.d[iy][lx - 1], dd(xcl, t.yc[er]), hcn, t.hc[iy][lx - 1]);
+            if (lx < TS) cand = relax1(cand, t.d[iy][lx + 1], dd(xcr, t.yc[er]), hcn, t.hc[iy][lx + 1]);
+          }
+          if (push_min(hy, lx, cand)) m |= sgn ? 2 : 1;
+        }
+      }
+      // left halo column (tile column 0) from interior column 1; right halo column (TP-1) from interior column TS
+#pragma unroll
+      for (int sgn = 0; sgn < 2; ++sgn) {
+        const int hx = sgn ? TP - 1 : 0, ix = sgn ? TS : 1;
+        {
+          const int ly = lane + 1;
+          const double hd = sgn ? hdr31 : hdl0;
+          const int xc = sgn ? xcr31 : xcl0;
+          const double hcn = t.hc[ly][hx];
+          double cand = CUDART_INF;
+          if (hcn < CUDART_INF) {
+            cand = relax1(cand, t.d[ly][ix], hd, hcn, t.hc[ly][ix]);
+            if (ly > 1) cand = relax1(cand, t.d[ly - 1][ix], dd(xc, t.yc[ly - 1]), hcn, t.hc[ly - 1][ix]);
+            if (ly < TS) cand = relax1(cand, t.d[ly + 1][ix], dd(xc, t.yc[ly]), hcn, t.hc[ly + 1][ix]);
+          }
+          if (push_min(ly, hx, cand)) m |= sgn ? 8 : 4;
+        }
+      }
+      // corners: NW NE SW SE from the diagonal interior cell
+      if (lane < 4) {
+        const int top = lane < 2, left = !(lane & 1);
+        const int hy = top ? 0 : TP - 1, hx = left ? 0 : TP - 1, iy = top ? 1 : TS, ix = left ? 1 : TS;
+        const double hcn = t.hc[hy][hx];
+        if (hcn < CUDART_INF) {
+          const double cand = relax1(CUDART_INF, t.d[iy][ix], dd(left ? xcl0 : xcr31, t.yc[top ? 0 : TS]), hcn, t.hc[iy][ix]);
+          if (push_min(hy, hx, cand)) m |= 16 << lane;
+        }
+      }
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xFFFFFFFFu, m, off);
+    SIPP_TICK(3)
     __threadfence();      // our field updates are visible before any neighbour can be told to look at them
     __syncwarp();
-    // neighbours: N S W E NW NE SW SE (a corner cell sets two edge bits; "both bits set" may over-activate a diagonal tile —
-    // harmless, an activation with nothing to do costs two sweeps)
-    if (lane < 8 && m) {
+    // neighbours: N S W E NW NE SW SE
+    if (lane < 8 && ((m >> lane) & 1)) {
       const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
       const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-      const int need[8] = {1, 2, 4, 8, 1 | 4, 1 | 8, 2 | 4, 2 | 8};
-      const bool on = (lane < 4) ? ((m & need[lane]) != 0) : ((m & need[lane]) == need[lane]);
       const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
-      if (on && ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
+      if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
         const int nt = nty_ * a.ntx + ntx_;
         if (atomicExch(&a.flags[nt], 1) == 0) {
           atomicAdd(&a.ctl[CTL_PENDING], 1);
@@ -322,7 +394,12 @@ k_relax(const RelaxArgs a) {
       __threadfence();
       atomicSub(&a.ctl[CTL_PENDING], 1);   // after our pushes were counted: pending reaches 0 only at the global fixed point
     }
+    SIPP_TICK(4)
   }
+#ifdef SIPP_RELAX_PROFILE
+  if (lane == 0)
+    for (int i = 0; i < 5; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + 16) + i, (unsigned long long)tp[i]);
+#endif
   // statistics
   atomicAdd(&a.ctl[CTL_PUSHES], push_local);
   if (lane == 0) {
@@ -337,7 +414,7 @@ __global__ void k_field_init(double* field, size_t n, int* flags, int* queue, in
   for (size_t k = i; k < n; k += stride) field[k] = CUDART_INF;
   for (size_t k = i; k < (size_t)ntiles; k += stride) flags[k] = 0;
   for (size_t k = i; k < (size_t)qcap; k += stride) queue[k] = -1;
-  if (i < 16) ctl[i] = 0;
+  if (i < 32) ctl[i] = 0;
 }
 __global__ void k_field_seed(double* field, int W, int H, int sx, int sy, int* flags, int* queue, int ntx, int* ctl) {
   if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
@@ -356,6 +433,8 @@ struct PathArgs {
   const double* field;
   const uint16_t* pcode;
   size_t pitch16;
+  const uint8_t* pred;   // canonical predecessor plane (k_pred)
+  size_t pitch;
   int* nodes;       // out, goal -> start, packed (x << 16) | y
   int cap;
   int* out;         // [0] len, [1] all explored, [2] found, [3] unused, [4] walk failed on a reachable goal
@@ -369,101 +448,175 @@ __device__ __forceinline__ double edge_len(const FieldGeom& g, int ax, int ay, i
   return g.ddist[g.xcls[mx] * g.Ky + g.ycls[my]];
 }
 
-// One warp. The walk runs inside a 32x32 window (plus halo) of d and half costs held in shared memory, centred on the
-// current node and re-loaded whenever the walk reaches the window's border; lanes 0..7 evaluate the 8 neighbours.
-__global__ void __launch_bounds__(32)
-k_backtrack(const PathArgs a) {
-  __shared__ TileSmem t;
-  __shared__ int s_xc[TP];
-  __shared__ double s_hd[TP];
+// ---- canonical predecessor of every cell (fully parallel), then the walk over predecessor bytes -------------------------
+// pred[y][x] = index k (0..7, neighbours in ascending node id x*H+y) of the canonical predecessor of (x,y): among the u with
+// d[u] + w(u,v) == d[v] bit for bit, the one with the smallest f = d[u] + h(u), lowest id on equal f;
+// PRED_NONE where there is none (start node, unreachable cells). One thread per cell, the 34x34 window of d / half costs of a
+// 32x32 tile staged in shared memory. Bandwidth-bound: 8 B + 2 B read, 1 B written per cell.
+constexpr uint8_t PRED_NONE = 255;
+constexpr int kPredThreads = 256;
+struct PredArgs {
+  FieldGeom g;
+  const double* field;
+  const uint16_t* pcode;
+  size_t pitch16;
+  uint8_t* pred;     // [H][pitch]
+  size_t pitch;
+  int ntx;
+};
+struct PredSmem {
+  double d[TP][TP + 1];
+  double hc[TP][TP + 1];
+  double dd[kMaxDd];
+  double hd[TP], vd[TP];
+  int xc[TP], yc[TP];
+};
+
+__global__ void __launch_bounds__(kPredThreads)
+k_pred(const PredArgs a) {
+  __shared__ PredSmem t;
   const FieldGeom& g = a.g;
-  const int lane = threadIdx.x;
-  int x = g.goal_x, y = g.goal_y;
-  const bool goal_ok = x >= 0 && x < g.W && y >= 0 && y < g.H;
-  const double dgoal = goal_ok ? a.field[(size_t)y * g.W + x] : CUDART_INF;
-  if (!(dgoal < CUDART_INF)) {
-    if (lane == 0) { a.out[0] = 0; a.out[1] = 0; a.out[2] = 0; a.out[3] = 0; a.out[4] = 0; *a.cost_out = -1.0; }
-    return;
+  const int tid = threadIdx.x;
+  const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
+  const int x0 = tx * TS, y0 = ty * TS;
+  const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
+  if (dd_in_smem)
+    for (int i = tid; i < g.Kx * g.Ky; i += kPredThreads) t.dd[i] = g.ddist[i];
+  const double* ddp = dd_in_smem ? t.dd : g.ddist;
+  {
+    // 34 x 34 window: 5 rounds of 256 threads, loads first, stores after (independent loads in flight together)
+    double dv[5];
+    uint32_t cv[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int idx = tid + k * kPredThreads;
+      const int ly = idx / TP, lx = idx - ly * TP;
+      const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+      const bool inb = idx < TP * TP && gx >= 0 && gx < g.W && gy >= 0 && gy < g.H;
+      dv[k] = inb ? a.field[(size_t)gy * g.W + gx] : CUDART_INF;
+      cv[k] = inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + gx] : (uint32_t)PCODE_REMOVED;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int idx = tid + k * kPredThreads;
+      if (idx < TP * TP) {
+        const int ly = idx / TP, lx = idx - ly * TP;
+        t.d[ly][lx] = dv[k];
+        t.hc[ly][lx] = half_cost(cv[k], g.init_half_cost);
+      }
+    }
   }
+  if (tid < TP) {
+    const int gy = y0 - 1 + tid, gx = x0 - 1 + tid;     // edges (gy, gy+1) and (gx, gx+1)
+    const bool oky = gy >= 0 && gy + 1 < g.H, okx = gx >= 0 && gx + 1 < g.W;
+    const int cy = oky ? g.ycls[gy] : -1, cx = okx ? g.xcls[gx] : -1;
+    t.yc[tid] = cy;
+    t.vd[tid] = oky ? g.vdist[cy] : CUDART_INF;
+    t.xc[tid] = cx;
+    t.hd[tid] = okx ? g.hdist[cx] : CUDART_INF;
+  }
+  __syncthreads();
   const int NDX[8] = {-1, -1, -1, 0, 0, 1, 1, 1};   // ascending node id = x*H + y
   const int NDY[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-  const int ndx = NDX[lane & 7], ndy = NDY[lane & 7];
-  int len = 0;
-  if (lane == 0) a.nodes[0] = (x << 16) | y;
-  len = 1;
-  bool fail = false;
-  while (!fail && !(x == g.start_x && y == g.start_y)) {
-    // ---- (re)load a window whose interior [x0, x0+32) x [y0, y0+32) has the current node at its centre
-    const int x0 = x - TS / 2, y0 = y - TS / 2;
-    load_tile(t, g, a.field, a.pcode, a.pitch16, x0, y0, lane);
+#pragma unroll 1
+  for (int c = tid; c < TS * TS; c += kPredThreads) {
+    const int lx = (c & (TS - 1)) + 1, ly = (c >> 5) + 1;
+    const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+    if (gx >= g.W || gy >= g.H) continue;
+    const double dv = t.d[ly][lx], hcv = t.hc[ly][lx];
+    int best = PRED_NONE;
+    if (dv < CUDART_INF && hcv < CUDART_INF) {
+      unsigned okmask = 0;
+      double du[8];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int e = lane + 32 * k;
-      if (e < TP) {
-        const int gy = y0 - 1 + e, gx = x0 - 1 + e;     // edges (gy, gy+1) and (gx, gx+1)
-        const bool oky = gy >= 0 && gy + 1 < g.H, okx = gx >= 0 && gx + 1 < g.W;
-        const int cy = oky ? g.ycls[gy] : -1, cx = okx ? g.xcls[gx] : -1;
-        t.yc[e] = cy;
-        t.vd[e] = oky ? g.vdist[cy] : CUDART_INF;
-        s_xc[e] = cx;
-        s_hd[e] = okx ? g.hdist[cx] : CUDART_INF;
-      }
-    }
-    __syncwarp();
-    // ---- walk while the node stays in the interior
-    int lx = x - x0 + 1, ly = y - y0 + 1;            // window coordinates incl. halo offset
-    while (lx >= 1 && lx <= TS && ly >= 1 && ly <= TS && !(x == g.start_x && y == g.start_y)) {
-      const double dv = t.d[ly][lx];
-      const double hcv = t.hc[ly][lx];
-      bool ok = false;
-      double du = CUDART_INF;
-      if (lane < 8) {
-        const int ux = lx + ndx, uy = ly + ndy;
-        const int ex = min(lx, ux), ey = min(ly, uy);  // local edge indices (edge e joins local e and e+1)
+      for (int k = 0; k < 8; ++k) {
+        const int ux = lx + NDX[k], uy = ly + NDY[k];
+        const int ex = min(lx, ux), ey = min(ly, uy);   // local edge indices (edge e joins local e and e+1)
         double dist;
-        if (ndy == 0) dist = s_hd[ex];
-        else if (ndx == 0) dist = t.vd[ey];
-        else dist = (s_xc[ex] >= 0 && t.yc[ey] >= 0) ? g.ddist[s_xc[ex] * g.Ky + t.yc[ey]] : CUDART_INF;
+        if (NDY[k] == 0) dist = t.hd[ex];
+        else if (NDX[k] == 0) dist = t.vd[ey];
+        else dist = (t.xc[ex] >= 0 && t.yc[ey] >= 0) ? ddp[t.xc[ex] * g.Ky + t.yc[ey]] : CUDART_INF;
         const double hcu = t.hc[uy][ux];
-        if (dist < CUDART_INF && hcu < CUDART_INF && hcv < CUDART_INF) {
-          du = t.d[uy][ux];
-          ok = __dadd_rn(du, __dmul_rn(dist, __dadd_rn(hcu, hcv))) == dv;
-        }
+        du[k] = t.d[uy][ux];
+        if (dist < CUDART_INF && hcu < CUDART_INF && __dadd_rn(du[k], __dmul_rn(dist, __dadd_rn(hcu, hcv))) == dv) okmask |= 1u << k;
       }
-      // tied predecessors: smallest f = d[u] + h(u), lowest neighbour id among equal f. Most nodes have a single
-      // predecessor, so the heuristic (a double sqrt) is only evaluated when there is a tie to break.
-      const unsigned okmask = __ballot_sync(0xFFFFFFFFu, ok);
-      int best_lane = 99;
-      if (okmask && (okmask & (okmask - 1)) == 0) {
-        best_lane = __ffs(okmask) - 1;
-      } else if (okmask) {
-        double f = CUDART_INF;
-        if (ok) {
-          const int gx = g.goal_x - (x + ndx), gy = g.goal_y - (y + ndy);
-          const double hh = __dmul_rn(__dmul_rn(__dsqrt_rn((double)(gx * gx + gy * gy)), g.min_cost), g.spacing);   // prm_star_planner.h:108-112
-          f = __dadd_rn(du, hh);
-        }
-        best_lane = ok ? lane : 99;
-        double best_f = f;
+      if (okmask) {
+        if ((okmask & (okmask - 1)) == 0) best = __ffs(okmask) - 1;
+        else {
+          double best_f = CUDART_INF;
 #pragma unroll
-        for (int off = 4; off > 0; off >>= 1) {
-          const double of = __shfl_xor_sync(0xFFFFFFFFu, best_f, off);
-          const int ol = __shfl_xor_sync(0xFFFFFFFFu, best_lane, off);
-          const bool take = (ol != 99) && (best_lane == 99 || of < best_f || (of == best_f && ol < best_lane));
-          if (take) { best_f = of; best_lane = ol; }
+          for (int k = 0; k < 8; ++k)
+            if (okmask & (1u << k)) {
+              const int hx = g.goal_x - (gx + NDX[k]), hy = g.goal_y - (gy + NDY[k]);
+              const double hh = __dmul_rn(__dmul_rn(__dsqrt_rn((double)(hx * hx + hy * hy)), g.min_cost), g.spacing);   // prm_star_planner.h:108-112
+              const double f = __dadd_rn(du[k], hh);
+              if (best == PRED_NONE || f < best_f) { best_f = f; best = k; }     // ascending k: the lowest id wins equal f
+            }
         }
-        best_lane = __shfl_sync(0xFFFFFFFFu, best_lane, 0);
       }
-      if (best_lane == 99 || len >= a.cap) { fail = true; break; }
-      x += NDX[best_lane]; y += NDY[best_lane];
-      lx += NDX[best_lane]; ly += NDY[best_lane];
-      if (lane == 0) a.nodes[len] = (x << 16) | y;
-      ++len;
     }
-    __syncwarp();
+    a.pred[(size_t)gy * a.pitch + gx] = (uint8_t)best;
   }
-  if (lane == 0) {
-    a.out[0] = fail ? 0 : len;
+}
+
+// One CTA. The walk runs over a 256x256 window of predecessor bytes held in shared memory, centred on the current node: all
+// threads (re)load the window whenever the walk leaves it (>= 112 steps per load), then thread 0 chases the bytes.
+constexpr int PW = 256;
+constexpr int kBackThreads = 256;
+__global__ void __launch_bounds__(kBackThreads)
+k_backtrack(const PathArgs a) {
+  extern __shared__ __align__(16) uint8_t win[];     // [PW][PW]
+  __shared__ int s_x, s_y, s_len, s_fail;
+  const FieldGeom& g = a.g;
+  const int tid = threadIdx.x;
+  const bool goal_ok = g.goal_x >= 0 && g.goal_x < g.W && g.goal_y >= 0 && g.goal_y < g.H;
+  const double dgoal = goal_ok ? a.field[(size_t)g.goal_y * g.W + g.goal_x] : CUDART_INF;
+  if (!(dgoal < CUDART_INF)) {
+    if (tid == 0) { a.out[0] = 0; a.out[1] = 0; a.out[2] = 0; a.out[3] = 0; a.out[4] = 0; *a.cost_out = -1.0; }
+    return;
+  }
+  if (tid == 0) {
+    s_x = g.goal_x; s_y = g.goal_y; s_len = 1; s_fail = 0;
+    a.nodes[0] = (g.goal_x << 16) | g.goal_y;
+  }
+  __syncthreads();
+  for (;;) {
+    int x = s_x, y = s_y, len = s_len;
+    bool fail = s_fail != 0;
+    if (fail || (x == g.start_x && y == g.start_y)) break;
+    // ---- (re)load: window [x0, x0+256) x [y0, y0+256) around the current node, x0 a multiple of 16 (the pred plane's
+    // pitch is a multiple of 128, so every 16-byte chunk below is aligned and inside the allocation row)
+    const int x0 = (x - PW / 2) & ~15, y0 = y - PW / 2;
+    {
+      const int gy = y0 + tid;                        // thread = window row
+      uint4 v[PW / 16];
+#pragma unroll
+      for (int k = 0; k < PW / 16; ++k) {
+        const int gx = x0 + 16 * k;
+        const bool inb = gy >= 0 && gy < g.H && gx >= 0 && gx < (int)a.pitch;
+        v[k] = inb ? *reinterpret_cast<const uint4*>(a.pred + (size_t)gy * a.pitch + gx) : make_uint4(~0u, ~0u, ~0u, ~0u);
+      }
+#pragma unroll
+      for (int k = 0; k < PW / 16; ++k) *reinterpret_cast<uint4*>(win + tid * PW + 16 * k) = v[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int lx = x - x0, ly = y - y0;
+      while ((unsigned)lx < (unsigned)PW && (unsigned)ly < (unsigned)PW && !(x == g.start_x && y == g.start_y)) {
+        const int p = win[ly * PW + lx];
+        if (p > 7 || len >= a.cap || x < 0 || x >= g.W) { fail = true; break; }
+        const int dx = (p >= 5) - (p <= 2);                                   // NDX = {-1,-1,-1,0,0,1,1,1}
+        const int dy = (p == 2 || p == 4 || p == 7) - (p == 0 || p == 3 || p == 5);   // NDY = {-1,0,1,-1,1,-1,0,1}
+        x += dx; y += dy; lx += dx; ly += dy;
+        a.nodes[len++] = (x << 16) | y;
+      }
+      s_x = x; s_y = y; s_len = len; s_fail = fail ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const bool fail = s_fail != 0;
+    a.out[0] = fail ? 0 : s_len;
     a.out[1] = 1;
     a.out[2] = fail ? 0 : 1;
     a.out[3] = 0;
@@ -550,6 +703,11 @@ static FieldGeom make_geom(const sipp_ctx* ctx) {
 }
 
 int field_plan(sipp_ctx* ctx, cudaStream_t s) {
+  // SIPP_PLAN_TIMING=1: per-phase device times of every plan on stderr (tuning aid)
+  static const bool timing = getenv("SIPP_PLAN_TIMING") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(ev[0], s);
   const FieldGeom g = make_geom(ctx);
   const size_t ncell = (size_t)ctx->W * ctx->H;
   const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
@@ -585,6 +743,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxWarps * 32), kargs, kRelaxWarps * sizeof(TileSmem), s));
   ctx->launches += 1;
 
+  if (timing) cudaEventRecord(ev[1], s);
   PathArgs pa;
   pa.g = g;
   pa.field = ctx->d_field;
@@ -594,10 +753,28 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   pa.cap = ctx->path_cap_nodes;
   pa.out = ctx->d_plan_out;
   pa.cost_out = reinterpret_cast<double*>(ctx->d_plan_out + 8);
-  k_backtrack<<<1, 32, 0, s>>>(pa);
+  static bool back_attr = false;
+  if (!back_attr) {
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
+    back_attr = true;
+  }
+  PredArgs pr;
+  pr.g = g;
+  pr.field = ctx->d_field;
+  pr.pcode = ctx->d_pcode;
+  pr.pitch16 = ctx->pitch16;
+  pr.pred = ctx->d_pred;
+  pr.pitch = ctx->pitch;
+  pr.ntx = ctx->n_tiles_x;
+  k_pred<<<ntiles, kPredThreads, 0, s>>>(pr);
+  pa.pred = ctx->d_pred;
+  pa.pitch = ctx->pitch;
+  k_backtrack<<<1, kBackThreads, PW * PW, s>>>(pa);
+  ctx->launches += 1;
   ctx->launches += 1;
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
 
+  if (timing) cudaEventRecord(ev[2], s);
   // new mask: computeCurrentPathEstimate swaps in a freshly zeroed map (map_server_planexp.cpp:894-899,904)
   SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_path, 0, ctx->pitch * ctx->H, s));
   RasterArgs rs;
@@ -617,5 +794,26 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   k_path_finish<<<blocks, 256, 0, s>>>(rs);
   ctx->launches += 2;
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(ev[3], s);
+    cudaEventSynchronize(ev[3]);
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, ev[0], ev[1]);
+    cudaEventElapsedTime(&t12, ev[1], ev[2]);
+    cudaEventElapsedTime(&t23, ev[2], ev[3]);
+    fprintf(stderr, "[sipp] plan phases: init+relax %.3f ms, backtrack %.3f ms, mask %.3f ms\n", t01, t12, t23);
+#ifdef SIPP_RELAX_PROFILE
+    {
+      int ctl[32];
+      cudaMemcpy(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
+      unsigned long long tp[5];
+      memcpy(tp, ctl + 16, sizeof(tp));
+      const double act = ctl[CTL_ACTIVATIONS] > 0 ? ctl[CTL_ACTIVATIONS] : 1;
+      fprintf(stderr, "[sipp] relax cycles per activation: pop %.0f  load %.0f  sweeps %.0f  merge+cross %.0f  push %.0f  (activations %d, sweeps %d)\n",
+              tp[0] / act, tp[1] / act, tp[2] / act, tp[3] / act, tp[4] / act, ctl[CTL_ACTIVATIONS], ctl[CTL_SWEEPS]);
+    }
+#endif
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   return SIPP_OK;
 }
