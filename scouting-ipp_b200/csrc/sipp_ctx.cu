@@ -270,7 +270,7 @@ void sipp_destroy(sipp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_closest_dist,
-                  ctx->d_recip, ctx->d_field, ctx->d_pred, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
+                  ctx->d_recip, ctx->d_field, ctx->d_pred, ctx->d_tile_w, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
                   ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_path_nodes, ctx->d_path_xy, ctx->d_plan_out, ctx->d_stage, ctx->d_tree_ws,
                   ctx->d_best, ctx->d_select_ws};
   for (void* p : ptrs)
@@ -326,7 +326,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   // zero all device pointers (sipp_ctx has non-trivial members, so no memset of the whole struct)
   ctx->d_state = ctx->d_path = ctx->d_rec = nullptr;
   ctx->d_label = ctx->d_pcode = ctx->d_freelab = ctx->d_closest = nullptr;
-  ctx->d_closest_dist = nullptr; ctx->d_recip = nullptr; ctx->d_field = nullptr; ctx->d_pred = nullptr;
+  ctx->d_closest_dist = nullptr; ctx->d_recip = nullptr; ctx->d_field = nullptr; ctx->d_pred = nullptr; ctx->d_tile_w = nullptr;
   ctx->d_xcls = ctx->d_ycls = nullptr; ctx->d_hdist = ctx->d_vdist = ctx->d_ddist = nullptr;
   ctx->d_tile_flags = nullptr; ctx->d_tile_list = nullptr; ctx->d_relax_ctl = nullptr;
   ctx->d_path_nodes = nullptr; ctx->d_path_xy = nullptr; ctx->d_plan_out = nullptr;
@@ -365,6 +365,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   rc |= dev_alloc(ctx, &ctx->d_freelab, n8);
   rc |= dev_alloc(ctx, &ctx->d_field, (size_t)ctx->W * ctx->H);
   rc |= dev_alloc(ctx, &ctx->d_pred, n8);
+  rc |= dev_alloc(ctx, &ctx->d_tile_w, ntiles * (size_t)(4 * 34 * 34));
   rc |= dev_alloc(ctx, &ctx->d_tile_flags, ntiles);
   rc |= dev_alloc(ctx, &ctx->d_tile_list, ntiles > 16384 ? ntiles : (size_t)16384);   // ring queue: >= tiles and >= resident warps
   rc |= dev_alloc(ctx, &ctx->d_relax_ctl, 32);

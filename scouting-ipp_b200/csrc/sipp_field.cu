@@ -32,7 +32,7 @@ namespace {
 
 constexpr int TS = 32;        // tile edge (cells)
 constexpr int TP = TS + 2;    // with a one-cell halo
-constexpr int kMaxDd = 1024;  // diagonal class table entries kept in shared memory
+constexpr int kMaxDd = 256;   // diagonal class table entries kept in shared memory (9..14 classes per axis in practice)
 
 struct RelaxArgs {
   FieldGeom g;
@@ -44,19 +44,20 @@ struct RelaxArgs {
   int* queue;               // [cap] ring buffer of tile ids, -1 = empty slot
   int cap;
   int* ctl;                 // see CTL_* below
+  const double* tile_w;     // [ntiles][4][TP][TP] edge-weight cache (k_weights)
   int spin_limit;           // watchdog: a warp that polls an empty queue this many times aborts the kernel
+  int mode;                 // bit0: publish after every sweep (else once per run); bit1: exclusive tile ownership (owner re-runs)
 };
 enum { CTL_HEAD = 0, CTL_TAIL = 1, CTL_PENDING = 2, CTL_ACTIVATIONS = 3, CTL_SWEEPS = 4, CTL_ABORT = 5, CTL_PUSHES = 6 };
 
 
-__device__ __forceinline__ double ld_relaxed(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
+// fire-and-forget minimum on the bit pattern of a non-negative double (integer order == numeric order). Must be RED (no
+// return value): with the returning form (ATOMG) every store of a tile waited for its L2 round trip.
+__device__ __forceinline__ void red_min_f64(double* p, double v) {
+  asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" ::"l"(p), "l"(__double_as_longlong(v)) : "memory");
 }
-__device__ __forceinline__ void st_relaxed(double* p, double v) {
-  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
+// orders this thread's earlier writes before its later ones at gpu scope (lighter than __threadfence's fence.sc)
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __forceinline__ int ld_volatile_i32(const int* p) {
   int v;
@@ -79,146 +80,238 @@ __device__ __forceinline__ double half_cost(uint32_t code, double init_half) {
 // warp-shuffle fixed-point loop, so information crosses the whole tile in one sweep in the sweep direction and along
 // rows. Sweeps alternate direction until one of them changes nothing: at that point every cell satisfies all eight
 // inequalities d[v] <= d[u] + w(u,v), i.e. the tile is at its local fixed point. No block barriers.
-constexpr int kRelaxWarps = 8;
+constexpr int kRelaxWarps = 5;
 
+constexpr int kTileWDoubles = 4 * TP * TP;   // per-tile block of the weight cache: we, ws, wse, wsw planes
 struct TileSmem {
   double d[TP][TP];      // tentative costs incl. one-cell halo
-  double hc[TP][TP];     // half costs incl. halo (+inf: removed node / off map)
-  double vd[TP];         // vd[r]: length of the vertical edge between local rows r and r+1
-  int yc[TP];            // its class (for the diagonal table), -1 off map
+  // edge weights of the tile (k_weights computes them once per plan; they depend on the map, not on d), copied in as ONE
+  // block by cp.async.bulk: weight of the edge from (r,c) to
+  double we[TP][TP];     //   (r, c+1)
+  double ws[TP][TP];     //   (r+1, c)
+  double wse[TP][TP];    //   (r+1, c+1)
+  double wsw[TP][TP];    //   (r+1, c-1)      +inf: edge missing (removed node, off map, diagonal not admitted)
 };
+static_assert(sizeof(TileSmem) == (TP * TP + kTileWDoubles) * sizeof(double), "weight planes must be contiguous");
+static_assert((TP * TP * sizeof(double)) % 16 == 0 && (kTileWDoubles * sizeof(double)) % 16 == 0, "bulk copy needs 16-byte granularity");
 
-__device__ __forceinline__ double relax1(double best, double dn, double dist, double hc0, double hcn) {
-  const double cand = __dadd_rn(dn, __dmul_rn(dist, __dadd_rn(hc0, hcn)));
-  return cand < best ? cand : best;
+// weight of an edge of length `dist` between cells with half costs hca / hcb: dist * (hca + hcb), the reference's
+// (dist * (ca + cb)) / 2.0 (prm_star_planner.cpp:178-181); +inf for a missing edge (never NaN, also for zero costs)
+__device__ __forceinline__ double edge_w(double dist, double hca, double hcb) {
+  return dist < CUDART_INF ? __dmul_rn(dist, __dadd_rn(hca, hcb)) : CUDART_INF;
 }
 
 // One sweep over the interior rows. DIR = +1: rows 1..32 using row r-1; DIR = -1: rows 32..1 using row r+1.
-// Returns (warp-uniform) whether any cell was lowered; `mask` collects which tile borders changed.
+// The previous row never goes through shared memory: its final values at columns lx-1, lx, lx+1 are exactly what the last
+// (change-free) iteration of its in-row loop held in (dl, d, dr), halo columns included, so they are carried in registers.
+// Row r is relaxed against them (N, NW, NE) and against itself (W, E) in a shuffle loop that runs until no lane changes; a
+// row nothing changes in costs one iteration. All edge weights come from the per-tile planes. Returns (warp-uniform)
+// whether any cell was lowered; bit r-1 of `rows_changed` = this lane's cell in row r was lowered.
 template <int DIR>
-__device__ __forceinline__ bool sweep_rows(TileSmem& t, const double* ddp, int Ky, int lane, int xcl, int xcr, double hdl, double hdr,
-                                           int& mask, uint32_t& rows_changed) {
+__device__ __forceinline__ bool sweep_rows(TileSmem& t, int lane, uint32_t& rows_changed) {
   const int lx = lane + 1;
   bool chg = false;
+  const int r_first = (DIR > 0) ? 0 : TP - 1;
+  double pl = t.d[r_first][lx - 1], pc = t.d[r_first][lx], pr = t.d[r_first][lx + 1];
+#pragma unroll 4
   for (int i = 0; i < TS; ++i) {
     const int r = (DIR > 0) ? (1 + i) : (TS - i);
-    const int pr = r - DIR;                       // the row this sweep has just finished (or the halo row)
-    const int er = (DIR > 0) ? pr : r;            // vertical / diagonal edges between rows er and er+1
-    const double hc0 = t.hc[r][lx];
+    // weights of the edges to the previous row's three cells and to the row neighbours
+    const double wn = (DIR > 0) ? t.ws[r - 1][lx] : t.ws[r][lx];
+    const double wnl = (DIR > 0) ? t.wse[r - 1][lx - 1] : t.wsw[r][lx];
+    const double wnr = (DIR > 0) ? t.wsw[r - 1][lx + 1] : t.wse[r][lx];
+    const double wl = t.we[r][lx - 1], wr = t.we[r][lx];
+    const double hl = t.d[r][0], hr = t.d[r][TP - 1];      // left / right halo of this row (constant during the sweep)
     double d = t.d[r][lx];
     const double d0 = d;
-    const double hl = t.d[r][0], hr = t.d[r][TP - 1];      // left / right halo of this row (constant during the activation)
-    const double hcl = t.hc[r][lx - 1], hcr = t.hc[r][lx + 1];
-    if (hc0 < CUDART_INF) {
-      const int yc = t.yc[er];
-      const double vdist = t.vd[er];
-      const double ddl = (yc >= 0 && xcl >= 0) ? ddp[xcl * Ky + yc] : CUDART_INF;   // quad left of this column
-      const double ddr = (yc >= 0 && xcr >= 0) ? ddp[xcr * Ky + yc] : CUDART_INF;   // quad right of this column
-      d = relax1(d, t.d[pr][lx], vdist, hc0, t.hc[pr][lx]);
-      d = relax1(d, t.d[pr][lx - 1], ddl, hc0, t.hc[pr][lx - 1]);
-      d = relax1(d, t.d[pr][lx + 1], ddr, hc0, t.hc[pr][lx + 1]);
-    }
-    // in-row fixed point (W / E neighbours) with shuffles
-    const double wl = __dmul_rn(hdl, __dadd_rn(hc0, hcl)), wr = __dmul_rn(hdr, __dadd_rn(hc0, hcr));
+    double ca = __dadd_rn(pc, wn);
+    { const double c1 = __dadd_rn(pl, wnl), c2 = __dadd_rn(pr, wnr); const double c3 = c1 < c2 ? c1 : c2; ca = c3 < ca ? c3 : ca; }
+    if (ca < d) d = ca;
+    double dl, dr;
     bool again;
     do {
-      double dl = __shfl_up_sync(0xFFFFFFFFu, d, 1), dr = __shfl_down_sync(0xFFFFFFFFu, d, 1);
+      dl = __shfl_up_sync(0xFFFFFFFFu, d, 1); dr = __shfl_down_sync(0xFFFFFFFFu, d, 1);
       if (lane == 0) dl = hl;
       if (lane == 31) dr = hr;
-      double nd = d;
-      if (hc0 < CUDART_INF) {
-        const double cl = __dadd_rn(dl, wl), cr = __dadd_rn(dr, wr);
-        if (cl < nd) nd = cl;
-        if (cr < nd) nd = cr;
-      }
-      again = nd < d;
-      d = nd;
+      const double cl = __dadd_rn(dl, wl), cr = __dadd_rn(dr, wr);
+      const double c = cl < cr ? cl : cr;
+      again = c < d;
+      if (again) d = c;
     } while (__any_sync(0xFFFFFFFFu, again));
+    pl = dl; pc = d; pr = dr;
     if (d < d0) {
       chg = true;
       rows_changed |= 1u << (r - 1);
       t.d[r][lx] = d;
-      if (r == 1) mask |= 1;
-      if (r == TS) mask |= 2;
-      if (lane == 0) mask |= 4;
-      if (lane == 31) mask |= 8;
     }
-    __syncwarp();                                  // row r is final and visible before the next row reads it
   }
+  __syncwarp();                                    // the sweep's stores are visible to the whole warp
   return __any_sync(0xFFFFFFFFu, chg);
 }
 
-// Loads d and the half costs of the 34x34 window whose interior starts at (x0, y0) into shared memory. Loads are issued in
-// batches (plain L2-coherent ld.global.cg: other warps update the field with L2 atomics while k_relax runs, so L1 is
-// bypassed; an aligned 8-byte load cannot tear) so that their latencies overlap instead of serialising on the stores.
-__device__ __forceinline__ void load_tile(TileSmem& t, const FieldGeom& g, const double* field, const uint16_t* pcode, size_t pitch16,
-                                          int x0, int y0, int lane) {
+// Loads d of the 34x34 window whose interior starts at (x0, y0) into shared memory. Loads are issued in batches (plain
+// L2-coherent ld.global.cg: other warps update the field with L2 atomics while k_relax runs, so L1 is bypassed; an aligned
+// 8-byte load cannot tear) so that their latencies overlap instead of serialising on the stores.
+__device__ __forceinline__ void load_d(TileSmem& t, const FieldGeom& g, const double* field, int x0, int y0, int lane) {
   const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
   const bool colin = gx >= 0 && gx < g.W;
-#pragma unroll 1
-  for (int lyb = 0; lyb < TP; lyb += 17) {
-    double dv[17];
-    uint32_t cv[17];
-#pragma unroll
-    for (int j = 0; j < 17; ++j) {
-      const int gy = y0 - 1 + lyb + j;
-      const bool inb = colin && gy >= 0 && gy < g.H;
-      dv[j] = inb ? __ldcg(field + (size_t)gy * g.W + gx) : CUDART_INF;
-      cv[j] = inb ? (uint32_t)pcode[(size_t)gy * pitch16 + gx] : (uint32_t)PCODE_REMOVED;
-    }
-#pragma unroll
-    for (int j = 0; j < 17; ++j) {
-      t.d[lyb + j][lane + 1] = dv[j];
-      t.hc[lyb + j][lane + 1] = half_cost(cv[j], g.init_half_cost);
-    }
-  }
-  // the two halo columns: 68 entries over the warp
   double hv[3];
-  uint32_t hcv[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < 3; ++j) {              // the two halo columns: 68 entries over the warp
     const int e = lane + 32 * j;
     const int ly = e >> 1, side_r = e & 1;
     const int hx = side_r ? x0 + TS : x0 - 1, gy = y0 - 1 + ly;
     const bool inb = e < 2 * TP && hx >= 0 && hx < g.W && gy >= 0 && gy < g.H;
     hv[j] = inb ? __ldcg(field + (size_t)gy * g.W + hx) : CUDART_INF;
-    hcv[j] = inb ? (uint32_t)pcode[(size_t)gy * pitch16 + hx] : (uint32_t)PCODE_REMOVED;
+  }
+#pragma unroll 1
+  for (int lyb = 0; lyb < TP; lyb += 17) {
+    double dv[17];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      const int gy = y0 - 1 + lyb + j;
+      const bool inb = colin && gy >= 0 && gy < g.H;
+      dv[j] = inb ? __ldcg(field + (size_t)gy * g.W + gx) : CUDART_INF;
+    }
+#pragma unroll
+    for (int j = 0; j < 17; ++j) t.d[lyb + j][lane + 1] = dv[j];
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int e = lane + 32 * j;
-    if (e < 2 * TP) {
-      const int ly = e >> 1, lxh = (e & 1) ? TP - 1 : 0;
-      t.d[ly][lxh] = hv[j];
-      t.hc[ly][lxh] = half_cost(hcv[j], g.init_half_cost);
-    }
+    if (e < 2 * TP) t.d[e >> 1][(e & 1) ? TP - 1 : 0] = hv[j];
   }
 }
 
-// Persistent, barrier-free worker kernel. Warps pull tile ids from a global ring queue, solve the tile to its local
-// fixed point and push the neighbours whose halo they lowered. Why this is still exact: (1) every value ever written is the
-// rounded length of a real path (an upper bound of the fixed point) and is merged with atomicMin on the bit pattern (for
-// non-negative doubles the integer order is the numeric order), so the field only ever decreases, even if two warps work
-// on the same tile at once; (2) a tile is re-queued whenever a neighbour lowers its halo after the tile last cleared its
-// "queued" flag, and the flag is cleared BEFORE the halo is loaded, so no update can be missed; (3) the kernel ends when
-// the number of queued + in-flight tiles drops to zero, i.e. at a global fixed point, which is unique.
+// Re-run of a tile by the warp that already holds it (exclusive ownership): only the border ring (rows / columns 1 and 32,
+// other tiles push into it) and the halo (rows / columns 0 and 33) can have changed. Loads them, keeps the lower of (held,
+// loaded) — they can only differ by a push — and returns the set of tile rows (0..33) that received a lower value.
+__device__ __forceinline__ uint64_t reload_ring(TileSmem& t, const FieldGeom& g, const double* field, int x0, int y0, int lane) {
+  const int rows4[4] = {0, 1, TS, TP - 1};
+  double rv[4], cv[4], kv = CUDART_INF;
+  const int gxc = x0 + lane, gyr = y0 + lane;          // this lane's interior column (tile col lane+1) / row (tile row lane+1)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int gy = y0 - 1 + rows4[k], gx = x0 - 1 + rows4[k];
+    rv[k] = (gxc < g.W && gy >= 0 && gy < g.H) ? __ldcg(field + (size_t)gy * g.W + gxc) : CUDART_INF;     // row rows4[k], column lane+1
+    cv[k] = (gyr < g.H && gx >= 0 && gx < g.W) ? __ldcg(field + (size_t)gyr * g.W + gx) : CUDART_INF;     // column rows4[k], row lane+1
+  }
+  int ky = 0, kx = 0;
+  if (lane < 4) {                                       // the four halo corners
+    ky = (lane < 2) ? 0 : TP - 1; kx = (lane & 1) ? TP - 1 : 0;
+    const int gy = y0 - 1 + ky, gx = x0 - 1 + kx;
+    if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H) kv = __ldcg(field + (size_t)gy * g.W + gx);
+  }
+  uint64_t E = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool lo = rv[k] < t.d[rows4[k]][lane + 1];
+    if (lo) t.d[rows4[k]][lane + 1] = rv[k];
+    if (__any_sync(0xFFFFFFFFu, lo)) E |= 1ull << rows4[k];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool lo = cv[k] < t.d[lane + 1][rows4[k]];
+    if (lo) t.d[lane + 1][rows4[k]] = cv[k];
+    E |= (uint64_t)__ballot_sync(0xFFFFFFFFu, lo) << 1;     // lane l holds tile row l+1
+  }
+  {
+    const bool lo = lane < 4 && kv < t.d[ky][kx];
+    if (lo) t.d[ky][kx] = kv;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, lo);
+    if (m & 3u) E |= 1ull;
+    if (m & 12u) E |= 1ull << (TP - 1);
+  }
+  __syncwarp();
+  return E;
+}
+
+// ---- edge-weight cache: one block of four 34x34 planes per tile (halo edges included, so neighbouring blocks overlap) -----
+struct WeightArgs {
+  FieldGeom g;
+  const uint16_t* pcode;
+  size_t pitch16;
+  double* tile_w;    // [ntiles][4][TP][TP]
+  int ntx;
+};
+constexpr int kWeightThreads = 256;
+__global__ void __launch_bounds__(kWeightThreads)
+k_weights(const WeightArgs a) {
+  __shared__ float hcf[TP][TP + 1];        // half costs (multiples of 0.5 <= 1799.5 or +inf: exact in fp32)
+  __shared__ int xc[TP], yc[TP];           // class of the edge between tile columns c, c+1 / rows r, r+1 (-1: off map)
+  __shared__ double hd[TP], vd[TP];
+  __shared__ double dd[kMaxDd];
+  const FieldGeom& g = a.g;
+  const int tid = threadIdx.x;
+  const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
+  const int x0 = tx * TS, y0 = ty * TS;
+  const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
+  if (dd_in_smem)
+    for (int i = tid; i < g.Kx * g.Ky; i += kWeightThreads) dd[i] = g.ddist[i];
+  const double* ddp = dd_in_smem ? dd : g.ddist;
+  for (int idx = tid; idx < TP * TP; idx += kWeightThreads) {
+    const int r = idx / TP, c = idx - r * TP;
+    const int gx = x0 - 1 + c, gy = y0 - 1 + r;
+    const bool inb = gx >= 0 && gx < g.W && gy >= 0 && gy < g.H;
+    hcf[r][c] = (float)half_cost(inb ? (uint32_t)a.pcode[(size_t)gy * a.pitch16 + gx] : (uint32_t)PCODE_REMOVED, g.init_half_cost);
+  }
+  if (tid < TP) {
+    const int gy = y0 - 1 + tid, gx = x0 - 1 + tid;     // edges (gy, gy+1) and (gx, gx+1)
+    const bool oky = gy >= 0 && gy + 1 < g.H, okx = gx >= 0 && gx + 1 < g.W;
+    const int cy = oky ? g.ycls[gy] : -1, cx = okx ? g.xcls[gx] : -1;
+    yc[tid] = cy;
+    vd[tid] = oky ? g.vdist[cy] : CUDART_INF;
+    xc[tid] = cx;
+    hd[tid] = okx ? g.hdist[cx] : CUDART_INF;
+  }
+  __syncthreads();
+  double* out = a.tile_w + (size_t)blockIdx.x * kTileWDoubles;
+  for (int idx = tid; idx < TP * TP; idx += kWeightThreads) {
+    const int r = idx / TP, c = idx - r * TP;
+    const double h0 = (double)hcf[r][c];
+    const bool rn = r + 1 < TP, cn = c + 1 < TP;
+    auto ddc = [&](int xcl_, int ycl_) { return (xcl_ >= 0 && ycl_ >= 0) ? ddp[xcl_ * g.Ky + ycl_] : CUDART_INF; };
+    out[idx] = cn ? edge_w(hd[c], h0, (double)hcf[r][c + 1]) : CUDART_INF;
+    out[TP * TP + idx] = rn ? edge_w(vd[r], h0, (double)hcf[r + 1][c]) : CUDART_INF;
+    out[2 * TP * TP + idx] = (rn && cn) ? edge_w(ddc(xc[c], yc[r]), h0, (double)hcf[r + 1][c + 1]) : CUDART_INF;
+    out[3 * TP * TP + idx] = (rn && c > 0) ? edge_w(ddc(xc[c - 1], yc[r]), h0, (double)hcf[r + 1][c - 1]) : CUDART_INF;
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Persistent, barrier-free worker kernel. Warps pull tile ids from a global ring queue, relax the tile in shared memory with
+// alternating row sweeps and, after EVERY sweep that lowered something, publish: store the lowered cells, relax across the
+// tile border into the neighbours' cells, queue the neighbours that received a lower value. Why this is exact:
+//  (1) every value ever written is the rounded length of a real path (an upper bound of the fixed point) and the field only
+//      ever decreases: cells other tiles may write too (our border ring, the neighbours' border rings) are merged with
+//      atomicMin on the bit pattern (for non-negative doubles the integer order is the numeric order); interior cells are
+//      written by the tile's owner only — a tile is run by at most one warp at a time (state bit RUN);
+//  (2) whoever lowers a cell of tile T afterwards sets T's QUEUED bit; if T is idle that queues it, if T is running its owner
+//      sees the bit when it finishes and runs T again (after clearing the bit and BEFORE re-loading the tile), so no update
+//      is missed; every activation offers all its border values to the neighbours at least once, so a border cell lowered by
+//      one neighbour is carried on to the others;
+//  (3) the kernel ends when the number of queued + running tiles drops to zero, i.e. at a global fixed point, which is unique.
+constexpr int ST_QUEUED = 1, ST_RUN = 2;
+
 __global__ void __launch_bounds__(kRelaxWarps * 32)
 k_relax(const RelaxArgs a) {
   extern __shared__ __align__(16) uint8_t relax_smem[];
-  __shared__ double s_dd[kMaxDd];
+  __shared__ __align__(8) uint64_t s_bar[kRelaxWarps];
 
   const FieldGeom& g = a.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TileSmem& t = reinterpret_cast<TileSmem*>(relax_smem)[warp];
-  const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
-  if (dd_in_smem)
-    for (int i = threadIdx.x; i < g.Kx * g.Ky; i += blockDim.x) s_dd[i] = g.ddist[i];
-  const double* ddp = dd_in_smem ? s_dd : g.ddist;
+  const uint32_t bar = smem_addr(&s_bar[warp]);
+  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
+  uint32_t bar_parity = 0;
 
   int sweeps_local = 0, act_local = 0, push_local = 0;
 #ifdef SIPP_RELAX_PROFILE
-  long long tp[6] = {0, 0, 0, 0, 0, 0};
+  long long tp[6] = {0, 0, 0, 0, 0, 0};   // pop, load d, sweeps, store+cross, push, weights
   long long tk = clock64();
 #define SIPP_TICK(i) { const long long now_ = clock64(); tp[i] += now_ - tk; tk = now_; }
 #else
@@ -246,9 +339,8 @@ k_relax(const RelaxArgs a) {
         __nanosleep(64);
       }
       if (ti >= 0) {
-        __threadfence();
-        atomicExch(&a.flags[ti], 0);   // from here on a neighbour that lowers our halo re-queues this tile
-        __threadfence();
+        atomicExch(&a.flags[ti], (a.mode & 2) ? ST_RUN : 0);   // queued -> running; a lowering from here on sets QUEUED again
+        fence_gpu();
       }
     }
     ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
@@ -257,148 +349,164 @@ k_relax(const RelaxArgs a) {
 
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
-    load_tile(t, g, a.field, a.pcode, a.pitch16, x0, y0, lane);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int r = lane + 32 * k;
-      if (r < TP) {
-        const int gy = y0 - 1 + r;               // edge between global rows gy and gy+1
-        const bool ok = gy >= 0 && gy + 1 < g.H;
-        const int cls = ok ? g.ycls[gy] : -1;
-        t.yc[r] = cls;
-        t.vd[r] = ok ? g.vdist[cls] : CUDART_INF;
-      }
-    }
-    // this lane's column: classes / lengths of the horizontal edges to its left and right
-    const int gxl = x0 + lane - 1, gxr = x0 + lane;       // edges (gxl, gxl+1) and (gxr, gxr+1)
-    const int xcl = (gxl >= 0 && gxl + 1 < g.W) ? g.xcls[gxl] : -1;
-    const int xcr = (gxr >= 0 && gxr + 1 < g.W) ? g.xcls[gxr] : -1;
-    const double hdl = xcl >= 0 ? g.hdist[xcl] : CUDART_INF, hdr = xcr >= 0 ? g.hdist[xcr] : CUDART_INF;
-    __syncwarp();
-
-    SIPP_TICK(1)
-    // alternate downward / upward sweeps until one of them changes nothing (its opposite was completed right before it)
-    int mask = 0;
-    uint32_t rows_changed = 0;
-    for (int it = 0;; ++it) {
-      const bool c = (it & 1) ? sweep_rows<-1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask, rows_changed)
-                              : sweep_rows<+1>(t, ddp, g.Ky, lane, xcl, xcr, hdl, hdr, mask, rows_changed);
-      ++sweeps_local;
-      if (!c && it >= 1) break;
-    }
-    ++act_local;
-    SIPP_TICK(2)
-
-    // merge what this lane lowered (monotone: atomicMin on the bit pattern of non-negative doubles)
-    {
-      const int gx = x0 + lane;
-      uint32_t rc = rows_changed;
-      while (rc) {
-        const int r = __ffs(rc) - 1;
-        rc &= rc - 1;
-        const int gy = y0 + r;
-        if (gx < g.W && gy < g.H)
-          atomicMin(reinterpret_cast<unsigned long long*>(a.field + (size_t)gy * g.W + gx),
-                    (unsigned long long)__double_as_longlong(t.d[r + 1][lane + 1]));
-      }
-    }
-    // ---- relax ACROSS the tile border: every halo cell n (it belongs to a neighbour tile) against its up to three
-    // neighbours c on our side, cand = d[c] + w(c,n) — bit for bit what the neighbour tile would compute from its own halo.
-    // A neighbour is queued only if one of its cells was actually lowered (the atomicMin returned a larger value), so a tile
-    // is not re-activated by the echo of the values it produced itself. Lane l handles column l+1 of the top / bottom halo
-    // rows and row l+1 of the left / right halo columns; lanes 0..3 the four corners.
-    // Done on EVERY activation, changed border or not: a border cell of ours may have been lowered by a neighbour's push since
-    // we last ran, and only we can carry that value on across our other borders.
-    int m = 0;   // bit k: neighbour k (N S W E NW NE SW SE) received a lower value
-    {
-      const int lx = lane + 1;
-      const double hdl0 = __shfl_sync(0xFFFFFFFFu, hdl, 0), hdr31 = __shfl_sync(0xFFFFFFFFu, hdr, 31);
-      const int xcl0 = __shfl_sync(0xFFFFFFFFu, xcl, 0), xcr31 = __shfl_sync(0xFFFFFFFFu, xcr, 31);
-      auto dd = [&](int xc, int yc) { return (xc >= 0 && yc >= 0) ? ddp[xc * g.Ky + yc] : CUDART_INF; };
-      auto push_min = [&](int hy, int hx, double cand) -> bool {   // (hy,hx): halo cell in tile coordinates
-        if (!(cand < t.d[hy][hx])) return false;                   // cannot beat the value we loaded, let alone the current one
-        const int gx = x0 - 1 + hx, gy = y0 - 1 + hy;              // on the map: hc of an off-map halo cell is +inf -> cand = +inf
-        const unsigned long long nb = (unsigned long long)__double_as_longlong(cand);
-        return atomicMin(reinterpret_cast<unsigned long long*>(a.field + (size_t)gy * g.W + gx), nb) > nb;
-      };
-      // top halo row (tile row 0) from interior row 1; bottom halo row (TP-1) from interior row TS
-#pragma unroll
-      for (int sgn = 0; sgn < 2; ++sgn) {
-        const int hy = sgn ? TP - 1 : 0, iy = sgn ? TS : 1, er = sgn ? TS : 0;   // edges between tile rows er and er+1
-        {
-          const double hcn = t.hc[hy][lx];
-          double cand = CUDART_INF;
-          if (hcn < CUDART_INF) {
-            cand = relax1(cand, t.d[iy][lx], t.vd[er], hcn, t.hc[iy][lx]);
-            if (lx > 1) cand = relax1(cand, t.d[iy][lx - 1], dd(xcl, t.yc[er]), hcn, t.hc[iy][lx - 1]);
-            if (lx < TS) cand = relax1(cand, t.d[iy][lx + 1], dd(xcr, t.yc[er]), hcn, t.hc[iy][lx + 1]);
-          }
-          if (push_min(hy, lx, cand)) m |= sgn ? 2 : 1;
-        }
-      }
-      // left halo column (tile column 0) from interior column 1; right halo column (TP-1) from interior column TS
-#pragma unroll
-      for (int sgn = 0; sgn < 2; ++sgn) {
-        const int hx = sgn ? TP - 1 : 0, ix = sgn ? TS : 1;
-        {
-          const int ly = lane + 1;
-          const double hd = sgn ? hdr31 : hdl0;
-          const int xc = sgn ? xcr31 : xcl0;
-          const double hcn = t.hc[ly][hx];
-          double cand = CUDART_INF;
-          if (hcn < CUDART_INF) {
-            cand = relax1(cand, t.d[ly][ix], hd, hcn, t.hc[ly][ix]);
-            if (ly > 1) cand = relax1(cand, t.d[ly - 1][ix], dd(xc, t.yc[ly - 1]), hcn, t.hc[ly - 1][ix]);
-            if (ly < TS) cand = relax1(cand, t.d[ly + 1][ix], dd(xc, t.yc[ly]), hcn, t.hc[ly + 1][ix]);
-          }
-          if (push_min(ly, hx, cand)) m |= sgn ? 8 : 4;
-        }
-      }
-      // corners: NW NE SW SE from the diagonal interior cell
-      if (lane < 4) {
-        const int top = lane < 2, left = !(lane & 1);
-        const int hy = top ? 0 : TP - 1, hx = left ? 0 : TP - 1, iy = top ? 1 : TS, ix = left ? 1 : TS;
-        const double hcn = t.hc[hy][hx];
-        if (hcn < CUDART_INF) {
-          const double cand = relax1(CUDART_INF, t.d[iy][ix], dd(left ? xcl0 : xcr31, t.yc[top ? 0 : TS]), hcn, t.hc[iy][ix]);
-          if (push_min(hy, hx, cand)) m |= 16 << lane;
-        }
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xFFFFFFFFu, m, off);
-    SIPP_TICK(3)
-    __threadfence();      // our field updates are visible before any neighbour can be told to look at them
-    __syncwarp();
-    // neighbours: N S W E NW NE SW SE
-    if (lane < 8 && ((m >> lane) & 1)) {
-      const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-      const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-      const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
-      if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
-        const int nt = nty_ * a.ntx + ntx_;
-        if (atomicExch(&a.flags[nt], 1) == 0) {
-          atomicAdd(&a.ctl[CTL_PENDING], 1);
-          const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
-          int* slot = a.queue + (pos % (unsigned)a.cap);
-          int spins = 0;
-          while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);   // never expected: cap >= number of tiles
-          __threadfence();
-          st_volatile_i32(slot, nt);
-          ++push_local;
-        }
-      }
-    }
-    __syncwarp();
+    // the tile's weight block: one bulk async copy global -> shared, completion on this warp's mbarrier; it overlaps with the
+    // loads of d below
+    __syncwarp();           // everyone is done reading the previous tile's planes
     if (lane == 0) {
-      __threadfence();
-      atomicSub(&a.ctl[CTL_PENDING], 1);   // after our pushes were counted: pending reaches 0 only at the global fixed point
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kTileWDoubles * sizeof(double))) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(&t.we[0][0])),
+                   "l"(a.tile_w + (size_t)ti * kTileWDoubles), "r"((uint32_t)(kTileWDoubles * sizeof(double))), "r"(bar)
+                   : "memory");
     }
-    SIPP_TICK(4)
+    bool weights_pending = true;
+
+    bool first_run = true;
+    for (;;) {   // runs of this tile: again whenever somebody lowered one of its cells while it was running
+      // first run: the whole window; re-run: only the border ring and the halo can have changed (the interior is ours alone
+      // and still in shared memory)
+      if (first_run) load_d(t, g, a.field, x0, y0, lane);
+      else reload_ring(t, g, a.field, x0, y0, lane);
+      first_run = false;
+      if (weights_pending) {
+        uint32_t ok = 0;
+        while (!ok)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(bar), "r"(bar_parity) : "memory");
+        bar_parity ^= 1u;
+        weights_pending = false;
+      }
+      __syncwarp();
+      ++act_local;
+      SIPP_TICK(1)
+
+      // alternate downward / upward sweeps until one of them changes nothing (its opposite was completed right before it);
+      // publish after every sweep that lowered something, and at least once per run
+      bool published = false, any_change = false;
+      for (int it = 0;; ++it) {
+        uint32_t rows_changed = 0;
+        const bool c = (it & 1) ? sweep_rows<-1>(t, lane, rows_changed) : sweep_rows<+1>(t, lane, rows_changed);
+        ++sweeps_local;
+        SIPP_TICK(2)
+        const bool last = !c && it >= 1;
+        if (c) any_change = true;
+        if ((a.mode & 1) ? (c || (last && !published)) : last) {
+          if (!(a.mode & 1)) rows_changed = any_change ? 0xFFFFFFFFu : 0u;   // one publish per run: store every row
+          published = true;
+          // ---- store what this lane lowered in this sweep
+          {
+            const int gx = x0 + lane;
+            const bool edge_col = lane == 0 || lane == 31;
+            uint32_t rc = rows_changed;
+            while (rc) {
+              const int r = __ffs(rc) - 1;
+              rc &= rc - 1;
+              const int gy = y0 + r;
+              double* dst = a.field + (size_t)gy * g.W + gx;
+              const double v = t.d[r + 1][lane + 1];
+              if (edge_col || r == 0 || r == TS - 1 || !(a.mode & 2))   // border ring: neighbours push into it concurrently
+                red_min_f64(dst, v);
+              else
+                *dst = v;                                 // interior: this warp is the only writer
+            }
+          }
+          // ---- relax ACROSS the tile border: every halo cell n (it belongs to a neighbour tile) against its up to three
+          // neighbours c on our side, cand = d[c] + w(c,n) — bit for bit what the neighbour would compute from its own halo.
+          // A neighbour is queued only if cand beats the value we hold for n (then our copy is updated too), so a tile is
+          // not re-activated by the echo of the values it produced itself. Lane l handles column l+1 of the top / bottom
+          // halo rows and row l+1 of the left / right halo columns; lanes 0..3 the four corners.
+          int m = 0;   // bit k: neighbour k (N S W E NW NE SW SE) received a lower value
+          {
+            const int lx = lane + 1, ly = lane + 1;
+            auto offer = [&](int hy, int hx, double cand) -> bool {   // (hy,hx): halo cell in tile coordinates
+              if (!(cand < t.d[hy][hx])) return false;               // +inf (edge missing / off map) never passes
+              t.d[hy][hx] = cand;
+              const int gx = x0 - 1 + hx, gy = y0 - 1 + hy;
+              red_min_f64(a.field + (size_t)gy * g.W + gx, cand);
+              return true;
+            };
+            auto min3 = [](double a_, double b_, double c_) { const double m_ = a_ < b_ ? a_ : b_; return m_ < c_ ? m_ : c_; };
+            // top halo row (0, lx) from interior row 1; bottom halo row (TP-1, lx) from interior row TS
+            {
+              double cl = CUDART_INF, cr = CUDART_INF;
+              if (lx > 1) cl = __dadd_rn(t.d[1][lx - 1], t.wsw[0][lx]);
+              if (lx < TS) cr = __dadd_rn(t.d[1][lx + 1], t.wse[0][lx]);
+              if (offer(0, lx, min3(__dadd_rn(t.d[1][lx], t.ws[0][lx]), cl, cr))) m |= 1;
+              cl = CUDART_INF; cr = CUDART_INF;
+              if (lx > 1) cl = __dadd_rn(t.d[TS][lx - 1], t.wse[TS][lx - 1]);
+              if (lx < TS) cr = __dadd_rn(t.d[TS][lx + 1], t.wsw[TS][lx + 1]);
+              if (offer(TP - 1, lx, min3(__dadd_rn(t.d[TS][lx], t.ws[TS][lx]), cl, cr))) m |= 2;
+            }
+            // left halo column (ly, 0) from interior column 1; right halo column (ly, TP-1) from interior column TS
+            {
+              double cu = CUDART_INF, cd = CUDART_INF;
+              if (ly > 1) cu = __dadd_rn(t.d[ly - 1][1], t.wsw[ly - 1][1]);
+              if (ly < TS) cd = __dadd_rn(t.d[ly + 1][1], t.wse[ly][0]);
+              if (offer(ly, 0, min3(__dadd_rn(t.d[ly][1], t.we[ly][0]), cu, cd))) m |= 4;
+              cu = CUDART_INF; cd = CUDART_INF;
+              if (ly > 1) cu = __dadd_rn(t.d[ly - 1][TS], t.wse[ly - 1][TS]);
+              if (ly < TS) cd = __dadd_rn(t.d[ly + 1][TS], t.wsw[ly][TP - 1]);
+              if (offer(ly, TP - 1, min3(__dadd_rn(t.d[ly][TS], t.we[ly][TS]), cu, cd))) m |= 8;
+            }
+            if (lane < 4) {                        // corners: NW NE SW SE from the diagonal interior cell
+              double cand;
+              int hy, hx;
+              if (lane == 0) { hy = 0; hx = 0; cand = __dadd_rn(t.d[1][1], t.wse[0][0]); }
+              else if (lane == 1) { hy = 0; hx = TP - 1; cand = __dadd_rn(t.d[1][TS], t.wsw[0][TP - 1]); }
+              else if (lane == 2) { hy = TP - 1; hx = 0; cand = __dadd_rn(t.d[TS][1], t.wsw[TS][1]); }
+              else { hy = TP - 1; hx = TP - 1; cand = __dadd_rn(t.d[TS][TS], t.wse[TS][TS]); }
+              if (offer(hy, hx, cand)) m |= 16 << lane;
+            }
+          }
+          m = __reduce_or_sync(0xFFFFFFFFu, (unsigned)m);
+          SIPP_TICK(3)
+          if (m) {
+            fence_gpu();      // the lowered neighbour cells are visible before the neighbour can be told to look
+            __syncwarp();
+            // neighbours: N S W E NW NE SW SE
+            if (lane < 8 && ((m >> lane) & 1)) {
+              const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+              const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+              const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
+              if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
+                const int nt = nty_ * a.ntx + ntx_;
+                if (atomicOr(&a.flags[nt], ST_QUEUED) == 0) {     // idle -> queued: ours to enqueue (a running tile re-runs itself)
+                  atomicAdd(&a.ctl[CTL_PENDING], 1);
+                  const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
+                  int* slot = a.queue + (pos % (unsigned)a.cap);
+                  int spins = 0;
+                  while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);   // never expected: cap >= number of tiles
+                  st_volatile_i32(slot, nt);
+                  ++push_local;
+                }
+              }
+            }
+            __syncwarp();
+          }
+          SIPP_TICK(4)
+        }
+        if (last) break;
+      }
+      // ---- done with this run: idle again, unless one of our cells was lowered meanwhile
+      int again = 0;
+      if (lane == 0) {
+        fence_gpu();
+        if (!(a.mode & 2)) atomicSub(&a.ctl[CTL_PENDING], 1);
+        else if (atomicCAS(&a.flags[ti], ST_RUN, 0) != ST_RUN) {
+          atomicExch(&a.flags[ti], ST_RUN);      // take the request; everything lowered before this point is re-loaded below
+          fence_gpu();
+          again = 1;
+        } else {
+          atomicSub(&a.ctl[CTL_PENDING], 1);     // after our pushes were counted: pending reaches 0 only at the global fixed point
+        }
+      }
+      again = __shfl_sync(0xFFFFFFFFu, again, 0);
+      SIPP_TICK(4)
+      if (!again) break;
+    }
   }
 #ifdef SIPP_RELAX_PROFILE
   if (lane == 0)
-    for (int i = 0; i < 5; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + 16) + i, (unsigned long long)tp[i]);
+    for (int i = 0; i < 6; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + 16) + i, (unsigned long long)tp[i]);
 #endif
   // statistics
   atomicAdd(&a.ctl[CTL_PUSHES], push_local);
@@ -440,13 +548,6 @@ struct PathArgs {
   int* out;         // [0] len, [1] all explored, [2] found, [3] unused, [4] walk failed on a reachable goal
   double* cost_out;
 };
-
-__device__ __forceinline__ double edge_len(const FieldGeom& g, int ax, int ay, int bx, int by) {
-  const int mx = min(ax, bx), my = min(ay, by);
-  if (ay == by) return g.hdist[g.xcls[mx]];
-  if (ax == bx) return g.vdist[g.ycls[my]];
-  return g.ddist[g.xcls[mx] * g.Ky + g.ycls[my]];
-}
 
 // ---- canonical predecessor of every cell (fully parallel), then the walk over predecessor bytes -------------------------
 // pred[y][x] = index k (0..7, neighbours in ascending node id x*H+y) of the canonical predecessor of (x,y): among the u with
@@ -722,10 +823,20 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   static int num_sms = 0, occ = 0;
   if (!num_sms) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
-    SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem)));
-    if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
   }
+  // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
+  WeightArgs wa;
+  wa.g = g;
+  wa.pcode = ctx->d_pcode;
+  wa.pitch16 = ctx->pitch16;
+  wa.tile_w = ctx->d_tile_w;
+  wa.ntx = ctx->n_tiles_x;
+  k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
+  ctx->launches += 1;
+  const size_t relax_smem = kRelaxWarps * sizeof(TileSmem);
+  SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem));
+  SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, relax_smem));
+  if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
   RelaxArgs ra;
   ra.g = g;
   ra.field = ctx->d_field;
@@ -736,11 +847,13 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   ra.queue = ctx->d_tile_list;
   ra.cap = qcap;
   ra.ctl = ctx->d_relax_ctl;
+  ra.tile_w = ctx->d_tile_w;
   ra.spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
+  ra.mode = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
   int grid = num_sms * occ;
   if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
   void* kargs[] = {(void*)&ra};
-  SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxWarps * 32), kargs, kRelaxWarps * sizeof(TileSmem), s));
+  SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxWarps * 32), kargs, relax_smem, s));
   ctx->launches += 1;
 
   if (timing) cudaEventRecord(ev[1], s);
@@ -806,11 +919,11 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     {
       int ctl[32];
       cudaMemcpy(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
-      unsigned long long tp[5];
+      unsigned long long tp[6];
       memcpy(tp, ctl + 16, sizeof(tp));
       const double act = ctl[CTL_ACTIVATIONS] > 0 ? ctl[CTL_ACTIVATIONS] : 1;
-      fprintf(stderr, "[sipp] relax cycles per activation: pop %.0f  load %.0f  sweeps %.0f  merge+cross %.0f  push %.0f  (activations %d, sweeps %d)\n",
-              tp[0] / act, tp[1] / act, tp[2] / act, tp[3] / act, tp[4] / act, ctl[CTL_ACTIVATIONS], ctl[CTL_SWEEPS]);
+      fprintf(stderr, "[sipp] relax cycles per activation: pop %.0f  load %.0f  sweeps %.0f  merge+cross %.0f  push %.0f  weights %.0f  (activations %d, sweeps %d)\n",
+              tp[0] / act, tp[1] / act, tp[2] / act, tp[3] / act, tp[4] / act, tp[5] / act, ctl[CTL_ACTIVATIONS], ctl[CTL_SWEEPS]);
     }
 #endif
     for (auto& e : ev) cudaEventDestroy(e);

@@ -97,6 +97,7 @@ struct sipp_ctx {
   float* d_closest_dist;
   double* d_recip;       // [65536] 1/label lookup for ExpandLowCost
   double* d_field;       // W*H doubles
+  double* d_tile_w;      // [ntiles][4][34][34] edge-weight cache of the relaxation tiles (k_weights)
   uint8_t* d_pred;       // canonical predecessor direction per cell (k_pred), [H][pitch]
   // geometry tables on device
   uint8_t *d_xcls, *d_ycls;
