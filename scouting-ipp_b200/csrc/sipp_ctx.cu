@@ -131,6 +131,8 @@ int host_clear(sipp_ctx* ctx) {
   ctx->field_valid = false;
   ctx->views_dirty = true;
   SIPP_CUDA_CHECK(ctx, launch_clear_planes(ctx, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, launch_closest_clear(ctx, ctx->stream));
+  ctx->lowcost_view_dirty = true;
   return SIPP_OK;
 }
 
@@ -200,7 +202,29 @@ bool same_bv(const sipp_eval_params& a, const sipp_eval_params& b) {
 
 // (re)build the evaluator view planes when the map, the path mask or the bounding volume changed
 int ensure_views(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, cudaStream_t s) {
+  if (p->evaluator == SIPP_EVAL_EXPAND_LOW_COST) {
+    // ExpandLowCostAreaEvaluator: its own view plane + the reciprocal table recip[idx] (idx = closest cost + 1)
+    const bool bv_changed = !(ctx->view_params_valid && same_bv(ctx->view_params, *p));
+    if (ctx->lowcost_view_dirty || bv_changed) {
+      SIPP_CUDA_CHECK(ctx, launch_build_lowcost_view(ctx, g, p->use_bounding_volume != 0, s));
+      ctx->lowcost_view_dirty = false;
+      if (bv_changed) ctx->views_dirty = true;    // the other views were built for another bounding volume
+      ctx->view_params = *p;
+      ctx->view_params_valid = true;
+    }
+    const int aug = p->augment_unknown_with_mean != 0;
+    if (!ctx->recip_valid || ctx->recip_augment != aug || memcmp(&ctx->recip_mean, &ctx->mean_cost, sizeof(double)) != 0) {
+      std::vector<double> r(4097, 0.0);
+      r[1] = aug ? 1.0 / ctx->mean_cost : 0.0;                  // cost <= 0: expand_low_cost_area_evaluator.cpp:55-57,64-66
+      for (int k = 2; k <= 4096; ++k) r[k] = 1.0 / (double)(k - 1);   // :53,62
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_recip, r.data(), r.size() * 8, cudaMemcpyHostToDevice, s));
+      SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));         // r goes out of scope
+      ctx->recip_valid = true; ctx->recip_augment = aug; ctx->recip_mean = ctx->mean_cost;
+    }
+    return SIPP_OK;
+  }
   if (!ctx->views_dirty && ctx->view_params_valid && same_bv(ctx->view_params, *p)) return SIPP_OK;
+  if (!(ctx->view_params_valid && same_bv(ctx->view_params, *p))) ctx->lowcost_view_dirty = true;   // built for another bounding volume
   SIPP_CUDA_CHECK(ctx, launch_build_views(ctx, g, p->use_bounding_volume != 0, s));
   if (int rc = sipp_debug_sync(ctx, s, "k_build_views")) return rc;
   ctx->views_dirty = false;
@@ -269,7 +293,7 @@ void sipp_destroy(sipp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_closest_dist,
+  void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_cclab, ctx->d_closest_dist,
                   ctx->d_recip, ctx->d_field, ctx->d_pred, ctx->d_tile_w, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
                   ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_path_nodes, ctx->d_path_xy, ctx->d_plan_out, ctx->d_stage, ctx->d_tree_ws,
                   ctx->d_best, ctx->d_select_ws};
@@ -277,6 +301,13 @@ void sipp_destroy(sipp_ctx* ctx) {
     if (p) cudaFree(p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->cycle_graph) cudaGraphExecDestroy(ctx->cycle_graph);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  for (int i = 0; i < 8; ++i) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+  }
   delete ctx;
 }
 
@@ -325,7 +356,8 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   memset(ctx->plan_stats, 0, sizeof(ctx->plan_stats));
   // zero all device pointers (sipp_ctx has non-trivial members, so no memset of the whole struct)
   ctx->d_state = ctx->d_path = ctx->d_rec = nullptr;
-  ctx->d_label = ctx->d_pcode = ctx->d_freelab = ctx->d_closest = nullptr;
+  ctx->d_label = ctx->d_pcode = ctx->d_freelab = ctx->d_closest = ctx->d_cclab = nullptr;
+  ctx->lowcost_view_dirty = true; ctx->recip_valid = false;
   ctx->d_closest_dist = nullptr; ctx->d_recip = nullptr; ctx->d_field = nullptr; ctx->d_pred = nullptr; ctx->d_tile_w = nullptr;
   ctx->d_xcls = ctx->d_ycls = nullptr; ctx->d_hdist = ctx->d_vdist = ctx->d_ddist = nullptr;
   ctx->d_tile_flags = nullptr; ctx->d_tile_list = nullptr; ctx->d_relax_ctl = nullptr;
@@ -333,6 +365,10 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; ctx->d_stage = nullptr; ctx->d_stage_bytes = 0;
   ctx->d_tree_ws = nullptr; ctx->d_tree_ws_bytes = 0; ctx->d_best = nullptr; ctx->d_select_ws = nullptr;
   ctx->stream = nullptr;
+  ctx->s_in = ctx->s_out = nullptr;
+  ctx->cycle_graph = nullptr;
+  ctx->cycle_graph_launches = 0;
+  for (int i = 0; i < 8; ++i) ctx->ev_in[i] = ctx->ev_k[i] = nullptr;
 
   auto fail = [&](int rc) {
     g_create_err = ctx->err;
@@ -345,6 +381,18 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
+  e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "copy streams / events: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
+  ctx->cycle_chunks = getenv("SIPP_CYCLE_CHUNKS") ? atoi(getenv("SIPP_CYCLE_CHUNKS")) : 0;
+  ctx->cycle_use_graph = !(getenv("SIPP_CYCLE_GRAPH") && atoi(getenv("SIPP_CYCLE_GRAPH")) == 0);
+  e = cudaMallocHost(&ctx->h_pinned, 256);
+  if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
+  ctx->h_pinned_bytes = 256;
 
   ctx->pitch = ((size_t)ctx->W + 127) & ~(size_t)127;
   ctx->pitch16 = ctx->pitch;
@@ -363,6 +411,12 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   rc |= dev_alloc(ctx, &ctx->d_label, n8);
   rc |= dev_alloc(ctx, &ctx->d_pcode, n8);
   rc |= dev_alloc(ctx, &ctx->d_freelab, n8);
+  rc |= dev_alloc(ctx, &ctx->d_closest, n8);
+  rc |= dev_alloc(ctx, &ctx->d_recip, (size_t)4097);
+  if (ctx->desc.compute_closest_observed) {
+    rc |= dev_alloc(ctx, &ctx->d_cclab, n8);
+    rc |= dev_alloc(ctx, &ctx->d_closest_dist, n8);
+  }
   rc |= dev_alloc(ctx, &ctx->d_field, (size_t)ctx->W * ctx->H);
   rc |= dev_alloc(ctx, &ctx->d_pred, n8);
   rc |= dev_alloc(ctx, &ctx->d_tile_w, ntiles * (size_t)(4 * 34 * 34));
@@ -426,6 +480,9 @@ static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, cons
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lab, labels, n * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (observed) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_obs, observed, n, cudaMemcpyHostToDevice, ctx->stream));
   SIPP_CUDA_CHECK(ctx, launch_ingest_patch(ctx, x0, y0, rows, cols, d_lab, d_obs, ctx->stream));
+  // setClosestObservedMaps runs per MapData patch (map_server_planexp.cpp:264); the masked whole-map upload is not one
+  if (ctx->desc.compute_closest_observed && !observed) SIPP_CUDA_CHECK(ctx, launch_closest_update(ctx, x0, y0, rows, cols, ctx->stream));
+  ctx->lowcost_view_dirty = true;
   ctx->views_dirty = true;
   ctx->field_valid = false;
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -688,20 +745,84 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
   cudaStream_t s = ctx->stream;
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, stage_bytes(n))) != SIPP_OK) return rc;
   const Stage st = carve(ctx->d_stage, n);
-  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
-  if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.start_xy, start_xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
-  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.cost, cost, (size_t)n * 8, cudaMemcpyHostToDevice, s));
   const GainGeom g = make_gain_geom(ctx, params);
   if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
-  if ((rc = gain_launch(ctx, params, g, n, st.xy, start_xy ? st.start_xy : nullptr, st.cost, st.gain, nullptr, st.terminal, st.value, s)) != SIPP_OK)
-    return rc;
-  SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, st.value, 0, ctx->d_best, nullptr, s));
-  BestRec br;
-  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(&br, ctx->d_best, sizeof(br), cudaMemcpyDeviceToHost, s));
-  if (gain) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain, st.gain, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-  if (terminal) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal, st.terminal, (size_t)n, cudaMemcpyDeviceToHost, s));
-  if (value) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value, st.value, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  // Chunked three-stage pipeline: host->device copies of chunk c+1 (stream s_in) and device->host copies of chunk c-1 (s_out)
+  // run under the gain kernel of chunk c (s); the argmax runs once over all values. Small batches go through in one piece.
+  // The whole pipeline (copies, kernels, cross-stream events) is captured once as a CUDA graph and replayed with a single
+  // launch while the caller keeps passing the same buffers and parameters — the per-call cost of ~25 driver calls was as
+  // large as the transfers themselves.
+  int chunks = ctx->cycle_chunks > 0 ? ctx->cycle_chunks : (n >= 16384 ? 2 : 1);
+  if (chunks > 8) chunks = 8;
+  const int per = (n + chunks - 1) / chunks;
+  BestRec* h_best = reinterpret_cast<BestRec*>(ctx->h_pinned);
+  auto enqueue = [&]() -> int {
+    int launched = 0;
+    for (int c = 0; c < chunks; ++c) {
+      const int lo = c * per, m = (lo + per <= n ? per : n - lo);
+      if (m <= 0) break;
+      cudaStream_t si = chunks > 1 ? ctx->s_in : s, so = chunks > 1 ? ctx->s_out : s;
+      if (chunks > 1 && c == 0) {   // fork the copy streams off s (required inside a capture, harmless outside)
+        SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_k[7], s));
+        SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(si, ctx->ev_k[7], 0));
+      }
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.xy + 2 * (size_t)lo, xy + 2 * (size_t)lo, (size_t)m * 16, cudaMemcpyHostToDevice, si));
+      if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.start_xy + 2 * (size_t)lo, start_xy + 2 * (size_t)lo, (size_t)m * 16, cudaMemcpyHostToDevice, si));
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.cost + lo, cost + lo, (size_t)m * 8, cudaMemcpyHostToDevice, si));
+      if (chunks > 1) {
+        SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_in[c], si));
+        SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_in[c], 0));
+      }
+      const int grc = gain_launch(ctx, params, g, m, st.xy + 2 * (size_t)lo, start_xy ? st.start_xy + 2 * (size_t)lo : nullptr, st.cost + lo, st.gain + lo,
+                                  nullptr, st.terminal + lo, st.value + lo, s);
+      if (grc != SIPP_OK) return grc;
+      ++launched;
+      if (chunks > 1) {
+        SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_k[c], s));
+        SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(so, ctx->ev_k[c], 0));
+      }
+      if (gain) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain + lo, st.gain + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
+      if (terminal) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal + lo, st.terminal + lo, (size_t)m, cudaMemcpyDeviceToHost, so));
+      if (value) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value + lo, st.value + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
+    }
+    SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, st.value, 0, ctx->d_best, nullptr, s));
+    ++launched;
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_best, ctx->d_best, sizeof(BestRec), cudaMemcpyDeviceToHost, s));
+    if (chunks > 1) {             // join the output stream back into s
+      SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_in[7], ctx->s_out));
+      SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_in[7], 0));
+    }
+    ctx->cycle_graph_launches = launched;
+    return SIPP_OK;
+  };
+  if (ctx->cycle_use_graph) {
+    // key: everything the captured nodes bake in
+    std::vector<unsigned char> key;
+    auto put = [&](const void* p, size_t nb) { const unsigned char* b = reinterpret_cast<const unsigned char*>(p); key.insert(key.end(), b, b + nb); };
+    const void* ptrs[8] = {xy, start_xy, cost, gain, terminal, value, ctx->d_stage, ctx->d_rec};
+    put(&n, sizeof(n)); put(&chunks, sizeof(chunks)); put(ptrs, sizeof(ptrs)); put(params, sizeof(*params)); put(&g, sizeof(g));
+    if (!ctx->cycle_graph || key != ctx->cycle_key) {
+      if (ctx->cycle_graph) { cudaGraphExecDestroy(ctx->cycle_graph); ctx->cycle_graph = nullptr; }
+      const int64_t launches_before = ctx->launches;
+      SIPP_CUDA_CHECK(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+      rc = enqueue();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      ctx->launches = launches_before;       // nothing ran yet
+      if (rc != SIPP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "graph capture of the cycle pipeline failed: %s", cudaGetErrorString(ce));
+      const cudaError_t ie = cudaGraphInstantiate(&ctx->cycle_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { ctx->cycle_graph = nullptr; return sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+      ctx->cycle_key = key;
+    }
+    SIPP_CUDA_CHECK(ctx, cudaGraphLaunch(ctx->cycle_graph, s));
+    ctx->launches += ctx->cycle_graph_launches;
+  } else {
+    if ((rc = enqueue()) != SIPP_OK) return rc;
+  }
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  const BestRec br = *h_best;
   if (best_index) *best_index = (int32_t)br.index;
   if (best_value) *best_value = br.value;
   return SIPP_OK;

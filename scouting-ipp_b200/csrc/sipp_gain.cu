@@ -329,12 +329,12 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           if (MODE == MODE_AVG_VIEW_COST) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) sum_aux2 += (wds[q] & 0xFFFFu) + (wds[q] >> 16);
-          } else {  // MODE_LOW_COST: entries are 0 (not unknown / off map / outside the bounding volume) or closest_label + 2
+          } else {  // MODE_LOW_COST: bit 15 = counted (UNKNOWN, inside the bounding volume), bits 0..11 = closest cost + 1
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t l0 = wds[q] & 0xFFFFu, l1 = wds[q] >> 16;
-              if (l0) { n_unk += 1; fsum += a.recip[l0]; }
-              if (l1) { n_unk += 1; fsum += a.recip[l1]; }
+              if (l0 & 0x8000u) { n_unk += 1; fsum += a.recip[l0 & 0x0FFFu]; }
+              if (l1 & 0x8000u) { n_unk += 1; fsum += a.recip[l1 & 0x0FFFu]; }
             }
           }
         }
@@ -386,7 +386,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           const uint32_t crec = my_crec, caux16 = my_caux16;
           bool c_unk, c_free = false, c_path = false, c_reach = false;
           if (MODE == MODE_LOW_COST) {
-            c_unk = c_in_bounds ? ((caux16 & 0x8000u) != 0) : true;
+            c_unk = c_in_bounds ? ((caux16 & 0x0FFFu) != 0) : true;      // idx != 0 <=> the cell is UNKNOWN
           } else {
             c_unk = c_in_bounds ? ((crec & REC_RAW_UNK) != 0) : true;
             c_free = c_in_bounds && (crec & REC_RAW_FREE) != 0;
@@ -409,7 +409,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
               const double dist = sqrt(dx * dx + dy * dy);
               fsum += (dist > a.inv_max_gain) ? 1.0 / dist : a.max_gain;
             } else if (MODE == MODE_LOW_COST) {
-              fsum += a.recip[c_in_bounds ? (caux16 & 0x7FFFu) : 0u];
+              fsum += a.recip[c_in_bounds ? (caux16 & 0x0FFFu) : 1u];   // outside the map server's bounds the lookup gives -1
             }
           } else if (MODE == MODE_AVG_VIEW_COST && c_free) {
             n_aux += 1;
@@ -583,10 +583,9 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   }
   if (mode == MODE_COUNT && p->evaluator == SIPP_EVAL_RRT_STAR && p->do_binary_check && p->use_distance_discount && !d_start_xy)
     return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "RRTStarEvaluator binary+discount mode needs start_xy (trajectory[0])");
-  if (mode == MODE_LOW_COST) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "ExpandLowCostAreaEvaluator is not built yet");
   const size_t rec_bytes = (size_t)a.box_w * side, aux_bytes = (size_t)a.box_w16 * 2 * side;
-  a.aux_off = (int)((rec_bytes + 127) & ~(size_t)127);
-  const bool need_aux = (mode == MODE_AVG_VIEW_COST);
+  const bool need_aux = (mode == MODE_AVG_VIEW_COST || mode == MODE_LOW_COST), need_rec = (mode != MODE_LOW_COST);
+  a.aux_off = need_rec ? (int)((rec_bytes + 127) & ~(size_t)127) : 0;
   a.slot_bytes = (int)((need_aux ? (a.aux_off + aux_bytes) : rec_bytes) + 127) & ~127;
   a.stages = ctx->gain_stages > 0 ? ctx->gain_stages : 2;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
@@ -596,7 +595,7 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   if (!tm_rec) return rc;
   const CUtensorMap* tm_aux = tm_rec;
   if (need_aux) {
-    tm_aux = cached_tmap(ctx, h, 1, &rc);
+    tm_aux = cached_tmap(ctx, h, mode == MODE_LOW_COST ? 2 : 1, &rc);
     if (!tm_aux) return rc;
   }
   switch (mode) {
@@ -604,6 +603,7 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
     case MODE_RRT_DISCOUNT: return launch_mode<MODE_RRT_DISCOUNT>(ctx, tm_rec, tm_aux, a, s);
     case MODE_GOAL_DISTANCE: return launch_mode<MODE_GOAL_DISTANCE>(ctx, tm_rec, tm_aux, a, s);
     case MODE_AVG_VIEW_COST: return launch_mode<MODE_AVG_VIEW_COST>(ctx, tm_rec, tm_aux, a, s);
+    case MODE_LOW_COST: return launch_mode<MODE_LOW_COST>(ctx, tm_rec, tm_aux, a, s);
   }
   return SIPP_OK;
 }

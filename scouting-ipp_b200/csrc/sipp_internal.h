@@ -67,6 +67,14 @@ struct sipp_ctx {
   sipp_map_desc desc;
   int device;
   cudaStream_t stream;
+  cudaStream_t s_in, s_out;          // copy streams of the chunked host-pointer pipeline (sipp_cycle)
+  cudaEvent_t ev_in[8], ev_k[8];
+  int cycle_chunks;                  // 0 = automatic; tuning knob SIPP_CYCLE_CHUNKS
+  // sipp_cycle's pipeline captured as a CUDA graph, replayed while the call's pointers / parameters stay the same
+  bool cycle_use_graph;
+  cudaGraphExec_t cycle_graph;
+  std::vector<unsigned char> cycle_key;
+  int cycle_graph_launches;
   std::mutex mu;
   std::string err;
   int64_t launches;
@@ -93,8 +101,11 @@ struct sipp_ctx {
   uint8_t* d_path;       // path mask 0/1
   uint8_t* d_rec;        // packed gain record (view)
   uint16_t* d_freelab;   // view: label where state == FREE (inside bv) else 0   (AverageViewCost)
-  uint16_t* d_closest;   // closest observed cost (label) for UNKNOWN cells       (ExpandLowCost)
-  float* d_closest_dist;
+  uint16_t* d_closest;   // ExpandLowCost view: closest-observed cost index + counted flag per cell (k_build_lowcost_view)
+  uint16_t* d_cclab;     // map_cost_closest_ (label of the closest observed cell), only with compute_closest_observed
+  float* d_closest_dist; // map_distance_closest_ as squared pixel distance
+  bool lowcost_view_dirty;
+  double recip_mean; int recip_augment; bool recip_valid;   // what d_recip was filled for
   double* d_recip;       // [65536] 1/label lookup for ExpandLowCost
   double* d_field;       // W*H doubles
   double* d_tile_w;      // [ntiles][4][34][34] edge-weight cache of the relaxation tiles (k_weights)
@@ -151,6 +162,9 @@ cudaError_t launch_ingest_patch(sipp_ctx* ctx, int x0, int y0, int rows, int col
                                 const uint8_t* d_observed, cudaStream_t s);
 cudaError_t launch_unknown_cost_noop(sipp_ctx* ctx, cudaStream_t s);
 cudaError_t launch_build_views(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cudaStream_t s);
+cudaError_t launch_closest_update(sipp_ctx* ctx, int x0, int y0, int rows, int cols, cudaStream_t s);
+cudaError_t launch_closest_clear(sipp_ctx* ctx, cudaStream_t s);
+cudaError_t launch_build_lowcost_view(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cudaStream_t s);
 cudaError_t launch_download_planes(sipp_ctx* ctx, uint8_t* d_state_out, int32_t* d_cost_out, uint8_t* d_reach_out,
                                    uint8_t* d_path_out, cudaStream_t s);
 cudaError_t launch_upload_mask(sipp_ctx* ctx, const uint8_t* d_mask_packed, cudaStream_t s);

@@ -5,6 +5,8 @@
 // planexp_base_planners/src/prm_star_planner.cpp:104-119). The sequential scalars of that loop
 // (mean_cost_, max_cost_, the goal-explored switch) are kept on the host in sipp_ctx.cu; everything
 // per-cell runs here.
+#include <cmath>
+
 #include "sipp_internal.h"
 
 namespace {
@@ -40,10 +42,53 @@ __global__ void k_ingest_patch(uint8_t* __restrict__ state, uint16_t* __restrict
     *pc = in_ids(rov, lab) ? (uint16_t)PCODE_REMOVED : (uint16_t)lab;   // :112-115
 }
 
+// MapServerPlanExp::setClosestObservedMaps (map_server_planexp.cpp:803-823) for one ingested patch [tlx,brx) x [tly,bry):
+// every UNKNOWN cell within 15 columns / 10 rows of the patch takes over the cost of the nearest cell of the closed box
+// [tlx..brx] x [tly..bry] if that is closer than what it had. One thread per window cell; a cell only writes its own
+// entries and only reads map_cost_, so the reference's sequential double loop is order independent.
+// dist2 holds the SQUARED pixel distance (an exact small integer in fp32): sqrt is monotone on distinct integers, so
+// `stored <= distance` of the reference is `stored2 <= distance2`; the initial value sqrt(width^2 + height^2) [metres!] is
+// represented by the sentinel qmax + 0.5, qmax = largest integer whose root is below it. The reference admits i == W /
+// j == H and a box that reaches one cell past the patch (and the map): those out-of-range accesses are skipped.
+__global__ void k_closest_update(const uint8_t* __restrict__ state, const uint16_t* __restrict__ label, uint16_t* __restrict__ cclab,
+                                 float* __restrict__ dist2, size_t pitch, size_t pitch16, int W, int H, int tlx, int tly, int brx, int bry) {
+  const int ww = brx - tlx + 31, wh = bry - tly + 21;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)ww * wh) return;
+  const int i = tlx - 15 + (int)(t % ww), j = tly - 10 + (int)(t / ww);
+  if (i < 0 || i >= W || j < 0 || j >= H) return;
+  if (state[(size_t)j * pitch + i] != SIPP_STATE_UNKNOWN) return;
+  const int cx = min(brx, max(tlx, i)), cy = min(bry, max(tly, j));
+  const float q = (float)((i - cx) * (i - cx) + (j - cy) * (j - cy));
+  float* dq = dist2 + (size_t)j * pitch16 + i;
+  if (*dq <= q) return;
+  if (cx < 0 || cx >= W || cy < 0 || cy >= H) return;
+  *dq = q;
+  cclab[(size_t)j * pitch16 + i] = label[(size_t)cy * pitch16 + cx];
+}
+
 __global__ void k_fill_f32(float* p, size_t n, float v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
+}
+
+// ExpandLowCostAreaEvaluator view (expand_low_cost_area_evaluator.cpp:50-69): per cell a 16-bit entry
+//   bits 0..11  idx = closest-observed cost + 1 when the cell is UNKNOWN (1 when there is no closest cost: plane not computed
+//               -> the lookup returns -1, or never set -> 0), 0 when the cell is observed
+//   bit 15      the corner voxel of the cell is counted: UNKNOWN and inside the bounding volume
+// The kernel adds recip[idx] per counted cell: recip[1] = augment ? 1/mean : 0, recip[k] = 1/(k-1).
+__global__ void k_build_lowcost_view(const uint8_t* __restrict__ state, const uint16_t* __restrict__ cclab, uint16_t* __restrict__ view,
+                                     size_t pitch, size_t pitch16, int W, int H, int bv_kx_lo, int bv_kx_hi, int bv_ky_lo, int bv_ky_hi) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)pitch16 * H) return;
+  const int y = (int)(t / (long long)pitch16), x = (int)(t % (long long)pitch16);
+  uint32_t e = 0;
+  if (x < W && state[(size_t)y * pitch + x] == SIPP_STATE_UNKNOWN) {
+    e = (cclab ? (uint32_t)cclab[(size_t)y * pitch16 + x] : 0u) + 1u;
+    if (x >= bv_kx_lo && x <= bv_kx_hi && y >= bv_ky_lo && y <= bv_ky_hi) e |= 0x8000u;
+  }
+  view[(size_t)y * pitch16 + x] = (uint16_t)e;
 }
 
 // Builds the evaluator view planes. 16 cells per thread, 128-bit loads/stores.
@@ -156,6 +201,41 @@ cudaError_t launch_build_views(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cu
   k_build_views<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_path, ctx->d_label, ctx->d_rec, ctx->d_freelab,
                                            ctx->pitch, ctx->pitch16, ctx->W, ctx->H, klo_x, khi_x, klo_y, khi_y,
                                            ctx->start_loc[0], ctx->start_loc[1], ctx->desc.compute_reachability);
+  ctx->launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_closest_update(sipp_ctx* ctx, int x0, int y0, int rows, int cols, cudaStream_t s) {
+  const long long n = (long long)(cols + 31) * (rows + 21);
+  const int threads = 256;
+  k_closest_update<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(ctx->d_state, ctx->d_label, ctx->d_cclab, ctx->d_closest_dist, ctx->pitch,
+                                                                             ctx->pitch16, ctx->W, ctx->H, x0, y0, x0 + cols, y0 + rows);
+  ctx->launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_closest_clear(sipp_ctx* ctx, cudaStream_t s) {
+  if (!ctx->d_cclab) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(ctx->d_cclab, 0, ctx->pitch16 * ctx->H * 2, s);
+  if (e != cudaSuccess) return e;
+  // sentinel for the initial distance sqrt(width^2 + height^2): qmax + 0.5 with qmax = max{q : sqrt(q) < that}
+  const double d0 = std::sqrt(ctx->desc.width * ctx->desc.width + ctx->desc.height * ctx->desc.height);
+  long long q = (long long)std::floor(d0 * d0);
+  while (q >= 0 && !(std::sqrt((double)q) < d0)) --q;
+  while (std::sqrt((double)(q + 1)) < d0) ++q;
+  const float sentinel = q > 8000000 ? 8.0e6f : (float)q + 0.5f;     // squared window distances never exceed 15^2 + 10^2
+  k_fill_f32<<<592, 256, 0, s>>>(ctx->d_closest_dist, ctx->pitch16 * ctx->H, sentinel);
+  ctx->launches += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_lowcost_view(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cudaStream_t s) {
+  const long long n = (long long)ctx->pitch16 * ctx->H;
+  const int threads = 256;
+  const int klo_x = use_bv ? g.bv_kx_lo : 0, khi_x = use_bv ? g.bv_kx_hi : ctx->W - 1;
+  const int klo_y = use_bv ? g.bv_ky_lo : 0, khi_y = use_bv ? g.bv_ky_hi : ctx->H - 1;
+  k_build_lowcost_view<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(ctx->d_state, ctx->d_cclab, ctx->d_closest, ctx->pitch, ctx->pitch16,
+                                                                                 ctx->W, ctx->H, klo_x, khi_x, klo_y, khi_y);
   ctx->launches += 1;
   return cudaGetLastError();
 }

@@ -71,6 +71,7 @@ static Module::ParamMap mapParams(int W, int H) {
   p["present_ids"] = "[0, 30, 45, 60, 90, 120]";
   p["unknown_init_cost"] = "max";
   p["compute_path"] = "true";
+  p["compute_closest_observed"] = "true";
   return p;
 }
 
@@ -241,6 +242,7 @@ static int testGpu() {
       {"GpuExpandReachableAreaEvaluator", "UpdateAllNonTerminal", "", SIPP_EVAL_EXPAND_REACHABLE},
       {"GpuAverageViewCostEvaluator", "ConstrainedUpdater", "UpdateAll", SIPP_EVAL_AVERAGE_VIEW_COST},
       {"GpuNaiveEvaluator", "RRTStarUpdater", "UpdateAll", SIPP_EVAL_NAIVE},
+      {"GpuExpandLowCostAreaEvaluator", "ConstrainedUpdater", "UpdateAll", SIPP_EVAL_EXPAND_LOW_COST},
   };
   for (const Config& cfg : cfgs) {
     std::printf("--- %s / %s / %s\n", cfg.type, cfg.updater, cfg.following);

@@ -153,6 +153,41 @@ def test_gain_and_cycle_config2_1024(golden):
             assert np.array_equal(gg, og) and np.array_equal(gv, ov) and gbv == obv
 
 
+def test_expand_low_cost_area_with_closest_observed_plane():
+    """A8: ExpandLowCostAreaEvaluator over the closest-observed plane that the patch ingest maintains
+    (setClosestObservedMaps, map_server_planexp.cpp:803-823), with and without augment_unknown_with_mean, with a bounding volume,
+    and without the plane (compute_closest_observed false: every lookup returns -1)."""
+    rng = np.random.default_rng(11)
+    W, H = 160, 128
+    for closest in (True, False):
+        mk = lambda f: f(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), 30, 120, 30,
+                         compute_closest_observed=closest)
+        g, o = both(mk)
+        for k in range(14):
+            rows, cols = (33, 33) if k % 3 else (17, 41)
+            x0, y0 = int(rng.integers(-12, W - 10)), int(rng.integers(-12, H - 10))
+            patch = rng.integers(0, 121, (rows, cols)).astype(np.int32)
+            g.map_update_patch(x0, y0, patch)
+            o.map_update_patch(x0, y0, patch)
+        assert g.map_stats() == o.map_stats()
+        xy = rng.uniform(-0.3, W * 0.0625 + 0.3, (300, 2))
+        xy[:, 1] = rng.uniform(-0.3, H * 0.0625 + 0.3, 300)
+        for half_fov in (1, 10, 32):
+            for aug in (False, True):
+                for bv in (None, (1.0, 7.5, 0.7, 6.1)):
+                    pg = sipp.make_params(sipp.EVAL_EXPAND_LOW_COST, half_fov=half_fov, augment_unknown_with_mean=aug, bounding_volume=bv)
+                    po = orc.make_params(orc.EVAL_EXPAND_LOW_COST, half_fov=half_fov, augment_unknown_with_mean=aug, bounding_volume=bv)
+                    gg, gc, gt = g.gain_batch(pg, xy)
+                    og, oc, ot = o.gain_batch(po, xy, variant=1, threads=4)
+                    assert np.array_equal(gc[:, :2], oc[:, :2]), (closest, half_fov, aug, bv)
+                    assert np.array_equal(gt, ot)
+                    assert np.allclose(gg, og, rtol=RTOL, atol=0.0, equal_nan=True), (closest, half_fov, aug, bv)
+        # the other evaluators still see their own views after the low-cost view was built (and vice versa)
+        g.set_path_mask(np.zeros((H, W), np.uint8)); o.set_path_mask(np.zeros((H, W), np.uint8))
+        assert_gain_parity(g, o, dict(evaluator=sipp.EVAL_NAIVE), xy)
+        assert_gain_parity(g, o, dict(evaluator=sipp.EVAL_AVERAGE_VIEW_COST), xy, bv=(1.0, 7.5, 0.7, 6.1))
+
+
 # ------------------------------------------------------------------------------------------------------------
 GOLDEN_NAMES = ["map_102", "map_110", "map_111", "map_112", "map_113", "map_115", "map_116", "map_122", "map_212", "map_312"]
 

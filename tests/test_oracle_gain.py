@@ -161,3 +161,48 @@ def test_faithful_and_linear_filters_agree():
             a = o.gain_batch(p, xy, start_xy=xy[::-1].copy(), variant=0)
             b = o.gain_batch(p, xy, start_xy=xy[::-1].copy(), variant=1, threads=3)
             assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_closest_observed_and_expand_low_cost_hand_case():
+    """setClosestObservedMaps (map_server_planexp.cpp:803-823) + ExpandLowCostAreaEvaluator (expand_low_cost_area_evaluator.cpp:33-72),
+    derived by hand: a 4x4 patch at cells [20,24)x[20,24) of an all-unknown 48x48 map. The reference clamps to the CLOSED box
+    [20..24]x[20..24] (bottom_right = top_left + size, one past the patch), so cells right of / below the patch take the cost of
+    the unobserved column / row 24 (0.0), cells left / above it the patch's first column / row."""
+    patch = (40 + np.arange(16).reshape(4, 4)).astype(np.int32)       # label(row r, col c) = 40 + 4 r + c
+    # unit quirk: the initial distance is sqrt(width^2 + height^2) in METRES (map_server_planexp.cpp:470-471) but it is compared
+    # with PIXEL distances (:817-818): on a 3 m x 3 m map (48 cells) nothing farther than 4.24 cells is ever updated
+    d = orc.make_desc(48, 48, 48 * VS, 48 * VS, (0.5, 0.5), (2.5, 2.5), 30, 120, 30, compute_closest_observed=True)
+    o = orc.Oracle(d)
+    o.map_update_patch(20, 20, patch)
+    cc, dc = o.closest_download()
+    assert dc[22, 16] == 4.0 and cc[22, 16] == patch[2, 0] and dc[22, 15] == np.sqrt(18.0) and cc[22, 15] == 0.0
+    W = H = 256                                                        # 16 m x 16 m: initial distance 22.6 > the 15 / 10 cell margins
+    d = orc.make_desc(W, H, W * VS, H * VS, (0.5, 0.5), (2.5, 2.5), 30, 120, 30, compute_closest_observed=True)
+    o = orc.Oracle(d)
+    o.map_update_patch(20, 20, patch)
+    cc, dc = o.closest_download()
+    d0 = np.sqrt((W * VS) ** 2 + (H * VS) ** 2)
+    assert cc[22, 18] == patch[2, 0] and dc[22, 18] == 2.0            # left of the patch: first patch column, distance 2
+    assert cc[17, 21] == patch[0, 1] and dc[17, 21] == 3.0            # above: first patch row
+    assert cc[22, 30] == 0.0 and dc[22, 30] == 6.0                    # right: column 24 is outside the patch and unobserved
+    assert cc[18, 17] == patch[0, 0] and dc[18, 17] == np.sqrt(13.0)  # corner
+    assert dc[22, 4] == d0 and cc[22, 4] == 0.0                       # 16 columns away: outside the 15-column margin
+    assert dc[9, 22] == d0 and dc[10, 22] == 10.0                     # 10-row margin
+    assert dc[21, 21] == d0                                           # observed cells are never touched
+    # a second, nearer patch replaces only where it is strictly closer (`<=` keeps the old value on ties)
+    o.map_update_patch(12, 20, (90 * np.ones((4, 4))).astype(np.int32))   # cells [12,16)x[20,24), closed box reaches column 16
+    cc2, dc2 = o.closest_download()
+    assert cc2[22, 18] == patch[2, 0] and dc2[22, 18] == 2.0          # tie (distance 2 to column 16, which is unobserved anyway)
+    assert cc2[22, 17] == 0.0 and dc2[22, 17] == 1.0                  # column 16 (unobserved, cost 0) is now the closest
+    # evaluator: window of half_fov 1 around cell (18, 22): the nine cells are all unknown; the centre voxel counts twice
+    p = orc.make_params(orc.EVAL_EXPAND_LOW_COST, half_fov=1)
+    gain, cnt, term = o.gain_batch(p, [[(18 + 0.3) * VS, (22 + 0.4) * VS]])
+    cells = [(x, y) for x in (17, 18, 19) for y in (21, 22, 23)] + [(18, 22)]
+    want = sum(1.0 / cc2[y, x] for x, y in cells if cc2[y, x] > 0)
+    assert cnt[0, 0] == 10 and cnt[0, 1] == 10 and term[0] == 0
+    assert abs(gain[0] - want) <= 1e-12 * want
+    # augment_unknown_with_mean: the cells without a closest cost add 1 / mean_cost_ each
+    p = orc.make_params(orc.EVAL_EXPAND_LOW_COST, half_fov=1, augment_unknown_with_mean=True)
+    gain2, _, _ = o.gain_batch(p, [[(18 + 0.3) * VS, (22 + 0.4) * VS]])
+    n0 = sum(1 for x, y in cells if not cc2[y, x] > 0)
+    assert n0 > 0 and abs(gain2[0] - (want + n0 / o.map_stats()[0])) <= 1e-9 * gain2[0]
