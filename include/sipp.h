@@ -232,6 +232,14 @@ int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, con
                    const double* d_start_xy, const double* d_cost, double* d_gain, uint8_t* d_terminal,
                    double* d_value, void* d_best, void* stream);
 
+/* ---- multi-GPU: merge of the per-shard best records ---------------------------------------------------- */
+/* d_recs: `world` 16-byte records {double value; int64 index} as gathered from the ranks (NCCL all_gather of the d_best
+ * of sipp_cycle_dev); record r holds a shard-local index that becomes global by adding r * shard_stride (pass 0 when the
+ * indices are already global). Picks what one rank scanning all candidates would select: the largest value, the lowest
+ * global index on ties; NaN never beats a number; a record with index < 0 (empty shard) never wins; if no record is
+ * comparable the first one is returned. Writes one 16-byte record with the GLOBAL index to d_out. One tiny kernel. */
+int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_t shard_stride, void* d_out, void* stream);
+
 /* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
 int64_t sipp_launch_count(const sipp_ctx* ctx);
 

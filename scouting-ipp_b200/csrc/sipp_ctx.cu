@@ -828,4 +828,12 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
   return SIPP_OK;
 }
 
+int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_t shard_stride, void* d_out, void* stream) {
+  SIPP_ENTER(ctx);
+  if (!d_recs || !d_out || world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad merge_best arguments");
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  SIPP_CUDA_CHECK(ctx, launch_merge_best(ctx, reinterpret_cast<const BestRec*>(d_recs), world, (long long)shard_stride, reinterpret_cast<BestRec*>(d_out), s));
+  return SIPP_OK;
+}
+
 }  // extern "C"

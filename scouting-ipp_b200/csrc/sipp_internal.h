@@ -178,6 +178,7 @@ cudaError_t launch_select_flat(sipp_ctx* ctx, int n, const double* d_value, long
 cudaError_t launch_value_flat(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, double* d_value, cudaStream_t s);
 cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_gain_below, const double* d_cost,
                               const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s);
+cudaError_t launch_merge_best(sipp_ctx* ctx, const BestRec* d_recs, int world, long long stride, BestRec* d_out, cudaStream_t s);
 size_t select_workspace_bytes();
 // sipp_field.cu
 int field_plan(sipp_ctx* ctx, cudaStream_t s);

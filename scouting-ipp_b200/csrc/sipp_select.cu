@@ -177,6 +177,27 @@ __global__ void k_tree_final(int n, const unsigned long long* __restrict__ best,
 
 }  // namespace
 
+// merge of the gathered per-shard records (multi-GPU): one warp, sequential-scan semantics (see sipp.h)
+__global__ void k_merge_best(const BestRec* __restrict__ recs, int world, long long stride, BestRec* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  BestRec best = recs[0];
+  if (best.index >= 0) best.index += 0;      // rank 0: offset 0
+  bool have = best.index >= 0 && !(best.value != best.value);
+  for (int r = 1; r < world; ++r) {
+    BestRec c = recs[r];
+    if (c.index < 0 || c.value != c.value) continue;
+    c.index += (long long)r * stride;
+    if (!have || c.value > best.value || (c.value == best.value && c.index < best.index)) { best = c; have = true; }
+  }
+  *out = best;
+}
+
+cudaError_t launch_merge_best(sipp_ctx* ctx, const BestRec* d_recs, int world, long long stride, BestRec* d_out, cudaStream_t s) {
+  k_merge_best<<<1, 32, 0, s>>>(d_recs, world, stride, d_out);
+  ctx->launches += 1;
+  return cudaGetLastError();
+}
+
 size_t select_workspace_bytes() { return sizeof(SelectWs); }
 
 static int sel_grid(int n) {

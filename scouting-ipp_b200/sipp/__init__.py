@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sipp_patch_origin", "sipp_map_update_patch", "sipp_map_upload_full", "sipp_update_unknown_cost", "sipp_map_stats",
     "sipp_map_download", "sipp_plan", "sipp_field_download", "sipp_path_mask_generation", "sipp_set_path_mask",
     "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
-    "sipp_cycle", "sipp_cycle_dev", "sipp_launch_count",
+    "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_launch_count",
 ]
 
 
@@ -149,6 +149,7 @@ def lib():
         L.sipp_value_preorder.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.sipp_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, pi32, pf64]
         L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.sipp_merge_best_dev.argtypes = [vp, vp, i32, i64, vp, vp]
         L.sipp_launch_count.argtypes = [vp]
         L.sipp_launch_count.restype = i64
         _lib = L
@@ -323,6 +324,9 @@ class Context:
     def cycle_dev(self, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, d_best, stream=None):
         self._check(self._L.sipp_cycle_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost),
                                            _ptr(d_gain), _ptr(d_terminal), _ptr(d_value), _ptr(d_best), _ptr(stream)))
+
+    def merge_best_dev(self, d_recs, world, shard_stride, d_out, stream=None):
+        self._check(self._L.sipp_merge_best_dev(self._h, _ptr(d_recs), int(world), int(shard_stride), _ptr(d_out), _ptr(stream)))
 
     def cycle_host_ptr(self, params, n, xy, start_xy, cost, gain, terminal, value):
         """sipp_cycle on caller-owned host buffers given as raw addresses (pinned memory for the e2e benchmark)."""

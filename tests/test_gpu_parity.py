@@ -153,6 +153,118 @@ def test_gain_and_cycle_config2_1024(golden):
             assert np.array_equal(gg, og) and np.array_equal(gv, ov) and gbv == obv
 
 
+def test_config3_and_bench_workload_4096():
+    """BASELINE config 3 (cost-to-go field on a 4096^2 synthetic map, partial map, init cost max) and the bench.py workload
+    (65536 candidates on that map): the whole field, the canonical path, the mask, every count and the selected candidate
+    against the oracle — the oracle's Dijkstra takes ~3 s at this size, so the full comparison is affordable."""
+    W = H = 4096
+    lab, obs, dg = synth.world(W, H, 1003, 1500, sipp.make_desc, init_cost="max")
+    _, _, do = synth.world(W, H, 1003, 1500, orc.make_desc, init_cost="max")
+    g, o = sipp.Context(dg), orc.Oracle(do)
+    g.map_upload_full(lab, obs)
+    o.map_upload_full(lab, obs)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+    fg, fo = g.field_download(), o.field_download()
+    assert np.array_equal(fg, fo), "field differs in %d cells" % int((fg != fo).sum())
+    assert np.array_equal(g.map_download()[3], o.map_download()[3])
+    # planning twice gives the same bits (the relaxation order differs from run to run, the fixed point does not)
+    rg2 = g.plan()
+    assert rg2[0] == rg[0] and np.array_equal(rg2[2], rg[2]) and np.array_equal(g.field_download(), fg)
+    xy, cost = synth.make_candidates(W, H, 1003, 65536)
+    for npg in (0.001, 0.0):
+        pgp = sipp.make_params(sipp.EVAL_RRT_STAR, non_path_voxel_gain=npg)
+        pop = orc.make_params(orc.EVAL_RRT_STAR, non_path_voxel_gain=npg)
+        gg, gc, gt = g.gain_batch(pgp, xy)
+        og, oc, ot = o.gain_batch(pop, xy, variant=1, threads=16)
+        assert np.array_equal(gc, oc) and np.array_equal(gt, ot)
+        gg2, gt2, gv, gi, gbv = g.cycle(pgp, xy, cost)
+        og2, ot2, ov, oi, obv = o.cycle(pop, xy, cost, variant=1, threads=16)
+        assert gi == oi and np.array_equal(gt2, ot2) and np.array_equal(gg2, gg)
+        assert np.allclose(gv, ov, rtol=RTOL, atol=0) and abs(gbv - obv) <= RTOL * abs(obv)
+        if npg == 0.0:
+            assert np.array_equal(gg, og) and np.array_equal(gv, ov) and gbv == obv
+
+
+def test_config4_field_properties_8192():
+    """BASELINE config 4 map size (8192^2): size-independent properties instead of a second full oracle run — (1) the field is a
+    fixed point: no edge can lower any cell, and every reachable cell but the start has a neighbour it is exactly derived from
+    (checked on the host with numpy over the axial edges, whose weights do not depend on the diagonal admission); (2) the path
+    is a chain of neighbouring cells from start to goal whose costs increase monotonically to d[goal]; (3) idempotence."""
+    W = H = 8192
+    lab, obs, dg = synth.world(W, H, 1004, 6000, sipp.make_desc, init_cost="max")
+    g = sipp.Context(dg)
+    g.map_upload_full(lab, obs)
+    cost, status, path, n = g.plan()
+    assert cost > 0 and n > 2 * 8000 // 2
+    f = g.field_download()
+    assert f[8, 8] == 0.0 and np.isfinite(cost)
+    # planner costs: observed label, init cost (max label) where unobserved, obstacle (label 0) = no node
+    ids = sorted(set(np.unique(lab).tolist()) - {0})
+    c = np.where(obs != 0, lab, max(ids)).astype(np.float64)
+    removed = (obs != 0) & (lab == 0)
+    s = (W * 0.0625) / (W + 1)
+    X = (W * 0.0625 - (W + 1) * s) / 2.0 + s * np.arange(W, dtype=np.float64)
+    dx = np.sqrt((X[1:] - X[:-1]) ** 2 + 0.0 * 0.0)
+    # (1a) horizontal edges: d[y, x+1] <= d[y, x] + dist * (c_a + c_b) / 2 and the reverse, wherever both ends are nodes
+    ok = ~removed[:, 1:] & ~removed[:, :-1]
+    w = dx[None, :] * (c[:, 1:] + c[:, :-1]) / 2.0
+    with np.errstate(invalid="ignore"):
+        assert not np.any(ok & (f[:, 1:] > f[:, :-1] + w)) and not np.any(ok & (f[:, :-1] > f[:, 1:] + w))
+    del w, ok
+    # (1b) vertical edges (the reference uses the x spacing for y as well)
+    Y = (H * 0.0625 - (H + 1) * s) / 2.0 + s * np.arange(H, dtype=np.float64)
+    dy = np.sqrt(0.0 * 0.0 + (Y[1:] - Y[:-1]) ** 2)
+    ok = ~removed[1:, :] & ~removed[:-1, :]
+    w = dy[:, None] * (c[1:, :] + c[:-1, :]) / 2.0
+    with np.errstate(invalid="ignore"):
+        assert not np.any(ok & (f[1:, :] > f[:-1, :] + w)) and not np.any(ok & (f[:-1, :] > f[1:, :] + w))
+    assert np.all(np.isinf(f[removed]))
+    # (2) the path: neighbouring nodes, strictly increasing cost-to-come, ends at d[goal]
+    px = np.rint((path[:, 0] - X[0]) / s).astype(int)
+    py = np.rint((path[:, 1] - Y[0]) / s).astype(int)
+    assert (px[0], py[0]) == (8, 8) and (px[-1], py[-1]) == (W - 8, H - 8)
+    assert np.all(np.abs(np.diff(px)) <= 1) and np.all(np.abs(np.diff(py)) <= 1)
+    along = f[py, px]
+    assert np.all(np.diff(along) > 0) and along[-1] == cost
+    # (3) idempotence: planning again reproduces the field bit for bit
+    cost2, _, path2, n2 = g.plan()
+    assert cost2 == cost and n2 == n and np.array_equal(path2, path) and np.array_equal(g.field_download(), f)
+
+
+def test_merge_best_records_matches_sequential_scan():
+    """sipp_merge_best_dev (the multi-GPU merge of the per-shard winners) against a sequential scan over the concatenated
+    candidate list: strictly greater wins, ties keep the lowest global index, NaN never beats a number, empty shards never win."""
+    import torch
+    g = sipp.Context(sipp.make_desc(64, 64, 4.0, 4.0, (0.5, 0.5), (3.5, 3.5), 30, 120, 30))
+    rng = np.random.default_rng(9)
+    dev = torch.device("cuda", 0)
+    for trial in range(200):
+        world = int(rng.integers(1, 9))
+        stride = int(rng.integers(1, 1000))
+        vals = rng.choice([0.0, 1.5, 1.5, 2.25, -3.0, np.nan, np.inf], size=world)
+        idx = np.array([int(rng.integers(0, stride)) if rng.random() > 0.25 else -1 for _ in range(world)], np.int64)
+        recs = np.empty((world, 2), np.int64)
+        recs[:, 0] = vals.view(np.int64)
+        recs[:, 1] = idx
+        # sequential scan (what one rank holding every candidate would do), first record kept when nothing is comparable
+        best = (vals[0], idx[0] if idx[0] >= 0 else idx[0])
+        have = idx[0] >= 0 and not np.isnan(vals[0])
+        for r in range(1, world):
+            if idx[r] < 0 or np.isnan(vals[r]):
+                continue
+            gi = idx[r] + r * stride
+            if not have or vals[r] > best[0] or (vals[r] == best[0] and gi < best[1]):
+                best, have = (vals[r], gi), True
+        d = torch.from_numpy(recs).to(dev)
+        out = torch.zeros(2, dtype=torch.int64, device=dev)
+        g.merge_best_dev(d.data_ptr(), world, stride, out.data_ptr())
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        ov = o[:1].view(np.float64)[0]
+        assert int(o[1]) == int(best[1]) and (ov == best[0] or (np.isnan(ov) and np.isnan(best[0]))), (trial, recs, o, best)
+
+
 def test_expand_low_cost_area_with_closest_observed_plane():
     """A8: ExpandLowCostAreaEvaluator over the closest-observed plane that the patch ingest maintains
     (setClosestObservedMaps, map_server_planexp.cpp:803-823), with and without augment_unknown_with_mean, with a bounding volume,
