@@ -223,7 +223,9 @@ def test_config4_field_properties_8192():
     # (2) the path: neighbouring nodes, strictly increasing cost-to-come, ends at d[goal]
     px = np.rint((path[:, 0] - X[0]) / s).astype(int)
     py = np.rint((path[:, 1] - Y[0]) / s).astype(int)
-    assert (px[0], py[0]) == (8, 8) and (px[-1], py[-1]) == (W - 8, H - 8)
+    snap = lambda p, off: int(np.floor((p - off) / s + 0.5))            # std::round of the reference (prm_star_planner.h:81), p > 0
+    assert (px[0], py[0]) == (snap(0.5, X[0]), snap(0.5, Y[0])) == (8, 8)
+    assert (px[-1], py[-1]) == (snap(W * 0.0625 - 0.5, X[0]), snap(H * 0.0625 - 0.5, Y[0]))
     assert np.all(np.abs(np.diff(px)) <= 1) and np.all(np.abs(np.diff(py)) <= 1)
     along = f[py, px]
     assert np.all(np.diff(along) > 0) and along[-1] == cost
