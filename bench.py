@@ -153,6 +153,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE line (the JSON): everything libraries print while the benchmark runs (NCCL's version banner,
+    # torchrun notices) is sent to stderr by pointing fd 1 at fd 2 until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import sipp
@@ -297,6 +303,7 @@ def main():
     h_term = torch.empty(T, dtype=torch.uint8).pin_memory()
     h_rec = torch.zeros(2, dtype=torch.int64).pin_memory()
     h_win = torch.zeros(2, dtype=torch.int64).pin_memory()
+    h_rec_np, h_win_np = h_rec.numpy(), h_win.numpy()      # same pinned memory, without the tensor-indexing overhead
 
     def e2e_cycle():
         """the call a user makes: host buffers in, host results out"""
@@ -304,8 +311,8 @@ def main():
 
     def e2e_exchange(bi_, bv_):
         """N > 1: exchange of the shard winners, enqueued on the collective's stream (it completes under the next cycle call)"""
-        h_rec[0:1].view(torch.float64)[0] = bv_
-        h_rec[1] = bi_
+        h_rec_np[:1].view(np.float64)[0] = bv_
+        h_rec_np[1] = bi_
         with torch.cuda.stream(cstream):
             d_best[0].copy_(h_rec, non_blocking=True)
             dist.all_gather_into_tensor(d_all[0], d_best[0])
@@ -322,7 +329,7 @@ def main():
                 e2e_exchange(bi_, bv_)
         if world > 1:
             cstream.synchronize()
-            bi_, bv_ = int(h_win[1]), float(h_win[0:1].view(torch.float64)[0])
+            bi_, bv_ = int(h_win_np[1]), float(h_win_np[:1].view(np.float64)[0])
         return bi_, bv_
 
     e2e_run(3)
@@ -395,7 +402,8 @@ def main():
                   "note": "plan = fp64 cost-to-go field + canonical path + mask through sipp_plan (host call, wall clock)"},
         "selected": {"index": best_index, "value": best_value}, "wall_s_timed_region": wall,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
