@@ -220,6 +220,20 @@ int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const 
 int sipp_value_preorder(sipp_ctx* ctx, int32_t n, const double* gain_new, const double* gain_old, const double* cost,
                         const int32_t* parent, double* value);
 
+/* ---- tree re-evaluation pass (A13 + A1-A8 + A14 in one call) ---------------------------------------------------------- */
+/* One pass of [upstream] OnlinePlanner::updateEvaluatorStep over a tree in pre-order (node 0 = root, parent[i] < i, children in
+ * index order), i.e. what the patched planner triggers with trajectory_evaluator_->updateSegment(root)
+ * (mav_active_3d_planning.patch:56): per node the updater chain RRTStarUpdater | ConstrainedUpdater | none ->
+ * UpdateAll | UpdateAllNonTerminal (rrt_star_updater.cpp:19-42, update_all_non_terminal.cpp:16-27) decides whether the
+ * node's gain (computeGain at end_xy) and value (GlobalNormalizedGain) are recomputed. The predicate runs on the device, only
+ * the eligible nodes are scored (one batched gain launch), values get the pre-order semantics of sipp_value_preorder.
+ * end_xy / start_xy: n x 2 (last / first trajectory point of each segment; start_xy may be NULL unless RRTStar binary+discount).
+ * gain, value, terminal: in/out (terminal is only ever set). cost: in. cur_xy: current robot position (2 doubles).
+ * path_changed: RRTStarUpdater's rrt_path_has_changed_ for this pass. n_rescored (optional out): nodes whose gain was recomputed. */
+int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n,
+                     const int32_t* parent, const double* end_xy, const double* start_xy, double* gain, const double* cost,
+                     double* value, uint8_t* terminal, const double* cur_xy, int32_t path_changed, int32_t* n_rescored);
+
 /* ---- fused evaluation cycle ------------------------------------------------------------------------ */
 /* gain for all n candidates (flat tree, candidate i is node i+1 under a virtual root) + value + argmax
  * in one call; what the batched root-first updateSegment (mav_active_3d_planning.patch:56) needs.

@@ -37,6 +37,27 @@ class MapDesc(C.Structure):
     ]
 
 
+UPD_RRT_STAR, UPD_CONSTRAINED, UPD_DIRECT = range(3)
+FOLLOW_UPDATE_ALL, FOLLOW_UPDATE_ALL_NON_TERMINAL = range(2)
+
+
+class UpdaterParams(C.Structure):  # sipp_updater_params
+    _fields_ = [
+        ("updater", C.c_int32), ("following", C.c_int32),
+        ("minimum_gain", C.c_double), ("update_range", C.c_double),
+        ("update_gain", C.c_int32), ("update_cost", C.c_int32), ("update_value", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+def make_updater(updater=UPD_RRT_STAR, following=FOLLOW_UPDATE_ALL, minimum_gain=-1e9, update_range=1e9, update_gain=True,
+                 update_cost=True, update_value=True):
+    u = UpdaterParams()
+    u.updater, u.following = int(updater), int(following)
+    u.minimum_gain, u.update_range = float(minimum_gain), float(update_range)
+    u.update_gain, u.update_cost, u.update_value = int(bool(update_gain)), int(bool(update_cost)), int(bool(update_value))
+    return u
+
+
 class EvalParams(C.Structure):
     _fields_ = [
         ("evaluator", C.c_int32), ("half_fov", C.c_int32),
@@ -130,6 +151,7 @@ def lib():
         L.orc_gain_batch.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, i32, i32]
         L.orc_value_select.argtypes = [i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64)]
         L.orc_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64), i32, i32]
+        L.orc_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
         _lib = L
     return _lib
 
@@ -284,6 +306,22 @@ class Oracle:
         self._L.orc_cycle(self._h, C.byref(params), n, _ptr(xy), _ptr(start_xy), _ptr(cost), _ptr(gain), _ptr(terminal),
                           _ptr(value), C.byref(bi), C.byref(bv), int(variant), int(threads))
         return gain, terminal, value, bi.value, bv.value
+
+
+    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, variant=1):
+        """literal pre-order emulation of one re-evaluation pass (orc_update_tree); returns (gain, value, terminal)"""
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        n = parent.shape[0]
+        end_xy = np.ascontiguousarray(end_xy, dtype=np.float64).reshape(n, 2)
+        sxy = None if start_xy is None else np.ascontiguousarray(start_xy, dtype=np.float64).reshape(n, 2)
+        g = np.array(gain, dtype=np.float64, copy=True)
+        v = np.array(value, dtype=np.float64, copy=True)
+        t = np.array(terminal, dtype=np.uint8, copy=True)
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        cur = np.ascontiguousarray(cur_xy, dtype=np.float64)
+        self._L.orc_update_tree(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g), _ptr(cost),
+                                _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), int(variant))
+        return g, v, t
 
 
 def value_select(gain, cost, parent=None):

@@ -828,6 +828,65 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
   return SIPP_OK;
 }
 
+int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
+                     const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                     const double* cur_xy, int32_t path_changed, int32_t* n_rescored) {
+  SIPP_ENTER(ctx);
+  int rc = check_params(ctx, params);
+  if (rc != SIPP_OK) return rc;
+  if (!updater || n < 1 || !parent || !end_xy || !gain || !cost || !value || !terminal || !cur_xy)
+    return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad update_tree arguments");
+  if (updater->updater < 0 || updater->updater > SIPP_UPD_DIRECT || updater->following < 0 || updater->following > SIPP_FOLLOW_UPDATE_ALL_NON_TERMINAL)
+    return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "unknown updater %d / following updater %d", updater->updater, updater->following);
+  for (int i = 1; i < n; ++i)
+    if (parent[i] < 0 || parent[i] >= i) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "parent[%d] = %d violates 0 <= parent[i] < i", i, parent[i]);
+  cudaStream_t s = ctx->stream;
+  // device staging: doubles end_xy[2n] start_xy[2n] gain_old gain_new gain_tmp cost value value_tmp | int32 parent sel n_sel | u8 flags x5
+  const size_t N = (size_t)n, need = N * (16 + 16 + 8 * 6) + N * 8 + 64 + N * 5 + 256;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
+  double* d_end = reinterpret_cast<double*>(ctx->d_stage);
+  double *d_start = d_end + 2 * N, *d_gold = d_start + 2 * N, *d_gnew = d_gold + N, *d_gtmp = d_gnew + N, *d_cost = d_gtmp + N, *d_val = d_cost + N,
+         *d_vtmp = d_val + N;
+  int32_t* d_parent = reinterpret_cast<int32_t*>(d_vtmp + N);
+  int* d_sel = d_parent + N;
+  int* d_nsel = d_sel + N;                       // 16 ints reserved
+  uint8_t* d_term = reinterpret_cast<uint8_t*>(d_nsel + 16);
+  uint8_t *d_ttmp = d_term + N, *d_dog = d_ttmp + N, *d_fol = d_dog + N, *d_dov = d_fol + N;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_end, end_xy, N * 16, cudaMemcpyHostToDevice, s));
+  if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_start, start_xy, N * 16, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_gold, gain, N * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cost, cost, N * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_val, value, N * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_parent, parent, N * 4, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_term, terminal, N, cudaMemcpyHostToDevice, s));
+  // 1. the updater predicate for every node + compaction of the nodes whose gain is recomputed
+  SIPP_CUDA_CHECK(ctx, launch_update_select(ctx, *updater, n, d_end, d_gold, d_term, cur_xy[0], cur_xy[1], path_changed != 0, d_dog, d_fol, d_sel, d_nsel, s));
+  // 2. one batched gain launch over the compacted list (count read on the device), results scattered by node index
+  const GainGeom g = make_gain_geom(ctx, params);
+  if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
+  if ((rc = gain_launch(ctx, params, g, n, d_end, start_xy ? d_start : nullptr, nullptr, d_gtmp, nullptr, d_ttmp, nullptr, s, d_sel, d_nsel)) != SIPP_OK) return rc;
+  // 3. new gains / terminal flags, which nodes get a new value
+  const int sets_terminal = params->evaluator == SIPP_EVAL_RRT_STAR || params->evaluator == SIPP_EVAL_EXPAND_REACHABLE;
+  SIPP_CUDA_CHECK(ctx, launch_update_apply(ctx, *updater, n, sets_terminal, d_dog, d_fol, d_gold, d_gtmp, d_ttmp, d_gnew, d_term, d_dov, s));
+  // 4. values with the pre-order semantics (new gains on the chain root..i, old gains below i)
+  if ((rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, N * 16 + 512)) != SIPP_OK) return rc;
+  SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_gnew, d_gold, d_cost, d_parent, d_vtmp, ctx->d_best, ctx->d_tree_ws, s));
+  SIPP_CUDA_CHECK(ctx, launch_update_value(ctx, n, d_dov, d_vtmp, d_val, s));
+  BestRec* h_best = reinterpret_cast<BestRec*>(ctx->h_pinned);
+  int* h_nsel = reinterpret_cast<int*>(h_best + 1);
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_best, ctx->d_best, sizeof(BestRec), cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_nsel, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (n > 1) {
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain + 1, d_gnew + 1, (N - 1) * 8, cudaMemcpyDeviceToHost, s));     // the root's gain is not ours to touch
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value + 1, d_val + 1, (N - 1) * 8, cudaMemcpyDeviceToHost, s));
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal + 1, d_term + 1, N - 1, cudaMemcpyDeviceToHost, s));
+  }
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  if (h_best->index == -2) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "tree deeper than 512 levels");
+  if (n_rescored) *n_rescored = *h_nsel;
+  return SIPP_OK;
+}
+
 int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_t shard_stride, void* d_out, void* stream) {
   SIPP_ENTER(ctx);
   if (!d_recs || !d_out || world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad merge_best arguments");

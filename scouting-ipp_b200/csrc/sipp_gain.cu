@@ -52,6 +52,8 @@ struct GainArgs {
   uint8_t* terminal;
   double* value;
   const double* recip;    // ExpandLowCost lookup
+  const int* sel;         // optional: candidate k of this launch is node sel[k] of the caller's arrays (outputs are scattered)
+  const int* n_dev;       // optional: number of candidates, read on the device (a.n is then only the upper bound for the grid)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -112,6 +114,7 @@ __device__ __forceinline__ uint32_t half_range_mask(int lo, int hi) {
 
 // ---- per-candidate window geometry (the reference's double-precision index math, restated) -------------
 struct Window {
+  int cid;           // index of the candidate in the caller's arrays
   int on_map;        // getVoxelCenter returned true (map_planexp.cpp:78,87)
   int cx, cy;        // centre cell of the window (center_voxel_loc, :89)
   double vcx, vcy;   // centre voxel coordinates ((loc + 0.5) * vs, :74-76)
@@ -172,7 +175,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   const int wpc = blockDim.x >> 5;
   const int gw = blockIdx.x * wpc + warp;
   const int nw = gridDim.x * wpc;
-  const int c0 = (int)(((long long)gw * a.n) / nw), c1 = (int)(((long long)(gw + 1) * a.n) / nw);
+  const int n_cand = a.n_dev ? min(a.n, *a.n_dev) : a.n;
+  const int c0 = (int)(((long long)gw * n_cand) / nw), c1 = (int)(((long long)(gw + 1) * n_cand) / nw);
   const int total = c1 - c0;
   const int h = a.half_fov;
   const int side = 2 * h + 1;
@@ -210,10 +214,12 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   Window cur, nxt;
   auto load_window = [&](int idx) {   // idx = index inside this warp's range
     Window w;
-    w.on_map = 0; w.cx = w.cy = -1000000; w.vcx = w.vcy = 0.0;
+    w.on_map = 0; w.cx = w.cy = -1000000; w.vcx = w.vcy = 0.0; w.cid = 0;
     if (idx < total) {
-      const double2 p = *reinterpret_cast<const double2*>(a.xy + 2 * (size_t)(c0 + idx));
+      const int cid = a.sel ? a.sel[c0 + idx] : c0 + idx;
+      const double2 p = *reinterpret_cast<const double2*>(a.xy + 2 * (size_t)cid);
       w = make_window(a.g, p.x, p.y);
+      w.cid = cid;
     }
     return w;
   };
@@ -361,7 +367,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
 
     // ---- centre voxel duplicate + evaluator epilogue: lane j finishes candidate base + j ------------------------
     if (lane < nb) {
-      const int cand = c0 + base + lane;
+      const int cand = cur.cid;
       const Window& w = cur;
       uint32_t n_unk = my_unk, n_aux = my_aux, sum_aux2 = my_sum2;
       double fsum = my_fsum;
@@ -539,7 +545,7 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
 
 int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
                 const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
-                cudaStream_t s) {
+                cudaStream_t s, const int* d_sel, const int* d_n) {
   if (n <= 0) return SIPP_OK;
   const int h = p->half_fov;
   if (h < 0 || h > 112) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d outside [0,112] (TMA box limit 256 columns)", h);
@@ -571,6 +577,8 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.terminal = d_terminal;
   a.value = d_cost ? d_value : nullptr;
   a.recip = ctx->d_recip;
+  a.sel = d_sel;
+  a.n_dev = d_n;
   int mode;
   switch (p->evaluator) {
     case SIPP_EVAL_RRT_STAR: mode = (p->use_distance_discount && !p->do_binary_check) ? MODE_RRT_DISCOUNT : MODE_COUNT; break;

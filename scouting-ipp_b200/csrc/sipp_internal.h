@@ -171,7 +171,15 @@ cudaError_t launch_upload_mask(sipp_ctx* ctx, const uint8_t* d_mask_packed, cuda
 // sipp_gain.cu
 int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy,
                 const double* d_start_xy, const double* d_cost, double* d_gain, uint32_t* d_counts,
-                uint8_t* d_terminal, double* d_value, cudaStream_t s);
+                uint8_t* d_terminal, double* d_value, cudaStream_t s, const int* d_sel = nullptr, const int* d_n = nullptr);
+// sipp_update.cu: evaluator-updater policy on the device (row A13)
+cudaError_t launch_update_select(sipp_ctx* ctx, const sipp_updater_params& u, int n, const double* d_end_xy, const double* d_gain,
+                                 const uint8_t* d_terminal, double cur_x, double cur_y, int path_changed, uint8_t* d_do_gain, uint8_t* d_follow,
+                                 int* d_sel, int* d_n_sel, cudaStream_t s);
+cudaError_t launch_update_apply(sipp_ctx* ctx, const sipp_updater_params& u, int n, int sets_terminal, const uint8_t* d_do_gain, const uint8_t* d_follow,
+                                const double* d_gain_old, const double* d_gain_tmp, const uint8_t* d_term_tmp, double* d_gain_new,
+                                uint8_t* d_terminal, uint8_t* d_do_value, cudaStream_t s);
+cudaError_t launch_update_value(sipp_ctx* ctx, int n, const uint8_t* d_do_value, const double* d_value_tmp, double* d_value, cudaStream_t s);
 // sipp_select.cu
 cudaError_t launch_select_flat(sipp_ctx* ctx, int n, const double* d_value, long long index_offset, BestRec* d_best, double* d_root_value,
                                cudaStream_t s);

@@ -353,49 +353,22 @@ bool GpuGainEvaluator::updateSegment(TrajectorySegment* segment) {
   const int n = (int)t.nodes.size();
   const Eigen::Vector3d cur = planner_.getCurrentPosition();
   const double cur_xy[2] = {cur[0], cur[1]};
-  std::vector<uint8_t> do_gain, maybe_value;
-  updaterMasks(updater_, t, cur_xy, updater_.updater == SIPP_UPD_RRT_STAR && rrt_path_has_changed_, &do_gain, &maybe_value);
-  // one batch for every selected node
-  std::vector<int> sel;
-  std::vector<double> xy, sxy;
-  for (int i = 1; i < n; ++i)
-    if (do_gain[i]) {
-      sel.push_back(i);
-      xy.push_back(t.end_xy[2 * i]); xy.push_back(t.end_xy[2 * i + 1]);
-      sxy.push_back(t.start_xy[2 * i]); sxy.push_back(t.start_xy[2 * i + 1]);
-    }
-  last_batch_ = (int)sel.size();
-  std::vector<double> gain_new(t.gain);
-  if (!sel.empty()) {
-    std::vector<double> g(sel.size());
-    std::vector<uint8_t> term(sel.size());
-    if (sipp_gain_batch(map_->ctx(), &params_, (int32_t)sel.size(), xy.data(), sxy.data(), g.data(), nullptr, term.data()) != SIPP_OK) {
-      planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
-      return false;
-    }
-    const bool sets_terminal = params_.evaluator == SIPP_EVAL_RRT_STAR || params_.evaluator == SIPP_EVAL_EXPAND_REACHABLE;
-    for (size_t k = 0; k < sel.size(); ++k) {
-      gain_new[sel[k]] = g[k];
-      t.nodes[sel[k]]->gain = g[k];
-      if (sets_terminal && term[k]) { t.nodes[sel[k]]->gain_terminal = true; t.terminal[sel[k]] = 1; }
-    }
+  // ONE call: updater predicate on the device, one batched gain launch over the eligible nodes, values with the pre-order
+  // semantics of the reference pass (sipp.h: sipp_update_tree). updaterMasks() above is the host statement of the same predicate.
+  std::vector<double> gain(t.gain), value(t.value);
+  std::vector<uint8_t> terminal(t.terminal);
+  int32_t rescored = 0;
+  if (sipp_update_tree(map_->ctx(), &params_, &updater_, n, t.parent.data(), t.end_xy.data(), t.start_xy.data(), gain.data(), t.cost.data(),
+                       value.data(), terminal.data(), cur_xy, (updater_.updater == SIPP_UPD_RRT_STAR && rrt_path_has_changed_) ? 1 : 0,
+                       &rescored) != SIPP_OK) {
+    planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
+    return false;
   }
-  // values with the pre-order semantics of the reference pass, written back where the following updater computes them
-  bool any_value = false;
+  last_batch_ = rescored;
   for (int i = 1; i < n; ++i) {
-    if (maybe_value[i] && updater_.following == SIPP_FOLLOW_UPDATE_ALL_NON_TERMINAL && t.terminal[i] && !updater_.update_cost) maybe_value[i] = 0;
-    any_value |= maybe_value[i] != 0;
-  }
-  if (any_value) {
-    gain_new[0] = 0.0;
-    std::vector<double> gain_old(t.gain), value(n);
-    gain_old[0] = 0.0;
-    if (sipp_value_preorder(map_->ctx(), n, gain_new.data(), gain_old.data(), t.cost.data(), t.parent.data(), value.data()) != SIPP_OK) {
-      planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
-      return false;
-    }
-    for (int i = 1; i < n; ++i)
-      if (maybe_value[i]) t.nodes[i]->value = value[i];
+    t.nodes[i]->gain = gain[i];
+    t.nodes[i]->value = value[i];
+    if (terminal[i]) t.nodes[i]->gain_terminal = true;
   }
   return true;
 }

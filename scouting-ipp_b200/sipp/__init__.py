@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sipp_patch_origin", "sipp_map_update_patch", "sipp_map_upload_full", "sipp_update_unknown_cost", "sipp_map_stats",
     "sipp_map_download", "sipp_plan", "sipp_field_download", "sipp_path_mask_generation", "sipp_set_path_mask",
     "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
-    "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_launch_count",
+    "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
 ]
 
 
@@ -42,6 +42,27 @@ class MapDesc(C.Structure):  # sipp_map_desc
         ("n_obstacle_ids_rov", C.c_int32), ("obstacle_ids_rov", C.c_int32 * MAX_IDS),
         ("compute_reachability", C.c_int32), ("compute_closest_observed", C.c_int32),
     ]
+
+
+UPD_RRT_STAR, UPD_CONSTRAINED, UPD_DIRECT = range(3)
+FOLLOW_UPDATE_ALL, FOLLOW_UPDATE_ALL_NON_TERMINAL = range(2)
+
+
+class UpdaterParams(C.Structure):  # sipp_updater_params
+    _fields_ = [
+        ("updater", C.c_int32), ("following", C.c_int32),
+        ("minimum_gain", C.c_double), ("update_range", C.c_double),
+        ("update_gain", C.c_int32), ("update_cost", C.c_int32), ("update_value", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+def make_updater(updater=UPD_RRT_STAR, following=FOLLOW_UPDATE_ALL, minimum_gain=-1e9, update_range=1e9, update_gain=True,
+                 update_cost=True, update_value=True):
+    u = UpdaterParams()
+    u.updater, u.following = int(updater), int(following)
+    u.minimum_gain, u.update_range = float(minimum_gain), float(update_range)
+    u.update_gain, u.update_cost, u.update_value = int(bool(update_gain)), int(bool(update_cost)), int(bool(update_value))
+    return u
 
 
 class EvalParams(C.Structure):  # sipp_eval_params
@@ -150,6 +171,7 @@ def lib():
         L.sipp_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, pi32, pf64]
         L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.sipp_merge_best_dev.argtypes = [vp, vp, i32, i64, vp, vp]
+        L.sipp_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, pi32]
         L.sipp_launch_count.argtypes = [vp]
         L.sipp_launch_count.restype = i64
         _lib = L
@@ -324,6 +346,22 @@ class Context:
     def cycle_dev(self, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, d_best, stream=None):
         self._check(self._L.sipp_cycle_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost),
                                            _ptr(d_gain), _ptr(d_terminal), _ptr(d_value), _ptr(d_best), _ptr(stream)))
+
+    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None):
+        """one re-evaluation pass over a pre-order tree; returns (gain, value, terminal, n_rescored) — inputs are not modified"""
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        n = parent.shape[0]
+        end_xy = np.ascontiguousarray(end_xy, dtype=np.float64).reshape(n, 2)
+        sxy = None if start_xy is None else np.ascontiguousarray(start_xy, dtype=np.float64).reshape(n, 2)
+        g = np.array(gain, dtype=np.float64, copy=True)
+        v = np.array(value, dtype=np.float64, copy=True)
+        t = np.array(terminal, dtype=np.uint8, copy=True)
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        cur = np.ascontiguousarray(cur_xy, dtype=np.float64)
+        nres = C.c_int32()
+        self._check(self._L.sipp_update_tree(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g),
+                                             _ptr(cost), _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), C.byref(nres)))
+        return g, v, t, nres.value
 
     def merge_best_dev(self, d_recs, world, shard_stride, d_out, stream=None):
         self._check(self._L.sipp_merge_best_dev(self._h, _ptr(d_recs), int(world), int(shard_stride), _ptr(d_out), _ptr(stream)))

@@ -234,6 +234,70 @@ def test_config4_field_properties_8192():
     assert cost2 == cost and n2 == n and np.array_equal(path2, path) and np.array_equal(g.field_download(), f)
 
 
+def _random_tree(rng, n, W, H):
+    """pre-order parent array of a random RRT-like tree (children in index order) + end / start points of the segments"""
+    par = np.full(n, -1, np.int32)
+    kids = [[] for _ in range(n)]
+    for i in range(1, n):                       # random attachment, then renumber in pre-order
+        p = int(rng.integers(0, i)) if rng.random() < 0.8 else int(rng.integers(max(0, i - 5), i))
+        kids[p].append(i)
+    order, stack = [], [0]
+    while stack:
+        v = stack.pop()
+        order.append(v)
+        stack.extend(reversed(kids[v]))
+    new = {v: k for k, v in enumerate(order)}
+    for p in range(n):
+        for c in kids[p]:
+            par[new[c]] = new[p]
+    end = np.empty((n, 2))
+    end[:, 0] = rng.uniform(-0.2, W * 0.0625 + 0.2, n)
+    end[:, 1] = rng.uniform(-0.2, H * 0.0625 + 0.2, n)
+    start = np.where(par[:, None] >= 0, end[np.maximum(par, 0)], end)
+    return par, end, start
+
+
+@pytest.mark.parametrize("upd,fol", [(0, 0), (0, 1), (1, 0), (2, 1), (2, 0)])
+def test_update_tree_pass_matches_preorder_emulation(upd, fol):
+    """Row A13 on the device: sipp_update_tree (predicate + compaction + one batched gain launch + pre-order values) against
+    the oracle's literal node-by-node emulation of the reference pass, for every updater chain the shipped cfgs use."""
+    rng = np.random.default_rng(100 + 10 * upd + fol)
+    W, H = 320, 240
+    lab, obs, dg = synth.world(W, H, 77, 14, sipp.make_desc, init_cost="max")
+    _, _, do = synth.world(W, H, 77, 14, orc.make_desc, init_cost="max")
+    g, o = sipp.Context(dg), orc.Oracle(do)
+    g.map_upload_full(lab, obs)
+    o.map_upload_full(lab, obs)
+    g.plan(); o.plan()
+    n = 1500
+    par, end, start = _random_tree(rng, n, W, H)
+    cost = rng.uniform(0.2, 5.0, n); cost[0] = 0.0
+    for kw in (dict(evaluator=sipp.EVAL_RRT_STAR, non_path_voxel_gain=0.0), dict(evaluator=sipp.EVAL_RRT_STAR, do_binary_check=True, use_distance_discount=True),
+               dict(evaluator=sipp.EVAL_GOAL_DISTANCE), dict(evaluator=sipp.EVAL_EXPAND_REACHABLE, discount_factor=0.0), dict(evaluator=sipp.EVAL_AVERAGE_VIEW_COST)):
+        pg, po = sipp.make_params(half_fov=32, **kw), orc.make_params(half_fov=32, **kw)
+        # state before the pass: last cycle's gains / values / terminal flags (from an older, smaller map: different numbers)
+        gain0 = np.where(rng.random(n) < 0.3, 0.0, rng.uniform(0.0, 50.0, n)); gain0[0] = 0.0
+        term0 = (rng.random(n) < 0.15).astype(np.uint8); term0[0] = 0
+        value0 = rng.uniform(0.0, 10.0, n)
+        for path_changed in (False, True):
+            for flags in ((True, False, True), (True, True, True), (False, False, True), (True, False, False)):
+                ug = sipp.make_updater(upd, fol, 0.001, 4.0, *flags)
+                uo = orc.make_updater(upd, fol, 0.001, 4.0, *flags)
+                cur = (rng.uniform(1.0, W * 0.0625 - 1.0), rng.uniform(1.0, H * 0.0625 - 1.0))
+                gg, gv, gt, nres = g.update_tree(pg, ug, par, end, gain0, cost, value0, term0, cur, path_changed, start_xy=start)
+                og, ov, ot = o.update_tree(po, uo, par, end, gain0, cost, value0, term0, cur, path_changed, start_xy=start)
+                assert np.array_equal(gt, ot)
+                assert nres == int(np.sum((gg != gain0) | (og != gain0))) or nres >= int(np.sum(og != gain0))
+                if EXACT_GAIN(kw):
+                    assert np.array_equal(gg, og, equal_nan=True)
+                else:
+                    assert np.allclose(gg, og, rtol=RTOL, atol=0.0, equal_nan=True)
+                assert np.allclose(gv, ov, rtol=RTOL, atol=0.0, equal_nan=True)
+                # nodes the pass must not touch keep their numbers bit for bit
+                same = (og == gain0) & (ov == value0)
+                assert np.array_equal(gv[same], value0[same])
+
+
 def test_merge_best_records_matches_sequential_scan():
     """sipp_merge_best_dev (the multi-GPU merge of the per-shard winners) against a sequential scan over the concatenated
     candidate list: strictly greater wins, ties keep the lowest global index, NaN never beats a number, empty shards never win."""
