@@ -147,6 +147,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the 16-byte shard winners travel. p2p (default): stored into the peers' mailboxes over NVLink by the argmax "
+                         "kernel itself (sipp_cycle_shard); nccl: all_gather + merge kernel. The other one is timed too and reported beside it.")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -199,7 +202,7 @@ def main():
     d_counts = torch.empty((T, 4), dtype=torch.int32, device=dev)
     d_best = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]     # {f64 value bits, i64 index}, double buffered
     d_all = [torch.zeros(2 * world, dtype=torch.int64, device=dev) for _ in range(2)]
-    d_glob = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_glob = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(3)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.Stream(device=dev)
     cstream = torch.cuda.Stream(device=dev)                          # the collective's stream
@@ -207,7 +210,39 @@ def main():
     e_done = [torch.cuda.Event() for _ in range(2)]
     g_done = [torch.cuda.Event() for _ in range(2)]
 
-    def step(k):
+    # ---- N > 1: map the peers' mailboxes (CUDA IPC handles moved with torch.distributed; plumbing only)
+    p2p_ok, p2p_note = False, None
+    if world > 1:
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.peer_export())
+            ctx.peer_attach(rank, handles)
+            p2p_ok = True
+        except Exception as exc:     # e.g. a container without CUDA IPC: the NCCL exchange below still runs on the GPU
+            p2p_note = str(exc)
+        flag = torch.tensor([1 if p2p_ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        p2p_ok = bool(flag.item())
+    exchange = "p2p" if (world > 1 and p2p_ok and args.exchange == "p2p") else ("nccl" if world > 1 else "none")
+
+    def step_p2p(k):
+        """gain + value + argmax of this rank's shard in ONE launch: the kernel's last CTA stores the shard's 16-byte winner into
+        every peer's mailbox over NVLink and collects the records of the PREVIOUS step (already there: the exchange latency hides
+        under this step's scan), merges them -> d_glob. No collective library, no second stream; the last step's records are
+        collected by a flush that is timed in full (tail)."""
+        b = k & 1
+        ctx.cycle_shard_pipelined_dev(params, T, d_xy.data_ptr(), None, d_cost.data_ptr(), d_gain.data_ptr(), d_term.data_ptr(),
+                                      d_value.data_ptr(), lo, d_glob[b].data_ptr(), sh)
+        return d_glob[b]
+
+    def step_p2p_sync(k):
+        """same, but every step waits for its own records (the latency a planner that needs the winner before it goes on sees)"""
+        b = k & 1
+        ctx.cycle_shard_dev(params, T, d_xy.data_ptr(), None, d_cost.data_ptr(), d_gain.data_ptr(), d_term.data_ptr(), d_value.data_ptr(),
+                            lo, d_glob[b].data_ptr(), sh)
+        return d_glob[b]
+
+    def step_nccl(k):
         """gain + value + argmax of this rank's shard; with N > 1 the only cross-GPU traffic: an all_gather of every shard's
         16-byte (value, index) record + one merge kernel (same argmax on every rank). The gather of step k runs on its own
         stream under the gain kernel of step k+1 (records double buffered); a step ends when the PREVIOUS gather is done."""
@@ -226,45 +261,73 @@ def main():
             stream.wait_event(g_done[1 - b])
         return d_glob[b]
 
-    tail_ms = 0.0
-    with torch.cuda.stream(stream):
-        for k in range(args.warmup):
-            flush.fill_(1)
-            best = step(k)
-        stream.synchronize()
-        cstream.synchronize()
+    def timed(step, overlapped_gather, flush_peers=False):
+        """W warm-up steps, then K timed ones: barrier + synchronize on both sides, CUDA events around every step on the
+        launching stream (the L2 flush between them is untimed), max over ranks of the summed step times."""
+        with torch.cuda.stream(stream):
+            for k in range(args.warmup):
+                flush.fill_(1)
+                best_ = step(k)
+            sampler = ClockSampler(local_rank)       # NVML init happens here, before the barrier
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            ev_tail = torch.cuda.Event(enable_timing=True)
+            stream.synchronize()
+            cstream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler.start()
+            if world > 1:
+                # one more untimed step: the ranks leave the host barrier hundreds of microseconds apart, and the first exchange
+                # after it would charge that host skew to step 0. Its exchange lines the GPUs up; the timed steps are queued behind it.
+                flush.fill_(2)
+                best_ = step(args.warmup)
+                if flush_peers:                # pipelined form: collecting this step's records is what waits for every rank
+                    ctx.peer_flush_dev(d_glob[2].data_ptr(), sh)
+            launches0 = ctx.launch_count()
+            wall0 = time.perf_counter()
+            k0 = args.warmup + 1 if world > 1 else 0        # keeps the double-buffer parity of the overlapped NCCL variant going
+            for k in range(args.steps):
+                flush.fill_(k & 0xFF)          # L2 flush between timed iterations (untimed)
+                ev[k][0].record(stream)
+                best_ = step(k0 + k)
+                ev[k][1].record(stream)
+            if overlapped_gather:              # the last gather has nothing to hide under: its full latency is added to the total
+                stream.wait_event(g_done[(k0 + args.steps - 1) & 1])
+            if flush_peers:                    # pipelined peer exchange: the last step's records are collected here, timed in full
+                best_ = d_glob[(k0 + args.steps) & 1]
+                ctx.peer_flush_dev(best_.data_ptr(), sh)
+            ev_tail.record(stream)
+            stream.synchronize()
+            cstream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            wall_ = time.perf_counter() - wall0
+            launches_ = ctx.launch_count() - launches0
+            clocks_ = sampler.result()
+        tail_ms = ev[-1][1].elapsed_time(ev_tail)
+        total = float(sum(a.elapsed_time(b) for a, b in ev)) + float(tail_ms)
+        if os.environ.get("SIPP_BENCH_DEBUG"):
+            print("[rank %d] %s step ms: %s tail %.4f gaps %s" % (rank, step.__name__, " ".join("%.3f" % a.elapsed_time(b) for a, b in ev), tail_ms,
+                                                                  " ".join("%.3f" % ev[i][1].elapsed_time(ev[i + 1][0]) for i in range(len(ev) - 1))), file=sys.stderr)
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = ctx.launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        ev_tail = torch.cuda.Event(enable_timing=True)
-        wall0 = time.perf_counter()
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)          # L2 flush between timed iterations (untimed)
-            ev[k][0].record(stream)
-            best = step(k)
-            ev[k][1].record(stream)
-        if world > 1:                      # the last gather has nothing to hide under: its full latency is added to the total
-            stream.wait_event(g_done[(args.steps - 1) & 1])
-        ev_tail.record(stream)
-        stream.synchronize()
-        cstream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - wall0
-        launches = ctx.launch_count() - launches0
-        clocks = sampler.result()
-    tail_ms = ev[-1][1].elapsed_time(ev_tail)
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms)) + float(tail_ms)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), best_, wall_, launches_, clocks_
+
+    other = None
+    if exchange == "p2p":
+        total_ms, best, wall, launches, clocks = timed(step_p2p, False, True)
+        s_ms, s_best, _, _, _ = timed(step_p2p_sync, False)  # every step waits for its own records
+        o_ms, o_best, _, _, _ = timed(step_nccl, True)      # the collective-library form of the same step, for comparison
+        assert torch.equal(o_best.cpu(), best.cpu()) and torch.equal(s_best.cpu(), best.cpu())
+        other = [{"exchange": "p2p, synchronous (every step ends with its own global winner)", "ms_per_step": s_ms / args.steps,
+                  "value": world * T * args.steps / (s_ms * 1e-3)},
+                 {"exchange": "nccl all_gather + merge kernel (gather of step k under the gain kernel of step k+1)", "ms_per_step": o_ms / args.steps,
+                  "value": world * T * args.steps / (o_ms * 1e-3)}]
+    else:
+        total_ms, best, wall, launches, clocks = timed(step_nccl, world > 1)
     value = world * T * args.steps / (total_ms * 1e-3)
     best_host = best.cpu().numpy()
     best_value = float(best_host[:1].view(np.float64)[0])
@@ -321,6 +384,11 @@ def main():
 
     def e2e_run(steps):
         bi_, bv_ = -1, 0.0
+        if exchange == "p2p":              # one call per cycle and rank: host buffers in, host results + the GLOBAL winner out
+            for _ in range(steps):
+                bi_, bv_ = ctx.cycle_shard_host_ptr(params, T, h_xy.data_ptr(), None, h_cost.data_ptr(), lo, h_gain.data_ptr(), h_term.data_ptr(),
+                                                    h_value.data_ptr())
+            return bi_, bv_
         for _ in range(steps):
             if world > 1:
                 cstream.synchronize()          # the previous exchange (h_rec / h_win are reused)
@@ -335,17 +403,24 @@ def main():
     e2e_run(3)
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    bi, bv = e2e_run(args.steps)
-    e2e_s = time.perf_counter() - t0
+    e2e_rep = []
+    for _ in range(5):                     # host-timed: median of 5 runs of K steps each (wall clock jitters more than CUDA events)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        bi, bv = e2e_run(args.steps)
+        e2e_rep.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_rep))
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e = {"value": world * T * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": T * 24, "d2h_bytes_per_step": T * 17 + 16,
            "ms_per_step": e2e_s / args.steps * 1e3,
-           "api": "sipp_cycle (host pointers, pinned; 2-chunk copy/compute pipeline replayed as a CUDA graph)"
-                  + (" + all_gather of the 16-byte shard winners + sipp_merge_best_dev, enqueued after each call and completing under the next one" if world > 1 else "")}
+           "api": ("sipp_cycle_shard (host pointers, pinned; copy/compute pipeline + argmax with the fused peer-memory exchange, replayed as a CUDA graph)"
+                   if exchange == "p2p" else
+                   "sipp_cycle (host pointers, pinned; 2-chunk copy/compute pipeline replayed as a CUDA graph)"
+                   + (" + all_gather of the 16-byte shard winners + sipp_merge_best_dev, enqueued after each call and completing under the next one" if world > 1 else ""))}
     assert bi == best_index and bv == best_value, (bi, best_index, bv, best_value)
 
     if rank != 0:
@@ -394,8 +469,13 @@ def main():
         "dtype": "u8 counts + f64 gain", "data": "synthetic",
         "config": {"workload": WORKLOAD, "candidates_per_gpu": T, "map": "%dx%d" % (W, H), "half_fov": HALF_FOV,
                    "l2": "flushed between timed steps (256 MiB write, untimed); the 16 MiB record plane is smaller than L2",
-                   "sharding": ("candidates sharded, map replicated, NCCL all_gather of one 16-byte record per rank per step + one merge kernel; "
-                                "the gather of step k overlaps the gain kernel of step k+1, the last gather is timed in full") if world > 1 else "single GPU"},
+                   "sharding": ("single GPU" if world == 1 else
+                                "candidates sharded, map replicated; the gain kernel's last CTA stores each shard's 16-byte winner into every peer's mailbox "
+                                "over NVLink (peer memory) and merges the peers' records of the previous step (pipelined; the last step is flushed inside the "
+                                "timed region): one launch per step, no collective call on the data path" if exchange == "p2p" else
+                                "candidates sharded, map replicated, NCCL all_gather of one 16-byte record per rank per step + one merge kernel; "
+                                "the gather of step k overlaps the gain kernel of step k+1, the last gather is timed in full"),
+                   "exchange": exchange, "exchange_note": p2p_note, "exchange_other": other},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "cycle": {"plan_ms": float(np.median(plan_ms)), "plan_cost": pcost, "plan_path_nodes": plen, "plan_stats": pstats,
                   "eval_ms": total_ms / args.steps, "ms_per_full_cycle": float(np.median(plan_ms)) + total_ms / args.steps,

@@ -254,6 +254,43 @@ int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, con
  * comparable the first one is returned. Writes one 16-byte record with the GLOBAL index to d_out. One tiny kernel. */
 int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_t shard_stride, void* d_out, void* stream);
 
+/* ---- multi-GPU: exchange of the shard winners through peer memory (NVLink / NVSwitch), fused into the argmax kernel ----- */
+/* One process per GPU (or several contexts in one process). Every rank exports a handle to its mailbox, the host program
+ * moves the handles between the ranks with whatever it has (MPI, torch.distributed, a ROS topic), and every rank attaches
+ * all of them. After that sipp_cycle_shard[_dev] scores this rank's shard and its argmax kernel (a) stores the shard's
+ * 16-byte winner into every peer's mailbox over NVLink, (b) waits for the peers' records of the same step in its own
+ * mailbox and (c) merges them: every rank ends the call with the GLOBAL winner — the candidate one GPU scanning all shards
+ * in index order would select (largest value, lowest global index on ties; NaN / empty shards never win). No collective
+ * library and no host round trip on the data path. All ranks must issue the same sequence of shard calls (lockstep); a rank
+ * that waits longer than the timeout (SIPP_PEER_TIMEOUT_MS, default 20000) returns index -3 and sipp_peer_status != 0.
+ * Replaces, for N GPUs, [upstream] SubsequentBest::selectNextBest over the whole candidate set. */
+#define SIPP_PEER_MAX_WORLD 16
+#define SIPP_PEER_HANDLE_BYTES 128
+int sipp_peer_export(sipp_ctx* ctx, void* handle /* SIPP_PEER_HANDLE_BYTES out */);
+int sipp_peer_attach(sipp_ctx* ctx, int32_t rank, int32_t world, const void* handles /* world x SIPP_PEER_HANDLE_BYTES */);
+int sipp_peer_detach(sipp_ctx* ctx);
+/* 0: healthy; 1: an exchange timed out. Synchronises the ctx stream. */
+int sipp_peer_status(sipp_ctx* ctx, int32_t* status, int64_t* steps_done);
+/* sipp_cycle_dev over this rank's shard + the fused exchange. index_offset = global index of this shard's candidate 0.
+ * d_best_global: 16-byte record {double value; int64 index} of the global winner (identical on every rank). */
+int sipp_cycle_shard_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy,
+                         const double* d_start_xy, const double* d_cost, double* d_gain, uint8_t* d_terminal,
+                         double* d_value, int64_t index_offset, void* d_best_global, void* stream);
+/* Pipelined form for back-to-back cycles: publishes this call's shard winner but collects the records of the PREVIOUS call
+ * (normally already there, so the exchange latency hides under this call's gain kernel). d_prev_best_global receives the
+ * global winner of the previous pipelined call ({0.0, -1} on the first one); sipp_peer_flush_dev collects the last one.
+ * Do not mix with the synchronous calls without a flush in between. */
+int sipp_cycle_shard_pipelined_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy,
+                                   const double* d_start_xy, const double* d_cost, double* d_gain, uint8_t* d_terminal,
+                                   double* d_value, int64_t index_offset, void* d_prev_best_global, void* stream);
+int sipp_peer_flush_dev(sipp_ctx* ctx, void* d_best_global, void* stream);
+/* host-pointer form (sipp_cycle + exchange): the call a host program makes per planning cycle on every rank */
+int sipp_cycle_shard(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy,
+                     const double* cost, int64_t index_offset, double* gain, uint8_t* terminal, double* value,
+                     int64_t* best_index_global, double* best_value);
+/* exchange of an arbitrary 16-byte record (e.g. the tree-mode winner): d_mine in, merged global record out */
+int sipp_peer_exchange_dev(sipp_ctx* ctx, const void* d_mine, void* d_out, void* stream);
+
 /* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
 int64_t sipp_launch_count(const sipp_ctx* ctx);
 

@@ -299,6 +299,8 @@ void sipp_destroy(sipp_ctx* ctx) {
                   ctx->d_best, ctx->d_select_ws};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  peer_release(ctx);
+  if (ctx->d_peer_box) cudaFree(ctx->d_peer_box);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->cycle_graph) cudaGraphExecDestroy(ctx->cycle_graph);
@@ -390,6 +392,9 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "copy streams / events: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
   ctx->cycle_chunks = getenv("SIPP_CYCLE_CHUNKS") ? atoi(getenv("SIPP_CYCLE_CHUNKS")) : 0;
   ctx->cycle_use_graph = !(getenv("SIPP_CYCLE_GRAPH") && atoi(getenv("SIPP_CYCLE_GRAPH")) == 0);
+  // opt-in: measured on B200 (tools/zerocopy_probe.py) it does not beat the copy-engine pipeline — every warp stores its results at
+  // the end of its one 32-candidate batch, so the 1.1 MB of PCIe writes land in a burst after the scan instead of under it
+  ctx->cycle_zero_copy = getenv("SIPP_CYCLE_ZEROCOPY") && atoi(getenv("SIPP_CYCLE_ZEROCOPY")) != 0;
   e = cudaMallocHost(&ctx->h_pinned, 256);
   if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
   ctx->h_pinned_bytes = 256;
@@ -722,26 +727,66 @@ int sipp_value_preorder(sipp_ctx* ctx, int32_t n, const double* gain_new, const 
 }
 
 // ---- fused cycle -----------------------------------------------------------------------------------------
-int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy, const double* d_cost,
-                   double* d_gain, uint8_t* d_terminal, double* d_value, void* d_best, void* stream) {
-  SIPP_ENTER(ctx);
+static int cycle_dev_impl(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy, const double* d_cost,
+                          double* d_gain, uint8_t* d_terminal, double* d_value, void* d_best, void* stream, bool shard, int64_t index_offset,
+                          int peer_mode = 0) {
   int rc = check_params(ctx, params);
   if (rc != SIPP_OK) return rc;
   if (n < 1 || !d_xy || !d_cost || !d_gain || !d_value || !d_best) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
+  if (shard && ctx->peer_world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "peers are not attached (sipp_peer_attach)");
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   const GainGeom g = make_gain_geom(ctx, params);
   if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
-  if ((rc = gain_launch(ctx, params, g, n, d_xy, d_start_xy, d_cost, d_gain, nullptr, d_terminal, d_value, s)) != SIPP_OK) return rc;
-  SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, d_value, 0, reinterpret_cast<BestRec*>(d_best), nullptr, s));
+  // one launch: the argmax (and, sharded, the exchange of the shard winners) is the tail of the gain kernel
+  static const bool fuse = !(getenv("SIPP_FUSED_SELECT") && atoi(getenv("SIPP_FUSED_SELECT")) == 0);
+  FusedSelect fs;
+  fs.best_out = reinterpret_cast<BestRec*>(d_best);
+  fs.index_offset = shard ? (long long)index_offset : 0;
+  fs.peer = shard ? &ctx->peer : nullptr;
+  fs.peer_mode = peer_mode;
+  if ((rc = gain_launch(ctx, params, g, n, d_xy, d_start_xy, d_cost, d_gain, nullptr, d_terminal, d_value, s, nullptr, nullptr, nullptr,
+                        fuse ? &fs : nullptr)) != SIPP_OK)
+    return rc;
+  if (!fuse)
+    SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, d_value, fs.index_offset, fs.best_out, nullptr, s, fs.peer, fs.peer_mode));
   return SIPP_OK;
 }
 
-int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy, const double* cost,
-               double* gain, uint8_t* terminal, double* value, int32_t* best_index, double* best_value) {
+int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy, const double* d_cost,
+                   double* d_gain, uint8_t* d_terminal, double* d_value, void* d_best, void* stream) {
   SIPP_ENTER(ctx);
+  return cycle_dev_impl(ctx, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, d_best, stream, false, 0);
+}
+
+int sipp_cycle_shard_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy,
+                         const double* d_cost, double* d_gain, uint8_t* d_terminal, double* d_value, int64_t index_offset,
+                         void* d_best_global, void* stream) {
+  SIPP_ENTER(ctx);
+  return cycle_dev_impl(ctx, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, d_best_global, stream, true, index_offset);
+}
+
+// device-side alias of a pinned (page-locked, mapped) host pointer; nullptr for pageable memory
+static void* pinned_alias(const void* p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+  cudaGetLastError();
+  return nullptr;
+}
+
+int sipp_cycle_shard_pipelined_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* d_xy, const double* d_start_xy,
+                                   const double* d_cost, double* d_gain, uint8_t* d_terminal, double* d_value, int64_t index_offset,
+                                   void* d_prev_best_global, void* stream) {
+  SIPP_ENTER(ctx);
+  return cycle_dev_impl(ctx, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, d_prev_best_global, stream, true, index_offset, 1);
+}
+
+static int cycle_host_impl(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy, const double* cost,
+                           double* gain, uint8_t* terminal, double* value, int64_t* best_index, double* best_value, bool shard, int64_t index_offset) {
   int rc = check_params(ctx, params);
   if (rc != SIPP_OK) return rc;
   if (n < 1 || !xy || !cost) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
+  if (shard && ctx->peer_world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "peers are not attached (sipp_peer_attach)");
   cudaStream_t s = ctx->stream;
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, stage_bytes(n))) != SIPP_OK) return rc;
   const Stage st = carve(ctx->d_stage, n);
@@ -756,6 +801,20 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
   if (chunks > 8) chunks = 8;
   const int per = (n + chunks - 1) / chunks;
   BestRec* h_best = reinterpret_cast<BestRec*>(ctx->h_pinned);
+  // Zero-copy results (SIPP_CYCLE_ZEROCOPY=1): when every result array the caller passed is pinned host memory, the gain kernel stores gain / terminal /
+  // value straight into it over PCIe (posted writes, coalesced 256-byte runs) and the argmax kernel writes the winner into the
+  // context's pinned record: no device->host copies, no output stream. Inputs still travel by copy engine, chunk c+1 under the
+  // gain kernel of chunk c — a kernel that reads its poses over PCIe cannot start a candidate before its pose has arrived.
+  double* a_gain = reinterpret_cast<double*>(pinned_alias(gain));
+  uint8_t* a_term = reinterpret_cast<uint8_t*>(pinned_alias(terminal));
+  double* a_value = reinterpret_cast<double*>(pinned_alias(value));
+  BestRec* a_best = reinterpret_cast<BestRec*>(pinned_alias(h_best));
+  const bool zc = ctx->cycle_zero_copy && a_best && (!gain || a_gain) && (!terminal || a_term) && (!value || a_value) && (gain || terminal || value);
+  FusedSelect fs;
+  fs.best_out = zc ? a_best : ctx->d_best;
+  fs.index_offset = shard ? (long long)index_offset : 0;
+  fs.peer = shard ? &ctx->peer : nullptr;
+  fs.peer_mode = 0;
   auto enqueue = [&]() -> int {
     int launched = 0;
     for (int c = 0; c < chunks; ++c) {
@@ -773,10 +832,12 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
         SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_in[c], si));
         SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_in[c], 0));
       }
-      const int grc = gain_launch(ctx, params, g, m, st.xy + 2 * (size_t)lo, start_xy ? st.start_xy + 2 * (size_t)lo : nullptr, st.cost + lo, st.gain + lo,
-                                  nullptr, st.terminal + lo, st.value + lo, s);
+      const int grc = gain_launch(ctx, params, g, m, st.xy + 2 * (size_t)lo, start_xy ? st.start_xy + 2 * (size_t)lo : nullptr, st.cost + lo,
+                                  (zc && gain) ? a_gain + lo : st.gain + lo, nullptr, (zc && terminal) ? a_term + lo : st.terminal + lo, st.value + lo, s,
+                                  nullptr, nullptr, (zc && value) ? a_value + lo : nullptr, chunks == 1 ? &fs : nullptr);
       if (grc != SIPP_OK) return grc;
       ++launched;
+      if (zc) continue;
       if (chunks > 1) {
         SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_k[c], s));
         SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(so, ctx->ev_k[c], 0));
@@ -785,10 +846,13 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
       if (terminal) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal + lo, st.terminal + lo, (size_t)m, cudaMemcpyDeviceToHost, so));
       if (value) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value + lo, st.value + lo, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
     }
-    SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, st.value, 0, ctx->d_best, nullptr, s));
-    ++launched;
-    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_best, ctx->d_best, sizeof(BestRec), cudaMemcpyDeviceToHost, s));
-    if (chunks > 1) {             // join the output stream back into s
+    // N GPUs: the argmax kernel also exchanges the shard winners through peer memory and leaves the global winner in d_best
+    if (chunks > 1) {           // several gain launches: one argmax over all values (a single launch carries it in its tail)
+      SIPP_CUDA_CHECK(ctx, launch_select_flat(ctx, n, st.value, fs.index_offset, fs.best_out, nullptr, s, fs.peer));
+      ++launched;
+    }
+    if (!zc) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_best, ctx->d_best, sizeof(BestRec), cudaMemcpyDeviceToHost, s));
+    if (chunks > 1 && !zc) {      // join the output stream back into s
       SIPP_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_in[7], ctx->s_out));
       SIPP_CUDA_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_in[7], 0));
     }
@@ -801,6 +865,8 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
     auto put = [&](const void* p, size_t nb) { const unsigned char* b = reinterpret_cast<const unsigned char*>(p); key.insert(key.end(), b, b + nb); };
     const void* ptrs[8] = {xy, start_xy, cost, gain, terminal, value, ctx->d_stage, ctx->d_rec};
     put(&n, sizeof(n)); put(&chunks, sizeof(chunks)); put(ptrs, sizeof(ptrs)); put(params, sizeof(*params)); put(&g, sizeof(g));
+    const int64_t shard_key[3] = {shard ? 1 : 0, shard ? index_offset : 0, zc ? 1 : 0};
+    put(shard_key, sizeof(shard_key));
     if (!ctx->cycle_graph || key != ctx->cycle_key) {
       if (ctx->cycle_graph) { cudaGraphExecDestroy(ctx->cycle_graph); ctx->cycle_graph = nullptr; }
       const int64_t launches_before = ctx->launches;
@@ -823,9 +889,25 @@ int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const d
   }
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
   const BestRec br = *h_best;
-  if (best_index) *best_index = (int32_t)br.index;
+  if (best_index) *best_index = br.index;
   if (best_value) *best_value = br.value;
+  if (shard && br.index == -3) return sipp_set_err(ctx, SIPP_ERR_CUDA, "peer exchange timed out (a rank died or the ranks are not calling in lockstep)");
   return SIPP_OK;
+}
+
+int sipp_cycle(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy, const double* cost,
+               double* gain, uint8_t* terminal, double* value, int32_t* best_index, double* best_value) {
+  SIPP_ENTER(ctx);
+  int64_t bi = -1;
+  const int rc = cycle_host_impl(ctx, params, n, xy, start_xy, cost, gain, terminal, value, &bi, best_value, false, 0);
+  if (rc == SIPP_OK && best_index) *best_index = (int32_t)bi;
+  return rc;
+}
+
+int sipp_cycle_shard(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const double* xy, const double* start_xy, const double* cost,
+                     int64_t index_offset, double* gain, uint8_t* terminal, double* value, int64_t* best_index_global, double* best_value) {
+  SIPP_ENTER(ctx);
+  return cycle_host_impl(ctx, params, n, xy, start_xy, cost, gain, terminal, value, best_index_global, best_value, true, index_offset);
 }
 
 int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,

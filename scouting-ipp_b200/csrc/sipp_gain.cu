@@ -18,7 +18,9 @@
 #include <cstdio>
 #include <cstring>
 
+#include "sipp_argmax.cuh"
 #include "sipp_internal.h"
+#include "sipp_peer.cuh"
 
 namespace {
 
@@ -51,9 +53,17 @@ struct GainArgs {
   uint32_t* counts;
   uint8_t* terminal;
   double* value;
+  double* value2;         // optional second copy of value (the caller's pinned host array, written over PCIe by the kernel)
   const double* recip;    // ExpandLowCost lookup
   const int* sel;         // optional: candidate k of this launch is node sel[k] of the caller's arrays (outputs are scattered)
   const int* n_dev;       // optional: number of candidates, read on the device (a.n is then only the upper bound for the grid)
+  // fused argmax (flat tree, value computed here): every lane keeps the best (value, index) of its candidates, warps / CTAs
+  // reduce, the last CTA to finish merges the per-CTA records — and, with peers attached, exchanges the winner over NVLink
+  BestRec* best_out;      // non-null: fused argmax on
+  SelectWs* sel_ws;
+  long long index_offset;
+  PeerDev peer;           // by value: the mailbox pointers sit in the kernel's parameter space
+  int peer_mode;          // < 0: single GPU
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -233,7 +243,12 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
     if (kNeedAux) tma_load_2d(dst + (uint32_t)a.aux_off, &tm_aux, bar, (w.cx - h) & ~7, w.cy - h);
   };
 
-  if (total <= 0) return;
+  const bool fused = a.best_out != nullptr;     // every warp takes part in the CTA reduction of the fused argmax
+  PeerCounters pcnt = {0, 0};                   // the exchange counters, fetched now so the tail does not wait for them
+  if (fused && a.peer_mode >= 0 && threadIdx.x == 0) pcnt = peer_preload(a.peer);
+  double best_v = -CUDART_INF;
+  long long best_i = LLONG_MAX;
+  if (total <= 0 && !fused) return;
   cur = load_window(lane);
   for (int k = 0; k < kStages - 1 && k < total; ++k)
     if (lane == k) issue(cur, k);   // kStages - 1 <= 7 < 32: all inside the first batch
@@ -464,10 +479,56 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
       if (a.value) {
         // flat tree: GlobalNormalizedGain with a zeroed root: value = gain / cost when cost > 0
         const double c = 0.0 + a.cost[cand];
-        a.value[cand] = c > 0 ? (0.0 + gain) / c : 0.0;
+        const double v = c > 0 ? (0.0 + gain) / c : 0.0;
+        a.value[cand] = v;
+        if (a.value2) a.value2[cand] = v;
+        if (better(v, (long long)cand, best_v, best_i)) { best_v = v; best_i = cand; }
       }
     }
     cur = nxt;
+  }
+  if (!fused) return;
+
+  // ---- fused argmax: warp -> CTA -> last CTA done (-> peers) -------------------------------------------------------------
+  __shared__ double s_bv[kMaxWarpsPerCta];
+  __shared__ long long s_bi[kMaxWarpsPerCta];
+  __shared__ int s_last;
+  __shared__ BestRec s_mine;
+  warp_argmax(best_v, best_i);
+  if (lane == 0) { s_bv[warp] = best_v; s_bi[warp] = best_i; }
+  __syncthreads();
+  if (warp == 0) {
+    best_v = lane < wpc ? s_bv[lane] : -CUDART_INF;
+    best_i = lane < wpc ? s_bi[lane] : LLONG_MAX;
+    warp_argmax(best_v, best_i);
+    if (lane == 0) {
+      a.sel_ws->partial[blockIdx.x].value = best_v;
+      a.sel_ws->partial[blockIdx.x].index = best_i;
+      __threadfence();                            // the partial record and this CTA's value[] stores before the ticket
+      s_last = (atomicAdd(&a.sel_ws->done, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp == 0) {
+    best_v = -CUDART_INF;
+    best_i = LLONG_MAX;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+      const double v = a.sel_ws->partial[b].value;
+      const long long i = a.sel_ws->partial[b].index;
+      if (better(v, i, best_v, best_i)) { best_v = v; best_i = i; }
+    }
+    warp_argmax(best_v, best_i);
+    if (lane == 0) {
+      s_mine = finalize_flat(n_cand, a.value, best_v, best_i, a.index_offset);
+      if (a.peer_mode < 0) *a.best_out = s_mine;
+      a.sel_ws->done = 0;                         // re-arm for the next launch on this stream
+    }
+  }
+  if (a.peer_mode >= 0) {
+    __syncthreads();
+    peer_exchange_block(a.peer, s_mine, a.best_out, a.peer_mode, pcnt);
   }
 }
 
@@ -533,7 +594,8 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gain<MODE>, wpc * 32, smem);
   if (e != cudaSuccess || occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
   const int want = (a.n + wpc - 1) / wpc;
-  const int grid = want < num_sms * occ ? want : num_sms * occ;   // persistent: a multiple of the SM count when saturated
+  int grid = want < num_sms * occ ? want : num_sms * occ;   // persistent: a multiple of the SM count when saturated
+  if (a.best_out && grid > kSelMaxBlocks) grid = kSelMaxBlocks;   // one partial record per CTA in the argmax workspace
   k_gain<MODE><<<grid, wpc * 32, smem, s>>>(*tm_rec, *tm_aux, a);
   ctx->launches += 1;
   e = cudaGetLastError();
@@ -545,7 +607,7 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
 
 int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
                 const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
-                cudaStream_t s, const int* d_sel, const int* d_n) {
+                cudaStream_t s, const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs) {
   if (n <= 0) return SIPP_OK;
   const int h = p->half_fov;
   if (h < 0 || h > 112) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d outside [0,112] (TMA box limit 256 columns)", h);
@@ -576,9 +638,18 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.counts = d_counts;
   a.terminal = d_terminal;
   a.value = d_cost ? d_value : nullptr;
+  a.value2 = d_cost ? d_value2 : nullptr;
   a.recip = ctx->d_recip;
   a.sel = d_sel;
   a.n_dev = d_n;
+  if (fs) {
+    if (!d_cost || !d_value || d_sel || d_n) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "fused argmax needs cost / value and a dense candidate list");
+    a.best_out = fs->best_out;
+    a.sel_ws = reinterpret_cast<SelectWs*>(ctx->d_select_ws);
+    a.index_offset = fs->index_offset;
+    if (fs->peer) a.peer = *fs->peer;
+    a.peer_mode = fs->peer ? fs->peer_mode : -1;
+  }
   int mode;
   switch (p->evaluator) {
     case SIPP_EVAL_RRT_STAR: mode = (p->use_distance_discount && !p->do_binary_check) ? MODE_RRT_DISCOUNT : MODE_COUNT; break;

@@ -63,6 +63,31 @@ struct BestRec {  // 16-byte record moved by the multi-GPU gather
   long long index;
 };
 
+// ---- multi-GPU peer exchange (protocol: sipp_peer.cuh) -------------------------------------------------------------------
+constexpr int kPeerSlots = 4;
+
+// One record = three self-validating 8-byte words, each carrying a tag derived from the step number, so neither side needs a
+// system-scope fence (measured: the release / acquire pair cost ~4 us per step, more than the NVLink hop itself): an aligned
+// 8-byte store is atomic, the words may arrive in any order, the reader polls until all three carry the tag of the step.
+struct PeerSlot {
+  unsigned long long w0;        // tag32 << 32 | low  half of the value's bit pattern
+  unsigned long long w1;        // tag32 << 32 | high half
+  unsigned long long w2;        // tag16 << 48 | global candidate index as a 48-bit two's complement (< 0: the shard was empty)
+  unsigned long long pad;
+};
+struct PeerBox {
+  PeerSlot slots[kPeerSlots][SIPP_PEER_MAX_WORLD];   // [step % 4][writer rank]
+  // device resident so a captured graph replays unchanged; only this rank's own kernels (one stream) touch them
+  unsigned long long published;  // records this rank has published
+  unsigned long long collected;  // steps this rank has collected (merged)
+  unsigned long long status;     // != 0: a wait timed out (a peer died or the ranks are not calling in lockstep)
+};
+struct PeerDev {
+  PeerBox* box[SIPP_PEER_MAX_WORLD];   // box[r]: rank r's mailbox as mapped into this rank's address space
+  int rank, world;
+  unsigned long long timeout_ns;
+};
+
 struct sipp_ctx {
   sipp_map_desc desc;
   int device;
@@ -72,6 +97,7 @@ struct sipp_ctx {
   int cycle_chunks;                  // 0 = automatic; tuning knob SIPP_CYCLE_CHUNKS
   // sipp_cycle's pipeline captured as a CUDA graph, replayed while the call's pointers / parameters stay the same
   bool cycle_use_graph;
+  bool cycle_zero_copy;              // results go straight into the caller's pinned host arrays (opt-in: SIPP_CYCLE_ZEROCOPY=1)
   cudaGraphExec_t cycle_graph;
   std::vector<unsigned char> cycle_key;
   int cycle_graph_launches;
@@ -141,6 +167,11 @@ struct sipp_ctx {
   void* d_tree_ws; size_t d_tree_ws_bytes;
   BestRec* d_best; void* d_select_ws;
   double* d_plan_cost_dummy;
+  // multi-GPU peer exchange (sipp_peer.cu): own mailbox, the peers' mailboxes as mapped here, device copy of the table
+  PeerBox* d_peer_box;
+  PeerDev peer;                             // the mailbox table, passed to the kernels by value
+  void* peer_mapped[SIPP_PEER_MAX_WORLD];   // cudaIpcOpenMemHandle results to close again (nullptr: not IPC-mapped)
+  int peer_rank, peer_world;                // peer_world == 0: not attached
 };
 
 // error helpers -----------------------------------------------------------------------------------------
@@ -169,9 +200,16 @@ cudaError_t launch_download_planes(sipp_ctx* ctx, uint8_t* d_state_out, int32_t*
                                    uint8_t* d_path_out, cudaStream_t s);
 cudaError_t launch_upload_mask(sipp_ctx* ctx, const uint8_t* d_mask_packed, cudaStream_t s);
 // sipp_gain.cu
+struct FusedSelect {       // argmax over value fused into the tail of k_gain (flat tree): one launch per evaluation cycle
+  BestRec* best_out;
+  long long index_offset;
+  const PeerDev* peer;     // non-null (host pointer, copied into the kernel parameters): exchange the winner with the peers, write the GLOBAL one
+  int peer_mode;           // PEER_SYNC / PEER_PIPELINED (sipp_peer.cuh)
+};
 int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy,
                 const double* d_start_xy, const double* d_cost, double* d_gain, uint32_t* d_counts,
-                uint8_t* d_terminal, double* d_value, cudaStream_t s, const int* d_sel = nullptr, const int* d_n = nullptr);
+                uint8_t* d_terminal, double* d_value, cudaStream_t s, const int* d_sel = nullptr, const int* d_n = nullptr,
+                double* d_value2 = nullptr, const FusedSelect* fs = nullptr);
 // sipp_update.cu: evaluator-updater policy on the device (row A13)
 cudaError_t launch_update_select(sipp_ctx* ctx, const sipp_updater_params& u, int n, const double* d_end_xy, const double* d_gain,
                                  const uint8_t* d_terminal, double cur_x, double cur_y, int path_changed, uint8_t* d_do_gain, uint8_t* d_follow,
@@ -182,7 +220,10 @@ cudaError_t launch_update_apply(sipp_ctx* ctx, const sipp_updater_params& u, int
 cudaError_t launch_update_value(sipp_ctx* ctx, int n, const uint8_t* d_do_value, const double* d_value_tmp, double* d_value, cudaStream_t s);
 // sipp_select.cu
 cudaError_t launch_select_flat(sipp_ctx* ctx, int n, const double* d_value, long long index_offset, BestRec* d_best, double* d_root_value,
-                               cudaStream_t s);
+                               cudaStream_t s, const PeerDev* d_peer = nullptr, int peer_mode = 0);
+// sipp_peer.cu: standalone exchange of one record (the fused form lives in k_select)
+cudaError_t launch_peer_exchange(sipp_ctx* ctx, const BestRec* d_mine, BestRec* d_out, int mode, cudaStream_t s);
+void peer_release(sipp_ctx* ctx);
 cudaError_t launch_value_flat(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, double* d_value, cudaStream_t s);
 cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_gain_below, const double* d_cost,
                               const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s);

@@ -13,32 +13,13 @@
 
 #include <climits>
 
+#include "sipp_argmax.cuh"
 #include "sipp_internal.h"
+#include "sipp_peer.cuh"
 
 namespace {
 
 constexpr int kSelThreads = 256;
-constexpr int kSelMaxBlocks = 296;
-
-struct SelectWs {
-  unsigned int done;       // last-block-done ticket
-  unsigned int pad[3];
-  BestRec partial[kSelMaxBlocks];
-};
-
-__device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) {
-  // "v beats bv": strictly greater, or equal with a lower index. NaN never beats anything.
-  return (v > bv) || (v == bv && i < bi);
-}
-
-__device__ __forceinline__ void warp_argmax(double& v, long long& i) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double ov = __shfl_xor_sync(0xFFFFFFFFu, v, off);
-    const long long oi = __shfl_xor_sync(0xFFFFFFFFu, i, off);
-    if (better(ov, oi, v, i)) { v = ov; i = oi; }
-  }
-}
 
 __device__ void block_argmax(double& v, long long& i) {
   __shared__ double sv[kSelThreads / 32];
@@ -60,7 +41,9 @@ __device__ void block_argmax(double& v, long long& i) {
 // allow scanning only the root's children in tree mode (sel[i] != 0).
 __global__ void __launch_bounds__(kSelThreads)
 k_select(int n, const double* __restrict__ value, const int32_t* __restrict__ parent, int tree_mode, long long index_offset,
-         SelectWs* ws, BestRec* out, double* root_value, const int* overflow_flag) {
+         SelectWs* ws, BestRec* out, double* root_value, const int* overflow_flag, const PeerDev peer, int peer_mode) {
+  PeerCounters pcnt = {0, 0};
+  if (peer_mode >= 0 && threadIdx.x == 0) pcnt = peer_preload(peer);
   double bv = -CUDART_INF;
   long long bi = LLONG_MAX;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -70,6 +53,7 @@ k_select(int n, const double* __restrict__ value, const int32_t* __restrict__ pa
   }
   block_argmax(bv, bi);
   __shared__ bool is_last;
+  __shared__ BestRec s_mine;
   if (threadIdx.x == 0) {
     ws->partial[blockIdx.x].value = bv;
     ws->partial[blockIdx.x].index = bi;
@@ -101,9 +85,14 @@ k_select(int n, const double* __restrict__ value, const int32_t* __restrict__ pa
     else if (value[first] != value[first]) { bv = value[first]; bi = first; }   // NaN first element sticks
     else if (bi == LLONG_MAX) { bv = value[first]; bi = first; }                // every other element was NaN / -inf ties
     if (overflow_flag && *overflow_flag) { bv = 0.0; bi = -2; }   // tree deeper than kMaxTreeDepth: in-band error
-    out->value = bv;
-    out->index = bi >= 0 ? bi + index_offset : bi;
+    s_mine.value = bv;
+    s_mine.index = bi >= 0 ? bi + index_offset : bi;
+    if (peer_mode < 0) *out = s_mine;
     ws->done = 0;   // re-arm for the next launch on this stream
+  }
+  if (peer_mode >= 0) {       // multi-GPU: publish the shard winner into every peer's mailbox, wait for theirs, merge (sipp_peer.cuh)
+    __syncthreads();
+    peer_exchange_block(peer, s_mine, out, peer_mode, pcnt);
   }
 }
 
@@ -208,9 +197,10 @@ static int sel_grid(int n) {
 }
 
 cudaError_t launch_select_flat(sipp_ctx* ctx, int n, const double* d_value, long long index_offset, BestRec* d_best, double* d_root_value,
-                               cudaStream_t s) {
+                               cudaStream_t s, const PeerDev* d_peer, int peer_mode) {
+  static const PeerDev no_peer = {};
   k_select<<<sel_grid(n), kSelThreads, 0, s>>>(n, d_value, nullptr, 0, index_offset, reinterpret_cast<SelectWs*>(ctx->d_select_ws), d_best,
-                                               d_root_value, nullptr);
+                                               d_root_value, nullptr, d_peer ? *d_peer : no_peer, d_peer ? peer_mode : -1);
   ctx->launches += 1;
   return cudaGetLastError();
 }
@@ -240,7 +230,7 @@ cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const 
   k_tree_init<<<blocks, threads, 0, s>>>(n, best, flags);
   k_tree_pairs<<<blocks, threads, 0, s>>>(n, d_gain, d_gain_below, d_cost, d_parent, best, own_nan, flags);
   k_tree_final<<<blocks, threads, 0, s>>>(n, best, own_nan, d_value);
-  k_select<<<sel_grid(n), kSelThreads, 0, s>>>(n, d_value, d_parent, 1, 0, reinterpret_cast<SelectWs*>(ctx->d_select_ws), d_best, nullptr, flags);
+  k_select<<<sel_grid(n), kSelThreads, 0, s>>>(n, d_value, d_parent, 1, 0, reinterpret_cast<SelectWs*>(ctx->d_select_ws), d_best, nullptr, flags, PeerDev{}, -1);
   ctx->launches += 4;
   return cudaGetLastError();
 }

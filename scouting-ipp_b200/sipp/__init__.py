@@ -27,7 +27,10 @@ ABI_SYMBOLS = [
     "sipp_map_download", "sipp_plan", "sipp_field_download", "sipp_path_mask_generation", "sipp_set_path_mask",
     "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
+    "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
+    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev",
 ]
+PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
 
 class MapDesc(C.Structure):  # sipp_map_desc
@@ -172,6 +175,15 @@ def lib():
         L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.sipp_merge_best_dev.argtypes = [vp, vp, i32, i64, vp, vp]
         L.sipp_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, pi32]
+        L.sipp_peer_export.argtypes = [vp, vp]
+        L.sipp_peer_attach.argtypes = [vp, i32, i32, vp]
+        L.sipp_peer_detach.argtypes = [vp]
+        L.sipp_peer_status.argtypes = [vp, pi32, C.POINTER(i64)]
+        L.sipp_cycle_shard_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, i64, vp, vp]
+        L.sipp_cycle_shard.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, i64, vp, vp, vp, C.POINTER(i64), pf64]
+        L.sipp_peer_exchange_dev.argtypes = [vp, vp, vp, vp]
+        L.sipp_cycle_shard_pipelined_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, i64, vp, vp]
+        L.sipp_peer_flush_dev.argtypes = [vp, vp, vp]
         L.sipp_launch_count.argtypes = [vp]
         L.sipp_launch_count.restype = i64
         _lib = L
@@ -365,6 +377,47 @@ class Context:
 
     def merge_best_dev(self, d_recs, world, shard_stride, d_out, stream=None):
         self._check(self._L.sipp_merge_best_dev(self._h, _ptr(d_recs), int(world), int(shard_stride), _ptr(d_out), _ptr(stream)))
+
+    # ---- multi-GPU: shard winners exchanged through peer memory (sipp_peer_*)
+    def peer_export(self):
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._check(self._L.sipp_peer_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def peer_attach(self, rank, handles):
+        """handles: list of the `world` byte strings returned by every rank's peer_export(), in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == PEER_HANDLE_BYTES * len(handles)
+        self._check(self._L.sipp_peer_attach(self._h, int(rank), len(handles), C.c_char_p(blob)))
+
+    def peer_detach(self):
+        self._check(self._L.sipp_peer_detach(self._h))
+
+    def peer_status(self):
+        st, n = C.c_int32(), C.c_int64()
+        self._check(self._L.sipp_peer_status(self._h, C.byref(st), C.byref(n)))
+        return st.value, n.value
+
+    def cycle_shard_dev(self, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, index_offset, d_best_global, stream=None):
+        self._check(self._L.sipp_cycle_shard_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost), _ptr(d_gain),
+                                                 _ptr(d_terminal), _ptr(d_value), int(index_offset), _ptr(d_best_global), _ptr(stream)))
+
+    def cycle_shard_pipelined_dev(self, params, n, d_xy, d_start_xy, d_cost, d_gain, d_terminal, d_value, index_offset, d_prev_best_global, stream=None):
+        self._check(self._L.sipp_cycle_shard_pipelined_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost), _ptr(d_gain),
+                                                           _ptr(d_terminal), _ptr(d_value), int(index_offset), _ptr(d_prev_best_global), _ptr(stream)))
+
+    def peer_flush_dev(self, d_best_global, stream=None):
+        self._check(self._L.sipp_peer_flush_dev(self._h, _ptr(d_best_global), _ptr(stream)))
+
+    def cycle_shard_host_ptr(self, params, n, xy, start_xy, cost, index_offset, gain, terminal, value):
+        """sipp_cycle_shard on caller-owned host buffers given as raw addresses; returns the GLOBAL winner"""
+        bi, bv = C.c_int64(), C.c_double()
+        self._check(self._L.sipp_cycle_shard(self._h, C.byref(params), int(n), _ptr(xy), _ptr(start_xy), _ptr(cost), int(index_offset),
+                                             _ptr(gain), _ptr(terminal), _ptr(value), C.byref(bi), C.byref(bv)))
+        return bi.value, bv.value
+
+    def peer_exchange_dev(self, d_mine, d_out, stream=None):
+        self._check(self._L.sipp_peer_exchange_dev(self._h, _ptr(d_mine), _ptr(d_out), _ptr(stream)))
 
     def cycle_host_ptr(self, params, n, xy, start_xy, cost, gain, terminal, value):
         """sipp_cycle on caller-owned host buffers given as raw addresses (pinned memory for the e2e benchmark)."""
