@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
 
 One "step" = one pass of the per-cycle evaluation over one candidate batch: footprint gain for every candidate
-(k_gain, TMA-tiled window scan) + value = gain/cost + argmax (k_select); with N > 1 the candidate set is sharded
-(weak scaling: 65536 candidates per GPU, map replicated) and each step ends with the NCCL gather of the
-16-byte best records. Metric: candidate-view evals/s on the 4096^2 map (BASELINE.json). The follower
+(k_gain, TMA-tiled window scan) + value = gain/cost + argmax (fused into the kernel's tail); with N > 1 the candidate set is sharded
+(weak scaling: 65536 candidates per GPU, map replicated) and each step ends with the exchange of the 16-byte shard
+winners through peer memory over NVLink, fused into the same kernel (an NCCL all_gather form is timed beside it). Metric: candidate-view evals/s on the 4096^2 map (BASELINE.json). The follower
 cost-to-go / path / mask step runs once per planning cycle; it is timed separately and reported under "cycle".
 
 --impl reference times the reference's own CPU algorithm (the oracle port of the C++ evaluators, faithful
@@ -318,12 +318,12 @@ def main():
 
     other = None
     if exchange == "p2p":
-        total_ms, best, wall, launches, clocks = timed(step_p2p, False, True)
-        s_ms, s_best, _, _, _ = timed(step_p2p_sync, False)  # every step waits for its own records
+        total_ms, best, wall, launches, clocks = timed(step_p2p_sync, False)   # every step ends with its own global winner
+        s_ms, s_best, _, _, _ = timed(step_p2p, False, True)
         o_ms, o_best, _, _, _ = timed(step_nccl, True)      # the collective-library form of the same step, for comparison
         assert torch.equal(o_best.cpu(), best.cpu()) and torch.equal(s_best.cpu(), best.cpu())
-        other = [{"exchange": "p2p, synchronous (every step ends with its own global winner)", "ms_per_step": s_ms / args.steps,
-                  "value": world * T * args.steps / (s_ms * 1e-3)},
+        other = [{"exchange": "p2p, pipelined (step k collects the records of step k-1; the ranks may drift up to one step apart and the final flush, "
+                              "timed in full, waits for the slowest)", "ms_per_step": s_ms / args.steps, "value": world * T * args.steps / (s_ms * 1e-3)},
                  {"exchange": "nccl all_gather + merge kernel (gather of step k under the gain kernel of step k+1)", "ms_per_step": o_ms / args.steps,
                   "value": world * T * args.steps / (o_ms * 1e-3)}]
     else:
@@ -471,8 +471,8 @@ def main():
                    "l2": "flushed between timed steps (256 MiB write, untimed); the 16 MiB record plane is smaller than L2",
                    "sharding": ("single GPU" if world == 1 else
                                 "candidates sharded, map replicated; the gain kernel's last CTA stores each shard's 16-byte winner into every peer's mailbox "
-                                "over NVLink (peer memory) and merges the peers' records of the previous step (pipelined; the last step is flushed inside the "
-                                "timed region): one launch per step, no collective call on the data path" if exchange == "p2p" else
+                                "over NVLink (peer memory), waits for the peers' records of the same step and merges them: every step ends with the global "
+                                "winner on every rank, one launch per step, no collective call on the data path" if exchange == "p2p" else
                                 "candidates sharded, map replicated, NCCL all_gather of one 16-byte record per rank per step + one merge kernel; "
                                 "the gather of step k overlaps the gain kernel of step k+1, the last gather is timed in full"),
                    "exchange": exchange, "exchange_note": p2p_note, "exchange_other": other},
