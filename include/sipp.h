@@ -254,6 +254,21 @@ int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, con
  * comparable the first one is returned. Writes one 16-byte record with the GLOBAL index to d_out. One tiny kernel. */
 int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_t shard_stride, void* d_out, void* stream);
 
+/* ---- episode replay (offline evaluation replay / ensembles of independent maps) ------------------ */
+/* The host loop of one exploration episode, run natively so that many episodes can be driven side by side from plain host
+ * threads (one context each; contexts are independent and their kernels overlap on the GPU): per cycle c
+ *   1. ingest the fov x fov patch of `truth` (W x H row-major labels) centred on the scout, as the simulator publishes it and
+ *      mapDataCallback ingests it (mav_simulator.cpp:438-479, map_server_planexp.cpp:222-276); before the first cycle the
+ *      init x init square at the map origin (mav_simulator.cpp:156-159; init == 0: none);
+ *   2. re-plan the follower path (sipp_plan);
+ *   3. score the n candidate views cand_xy[c][n][2] with travel costs cand_cost[c][n] and select (sipp_cycle);
+ *   4. move the scout to the selected candidate (it stays where it is when none wins).
+ * Outputs (any may be NULL), one entry per cycle: path cost, SIPP_PLAN_* status, path nodes, selected candidate, its value.
+ * Replaces, for evaluation runs, the loop data_analysis/evaluation.py:39-62 + planexp_eval_planner.cpp:201-303 drive. */
+int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params* params, int32_t cycles, int32_t n,
+                     const double* cand_xy, const double* cand_cost, int32_t fov, int32_t init, double start_x, double start_y,
+                     double* path_cost, int32_t* plan_status, int32_t* path_len, int32_t* best_index, double* best_value);
+
 /* ---- multi-GPU: exchange of the shard winners through peer memory (NVLink / NVSwitch), fused into the argmax kernel ----- */
 /* One process per GPU (or several contexts in one process). Every rank exports a handle to its mailbox, the host program
  * moves the handles between the ranks with whatever it has (MPI, torch.distributed, a ROS topic), and every rank attaches

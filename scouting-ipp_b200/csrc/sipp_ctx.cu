@@ -550,14 +550,14 @@ int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask) {
 
 int sipp_path_mask_generation(const sipp_ctx* ctx) { return ctx ? ctx->path_generation : -1; }
 
-int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
-  SIPP_ENTER(ctx);
+static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
   int rc = field_plan(ctx, ctx->stream);
   if (rc != SIPP_OK) return rc;
-  int out[10];
-  int ctl[8];   // CTL_* of sipp_field.cu: head, tail, pending, activations, sweeps, abort, pushes
-  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
-  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->stream));
+  // results come back through the context's pinned block (a copy into pageable memory is staged by the driver under a global lock)
+  int* out = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->h_pinned) + 64);   // [10]
+  int* ctl = out + 16;   // [8] CTL_* of sipp_field.cu: head, tail, pending, activations, sweeps, abort, pushes
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, 10 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->plan_stats[0] = ctl[6];
   ctx->plan_stats[1] = ctl[3];
@@ -588,6 +588,11 @@ int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int
   ctx->field_valid = true;
   ctx->views_dirty = true;
   return SIPP_OK;
+}
+
+int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
+  SIPP_ENTER(ctx);
+  return plan_impl(ctx, cost, status, path_xy, path_cap, path_len);
 }
 
 int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]) {
@@ -859,7 +864,7 @@ static int cycle_host_impl(sipp_ctx* ctx, const sipp_eval_params* params, int32_
     ctx->cycle_graph_launches = launched;
     return SIPP_OK;
   };
-  if (ctx->cycle_use_graph) {
+  if (ctx->cycle_use_graph && chunks > 1) {   // a single chunk is seven driver calls: capturing / instantiating a graph costs more
     // key: everything the captured nodes bake in
     std::vector<unsigned char> key;
     auto put = [&](const void* p, size_t nb) { const unsigned char* b = reinterpret_cast<const unsigned char*>(p); key.insert(key.end(), b, b + nb); };
@@ -908,6 +913,50 @@ int sipp_cycle_shard(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, c
                      int64_t index_offset, double* gain, uint8_t* terminal, double* value, int64_t* best_index_global, double* best_value) {
   SIPP_ENTER(ctx);
   return cycle_host_impl(ctx, params, n, xy, start_xy, cost, gain, terminal, value, best_index_global, best_value, true, index_offset);
+}
+
+// ---- episode replay --------------------------------------------------------------------------------------
+int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params* params, int32_t cycles, int32_t n, const double* cand_xy,
+                     const double* cand_cost, int32_t fov, int32_t init, double start_x, double start_y, double* path_cost,
+                     int32_t* plan_status, int32_t* path_len, int32_t* best_index, double* best_value) {
+  SIPP_ENTER(ctx);
+  if (!truth || !params || cycles < 0 || n < 1 || !cand_xy || !cand_cost || fov < 1 || fov > 4096 || init < 0)
+    return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad episode arguments");
+  const int W = ctx->W, H = ctx->H;
+  int rc;
+  std::vector<int32_t> patch;
+  auto ingest_window = [&](int x0, int y0, int rows, int cols) -> int {   // the simulator's MapData patch: truth labels, 0 off the image
+    patch.assign((size_t)rows * cols, 0);
+    for (int i = 0; i < rows; ++i) {
+      const int y = y0 + i;
+      if (y < 0 || y >= H) continue;
+      for (int j = 0; j < cols; ++j) {
+        const int x = x0 + j;
+        if (x >= 0 && x < W) patch[(size_t)i * cols + j] = truth[(size_t)y * W + x];
+      }
+    }
+    return ingest_common(ctx, x0, y0, rows, cols, patch.data(), nullptr);
+  };
+  if (init > 0 && (rc = ingest_window(0, 0, init < H ? init : H, init < W ? init : W)) != SIPP_OK) return rc;   // mav_simulator.cpp:156-159
+  double px = start_x, py = start_y;
+  for (int c = 0; c < cycles; ++c) {
+    const int ix = (int)(px * (long)W / ctx->desc.width), iy = (int)(py * (long)H / ctx->desc.height);   // sipp_patch_origin
+    if ((rc = ingest_window(ix - fov / 2, iy - fov / 2, fov, fov)) != SIPP_OK) return rc;
+    double pc = -1.0;
+    int32_t st = 0, len = 0;
+    if ((rc = plan_impl(ctx, &pc, &st, nullptr, 0, &len)) != SIPP_OK) return rc;
+    int64_t bi = -1;
+    double bv = 0.0;
+    const double* xy = cand_xy + (size_t)c * n * 2;
+    if ((rc = cycle_host_impl(ctx, params, n, xy, nullptr, cand_cost + (size_t)c * n, nullptr, nullptr, nullptr, &bi, &bv, false, 0)) != SIPP_OK) return rc;
+    if (path_cost) path_cost[c] = pc;
+    if (plan_status) plan_status[c] = st;
+    if (path_len) path_len[c] = len;
+    if (best_index) best_index[c] = (int32_t)bi;
+    if (best_value) best_value[c] = bv;
+    if (bi >= 0) { px = xy[2 * bi]; py = xy[2 * bi + 1]; }
+  }
+  return SIPP_OK;
 }
 
 int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,

@@ -834,9 +834,11 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
   ctx->launches += 1;
   const size_t relax_smem = kRelaxWarps * sizeof(TileSmem);
-  SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem));
-  SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, relax_smem));
-  if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
+  if (!occ) {   // once per process (per device would be the same answer: sm_100a only)
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem));
+    SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, relax_smem));
+    if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
+  }
   RelaxArgs ra;
   ra.g = g;
   ra.field = ctx->d_field;
@@ -850,10 +852,19 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   ra.tile_w = ctx->d_tile_w;
   ra.spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
   ra.mode = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
+  // persistent workers: one CTA per SM for a large map; a small map (an ensemble of 640x480 maps runs many plans side by side on
+  // their contexts' streams) gets one warp per ~3 tiles so that several relaxations share the GPU instead of queueing for all SMs
+  static const int grid_env = getenv("SIPP_RELAX_GRID") ? atoi(getenv("SIPP_RELAX_GRID")) : 0;
   int grid = num_sms * occ;
+  const int want = grid_env > 0 ? grid_env : (ntiles + 15) / 16;
+  if (want < grid) grid = want;
+  if (grid < 1) grid = 1;
   if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
-  void* kargs[] = {(void*)&ra};
-  SIPP_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_relax, dim3(grid), dim3(kRelaxWarps * 32), kargs, relax_smem, s));
+  // a plain launch: the workers never wait for each other (no grid barrier; any one warp can drain the queue alone), so CTAs that
+  // only become resident later — e.g. while other contexts' kernels hold SMs — just join late. Cooperative launches of different
+  // streams do not overlap, which serialised the plans of an ensemble.
+  k_relax<<<grid, kRelaxWarps * 32, relax_smem, s>>>(ra);
+  SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   ctx->launches += 1;
 
   if (timing) cudaEventRecord(ev[1], s);

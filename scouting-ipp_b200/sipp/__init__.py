@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
-    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev",
+    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -184,6 +184,7 @@ def lib():
         L.sipp_peer_exchange_dev.argtypes = [vp, vp, vp, vp]
         L.sipp_cycle_shard_pipelined_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, i64, vp, vp]
         L.sipp_peer_flush_dev.argtypes = [vp, vp, vp]
+        L.sipp_episode_run.argtypes = [vp, vp, C.POINTER(EvalParams), i32, i32, vp, vp, i32, i32, f64, f64, vp, vp, vp, vp, vp]
         L.sipp_launch_count.argtypes = [vp]
         L.sipp_launch_count.restype = i64
         _lib = L
@@ -377,6 +378,20 @@ class Context:
 
     def merge_best_dev(self, d_recs, world, shard_stride, d_out, stream=None):
         self._check(self._L.sipp_merge_best_dev(self._h, _ptr(d_recs), int(world), int(shard_stride), _ptr(d_out), _ptr(stream)))
+
+    def episode_run(self, truth, params, cand_xy, cand_cost, fov=65, init=320, start=(0.5, 0.5)):
+        """sipp_episode_run: cand_xy [cycles][n][2], cand_cost [cycles][n]; returns the per-cycle trace as a list of
+        (path cost, plan status, path nodes, selected candidate, value) — the format of sipp.episode.run_episode"""
+        truth = np.ascontiguousarray(truth, dtype=np.int32)
+        cand_xy = np.ascontiguousarray(cand_xy, dtype=np.float64)
+        cand_cost = np.ascontiguousarray(cand_cost, dtype=np.float64)
+        cycles, n = cand_cost.shape
+        assert truth.shape == (self.H, self.W) and cand_xy.shape == (cycles, n, 2)
+        pc, bv = np.zeros(cycles, np.float64), np.zeros(cycles, np.float64)
+        st, ln, bi = np.zeros(cycles, np.int32), np.zeros(cycles, np.int32), np.zeros(cycles, np.int32)
+        self._check(self._L.sipp_episode_run(self._h, _ptr(truth), C.byref(params), cycles, n, _ptr(cand_xy), _ptr(cand_cost), int(fov), int(init),
+                                             float(start[0]), float(start[1]), _ptr(pc), _ptr(st), _ptr(ln), _ptr(bi), _ptr(bv)))
+        return [(float(pc[c]), int(st[c]), int(ln[c]), int(bi[c]), float(bv[c])) for c in range(cycles)]
 
     # ---- multi-GPU: shard winners exchanged through peer memory (sipp_peer_*)
     def peer_export(self):

@@ -532,3 +532,24 @@ def test_empty_and_error_paths():
     with pytest.raises(sipp.SippError):
         g.map_update_patch(0, 0, np.full((4, 4), 70000, np.int32))
     assert g.launch_count() > 0
+
+
+def test_episode_loop_matches_oracle_trace():
+    """config 5 in small: episodes of {ingest the 65x65 patch at the scout, re-plan, score, select} on 640x480-style maps; the
+    trace of every cycle — path cost, plan status, path length, selected candidate bit-identical, the winner's value within RTOL
+    (bit-identical too where the gain is integer valued) — matches the oracle's"""
+    from sipp import episode
+    W, H = 320, 240
+    for seed in (2000, 2001):
+        lab = synth.make_labels(W, H, seed)
+        ids = sorted(set(np.unique(lab).tolist()) - {0})
+        mk = lambda f: f(W, H, W * synth.MPP, H * synth.MPP, (0.5, 0.5), (W * synth.MPP - 0.5, H * synth.MPP - 0.5), min(ids), max(ids), max(ids))
+        kw = dict(half_fov=32, non_path_voxel_gain=0.001 if seed % 2 else 0.0)
+        tg = episode.run_episode(sipp.Context(mk(sipp.make_desc)), lab, sipp.make_params(sipp.EVAL_RRT_STAR, **kw), seed, cycles=8, T=256, init=96)
+        to = episode.run_episode(orc.Oracle(mk(orc.make_desc)), lab, orc.make_params(orc.EVAL_RRT_STAR, **kw), seed, cycles=8, T=256, init=96)
+        assert episode.traces_match(tg, to, RTOL), (seed, tg, to)
+        # the native loop (sipp_episode_run, what ensembles are driven with) leaves exactly the Python loop's trace
+        cxy, cc = episode.episode_candidates(W, H, seed, 8, 256)
+        assert sipp.Context(mk(sipp.make_desc)).episode_run(lab, sipp.make_params(sipp.EVAL_RRT_STAR, **kw), cxy, cc, fov=65, init=96) == tg
+        if kw['non_path_voxel_gain'] == 0.0:
+            assert tg == to          # integer-valued gains: the whole trace is bit-identical
