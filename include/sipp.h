@@ -254,6 +254,24 @@ int sipp_cycle_dev(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, con
  * comparable the first one is returned. Writes one 16-byte record with the GLOBAL index to d_out. One tiny kernel. */
 int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_t shard_stride, void* d_out, void* stream);
 
+/* ---- trajectory cost: line integral of the map cost --------------------------------------------- */
+/* "CostPlanExpMapIntegral" (advanced_planner_modules/src/cost_computer/cost_planexp_map_integral.cpp:15-73,
+ * cfg/evaluators/baseline.yaml:14-15): parameters as in setupFromParamMap (:15-18). */
+typedef struct sipp_cost_params {
+  int32_t accumulate;            /* default false: add the parent's cost                         */
+  int32_t pad_;
+  double max_sample_distance;    /* default 0.05 m                                               */
+} sipp_cost_params;
+/* computeCost for n trajectory segments at once. Segment i owns the points [point_offset[i], point_offset[i+1]) of
+ * points_xyz (x, y, z doubles: trajectory[k].position_W). cost[i] = sum over the consecutive point pairs of the sampled
+ * integral (sub-samples every max_sample_distance along the pair, each charged distance * mean of the two map costs, or
+ * distance * mean map cost when either sample lies on an unobserved cell; off-map samples read -1 like getCostAtLocation);
+ * + parent_cost[i] when accumulate is set and parent_cost != NULL. valid[i] (optional) = computeCost's return value: 0 for
+ * segments with fewer than two points (their cost is 0). Every segment is integrated sequentially in the reference's
+ * operation order (one thread per segment), so the result is bit-identical to the C++ loop. */
+int sipp_cost_integral(sipp_ctx* ctx, const sipp_cost_params* params, int32_t n, const int32_t* point_offset,
+                       const double* points_xyz, const double* parent_cost, double* cost, uint8_t* valid);
+
 /* ---- episode replay (offline evaluation replay / ensembles of independent maps) ------------------ */
 /* The host loop of one exploration episode, run natively so that many episodes can be driven side by side from plain host
  * threads (one context each; contexts are independent and their kernels overlap on the GPU): per cycle c

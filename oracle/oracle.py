@@ -71,6 +71,16 @@ class EvalParams(C.Structure):
     ]
 
 
+class CostParams(C.Structure):  # sipp_cost_params
+    _fields_ = [("accumulate", C.c_int32), ("pad_", C.c_int32), ("max_sample_distance", C.c_double)]
+
+
+def make_cost_params(accumulate=False, max_sample_distance=0.05):
+    p = CostParams()
+    p.accumulate, p.max_sample_distance = int(bool(accumulate)), float(max_sample_distance)
+    return p
+
+
 def make_desc(W, H, width, height, start, goal, min_cost, max_cost, init_cost, obstacle_ids_mav=(0,),
               obstacle_ids_rov=(0,), unknown_id=3599, compute_reachability=True, compute_closest_observed=False):
     d = MapDesc()
@@ -150,6 +160,7 @@ def lib():
         L.orc_set_path_mask.argtypes = [vp, vp]
         L.orc_gain_batch.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, i32, i32]
         L.orc_value_select.argtypes = [i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64)]
+        L.orc_cost_integral.argtypes = [vp, C.POINTER(CostParams), i32, vp, vp, vp, vp, vp]
         L.orc_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64), i32, i32]
         L.orc_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
         _lib = L
@@ -292,6 +303,15 @@ class Oracle:
         self._L.orc_gain_batch(self._h, C.byref(params), n, _ptr(xy), _ptr(start_xy), _ptr(gain), _ptr(counts),
                                _ptr(terminal), int(variant), int(threads))
         return gain, counts, terminal
+
+    def cost_integral(self, cparams, point_offset, points_xyz, parent_cost=None):
+        off = np.ascontiguousarray(point_offset, dtype=np.int32)
+        n = off.shape[0] - 1
+        pts = np.ascontiguousarray(points_xyz, dtype=np.float64).reshape(-1, 3)
+        pc = None if parent_cost is None else np.ascontiguousarray(parent_cost, dtype=np.float64)
+        cost, valid = np.zeros(n, np.float64), np.zeros(n, np.uint8)
+        self._L.orc_cost_integral(self._h, C.byref(cparams), n, _ptr(off), _ptr(pts), _ptr(pc), _ptr(cost), _ptr(valid))
+        return cost, valid
 
     def cycle(self, params, xy, cost, start_xy=None, variant=0, threads=1):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

@@ -903,6 +903,59 @@ int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_pa
 }
 
 // flat-tree cycle: candidate i is node i+1 under a virtual root.
+// CostPlanExpMapIntegral::computeCost (advanced_planner_modules/src/cost_computer/cost_planexp_map_integral.cpp:21-73): line integral of
+// the map cost along the piecewise-linear trajectory, sampled every max_sample_distance; a sample pair touching an unobserved cell
+// (weight 0) is charged the mean map cost; off-map samples read -1 (getCostAtLocation :757-762) and are used as they are.
+// Segment i has points pts[off[i] .. off[i+1]) (x, y, z); valid[i] = the reference's return value (false for < 2 points).
+int orc_cost_integral(orc_ctx* c, const sipp_cost_params* cp, int32_t n, const int32_t* off, const double* pts, const double* parent_cost,
+                      double* cost_out, uint8_t* valid) {
+  Oracle& o = c->o;
+  const double msd = cp->max_sample_distance;
+  auto weight = [&](const Vec3& p) { return cost_at(o, p); };                       // MapPlanExp::getVoxelWeight map_planexp.cpp:110-112
+  auto norm3 = [](const Vec3& a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); };
+  for (int s = 0; s < n; ++s) {
+    const int np = off[s + 1] - off[s];
+    const double* P = pts + 3 * (size_t)off[s];
+    if (np < 2) {                                                                    // :22-25
+      cost_out[s] = 0.0;
+      if (valid) valid[s] = 0;
+      continue;
+    }
+    double cost = 0.0, segment_cost = 0.0;
+    Vec3 last{P[0], P[1], P[2]};
+    for (int i = 1; i < np; ++i) {
+      const Vec3 pi{P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+      const Vec3 diff{pi.x - last.x, pi.y - last.y, pi.z - last.z};
+      const double segment_distance = norm3(diff);                                   // :37
+      if (segment_distance > 0.005) {
+        const Vec3 dir{diff.x / segment_distance, diff.y / segment_distance, diff.z / segment_distance};   // :39
+        const int n_sub = (int)(segment_distance / msd);                             // :40
+        segment_cost = 0;
+        Vec3 start = last, end = last;
+        for (int j = 0; j <= n_sub; ++j) {
+          double sub = msd;
+          if (j == n_sub) sub = segment_distance - n_sub * msd;                      // :46
+          end.x += dir.x * sub; end.y += dir.y * sub; end.z += dir.z * sub;          // :47
+          const double ws = weight(start), we = weight(end);
+          double sub_cost = sub * (ws + we) / 2.0;                                   // :48-49
+          if (ws == 0 || we == 0) sub_cost = sub * o.mean_cost;                      // :50-51
+          segment_cost += sub_cost;
+          start = end;
+        }
+      } else {                                                                       // :55-61
+        const double w = weight(pi);
+        segment_cost = (w == 0) ? segment_distance * o.mean_cost : segment_distance * w;
+      }
+      cost += segment_cost;
+      last = pi;
+    }
+    if (cp->accumulate && parent_cost) cost += parent_cost[s];                       // :68-70
+    cost_out[s] = cost;
+    if (valid) valid[s] = 1;
+  }
+  return 0;
+}
+
 int orc_cycle(orc_ctx* c, const sipp_eval_params* p, int32_t n, const double* xy, const double* start_xy, const double* cost,
               double* gain, uint8_t* terminal, double* value, int32_t* best_index, double* best_value, int variant, int threads) {
   orc_gain_batch(c, p, n, xy, start_xy, gain, nullptr, terminal, variant, threads);

@@ -915,6 +915,37 @@ int sipp_cycle_shard(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, c
   return cycle_host_impl(ctx, params, n, xy, start_xy, cost, gain, terminal, value, best_index_global, best_value, true, index_offset);
 }
 
+// ---- trajectory cost integral --------------------------------------------------------------------------
+int sipp_cost_integral(sipp_ctx* ctx, const sipp_cost_params* params, int32_t n, const int32_t* point_offset, const double* points_xyz,
+                       const double* parent_cost, double* cost, uint8_t* valid) {
+  SIPP_ENTER(ctx);
+  if (!params || n < 0 || (n > 0 && (!point_offset || !cost))) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cost_integral arguments");
+  if (!(params->max_sample_distance > 0)) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "max_sample_distance must be positive");
+  if (n == 0) return SIPP_OK;
+  if (point_offset[0] != 0) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "point_offset[0] must be 0");
+  for (int i = 0; i < n; ++i)
+    if (point_offset[i + 1] < point_offset[i]) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "point_offset is not non-decreasing at %d", i);
+  const size_t np = (size_t)point_offset[n];
+  if (np > 0 && !points_xyz) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "points_xyz == NULL");
+  cudaStream_t s = ctx->stream;
+  int rc;
+  const size_t N = (size_t)n, need = np * 24 + N * 8 * 2 + (N + 1) * 4 + N + 512;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
+  double* d_pts = reinterpret_cast<double*>(ctx->d_stage);
+  double *d_parent = d_pts + 3 * np, *d_cost = d_parent + N;
+  int32_t* d_off = reinterpret_cast<int32_t*>(d_cost + N);
+  uint8_t* d_valid = reinterpret_cast<uint8_t*>(d_off + N + 1);
+  if (np) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pts, points_xyz, np * 24, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_off, point_offset, (N + 1) * 4, cudaMemcpyHostToDevice, s));
+  const bool acc = params->accumulate && parent_cost;
+  if (acc) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_parent, parent_cost, N * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, launch_cost_integral(ctx, *params, n, d_off, d_pts, acc ? d_parent : nullptr, d_cost, d_valid, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(cost, d_cost, N * 8, cudaMemcpyDeviceToHost, s));
+  if (valid) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(valid, d_valid, N, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  return SIPP_OK;
+}
+
 // ---- episode replay --------------------------------------------------------------------------------------
 int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params* params, int32_t cycles, int32_t n, const double* cand_xy,
                      const double* cand_cost, int32_t fov, int32_t init, double start_x, double start_y, double* path_cost,

@@ -229,6 +229,9 @@ cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const 
                               const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s);
 cudaError_t launch_merge_best(sipp_ctx* ctx, const BestRec* d_recs, int world, long long stride, BestRec* d_out, cudaStream_t s);
 size_t select_workspace_bytes();
+// sipp_cost.cu
+cudaError_t launch_cost_integral(sipp_ctx* ctx, const sipp_cost_params& p, int n, const int32_t* d_off, const double* d_pts, const double* d_parent_cost,
+                                 double* d_cost, uint8_t* d_valid, cudaStream_t s);
 // sipp_field.cu
 int field_plan(sipp_ctx* ctx, cudaStream_t s);
 

@@ -248,6 +248,14 @@ void GpuGainEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
   setParam<double>(param_map, "bounding_volume/x_max", &params_.bv_x_max, 0.0);
   setParam<double>(param_map, "bounding_volume/y_min", &params_.bv_y_min, 0.0);
   setParam<double>(param_map, "bounding_volume/y_max", &params_.bv_y_max, 0.0);
+  // cost_computer block (cfg/evaluators/baseline.yaml:14-15): [upstream] "SegmentTime" or the map line integral
+  std::string ct;
+  setParam<std::string>(param_map, "cost_computer/type", &ct, "SegmentTime");
+  cost_is_integral_ = (ct == "GpuCostPlanExpMapIntegral" || ct == "CostPlanExpMapIntegral");
+  if (!cost_is_integral_ && ct != "SegmentTime") config_error_ = "unknown cost_computer type '" + ct + "'";
+  setParam<bool>(param_map, "cost_computer/accumulate", &b, false);                                    // cost_planexp_map_integral.cpp:16-17
+  cost_params_.accumulate = b;
+  setParam<double>(param_map, "cost_computer/max_sample_distance", &cost_params_.max_sample_distance, 0.05);
   // evaluator_updater block (cfg/evaluators/rrt_star.yaml:24-32, example_config.yaml:109-117)
   std::string ut, ft;
   setParam<std::string>(param_map, "evaluator_updater/type", &ut, "RRTStarUpdater");
@@ -298,7 +306,21 @@ bool GpuGainEvaluator::computeGain(TrajectorySegment* traj_in) {
   return true;
 }
 
-bool GpuGainEvaluator::computeCost(TrajectorySegment* traj_in) {   // [upstream] SegmentTime: duration of the segment in seconds
+bool GpuGainEvaluator::computeCost(TrajectorySegment* traj_in) {
+  if (cost_is_integral_) {   // CostPlanExpMapIntegral::computeCost (cost_planexp_map_integral.cpp:21-73) as a batch of one segment
+    if (!map_) return false;
+    std::vector<double> pts;
+    pts.reserve(traj_in->trajectory.size() * 3);
+    for (const auto& p : traj_in->trajectory) { pts.push_back(p.position_W.x()); pts.push_back(p.position_W.y()); pts.push_back(p.position_W.z()); }
+    const int32_t off[2] = {0, (int32_t)traj_in->trajectory.size()};
+    const double parent_cost = traj_in->parent ? traj_in->parent->cost : 0.0;
+    double cost = 0.0;
+    uint8_t valid = 0;
+    if (sipp_cost_integral(map_->ctx(), &cost_params_, 1, off, pts.data(), traj_in->parent ? &parent_cost : nullptr, &cost, &valid) != SIPP_OK) return false;
+    traj_in->cost = cost;
+    return valid != 0;
+  }
+  // [upstream] SegmentTime: duration of the segment in seconds
   if (traj_in->trajectory.empty()) { traj_in->cost = 0.0; return false; }
   traj_in->cost = static_cast<double>(traj_in->trajectory.back().time_from_start_ns) * 1.0e-9;
   return true;

@@ -119,6 +119,8 @@ class GpuGainEvaluator : public TrajectoryEvaluator {
   map::GpuMapPlanExp* map_ = nullptr;
   sipp_eval_params params_;
   sipp_updater_params updater_;
+  bool cost_is_integral_ = false;     // cost_computer/type: "SegmentTime" [upstream] or "(Gpu)CostPlanExpMapIntegral"
+  sipp_cost_params cost_params_ = {0, 0, 0.05};
   int last_rrt_path_id_ = 0;          // rrt_star_updater.h:30-31
   bool rrt_path_has_changed_ = true;
   int last_batch_ = 0;

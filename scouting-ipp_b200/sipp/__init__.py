@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
-    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run",
+    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -79,6 +79,16 @@ class EvalParams(C.Structure):  # sipp_eval_params
         ("augment_unknown_with_mean", C.c_int32), ("use_bounding_volume", C.c_int32),
         ("bv_x_min", C.c_double), ("bv_x_max", C.c_double), ("bv_y_min", C.c_double), ("bv_y_max", C.c_double),
     ]
+
+
+class CostParams(C.Structure):  # sipp_cost_params
+    _fields_ = [("accumulate", C.c_int32), ("pad_", C.c_int32), ("max_sample_distance", C.c_double)]
+
+
+def make_cost_params(accumulate=False, max_sample_distance=0.05):
+    p = CostParams()
+    p.accumulate, p.max_sample_distance = int(bool(accumulate)), float(max_sample_distance)
+    return p
 
 
 class SippError(RuntimeError):
@@ -185,6 +195,7 @@ def lib():
         L.sipp_cycle_shard_pipelined_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, i64, vp, vp]
         L.sipp_peer_flush_dev.argtypes = [vp, vp, vp]
         L.sipp_episode_run.argtypes = [vp, vp, C.POINTER(EvalParams), i32, i32, vp, vp, i32, i32, f64, f64, vp, vp, vp, vp, vp]
+        L.sipp_cost_integral.argtypes = [vp, C.POINTER(CostParams), i32, vp, vp, vp, vp, vp]
         L.sipp_launch_count.argtypes = [vp]
         L.sipp_launch_count.restype = i64
         _lib = L
@@ -378,6 +389,16 @@ class Context:
 
     def merge_best_dev(self, d_recs, world, shard_stride, d_out, stream=None):
         self._check(self._L.sipp_merge_best_dev(self._h, _ptr(d_recs), int(world), int(shard_stride), _ptr(d_out), _ptr(stream)))
+
+    def cost_integral(self, cparams, point_offset, points_xyz, parent_cost=None):
+        """CostPlanExpMapIntegral for a batch of segments: returns (cost, valid)"""
+        off = np.ascontiguousarray(point_offset, dtype=np.int32)
+        n = off.shape[0] - 1
+        pts = np.ascontiguousarray(points_xyz, dtype=np.float64).reshape(-1, 3)
+        pc = None if parent_cost is None else np.ascontiguousarray(parent_cost, dtype=np.float64)
+        cost, valid = np.zeros(n, np.float64), np.zeros(n, np.uint8)
+        self._check(self._L.sipp_cost_integral(self._h, C.byref(cparams), n, _ptr(off), _ptr(pts), _ptr(pc), _ptr(cost), _ptr(valid)))
+        return cost, valid
 
     def episode_run(self, truth, params, cand_xy, cand_cost, fov=65, init=320, start=(0.5, 0.5)):
         """sipp_episode_run: cand_xy [cycles][n][2], cand_cost [cycles][n]; returns the per-cycle trace as a list of

@@ -24,6 +24,8 @@ int orc_plan(orc_ctx* c, double* cost, int32_t* status, double* path_xy, int32_t
 int orc_path_mask_generation(orc_ctx* c);
 int orc_gain_batch(orc_ctx* c, const sipp_eval_params* p, int32_t n, const double* xy, const double* start_xy, double* gain,
                    uint32_t* counts, uint8_t* terminal, int variant, int threads);
+int orc_cost_integral(orc_ctx* c, const sipp_cost_params* cp, int32_t n, const int32_t* off, const double* pts, const double* parent_cost,
+                      double* cost_out, uint8_t* valid);
 int orc_value_select(int32_t n, const double* gain_in, const double* cost_in, const int32_t* parent, double* value,
                      int32_t* best_child, double* best_value);
 int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
@@ -326,6 +328,32 @@ static int testGpu() {
     for (int i : {1, 7, 133, N - 1}) {
       CHECK(gev->computeValue(t.nodes[i]), "computeValue");
       CHECK(t.nodes[i]->value == ov[i], "computeValue node %d: %.17g vs %.17g", i, t.nodes[i]->value, ov[i]);
+    }
+    if (&cfg == &cfgs[0]) {
+      // cost_computer/type: CostPlanExpMapIntegral (cfg/evaluators/baseline.yaml:14-15) — computeCost node by node, parents first,
+      // accumulate on; against the oracle's statement of cost_planexp_map_integral.cpp:21-73
+      Module::ParamMap cp2 = evalParams(cfg.type, cfg.updater, cfg.following);
+      cp2["cost_computer/type"] = "CostPlanExpMapIntegral";
+      cp2["cost_computer/accumulate"] = "true";
+      cp2["cost_computer/max_sample_distance"] = "0.05";
+      auto cev = ModuleFactoryRegistry::createModule<TrajectoryEvaluator>(&cp2, planner, &err);
+      CHECK(cev != nullptr, "evaluator with the map-integral cost: %s", err.c_str());
+      const sipp_cost_params CP = {1, 0, 0.05};
+      std::vector<double> saved(N);
+      for (int i = 0; i < N; ++i) saved[i] = t.nodes[i]->cost;
+      int bad_cost = 0;
+      for (int i = 1; i < N && cev; ++i) {
+        std::vector<double> pts;
+        for (const auto& p : t.nodes[i]->trajectory) { pts.push_back(p.position_W.x()); pts.push_back(p.position_W.y()); pts.push_back(p.position_W.z()); }
+        const int32_t off[2] = {0, (int32_t)t.nodes[i]->trajectory.size()};
+        const double pc = t.nodes[i]->parent->cost;      // already the integral cost (parents come first in the flat order)
+        double want; uint8_t wv;
+        orc_cost_integral(orc, &CP, 1, off, pts.data(), &pc, &want, &wv);
+        const bool rv = cev->computeCost(t.nodes[i]);
+        bad_cost += (rv != (wv != 0)) || t.nodes[i]->cost != want;
+      }
+      CHECK(bad_cost == 0, "%d map-integral costs differ", bad_cost);
+      for (int i = 0; i < N; ++i) t.nodes[i]->cost = saved[i];
     }
     for (int i = 1; i < N; ++i) t.nodes[i]->value = ov[i];
 
