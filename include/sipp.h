@@ -184,6 +184,18 @@ int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask);
 /* relaxation statistics of the last sipp_plan: [0]=tile queue pushes, [1]=tile activations, [2]=tile sweeps, [3]=aborted */
 int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]);
 
+/* Incremental re-plan. Between two plans only ingested patches change the planner's map, so sipp_plan
+ * reuses the previous fixed point: cells first observed at a HIGHER cost than the planner assumed (obstacles, labels above the
+ * init cost) invalidate — along the predecessor plane of the last plan — exactly the cost-to-go values whose path ran through
+ * them; those are reset to +inf and the relaxation restarts from the patch tiles and the rim of the invalidated region. The
+ * result is bit-identical to a plan from scratch (the least fixed point is unique and every surviving value is an upper bound
+ * of it). A plan falls back to a full one after sipp_map_clear / sipp_update_unknown_cost / a change of the init cost, or when
+ * the patches cover more than half of the tiles. On by default; SIPP_INCREMENTAL=0 or sipp_set_incremental(ctx, 0) turn it off.
+ * info: [0] 1 = the last plan was incremental, [1] tiles touched by patches, [2] tiles the relaxation started from,
+ * [3] cells invalidated. */
+int sipp_set_incremental(sipp_ctx* ctx, int32_t enable);
+int sipp_plan_info(const sipp_ctx* ctx, int64_t info[4]);
+
 /* ---- batched footprint gain (A1-A8) ---------------------------------------------------------------- */
 /* Replaces, for n candidates at once, SimulatedSensorEvaluator::computeGain -> getVisibleVoxelsFromTrajectory
  * -> MapPlanExp::getVoxelArea -> <Evaluator>::computeGainFromVisibleVoxels

@@ -129,6 +129,8 @@ int host_clear(sipp_ctx* ctx) {
   ctx->init_cost = ctx->desc.unknown_init_cost;
   ctx->path_valid = false;
   ctx->field_valid = false;
+  ctx->warm_valid = false;
+  ctx->pending_rects.clear();
   ctx->views_dirty = true;
   SIPP_CUDA_CHECK(ctx, launch_clear_planes(ctx, ctx->stream));
   SIPP_CUDA_CHECK(ctx, launch_closest_clear(ctx, ctx->stream));
@@ -296,7 +298,7 @@ void sipp_destroy(sipp_ctx* ctx) {
   void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_cclab, ctx->d_closest_dist,
                   ctx->d_recip, ctx->d_field, ctx->d_pred, ctx->d_tile_w, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
                   ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_path_nodes, ctx->d_path_xy, ctx->d_plan_out, ctx->d_stage, ctx->d_tree_ws,
-                  ctx->d_best, ctx->d_select_ws};
+                  ctx->d_best, ctx->d_select_ws, ctx->d_mark, ctx->d_tile_seed, ctx->d_seed_list};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   peer_release(ctx);
@@ -391,6 +393,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   }
   if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "copy streams / events: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
   ctx->cycle_chunks = getenv("SIPP_CYCLE_CHUNKS") ? atoi(getenv("SIPP_CYCLE_CHUNKS")) : 0;
+  ctx->inc_enabled = !(getenv("SIPP_INCREMENTAL") && atoi(getenv("SIPP_INCREMENTAL")) == 0);
   ctx->cycle_use_graph = !(getenv("SIPP_CYCLE_GRAPH") && atoi(getenv("SIPP_CYCLE_GRAPH")) == 0);
   // opt-in: measured on B200 (tools/zerocopy_probe.py) it does not beat the copy-engine pipeline — every warp stores its results at
   // the end of its one 32-candidate batch, so the 1.1 MB of PCIe writes land in a burst after the scan instead of under it
@@ -424,6 +427,9 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   }
   rc |= dev_alloc(ctx, &ctx->d_field, (size_t)ctx->W * ctx->H);
   rc |= dev_alloc(ctx, &ctx->d_pred, n8);
+  rc |= dev_alloc(ctx, &ctx->d_mark, n8);
+  rc |= dev_alloc(ctx, &ctx->d_tile_seed, ntiles);
+  rc |= dev_alloc(ctx, &ctx->d_seed_list, ntiles);
   rc |= dev_alloc(ctx, &ctx->d_tile_w, ntiles * (size_t)(4 * 34 * 34));
   rc |= dev_alloc(ctx, &ctx->d_tile_flags, ntiles);
   rc |= dev_alloc(ctx, &ctx->d_tile_list, ntiles > 16384 ? ntiles : (size_t)16384);   // ring queue: >= tiles and >= resident warps
@@ -477,6 +483,17 @@ static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, cons
   if (!labels || rows <= 0 || cols <= 0) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad patch %d x %d", rows, cols);
   int rc = host_ingest(ctx, x0, y0, rows, cols, labels, observed);
   if (rc != SIPP_OK) return rc;
+  // incremental re-plan bookkeeping: the patch rectangle joins the list the next plan starts from; a change of the init cost
+  // (goal explored, map_server_planexp.cpp:276) changes every unexplored cell and ends the warm start
+  if (ctx->warm_valid && ctx->init_cost != ctx->warm_init_cost) ctx->warm_valid = false;
+  if (ctx->warm_valid) {
+    const int xa = x0 < 0 ? 0 : x0, ya = y0 < 0 ? 0 : y0, xb = x0 + cols - 1 >= ctx->W ? ctx->W - 1 : x0 + cols - 1,
+              yb = y0 + rows - 1 >= ctx->H ? ctx->H - 1 : y0 + rows - 1;
+    if (xa <= xb && ya <= yb) {
+      if (ctx->pending_rects.size() >= 4 * 64) ctx->warm_valid = false;      // too many patches since the last plan: start over
+      else { ctx->pending_rects.push_back(xa); ctx->pending_rects.push_back(ya); ctx->pending_rects.push_back(xb); ctx->pending_rects.push_back(yb); }
+    }
+  }
   const size_t n = (size_t)rows * cols;
   const size_t need = n * 4 + (observed ? n : 0) + 256;
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
@@ -506,6 +523,7 @@ int sipp_map_upload_full(sipp_ctx* ctx, const int32_t* labels, const uint8_t* ob
 
 int sipp_update_unknown_cost(sipp_ctx* ctx, double new_cost) {
   SIPP_ENTER(ctx);
+  if (new_cost != ctx->init_cost) ctx->warm_valid = false;
   ctx->init_cost = new_cost;   // unexplored cells carry PCODE_UNEXPLORED; their cost is resolved at plan time
   ctx->field_valid = false;
   return SIPP_OK;
@@ -552,7 +570,7 @@ int sipp_path_mask_generation(const sipp_ctx* ctx) { return ctx ? ctx->path_gene
 
 static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
   int rc = field_plan(ctx, ctx->stream);
-  if (rc != SIPP_OK) return rc;
+  if (rc != SIPP_OK) { ctx->warm_valid = false; return rc; }
   // results come back through the context's pinned block (a copy into pageable memory is staged by the driver under a global lock)
   int* out = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->h_pinned) + 64);   // [10]
   int* ctl = out + 16;   // [8] CTL_* of sipp_field.cu: head, tail, pending, activations, sweeps, abort, pushes
@@ -563,7 +581,16 @@ static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_
   ctx->plan_stats[1] = ctl[3];
   ctx->plan_stats[2] = ctl[4];
   ctx->plan_stats[3] = ctl[5];
-  if (ctl[5]) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation aborted by its watchdog (work queue starved)");
+  ctx->pending_rects.clear();
+  ctx->plan_info[2] = out[6];
+  ctx->plan_info[3] = out[5];
+  if (ctl[5]) {
+    ctx->warm_valid = false;
+    return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation aborted by its watchdog (work queue starved)");
+  }
+  // the converged field + predecessor plane are the warm start of the next plan
+  ctx->warm_valid = ctx->inc_enabled;
+  ctx->warm_init_cost = ctx->init_cost;
   double c;
   memcpy(&c, &out[8], sizeof(double));
   const int len = out[0];
@@ -593,6 +620,19 @@ static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_
 int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
   SIPP_ENTER(ctx);
   return plan_impl(ctx, cost, status, path_xy, path_cap, path_len);
+}
+
+int sipp_plan_info(const sipp_ctx* ctx, int64_t info[4]) {
+  if (!ctx || !info) return SIPP_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) info[i] = ctx->plan_info[i];
+  return SIPP_OK;
+}
+
+int sipp_set_incremental(sipp_ctx* ctx, int32_t enable) {
+  SIPP_ENTER(ctx);
+  ctx->inc_enabled = enable != 0;
+  if (!enable) ctx->warm_valid = false;
+  return SIPP_OK;
 }
 
 int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]) {

@@ -234,6 +234,7 @@ struct WeightArgs {
   size_t pitch16;
   double* tile_w;    // [ntiles][4][TP][TP]
   int ntx;
+  const int* tile_list;   // optional: block b rebuilds tile tile_list[b] (incremental re-plan: only the tiles a patch touched)
 };
 constexpr int kWeightThreads = 256;
 __global__ void __launch_bounds__(kWeightThreads)
@@ -244,7 +245,8 @@ k_weights(const WeightArgs a) {
   __shared__ double dd[kMaxDd];
   const FieldGeom& g = a.g;
   const int tid = threadIdx.x;
-  const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
+  const int tile = a.tile_list ? a.tile_list[blockIdx.x] : (int)blockIdx.x;
+  const int tx = tile % a.ntx, ty = tile / a.ntx;
   const int x0 = tx * TS, y0 = ty * TS;
   const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
   if (dd_in_smem)
@@ -266,7 +268,7 @@ k_weights(const WeightArgs a) {
     hd[tid] = okx ? g.hdist[cx] : CUDART_INF;
   }
   __syncthreads();
-  double* out = a.tile_w + (size_t)blockIdx.x * kTileWDoubles;
+  double* out = a.tile_w + (size_t)tile * kTileWDoubles;
   for (int idx = tid; idx < TP * TP; idx += kWeightThreads) {
     const int r = idx / TP, c = idx - r * TP;
     const double h0 = (double)hcf[r][c];
@@ -519,7 +521,7 @@ k_relax(const RelaxArgs a) {
 __global__ void k_field_init(double* field, size_t n, int* flags, int* queue, int ntiles, int qcap, int* ctl) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = i; k < n; k += stride) field[k] = CUDART_INF;
+  for (size_t k = i; k < n; k += stride) field[k] = CUDART_INF;   // n == 0: queue reset only (incremental re-plan keeps the field)
   for (size_t k = i; k < (size_t)ntiles; k += stride) flags[k] = 0;
   for (size_t k = i; k < (size_t)qcap; k += stride) queue[k] = -1;
   if (i < 32) ctl[i] = 0;
@@ -533,6 +535,206 @@ __global__ void k_field_seed(double* field, int W, int H, int sx, int sy, int* f
     ctl[CTL_TAIL] = 1;
     ctl[CTL_PENDING] = 1;
   }
+}
+
+
+// ---- incremental re-plan -------------------------------------------------------------------------------------------------
+// Between two plans only ingested patches change the planner's map, and only cells observed for the first time change cost
+// (prm_star_planner.cpp:111-115). The previous fixed point d is reused:
+//  (1) cells whose cost went UP (first seen as an obstacle, or at a label above the init cost) were marked by k_ingest_patch.
+//      k_inval follows the canonical predecessor plane of the last plan FORWARD from these marks — a cell whose predecessor is
+//      marked is marked — and sets d = +inf on everything marked: exactly the cells whose shortest path ran through a cell or
+//      edge that got more expensive. Every value that survives is still the (rounded) length of a path whose edges kept or
+//      lowered their weight, i.e. an upper bound of the new fixed point;
+//  (2) the relaxation restarts from the tiles the patches touched (lower weights) and the tiles in and around the invalidated
+//      region; from upper bounds it converges to the same least fixed point as from +inf (the operator is monotone, also in
+//      rounded arithmetic), so the field has the bits of a from-scratch plan — tests compare the two.
+// k_inval is a persistent tile work-queue kernel like k_relax, one warp per 32x32 tile, bytes instead of doubles.
+constexpr int kInvalWarps = 8;
+struct InvalSmem {
+  uint8_t m[TP][TP + 2];    // marks incl. halo (row pitch 36)
+  uint8_t p[TS][TS];        // predecessor directions
+};
+struct InvalArgs {
+  int W, H, ntx, nty;
+  uint8_t* mark;            // [H][pitch]
+  const uint8_t* pred;      // [H][pitch]
+  size_t pitch;
+  double* field;
+  int start_x, start_y;
+  int* flags; int* queue; int cap; int* ctl;
+  uint8_t* tile_seed;       // [ntiles] out: tile holds invalidated cells
+  int spin_limit;
+};
+enum { CTL_MARKED = 7 };
+
+__global__ void __launch_bounds__(kInvalWarps * 32)
+k_inval(const InvalArgs a) {
+  __shared__ InvalSmem sm[kInvalWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  InvalSmem& t = sm[warp];
+  const int NDX[8] = {-1, -1, -1, 0, 0, 1, 1, 1};   // k_pred's neighbour order
+  const int NDY[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  int marked_local = 0;
+  for (;;) {
+    int ti = -2;
+    if (lane == 0) {
+      const unsigned ticket = (unsigned)atomicAdd(&a.ctl[CTL_HEAD], 1);
+      int* slot = a.queue + (ticket % (unsigned)a.cap);
+      int spins = 0;
+      for (;;) {
+        const int v = ld_volatile_i32(slot);
+        if (v >= 0) { st_volatile_i32(slot, -1); ti = v; break; }
+        if (ld_volatile_i32(&a.ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) break;
+        if (++spins > a.spin_limit) { atomicExch(&a.ctl[CTL_ABORT], 1); break; }
+        __nanosleep(64);
+      }
+      if (ti >= 0) {
+        atomicExch(&a.flags[ti], 0);      // queued -> running: a mark arriving from now on queues the tile again
+        fence_gpu();
+      }
+    }
+    ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+    if (ti < 0) break;
+    const int tx = ti % a.ntx, ty = ti / a.ntx;
+    const int x0 = tx * TS, y0 = ty * TS;
+    // ---- load: lane = tile column (+ the two halo columns by lanes 0 / 1), all rows
+    {
+      const int gx = x0 + lane;
+      const bool colin = gx < a.W;
+      for (int r = 0; r < TP; ++r) {
+        const int gy = y0 - 1 + r;
+        const bool rowin = gy >= 0 && gy < a.H;
+        t.m[r][lane + 1] = (rowin && colin) ? __ldcg(a.mark + (size_t)gy * a.pitch + gx) : (uint8_t)0;
+        if (lane < 2) {
+          const int hx = lane ? x0 + TS : x0 - 1;
+          t.m[r][lane ? TP - 1 : 0] = (rowin && hx >= 0 && hx < a.W) ? __ldcg(a.mark + (size_t)gy * a.pitch + hx) : (uint8_t)0;
+        }
+        if (r >= 1 && r <= TS) t.p[r - 1][lane] = (rowin && colin) ? a.pred[(size_t)gy * a.pitch + gx] : (uint8_t)255;
+      }
+    }
+    __syncwarp();
+    // ---- propagate to the tile-local fixed point: a cell is marked when its predecessor is. Alternating down / up sweeps; inside a
+    // row the W / E dependencies are iterated with shuffles until nothing changes.
+    uint32_t newly[2] = {0u, 0u};          // bit r (of word r >> 5... TS == 32: one word) : this lane's cell in row r was marked here
+    uint32_t fresh = 0;                    // rows where this lane's cell carries an unpublished ingest mark (value 1)
+    for (int r = 0; r < TS; ++r) if (t.m[r + 1][lane + 1] == 1) fresh |= 1u << r;
+    for (int it = 0;; ++it) {
+      bool chg = false;
+      for (int i = 0; i < TS; ++i) {
+        const int r = (it & 1) ? (TS - 1 - i) : i;
+        int mk = t.m[r + 1][lane + 1] != 0;
+        const int p = t.p[r][lane];
+        int dx = 0, dy = 0;
+        if (p < 8) { dx = NDX[p]; dy = NDY[p]; }
+        if (!mk && p < 8 && dy != 0 && t.m[r + 1 + dy][lane + 1 + dx] != 0) mk = 1;     // predecessor in the row above / below
+        // predecessor in this row: W / E chains
+        const int hl = t.m[r + 1][0] != 0, hr = t.m[r + 1][TP - 1] != 0;
+        bool again;
+        int mk0 = t.m[r + 1][lane + 1] != 0;
+        do {
+          int ml = __shfl_up_sync(0xFFFFFFFFu, mk, 1), mr = __shfl_down_sync(0xFFFFFFFFu, mk, 1);
+          if (lane == 0) ml = hl;
+          if (lane == 31) mr = hr;
+          again = !mk && p < 8 && dy == 0 && ((dx < 0 && ml) || (dx > 0 && mr));
+          if (again) mk = 1;
+        } while (__any_sync(0xFFFFFFFFu, again));
+        if (mk && !mk0) {
+          t.m[r + 1][lane + 1] = 2;
+          newly[0] |= 1u << r;
+          chg = true;
+        }
+        __syncwarp();
+      }
+      if (!__any_sync(0xFFFFFFFFu, chg) && it >= 1) break;
+    }
+    // ---- publish: marks (value 2) and d = +inf for every cell marked here or carrying a fresh ingest mark
+    const uint32_t pub = newly[0] | fresh;
+    {
+      const int gx = x0 + lane;
+      uint32_t rc = pub;
+      while (rc) {
+        const int r = __ffs(rc) - 1;
+        rc &= rc - 1;
+        const int gy = y0 + r;
+        a.mark[(size_t)gy * a.pitch + gx] = 2;
+        if (!(gx == a.start_x && gy == a.start_y)) a.field[(size_t)gy * a.W + gx] = CUDART_INF;   // the start keeps d = 0
+        ++marked_local;
+      }
+    }
+    const uint32_t any_pub = __reduce_or_sync(0xFFFFFFFFu, pub);
+    uint32_t any_mark = 0;
+    for (int r = 0; r < TS; ++r) if (t.m[r + 1][lane + 1] != 0) any_mark |= 1u << r;
+    any_mark = __reduce_or_sync(0xFFFFFFFFu, any_mark);
+    if (lane == 0 && any_mark) a.tile_seed[ti] = 1;
+    // neighbours whose cells may hang off a cell published here: the side / corner of the border ring it lies on
+    int m = 0;   // N S W E NW NE SW SE
+    if (pub & 1u) m |= 1;
+    if (pub & (1u << (TS - 1))) m |= 2;
+    if (lane == 0 && pub) m |= 4;
+    if (lane == 31 && pub) m |= 8;
+    if (lane == 0 && (pub & 1u)) m |= 16;
+    if (lane == 31 && (pub & 1u)) m |= 32;
+    if (lane == 0 && (pub & (1u << (TS - 1)))) m |= 64;
+    if (lane == 31 && (pub & (1u << (TS - 1)))) m |= 128;
+    m = __reduce_or_sync(0xFFFFFFFFu, (unsigned)m);
+    if (m & 16) m |= 1 | 4;      // a corner cell also borders the two side neighbours
+    if (m & 32) m |= 1 | 8;
+    if (m & 64) m |= 2 | 4;
+    if (m & 128) m |= 2 | 8;
+    if (any_pub) fence_gpu();
+    __syncwarp();
+    if (m && lane < 8 && ((m >> lane) & 1)) {
+      const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+      const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+      const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
+      if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
+        const int nt = nty_ * a.ntx + ntx_;
+        if (atomicOr(&a.flags[nt], ST_QUEUED) == 0) {
+          atomicAdd(&a.ctl[CTL_PENDING], 1);
+          const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
+          int* slot = a.queue + (pos % (unsigned)a.cap);
+          int spins = 0;
+          while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);
+          st_volatile_i32(slot, nt);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      fence_gpu();
+      atomicSub(&a.ctl[CTL_PENDING], 1);
+    }
+  }
+  if (marked_local) atomicAdd(&a.ctl[CTL_MARKED], marked_local);
+}
+
+// queue <- the listed tiles (the tiles the patches touched); also flags them as seeds of the relaxation
+__global__ void k_seed_from_list(const int* list, int n, int* flags, int* queue, int* ctl, uint8_t* tile_seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int t = list[i];
+    flags[t] = ST_QUEUED;
+    queue[i] = t;
+    tile_seed[t] = 1;
+  }
+  if (i == 0) { ctl[CTL_TAIL] = n; ctl[CTL_PENDING] = n; }
+}
+// queue <- every tile that is a seed or touches one (the invalidated region and its rim, the patch tiles)
+__global__ void k_seed_relax(const uint8_t* tile_seed, int ntx, int nty, int* flags, int* queue, int* ctl) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntx * nty) return;
+  const int tx = t % ntx, ty = t / ntx;
+  bool on = false;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = tx + dx, y = ty + dy;
+      if (x >= 0 && x < ntx && y >= 0 && y < nty && tile_seed[y * ntx + x]) on = true;
+    }
+  if (!on) return;
+  flags[t] = ST_QUEUED;
+  atomicAdd(&ctl[CTL_PENDING], 1);
+  queue[atomicAdd(&ctl[CTL_TAIL], 1)] = t;
 }
 
 // ---- canonical backtrack: one warp, lanes 0..7 = the 8 neighbours in ascending node-id order ------------
@@ -814,25 +1016,85 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
   // ring capacity: every tile can be queued at most once, and every waiting warp must own a distinct slot (ticket % cap)
   const int qcap = ntiles > 16384 ? ntiles : 16384;
-  k_field_init<<<592, 256, 0, s>>>(ctx->d_field, ncell, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
-  k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->n_tiles_x,
-                               ctx->d_relax_ctl);
-  ctx->launches += 2;
-  SIPP_CUDA_CHECK(ctx, cudaGetLastError());
-
   static int num_sms = 0, occ = 0;
   if (!num_sms) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
   }
-  // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
   WeightArgs wa;
   wa.g = g;
   wa.pcode = ctx->d_pcode;
   wa.pitch16 = ctx->pitch16;
   wa.tile_w = ctx->d_tile_w;
   wa.ntx = ctx->n_tiles_x;
-  k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
-  ctx->launches += 1;
+  wa.tile_list = nullptr;
+
+  // ---- incremental start? the tiles the patches since the last plan touched (one cell of margin: a tile's weight block and
+  // halo reach one cell into its neighbours)
+  std::vector<int> seed_tiles;
+  bool incremental = ctx->inc_enabled && ctx->warm_valid && ctx->warm_init_cost == ctx->init_cost;
+  if (incremental) {
+    std::vector<uint8_t> seen((size_t)ntiles, 0);
+    for (size_t r = 0; r + 3 < ctx->pending_rects.size(); r += 4) {
+      const int xa = ctx->pending_rects[r] - 1, ya = ctx->pending_rects[r + 1] - 1, xb = ctx->pending_rects[r + 2] + 1, yb = ctx->pending_rects[r + 3] + 1;
+      const int ta = (xa < 0 ? 0 : xa) / TS, tb = (xb >= ctx->W ? ctx->W - 1 : xb) / TS;
+      const int ua = (ya < 0 ? 0 : ya) / TS, ub = (yb >= ctx->H ? ctx->H - 1 : yb) / TS;
+      for (int ty = ua; ty <= ub; ++ty)
+        for (int tx = ta; tx <= tb; ++tx) {
+          const int t = ty * ctx->n_tiles_x + tx;
+          if (!seen[t]) { seen[t] = 1; seed_tiles.push_back(t); }
+        }
+    }
+    if ((int)seed_tiles.size() * 2 > ntiles) incremental = false;     // most of the map changed: start over
+  }
+  ctx->plan_info[0] = incremental ? 1 : 0;
+  ctx->plan_info[1] = (int64_t)seed_tiles.size();
+
+  if (!incremental) {
+    if (ctx->warm_valid || !ctx->pending_rects.empty())   // ingest marks of an abandoned warm start must not leak into a later one
+      SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_mark, 0, ctx->pitch * ctx->H, s));
+    k_field_init<<<592, 256, 0, s>>>(ctx->d_field, ncell, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
+    k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->n_tiles_x,
+                                 ctx->d_relax_ctl);
+    ctx->launches += 2;
+    SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+    // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
+    k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
+    ctx->launches += 1;
+    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_plan_out + 5, 0, 2 * sizeof(int), s));
+  } else {
+    const int nl = (int)seed_tiles.size();
+    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_tile_seed, 0, (size_t)ntiles, s));
+    k_field_init<<<64, 256, 0, s>>>(ctx->d_field, 0, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
+    ctx->launches += 1;
+    if (nl > 0) {
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_seed_list, seed_tiles.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, s));
+      k_seed_from_list<<<(nl + 255) / 256, 256, 0, s>>>(ctx->d_seed_list, nl, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_tile_seed);
+      wa.tile_list = ctx->d_seed_list;
+      k_weights<<<nl, kWeightThreads, 0, s>>>(wa);
+      InvalArgs ia;
+      ia.W = ctx->W; ia.H = ctx->H; ia.ntx = ctx->n_tiles_x; ia.nty = ctx->n_tiles_y;
+      ia.mark = ctx->d_mark; ia.pred = ctx->d_pred; ia.pitch = ctx->pitch; ia.field = ctx->d_field;
+      ia.start_x = g.start_x; ia.start_y = g.start_y;
+      ia.flags = ctx->d_tile_flags; ia.queue = ctx->d_tile_list; ia.cap = qcap; ia.ctl = ctx->d_relax_ctl;
+      ia.tile_seed = ctx->d_tile_seed;
+      ia.spin_limit = 20 * 1000 * 1000;
+      int igrid = (ntiles + 8 * kInvalWarps - 1) / (8 * kInvalWarps);
+      if (igrid > 2 * num_sms) igrid = 2 * num_sms;
+      if (igrid * kInvalWarps > qcap) igrid = qcap / kInvalWarps;
+      k_inval<<<igrid, kInvalWarps * 32, 0, s>>>(ia);
+      ctx->launches += 3;
+      SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_plan_out + 5, ctx->d_relax_ctl + CTL_MARKED, sizeof(int), cudaMemcpyDeviceToDevice, s));
+      k_field_init<<<64, 256, 0, s>>>(ctx->d_field, 0, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
+      k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl);
+      ctx->launches += 2;
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_plan_out + 6, ctx->d_relax_ctl + CTL_TAIL, sizeof(int), cudaMemcpyDeviceToDevice, s));
+      SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_mark, 0, ctx->pitch * ctx->H, s));
+    } else {
+      SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_plan_out + 5, 0, 2 * sizeof(int), s));
+    }
+    SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+  }
   const size_t relax_smem = kRelaxWarps * sizeof(TileSmem);
   if (!occ) {   // once per process (per device would be the same answer: sm_100a only)
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem));

@@ -154,6 +154,16 @@ struct sipp_ctx {
   bool path_valid;
   bool field_valid;
   int64_t plan_stats[4];
+  // incremental re-plan (sipp_field.cu): the converged field + predecessor plane of the last plan stay valid as a warm start while
+  // the only changes since are ingested patches
+  bool inc_enabled;            // SIPP_INCREMENTAL=0 turns it off
+  bool warm_valid;             // d_field / d_pred hold the fixed point of the planner map as it was at the last plan
+  double warm_init_cost;       // init cost the last plan used
+  std::vector<int> pending_rects;   // x0, y0, x1, y1 (cell ranges, inclusive) of the patches ingested since the last plan
+  uint8_t* d_mark;             // [H][pitch] cells whose cost-to-go lost its support: 1 = first observed at a higher cost (k_ingest_patch), 2 = published
+  uint8_t* d_tile_seed;        // [ntiles] tile holds invalidated cells / was touched by a patch
+  int* d_seed_list;            // [ntiles] tile ids of the patches since the last plan
+  int64_t plan_info[4];        // last plan: [0] 1 = incremental, [1] tiles seeded from patches, [2] tiles seeded for the relaxation, [3] cells invalidated
   // views
   bool views_dirty;
   sipp_eval_params view_params;   // bounding volume the views were built for

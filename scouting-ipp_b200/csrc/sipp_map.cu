@@ -27,7 +27,7 @@ __device__ __forceinline__ bool in_ids(const IdList& l, int v) {
 __global__ void k_ingest_patch(uint8_t* __restrict__ state, uint16_t* __restrict__ label, uint16_t* __restrict__ pcode,
                                size_t pitch, size_t pitch16, int W, int H, int x0, int y0, int rows, int cols,
                                const int32_t* __restrict__ labels, const uint8_t* __restrict__ observed, IdList mav,
-                               IdList rov) {
+                               IdList rov, uint8_t* __restrict__ mark, int init_cost_ceil) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * cols) return;
   const int i = (int)(t / cols), j = (int)(t % cols);
@@ -38,8 +38,13 @@ __global__ void k_ingest_patch(uint8_t* __restrict__ state, uint16_t* __restrict
   label[(size_t)y * pitch16 + x] = (uint16_t)lab;                  // map_cost_ = label  :242
   state[(size_t)y * pitch + x] = in_ids(mav, lab) ? SIPP_STATE_OCCUPIED : SIPP_STATE_FREE;  // :252-256
   uint16_t* pc = pcode + (size_t)y * pitch16 + x;
-  if (*pc == PCODE_UNEXPLORED)                                     // is_new  prm_star_planner.cpp:111
-    *pc = in_ids(rov, lab) ? (uint16_t)PCODE_REMOVED : (uint16_t)lab;   // :112-115
+  if (*pc == PCODE_UNEXPLORED) {                                   // is_new  prm_star_planner.cpp:111
+    const bool removed = in_ids(rov, lab);
+    *pc = removed ? (uint16_t)PCODE_REMOVED : (uint16_t)lab;       // :112-115
+    // incremental re-plan: the planner believed init_cost here; a cell whose cost went UP (or whose edges are gone) invalidates
+    // every cost-to-go value whose path runs through it (k_inval follows the predecessor plane from these marks)
+    if (mark && (removed || lab > init_cost_ceil)) mark[(size_t)y * pitch + x] = 1;
+  }
 }
 
 // MapServerPlanExp::setClosestObservedMaps (map_server_planexp.cpp:803-823) for one ingested patch [tlx,brx) x [tly,bry):
@@ -172,6 +177,7 @@ cudaError_t launch_clear_planes(sipp_ctx* ctx, cudaStream_t s) {
   if ((e = cudaMemsetAsync(ctx->d_label, 0, n16 * 2, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_pcode, 0xFF, n16 * 2, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_path, 0, n8, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_mark, 0, n8, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_rec, 0, n8, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_freelab, 0, n16 * 2, s)) != cudaSuccess) return e;
   ctx->launches += 6;
@@ -187,7 +193,8 @@ cudaError_t launch_ingest_patch(sipp_ctx* ctx, int x0, int y0, int rows, int col
   k_ingest_patch<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->pitch, ctx->pitch16, ctx->W,
                                             ctx->H, x0, y0, rows, cols, d_labels, d_observed,
                                             make_ids(ctx->desc.obstacle_ids_mav, ctx->desc.n_obstacle_ids_mav),
-                                            make_ids(ctx->desc.obstacle_ids_rov, ctx->desc.n_obstacle_ids_rov));
+                                            make_ids(ctx->desc.obstacle_ids_rov, ctx->desc.n_obstacle_ids_rov),
+                                            ctx->warm_valid ? ctx->d_mark : nullptr, (int)floor(ctx->warm_init_cost));
   ctx->launches += 1;
   return cudaGetLastError();
 }

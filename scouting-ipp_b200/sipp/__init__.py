@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "sipp_plan_stats", "sipp_gain_batch", "sipp_gain_batch_dev", "sipp_value_select", "sipp_value_select_dev", "sipp_value_preorder",
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
-    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral",
+    "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -196,6 +196,8 @@ def lib():
         L.sipp_peer_flush_dev.argtypes = [vp, vp, vp]
         L.sipp_episode_run.argtypes = [vp, vp, C.POINTER(EvalParams), i32, i32, vp, vp, i32, i32, f64, f64, vp, vp, vp, vp, vp]
         L.sipp_cost_integral.argtypes = [vp, C.POINTER(CostParams), i32, vp, vp, vp, vp, vp]
+        L.sipp_set_incremental.argtypes = [vp, i32]
+        L.sipp_plan_info.argtypes = [vp, vp]
         L.sipp_launch_count.argtypes = [vp]
         L.sipp_launch_count.restype = i64
         _lib = L
@@ -299,6 +301,14 @@ class Context:
         st = np.zeros(4, np.int64)
         self._check(self._L.sipp_plan_stats(self._h, _ptr(st)))
         return dict(pushes=int(st[0]), tile_activations=int(st[1]), tile_sweeps=int(st[2]), aborted=int(st[3]))
+
+    def set_incremental(self, enable):
+        self._check(self._L.sipp_set_incremental(self._h, int(bool(enable))))
+
+    def plan_info(self):
+        st = np.zeros(4, np.int64)
+        self._check(self._L.sipp_plan_info(self._h, _ptr(st)))
+        return dict(incremental=bool(st[0]), patch_tiles=int(st[1]), relax_seed_tiles=int(st[2]), invalidated_cells=int(st[3]))
 
     def field_download(self):
         f = np.empty((self.H, self.W), np.float64)

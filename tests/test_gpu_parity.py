@@ -553,3 +553,49 @@ def test_episode_loop_matches_oracle_trace():
         assert sipp.Context(mk(sipp.make_desc)).episode_run(lab, sipp.make_params(sipp.EVAL_RRT_STAR, **kw), cxy, cc, fov=65, init=96) == tg
         if kw['non_path_voxel_gain'] == 0.0:
             assert tg == to          # integer-valued gains: the whole trace is bit-identical
+
+
+@pytest.mark.parametrize("init", ["max", "min", 75])
+def test_incremental_replan_is_bit_identical_to_a_plan_from_scratch(init):
+    """A sequence of patch ingests + plans: the incremental re-plan (warm start from the previous fixed point, invalidation along the
+    predecessor plane where costs went up) leaves the same field, path, mask and cost as a context that plans from scratch every
+    time and as the oracle. init = 75 makes labels fall on both sides of the assumed cost (lower AND higher), obstacles always raise."""
+    from sipp import episode
+    W, H = 384, 288
+    lab = synth.make_labels(W, H, 31)
+    ids = sorted(set(np.unique(lab).tolist()) - {0})
+    ic = max(ids) if init == "max" else (min(ids) if init == "min" else float(init))
+    mk = lambda f: f(W, H, W * synth.MPP, H * synth.MPP, (0.5, 0.5), (W * synth.MPP - 0.5, H * synth.MPP - 0.5), min(ids), max(ids), ic)
+    gi, gf, o = sipp.Context(mk(sipp.make_desc)), sipp.Context(mk(sipp.make_desc)), orc.Oracle(mk(orc.make_desc))
+    gf.set_incremental(False)
+    rng = np.random.default_rng(77)
+    used = 0
+    for step in range(14):
+        k = 1 if step % 5 else 3                       # sometimes several patches between two plans
+        for _ in range(k):
+            if step == 0:
+                x0, y0, rows, cols = 0, 0, 96, 96      # the simulator's initial square
+            else:
+                rows = cols = int(rng.choice([1, 17, 65]))
+                x0, y0 = int(rng.integers(-20, W)), int(rng.integers(-20, H))
+            patch = episode.extract_patch(lab, x0, y0, rows, cols)
+            for b in (gi, gf, o):
+                b.map_update_patch(x0, y0, patch)
+        ri, rf, ro = gi.plan(), gf.plan(), o.plan()
+        info = gi.plan_info()
+        used += info["incremental"]
+        assert not gf.plan_info()["incremental"]
+        assert ri[0] == rf[0] == ro[0] and ri[1] == rf[1] == ro[1] and ri[3] == rf[3] == ro[3], (step, ri[0], rf[0], ro[0], info)
+        assert np.array_equal(ri[2], ro[2]) and np.array_equal(rf[2], ro[2])
+        fi, ff = gi.field_download(), gf.field_download()
+        assert np.array_equal(fi, ff), (step, info, int((fi != ff).sum()))
+        assert np.array_equal(fi, o.field_download())
+        assert np.array_equal(gi.map_download()[3], o.map_download()[3])
+    assert used >= 10, used                            # the goal-explored switch of the init cost may force a few full plans
+    # a plan right after a plan (nothing ingested) and after an init-cost change
+    r2 = gi.plan()
+    assert gi.plan_info() == dict(incremental=True, patch_tiles=0, relax_seed_tiles=0, invalidated_cells=0) and r2[0] == ri[0]
+    for b in (gi, gf, o):
+        b.update_unknown_cost(45.0)
+    assert gi.plan()[0] == gf.plan()[0] == o.plan()[0] and not gi.plan_info()["incremental"]
+    assert np.array_equal(gi.field_download(), o.field_download())
