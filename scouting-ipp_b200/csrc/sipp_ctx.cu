@@ -558,6 +558,7 @@ int sipp_map_download(sipp_ctx* ctx, uint8_t* state, int32_t* cost, uint8_t* rea
 
 int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask) {
   SIPP_ENTER(ctx);
+  ctx->path_mask_foreign = true;
   if (!mask) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "mask == NULL");
   SIPP_CUDA_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_path, ctx->pitch, mask, ctx->W, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -47,6 +47,7 @@ struct RelaxArgs {
   const double* tile_w;     // [ntiles][4][TP][TP] edge-weight cache (k_weights)
   int spin_limit;           // watchdog: a warp that polls an empty queue this many times aborts the kernel
   int mode;                 // bit0: publish after every sweep (else once per run); bit1: exclusive tile ownership (owner re-runs)
+  uint8_t* touched;         // optional [ntiles]: set for every tile that was activated (incremental re-plan: where d may have changed)
 };
 enum { CTL_HEAD = 0, CTL_TAIL = 1, CTL_PENDING = 2, CTL_ACTIVATIONS = 3, CTL_SWEEPS = 4, CTL_ABORT = 5, CTL_PUSHES = 6 };
 
@@ -351,6 +352,7 @@ k_relax(const RelaxArgs a) {
 
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
+    if (a.touched && lane == 0) a.touched[ti] = 1;
     // the tile's weight block: one bulk async copy global -> shared, completion on this warp's mbarrier; it overlaps with the
     // loads of d below
     __syncwarp();           // everyone is done reading the previous tile's planes
@@ -749,6 +751,7 @@ struct PathArgs {
   int cap;
   int* out;         // [0] len, [1] all explored, [2] found, [3] unused, [4] walk failed on a reachable goal
   double* cost_out;
+  const int* redo;  // optional: 0 = the previous plan's path is still the canonical one (nothing on or next to it changed): keep everything
 };
 
 // ---- canonical predecessor of every cell (fully parallel), then the walk over predecessor bytes -------------------------
@@ -765,7 +768,8 @@ struct PredArgs {
   size_t pitch16;
   uint8_t* pred;     // [H][pitch]
   size_t pitch;
-  int ntx;
+  int ntx, nty;
+  const uint8_t* sel;   // optional [ntiles]: recompute a tile only if it or one of its 8 neighbours is flagged (d unchanged elsewhere)
 };
 struct PredSmem {
   double d[TP][TP + 1];
@@ -782,6 +786,15 @@ k_pred(const PredArgs a) {
   const int tid = threadIdx.x;
   const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
   const int x0 = tx * TS, y0 = ty * TS;
+  if (a.sel) {
+    bool on = false;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = tx + dx, y = ty + dy;
+        if (x >= 0 && x < a.ntx && y >= 0 && y < a.nty && a.sel[y * a.ntx + x]) on = true;
+      }
+    if (!on) return;
+  }
   const bool dd_in_smem = g.Kx * g.Ky <= kMaxDd;
   if (dd_in_smem)
     for (int i = tid; i < g.Kx * g.Ky; i += kPredThreads) t.dd[i] = g.ddist[i];
@@ -872,6 +885,7 @@ k_backtrack(const PathArgs a) {
   __shared__ int s_x, s_y, s_len, s_fail;
   const FieldGeom& g = a.g;
   const int tid = threadIdx.x;
+  if (a.redo && *a.redo == 0) return;
   const bool goal_ok = g.goal_x >= 0 && g.goal_x < g.W && g.goal_y >= 0 && g.goal_y < g.H;
   const double dgoal = goal_ok ? a.field[(size_t)g.goal_y * g.W + g.goal_x] : CUDART_INF;
   if (!(dgoal < CUDART_INF)) {
@@ -940,6 +954,7 @@ struct RasterArgs {
   uint8_t* path;      // mask plane
   size_t pitch;
   double map_width, map_height, mpp_third;
+  const int* redo;    // optional: 0 = path unchanged, the mask of the previous plan stands
 };
 
 __device__ __forceinline__ void pos2pix(const RasterArgs& a, double px, double py, int* ix, int* iy) {
@@ -955,7 +970,30 @@ __device__ __forceinline__ void node_pose(const FieldGeom& g, int packed, double
   *py = __dadd_rn(g.off_y, __dmul_rn(g.spacing, (double)y));
 }
 
+// Incremental re-plan: does the previous plan's path touch a tile whose predecessor bytes were recomputed (the tile or a neighbour
+// was relaxed / invalidated / hit by a patch)? If not, the walk from the goal would read exactly the bytes it read last time.
+__global__ void k_path_check(const int* nodes, const int* out, const uint8_t* touched, int ntx, int nty, int* redo) {
+  const int len = out[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (out[2] == 0 || len <= 0)) *redo = 1;     // no path last time: look again
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  const int nj = nodes[j];
+  const int tx = (nj >> 16) / TS, ty = (nj & 0xFFFF) / TS;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = tx + dx, y = ty + dy;
+      if (x >= 0 && x < ntx && y >= 0 && y < nty && touched[y * ntx + x]) { *redo = 1; return; }
+    }
+}
+__global__ void k_mask_clear(uint8_t* path, size_t n16, const int* redo) {
+  if (redo && *redo == 0) return;
+  uint4* p = reinterpret_cast<uint4*>(path);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += stride) p[k] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void k_path_finish(const RasterArgs a) {
+  if (a.redo && *a.redo == 0) return;
   const int len = a.out[0];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;   // path point index, start -> goal
   if (j >= len) return;
@@ -1114,6 +1152,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   ra.tile_w = ctx->d_tile_w;
   ra.spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
   ra.mode = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
+  ra.touched = incremental ? ctx->d_tile_seed : nullptr;
   // persistent workers: one CTA per SM for a large map; a small map (an ensemble of 640x480 maps runs many plans side by side on
   // their contexts' streams) gets one warp per ~3 tiles so that several relaxations share the GPU instead of queueing for all SMs
   static const int grid_env = getenv("SIPP_RELAX_GRID") ? atoi(getenv("SIPP_RELAX_GRID")) : 0;
@@ -1139,6 +1178,18 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   pa.cap = ctx->path_cap_nodes;
   pa.out = ctx->d_plan_out;
   pa.cost_out = reinterpret_cast<double*>(ctx->d_plan_out + 8);
+  // incremental: predecessor bytes are recomputed around the touched tiles only, and the walk / mask are skipped when the previous
+  // path runs nowhere near them (d_plan_out[7] = "redo")
+  int* d_redo = ctx->d_plan_out + 7;
+  static const bool reuse_env = !(getenv("SIPP_PATH_REUSE") && atoi(getenv("SIPP_PATH_REUSE")) == 0);
+  const bool reuse = incremental && reuse_env && !ctx->path_mask_foreign;
+  ctx->path_mask_foreign = false;
+  pa.redo = reuse ? d_redo : nullptr;
+  if (reuse) {
+    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_redo, 0, sizeof(int), s));
+    k_path_check<<<(ctx->path_cap_nodes + 255) / 256, 256, 0, s>>>(ctx->d_path_nodes, ctx->d_plan_out, ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, d_redo);
+    ctx->launches += 1;
+  }
   static bool back_attr = false;
   if (!back_attr) {
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
@@ -1151,7 +1202,8 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   pr.pitch16 = ctx->pitch16;
   pr.pred = ctx->d_pred;
   pr.pitch = ctx->pitch;
-  pr.ntx = ctx->n_tiles_x;
+  pr.ntx = ctx->n_tiles_x; pr.nty = ctx->n_tiles_y;
+  pr.sel = incremental ? ctx->d_tile_seed : nullptr;
   k_pred<<<ntiles, kPredThreads, 0, s>>>(pr);
   pa.pred = ctx->d_pred;
   pa.pitch = ctx->pitch;
@@ -1162,8 +1214,9 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
 
   if (timing) cudaEventRecord(ev[2], s);
   // new mask: computeCurrentPathEstimate swaps in a freshly zeroed map (map_server_planexp.cpp:894-899,904)
-  SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_path, 0, ctx->pitch * ctx->H, s));
+  k_mask_clear<<<592, 256, 0, s>>>(ctx->d_path, ctx->pitch * ctx->H / 16, pa.redo);
   RasterArgs rs;
+  rs.redo = pa.redo;
   rs.g = g;
   rs.nodes = ctx->d_path_nodes;
   rs.out = ctx->d_plan_out;

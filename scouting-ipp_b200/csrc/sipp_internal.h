@@ -157,6 +157,7 @@ struct sipp_ctx {
   // incremental re-plan (sipp_field.cu): the converged field + predecessor plane of the last plan stay valid as a warm start while
   // the only changes since are ingested patches
   bool inc_enabled;            // SIPP_INCREMENTAL=0 turns it off
+  bool path_mask_foreign;      // d_path was written by sipp_set_path_mask since the last plan: the next plan must rasterise again
   bool warm_valid;             // d_field / d_pred hold the fixed point of the planner map as it was at the last plan
   double warm_init_cost;       // init cost the last plan used
   std::vector<int> pending_rects;   // x0, y0, x1, y1 (cell ranges, inclusive) of the patches ingested since the last plan
