@@ -87,6 +87,35 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Host placement: run this process (and allocate its pinned buffers) on the NUMA node the GPU hangs off. The end-to-end path
+    is PCIe bound; from the far socket every copy crosses the inter-socket link. Returns a note for the JSON line."""
+    if os.environ.get("SIPP_BENCH_NO_NUMA"):
+        return "not bound (SIPP_BENCH_NO_NUMA)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+        base = "/sys/bus/pci/devices/%s" % bus
+        node = int(open(base + "/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as exc:
+        return "not bound (%s)" % type(exc).__name__
+
+
 def build_inputs(n_gpus):
     from sipp import synth
     lab = synth.make_labels(W, H, SEED)
@@ -171,6 +200,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit("WORLD_SIZE (%d) != --gpus (%d): launch with torchrun --nproc-per-node %d" % (world, args.gpus, args.gpus))
+    numa_note = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -417,7 +447,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e = {"value": world * T * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": T * 24, "d2h_bytes_per_step": T * 17 + 16,
-           "ms_per_step": e2e_s / args.steps * 1e3,
+           "ms_per_step": e2e_s / args.steps * 1e3, "host_placement": numa_note,
            "api": ("sipp_cycle_shard (host pointers, pinned; copy/compute pipeline + argmax with the fused peer-memory exchange, replayed as a CUDA graph)"
                    if exchange == "p2p" else
                    "sipp_cycle (host pointers, pinned; 2-chunk copy/compute pipeline replayed as a CUDA graph)"

@@ -600,20 +600,33 @@ k_inval(const InvalArgs a) {
     if (ti < 0) break;
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
-    // ---- load: lane = tile column (+ the two halo columns by lanes 0 / 1), all rows
+    // ---- load: lane = tile column (+ the two halo columns by lanes 0 / 1), all rows. Every load is issued before the first
+    // store (registers), so their latencies overlap instead of queueing behind the shared-memory stores
     {
       const int gx = x0 + lane;
       const bool colin = gx < a.W;
+      const int hx = (lane & 1) ? x0 + TS : x0 - 1;
+      const bool hin = lane < 2 && hx >= 0 && hx < a.W;
+      uint8_t mv[TP], hv[TP], pv[TS];
+#pragma unroll
       for (int r = 0; r < TP; ++r) {
         const int gy = y0 - 1 + r;
         const bool rowin = gy >= 0 && gy < a.H;
-        t.m[r][lane + 1] = (rowin && colin) ? __ldcg(a.mark + (size_t)gy * a.pitch + gx) : (uint8_t)0;
-        if (lane < 2) {
-          const int hx = lane ? x0 + TS : x0 - 1;
-          t.m[r][lane ? TP - 1 : 0] = (rowin && hx >= 0 && hx < a.W) ? __ldcg(a.mark + (size_t)gy * a.pitch + hx) : (uint8_t)0;
-        }
-        if (r >= 1 && r <= TS) t.p[r - 1][lane] = (rowin && colin) ? a.pred[(size_t)gy * a.pitch + gx] : (uint8_t)255;
+        mv[r] = (rowin && colin) ? __ldcg(a.mark + (size_t)gy * a.pitch + gx) : (uint8_t)0;
+        hv[r] = (rowin && hin) ? __ldcg(a.mark + (size_t)gy * a.pitch + hx) : (uint8_t)0;
       }
+#pragma unroll
+      for (int r = 0; r < TS; ++r) {
+        const int gy = y0 + r;
+        pv[r] = (gy < a.H && colin) ? a.pred[(size_t)gy * a.pitch + gx] : (uint8_t)255;
+      }
+#pragma unroll
+      for (int r = 0; r < TP; ++r) {
+        t.m[r][lane + 1] = mv[r];
+        if (lane < 2) t.m[r][lane ? TP - 1 : 0] = hv[r];
+      }
+#pragma unroll
+      for (int r = 0; r < TS; ++r) t.p[r][lane] = pv[r];
     }
     __syncwarp();
     // ---- propagate to the tile-local fixed point: a cell is marked when its predecessor is. Alternating down / up sweeps; inside a
