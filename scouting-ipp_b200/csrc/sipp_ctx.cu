@@ -298,7 +298,7 @@ void sipp_destroy(sipp_ctx* ctx) {
   void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_cclab, ctx->d_closest_dist,
                   ctx->d_recip, ctx->d_field, ctx->d_pred, ctx->d_tile_w, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
                   ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_path_nodes, ctx->d_path_xy, ctx->d_plan_out, ctx->d_stage, ctx->d_tree_ws,
-                  ctx->d_best, ctx->d_select_ws, ctx->d_mark, ctx->d_tile_seed, ctx->d_seed_list};
+                  ctx->d_best, ctx->d_select_ws, ctx->d_mark, ctx->d_tile_seed, ctx->d_seed_list, ctx->d_rec2[0], ctx->d_rec2[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   peer_release(ctx);
@@ -416,6 +416,8 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   rc |= dev_alloc(ctx, &ctx->d_state, n8);
   rc |= dev_alloc(ctx, &ctx->d_path, n8);
   rc |= dev_alloc(ctx, &ctx->d_rec, n8);
+  rc |= dev_alloc(ctx, &ctx->d_rec2[0], n8 / 4);
+  rc |= dev_alloc(ctx, &ctx->d_rec2[1], n8 / 4);
   rc |= dev_alloc(ctx, &ctx->d_label, n8);
   rc |= dev_alloc(ctx, &ctx->d_pcode, n8);
   rc |= dev_alloc(ctx, &ctx->d_freelab, n8);

@@ -53,6 +53,10 @@ struct GainArgs {
   uint32_t* counts;
   uint8_t* terminal;
   double* value;
+  const uint8_t* rec_plane;   // packed scan: the byte record plane, read once per candidate for the duplicated centre voxel
+  size_t rec_pitch;
+  const uint8_t* rec2_plane;  // packed scan: the 2-bit plane of the evaluator (path or reachability flavour)
+  size_t rec2_pitch;
   double* value2;         // optional second copy of value (the caller's pinned host array, written over PCIe by the kernel)
   const double* recip;    // ExpandLowCost lookup
   const int* sel;         // optional: candidate k of this launch is node sel[k] of the caller's arrays (outputs are scattered)
@@ -106,6 +110,13 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// carry-save adder on 32 bit columns at once: h:l = a + b + c per bit (two LOP3)
+#define SIPP_CSA(h, l, a, b, c) { const uint32_t u_ = (a) ^ (b); h = ((a) & (b)) | (u_ & (c)); l = u_ ^ (c); }
 __device__ __forceinline__ uint32_t bytesum(uint32_t v) { return __dp4a(v, 0x01010101u, 0u); }
 // mask with bytes [lo, hi) of a 4-byte word set, 0 <= lo, hi <= 4 after clamping
 __device__ __forceinline__ uint32_t byte_range_mask(int lo, int hi) {
@@ -113,6 +124,14 @@ __device__ __forceinline__ uint32_t byte_range_mask(int lo, int hi) {
   hi = min(hi, 4);
   if (hi <= lo) return 0u;
   return (0xFFFFFFFFu >> (8 * (4 - hi))) & (0xFFFFFFFFu << (8 * lo));
+}
+// mask with bits [lo, hi) of a 32-bit word set, after clamping to [0, 32]
+__device__ __forceinline__ uint32_t bit_range_mask(int lo, int hi) {
+  lo = max(lo, 0);
+  hi = min(hi, 32);
+  if (hi <= lo) return 0u;
+  const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+  return upto_hi & (0xFFFFFFFFu << lo);
 }
 // same for the two halfwords of a word, 0 <= lo, hi <= 2
 __device__ __forceinline__ uint32_t half_range_mask(int lo, int hi) {
@@ -128,6 +147,7 @@ struct Window {
   int on_map;        // getVoxelCenter returned true (map_planexp.cpp:78,87)
   int cx, cy;        // centre cell of the window (center_voxel_loc, :89)
   double vcx, vcy;   // centre voxel coordinates ((loc + 0.5) * vs, :74-76)
+  uint32_t crec;     // packed scan: byte record of the window's centre cell (the tile holds 2-bit records only)
 };
 
 __device__ __forceinline__ int trunc_to_int(double v) {
@@ -164,8 +184,14 @@ __device__ __forceinline__ int clipped_extent(int c, int h, int lo, int hi) {
 // Lane layout over a tile whose rows are `ncr` 16-byte chunks wide: lane = lrow * ncr + lcc for the first
 // rpi * ncr lanes (rpi = 32 / ncr rows are covered per iteration), the remaining lanes idle. A lane keeps its chunk
 // column for the whole scan, so the column masks of the (unaligned) window are computed once per candidate.
-template <int MODE>
-__global__ void __launch_bounds__(kMaxWarpsPerCta * 32)
+// PACKED (count-type evaluators): the window is read from the 2-bit-per-cell plane (bit 0 UNKNOWN, bit 1 UNKNOWN & path /
+// reachable; a 65-cell window row is 17 bytes instead of 65) with plain read-only loads straight into registers — no TMA, no
+// shared-memory tile, no mbarrier. Measured: a cp.async.bulk.tensor costs the SM ~130 cycles of TMA-unit time however small the
+// box (tools/gain_rows_probe.py: 30 us for 65536 candidates at 17 rows, 45 us at 65), which bounds the tiled form at one
+// candidate per ~200 cycles per SM; the direct form has no per-candidate fixed cost beyond its own instructions and runs two
+// CTAs per SM (no dynamic shared memory).
+template <int MODE, bool PACKED = false>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, PACKED ? 2 : 1)
 k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_aux, const GainArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[kMaxWarpsPerCta * kMaxStages];
@@ -212,6 +238,16 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   const int my_iters = (lane_on && lrow < side) ? (side - lrow + rpi - 1) / rpi : 0;
   // column masks of the unaligned window, tabulated once per CTA: entry [r0 * ncr + chunk] holds the four byte masks of
   // 16-byte chunk `chunk` when the window starts at byte r0 of the tile row (r0 = (cx - h) & 15)
+  uint32_t* mask32 = reinterpret_cast<uint32_t*>(mask_tbl);
+  if (PACKED) {
+    // entry [r0 * wpr + word]: window bits of 32-bit word `word` of a box row (16 cells each) when the window starts at cell r0
+    // of the box (0..63)
+    const int wpr_ = a.box_w >> 2;
+    for (int e = threadIdx.x; e < 64 * wpr_; e += blockDim.x) {
+      const int r0 = e / wpr_, wd = e - r0 * wpr_;
+      mask32[e] = bit_range_mask(2 * r0 - 32 * wd, 2 * (r0 + side) - 32 * wd);
+    }
+  } else
   for (int e = threadIdx.x; e < 16 * ncr; e += blockDim.x) {
     const int r0 = e / ncr, cc = e - r0 * ncr;
     const int lo = r0 - 16 * cc, hi = r0 + side - 16 * cc;   // valid bytes of the chunk: [lo, hi) clipped to [0,16)
@@ -220,16 +256,26 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   }
   __syncthreads();
 
+  // packed scan: lane = (row slot g, word column k) of the box; constants of the whole kernel
+  const int pk_wpr = PACKED ? (a.box_w >> 2) : 8, pk_rpp = 32 / pk_wpr;
+  const int pk_g = lane / pk_wpr, pk_k = lane - pk_g * pk_wpr;
+  const int pk_nrows = (PACKED && pk_g < pk_rpp) ? (side - pk_g + pk_rpp - 1) / pk_rpp : 0;     // rows pk_g, pk_g + rpp, ... < side
+  const int pk_span = pk_rpp * (pk_nrows > 0 ? pk_nrows - 1 : 0);                              // last row offset of this lane
+  const size_t pk_stride = (size_t)pk_rpp * a.rec2_pitch;
+
   // ---- per-batch lane state: the window of candidate (batch base + lane)
   Window cur, nxt;
   auto load_window = [&](int idx) {   // idx = index inside this warp's range
     Window w;
-    w.on_map = 0; w.cx = w.cy = -1000000; w.vcx = w.vcy = 0.0; w.cid = 0;
+    w.on_map = 0; w.cx = w.cy = -1000000; w.vcx = w.vcy = 0.0; w.cid = 0; w.crec = 0;
     if (idx < total) {
       const int cid = a.sel ? a.sel[c0 + idx] : c0 + idx;
       const double2 p = *reinterpret_cast<const double2*>(a.xy + 2 * (size_t)cid);
       w = make_window(a.g, p.x, p.y);
       w.cid = cid;
+      w.crec = 0;
+      if (PACKED && w.on_map && w.cx >= 0 && w.cx < a.g.W && w.cy >= 0 && w.cy < a.g.H)
+        w.crec = __ldg(a.rec_plane + (size_t)w.cy * a.rec_pitch + w.cx);      // needed only in the epilogue, a batch later
     }
     return w;
   };
@@ -250,8 +296,9 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   long long best_i = LLONG_MAX;
   if (total <= 0 && !fused) return;
   cur = load_window(lane);
-  for (int k = 0; k < kStages - 1 && k < total; ++k)
-    if (lane == k) issue(cur, k);   // kStages - 1 <= 7 < 32: all inside the first batch
+  if (!PACKED)
+    for (int k = 0; k < kStages - 1 && k < total; ++k)
+      if (lane == k) issue(cur, k);   // kStages - 1 <= 7 < 32: all inside the first batch
 
   int s = 0, s_issue = kStages - 1;   // slot being scanned / slot refilled next (the one scanned in the previous iteration)
   uint32_t parity = 0;
@@ -264,21 +311,99 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
 
     for (int j = 0; j < nb; ++j) {
       const int ahead = j + kStages - 1;
-      if (base + ahead < total) {
+      if (!PACKED && base + ahead < total) {
         __syncwarp();   // every lane is done reading the slot that is about to be refilled
         if (ahead < 32) { if (lane == ahead) issue(cur, s_issue); }
         else            { if (lane == ahead - 32) issue(nxt, s_issue); }
       }
       const uint32_t tile = slot_base + (uint32_t)s * (uint32_t)a.slot_bytes;
       const int wcx = __shfl_sync(0xFFFFFFFFu, cur.cx, j), wcy = __shfl_sync(0xFFFFFFFFu, cur.cy, j);
-      while (!mbar_try_wait(bar_base + 8u * s, parity)) {
-      }
+      if (!PACKED)
+        while (!mbar_try_wait(bar_base + 8u * s, parity)) {
+        }
 
       // ---- window scan -------------------------------------------------------------------------------
       uint32_t n_unk = 0, n_aux = 0;       // per-lane totals
       uint32_t sum_aux2 = 0;               // AverageViewCost: sum of labels
       double fsum = 0.0;                   // floating-point modes
-      if (kNeedRec && lane_on) {
+      if (PACKED) {
+        // lane = (row slot g, word column k): the 32 lanes of one load instruction read rpp consecutive rows x wpr words (one
+        // 16-byte-aligned run of 4 * wpr bytes per row). A lane sums ITS word column over its rows with
+        // bit-sliced carry-save adders (Harley-Seal, blocks of eight rows): the window mask is the same for every row of a
+        // column, so it is applied once to the counter planes, and eight rows cost 14 LOP3 + 2 POPC instead of 16 AND + 16 POPC.
+        // All loads of a block are issued before the first use; rows / words outside the plane read as 0.
+        const uint32_t m = mask32[((wcx - h) & 63) * pk_wpr + pk_k];
+        const int colbyte = (((wcx - h) >> 2) & ~15) + 4 * pk_k;              // byte column of this lane's word (may be off the plane)
+        const bool colok = colbyte >= 0 && colbyte + 4 <= (int)a.rec2_pitch;
+        int nrows = (m != 0u && colok) ? pk_nrows : 0;
+        int y = wcy - h + pk_g;                                               // this lane's rows: y, y + rpp, ...
+        uint32_t ones = 0, twos = 0, fours = 0, c8b = 0, c8a = 0, sb = 0, sa = 0;
+        if (y >= 0 && y + pk_span < a.g.H) {
+          // every row is on the plane (all candidates except those within half_fov of the top / bottom edge): no per-load tests
+          const uint8_t* ptr = a.rec2_plane + (size_t)y * a.rec2_pitch + colbyte;
+#define SIPP_LD(j) __ldg(reinterpret_cast<const uint32_t*>(ptr + (j) * pk_stride))
+#define SIPP_HS8(x0, x1, x2, x3, x4, x5, x6, x7)                                   \
+  {                                                                                \
+    uint32_t ta, tb, fa, fb, e8;                                                   \
+    SIPP_CSA(ta, ones, ones, x0, x1);                                              \
+    SIPP_CSA(tb, ones, ones, x2, x3);                                              \
+    SIPP_CSA(fa, twos, twos, ta, tb);                                              \
+    SIPP_CSA(ta, ones, ones, x4, x5);                                              \
+    SIPP_CSA(tb, ones, ones, x6, x7);                                              \
+    SIPP_CSA(fb, twos, twos, ta, tb);                                              \
+    SIPP_CSA(e8, fours, fours, fa, fb);                                            \
+    e8 &= m;                                                                       \
+    c8b += __popc(e8);                                                             \
+    c8a += __popc(e8 & 0xAAAAAAAAu);                                               \
+  }
+          // every load of the window is issued before the first use (one L2 round trip per candidate, not one per block): an odd
+          // last row first, then blocks of sixteen / eight rows
+          uint32_t xl = 0;
+          if (nrows & 1) xl = __ldg(reinterpret_cast<const uint32_t*>(ptr + (size_t)(nrows - 1) * pk_stride)) & m;
+          nrows &= ~1;
+          for (; nrows >= 16; nrows -= 16) {
+            const uint32_t x0 = SIPP_LD(0), x1 = SIPP_LD(1), x2 = SIPP_LD(2), x3 = SIPP_LD(3), x4 = SIPP_LD(4), x5 = SIPP_LD(5), x6 = SIPP_LD(6),
+                           x7 = SIPP_LD(7), x8 = SIPP_LD(8), x9 = SIPP_LD(9), xa = SIPP_LD(10), xb = SIPP_LD(11), xc = SIPP_LD(12), xd = SIPP_LD(13),
+                           xe = SIPP_LD(14), xf = SIPP_LD(15);
+            ptr += 16 * pk_stride;
+            SIPP_HS8(x0, x1, x2, x3, x4, x5, x6, x7)
+            SIPP_HS8(x8, x9, xa, xb, xc, xd, xe, xf)
+          }
+          if (nrows >= 8) {
+            const uint32_t x0 = SIPP_LD(0), x1 = SIPP_LD(1), x2 = SIPP_LD(2), x3 = SIPP_LD(3), x4 = SIPP_LD(4), x5 = SIPP_LD(5), x6 = SIPP_LD(6),
+                           x7 = SIPP_LD(7);
+            ptr += 8 * pk_stride;
+            nrows -= 8;
+            SIPP_HS8(x0, x1, x2, x3, x4, x5, x6, x7)
+          }
+          for (; nrows > 0; --nrows) {
+            const uint32_t x = SIPP_LD(0) & m;
+            ptr += pk_stride;
+            sb += __popc(x);
+            sa += __popc(x & 0xAAAAAAAAu);
+          }
+          sb += __popc(xl);
+          sa += __popc(xl & 0xAAAAAAAAu);
+#undef SIPP_LD
+#undef SIPP_HS8
+        } else {
+          // window cut by the top / bottom edge: rows off the plane read as 0
+          const uint8_t* col = a.rec2_plane + colbyte;
+          for (; nrows > 0; --nrows) {
+            if (y >= 0 && y < a.g.H) {
+              const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)y * a.rec2_pitch)) & m;
+              sb += __popc(x);
+              sa += __popc(x & 0xAAAAAAAAu);
+            }
+            y += pk_rpp;
+          }
+        }
+        ones &= m; twos &= m; fours &= m;
+        const uint32_t both = __popc(ones) + 2u * __popc(twos) + 4u * __popc(fours) + 8u * c8b + sb;
+        const uint32_t aux = __popc(ones & 0xAAAAAAAAu) + 2u * __popc(twos & 0xAAAAAAAAu) + 4u * __popc(fours & 0xAAAAAAAAu) + 8u * c8a + sa;
+        n_unk = both - aux;                            // bit 1 (aux) is only ever set together with bit 0
+        n_aux = aux;
+      } else if (kNeedRec && lane_on) {
         const int r0 = (wcx - h) & 15;                 // the window occupies tile columns [r0, r0 + side)
         const uint4 m = mask_tbl[r0 * ncr + lcc];      // byte masks of this lane's 16-byte chunk column for that offset
         const uint32_t m0 = m.x, m1 = m.y, m2 = m.z, m3 = m.w;
@@ -373,7 +498,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
         my_unk = n_unk; my_aux = n_aux; my_sum2 = sum_aux2;
         if (kFloat) my_fsum = fsum;
         // the window centre cell sits at tile position (h, cx - aligned box start); only meaningful for on-map candidates
-        if (kNeedRec) my_crec = lds8(tile + (uint32_t)(h * a.box_w + (wcx - ((wcx - h) & ~15))));
+        if (PACKED) my_crec = cur.crec;
+        else if (kNeedRec) my_crec = lds8(tile + (uint32_t)(h * a.box_w + (wcx - ((wcx - h) & ~15))));
         if (kNeedAux) my_caux16 = lds16(tile + (uint32_t)a.aux_off + 2u * (uint32_t)(h * a.box_w16 + (wcx - ((wcx - h) & ~7))));
       }
       s_issue = s;
@@ -548,10 +674,10 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_tmap(sipp_ctx* ctx, CUtensorMap* out, void* base, int elem_bytes, size_t pitch_bytes, int box_w_elems, int box_h) {
+int make_tmap(sipp_ctx* ctx, CUtensorMap* out, void* base, int elem_bytes, size_t pitch_bytes, int box_w_elems, int box_h, int width_elems = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)ctx->W, (cuuint64_t)ctx->H};
+  cuuint64_t dims[2] = {(cuuint64_t)(width_elems > 0 ? width_elems : ctx->W), (cuuint64_t)ctx->H};
   cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_w_elems, (cuuint32_t)box_h};
   cuuint32_t estr[2] = {1, 1};
@@ -561,6 +687,10 @@ int make_tmap(sipp_ctx* ctx, CUtensorMap* out, void* base, int elem_bytes, size_
   if (r != CUDA_SUCCESS) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) box %dx%d", (int)r, box_w_elems, box_h);
   return SIPP_OK;
 }
+
+// bytes of a 2-bit-plane row that `side` cells can touch ((side + 2) / 4 + 1), plus up to 15 bytes of slack for the 16-byte
+// alignment of the box start, rounded up to the 16-byte granularity of TMA
+int packed_box_w(int side) { return (15 + (side + 2) / 4 + 1 + 15) & ~15; }
 
 const CUtensorMap* cached_tmap(sipp_ctx* ctx, int half_fov, int kind, int* rc) {
   for (auto& e : ctx->tma_cache)
@@ -572,13 +702,14 @@ const CUtensorMap* cached_tmap(sipp_ctx* ctx, int half_fov, int kind, int* rc) {
   // box width: the window plus up to 15 (7) cells of slack for the 16-byte alignment of the box start
   if (kind == 0) *rc = make_tmap(ctx, &e.map, ctx->d_rec, 1, ctx->pitch, (side + 15 + 15) & ~15, side);
   else if (kind == 1) *rc = make_tmap(ctx, &e.map, ctx->d_freelab, 2, ctx->pitch16 * 2, (side + 7 + 7) & ~7, side);
-  else *rc = make_tmap(ctx, &e.map, ctx->d_closest, 2, ctx->pitch16 * 2, (side + 7 + 7) & ~7, side);
+  else if (kind == 2) *rc = make_tmap(ctx, &e.map, ctx->d_closest, 2, ctx->pitch16 * 2, (side + 7 + 7) & ~7, side);
+  else *rc = sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "unknown tensor map kind %d", kind);
   if (*rc != SIPP_OK) return nullptr;
   ctx->tma_cache.push_back(e);
   return &ctx->tma_cache.back().map;
 }
 
-template <int MODE>
+template <int MODE, bool PACKED = false>
 int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_aux, const GainArgs& a, cudaStream_t s) {
   static int num_sms = 0;
   if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -586,17 +717,18 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
   const int kStages = a.stages;
   int wpc = ctx->gain_warps > 0 ? ctx->gain_warps : kMaxWarpsPerCta;
   while (wpc > 1 && (size_t)wpc * kStages * a.slot_bytes > 220 * 1024) --wpc;
-  const size_t smem = (size_t)wpc * kStages * a.slot_bytes;
+  const size_t smem = PACKED ? 0 : (size_t)wpc * kStages * a.slot_bytes;     // the packed form keeps no tiles
   if (smem > 227 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %zu bytes of shared memory per CTA", a.half_fov, smem);
-  cudaError_t e = cudaFuncSetAttribute(k_gain<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = k_gain<MODE, PACKED>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gain<MODE>, wpc * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem);
   if (e != cudaSuccess || occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
   const int want = (a.n + wpc - 1) / wpc;
   int grid = want < num_sms * occ ? want : num_sms * occ;   // persistent: a multiple of the SM count when saturated
   if (a.best_out && grid > kSelMaxBlocks) grid = kSelMaxBlocks;   // one partial record per CTA in the argmax workspace
-  k_gain<MODE><<<grid, wpc * 32, smem, s>>>(*tm_rec, *tm_aux, a);
+  kern<<<grid, wpc * 32, smem, s>>>(*tm_rec, *tm_aux, a);
   ctx->launches += 1;
   e = cudaGetLastError();
   if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_gain launch: %s", cudaGetErrorString(e));
@@ -662,15 +794,25 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   }
   if (mode == MODE_COUNT && p->evaluator == SIPP_EVAL_RRT_STAR && p->do_binary_check && p->use_distance_discount && !d_start_xy)
     return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "RRTStarEvaluator binary+discount mode needs start_xy (trajectory[0])");
+  // count-type evaluators scan the 2-bit plane (SIPP_GAIN_PACKED=0: the byte record, as the other evaluators do)
+  static const bool packed_env = !(getenv("SIPP_GAIN_PACKED") && atoi(getenv("SIPP_GAIN_PACKED")) == 0);
+  const bool packed = packed_env && mode == MODE_COUNT && packed_box_w(side) <= 64;   // mask table: 64 cell offsets x <= 4 chunks
+  if (packed) {
+    a.box_w = packed_box_w(side);
+    a.rec_plane = ctx->d_rec;
+    a.rec_pitch = ctx->pitch;
+    a.rec2_plane = ctx->d_rec2[p->evaluator == SIPP_EVAL_EXPAND_REACHABLE ? 1 : 0];
+    a.rec2_pitch = ctx->pitch / 4;
+  }
   const size_t rec_bytes = (size_t)a.box_w * side, aux_bytes = (size_t)a.box_w16 * 2 * side;
   const bool need_aux = (mode == MODE_AVG_VIEW_COST || mode == MODE_LOW_COST), need_rec = (mode != MODE_LOW_COST);
   a.aux_off = need_rec ? (int)((rec_bytes + 127) & ~(size_t)127) : 0;
   a.slot_bytes = (int)((need_aux ? (a.aux_off + aux_bytes) : rec_bytes) + 127) & ~127;
-  a.stages = ctx->gain_stages > 0 ? ctx->gain_stages : 2;
+  a.stages = ctx->gain_stages > 0 ? ctx->gain_stages : (packed ? 4 : 2);
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   while (a.stages > 2 && (size_t)a.stages * a.slot_bytes > 220 * 1024) --a.stages;
   int rc = SIPP_OK;
-  const CUtensorMap* tm_rec = cached_tmap(ctx, h, 0, &rc);
+  const CUtensorMap* tm_rec = cached_tmap(ctx, h, 0, &rc);      // the packed form does not use it (plain loads)
   if (!tm_rec) return rc;
   const CUtensorMap* tm_aux = tm_rec;
   if (need_aux) {
@@ -678,7 +820,7 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
     if (!tm_aux) return rc;
   }
   switch (mode) {
-    case MODE_COUNT: return launch_mode<MODE_COUNT>(ctx, tm_rec, tm_aux, a, s);
+    case MODE_COUNT: return packed ? launch_mode<MODE_COUNT, true>(ctx, tm_rec, tm_aux, a, s) : launch_mode<MODE_COUNT>(ctx, tm_rec, tm_aux, a, s);
     case MODE_RRT_DISCOUNT: return launch_mode<MODE_RRT_DISCOUNT>(ctx, tm_rec, tm_aux, a, s);
     case MODE_GOAL_DISTANCE: return launch_mode<MODE_GOAL_DISTANCE>(ctx, tm_rec, tm_aux, a, s);
     case MODE_AVG_VIEW_COST: return launch_mode<MODE_AVG_VIEW_COST>(ctx, tm_rec, tm_aux, a, s);

@@ -126,6 +126,8 @@ struct sipp_ctx {
   uint16_t* d_pcode;     // planner code
   uint8_t* d_path;       // path mask 0/1
   uint8_t* d_rec;        // packed gain record (view)
+  uint8_t* d_rec2[2];    // 2 bits per cell (4 cells per byte, row pitch = pitch / 4): bit 0 UNKNOWN, bit 1 UNKNOWN & path [0] / & reachable [1]
+                         // (both inside the bounding volume) — what the count-type evaluators scan
   uint16_t* d_freelab;   // view: label where state == FREE (inside bv) else 0   (AverageViewCost)
   uint16_t* d_closest;   // ExpandLowCost view: closest-observed cost index + counted flag per cell (k_build_lowcost_view)
   uint16_t* d_cclab;     // map_cost_closest_ (label of the closest observed cell), only with compute_closest_observed

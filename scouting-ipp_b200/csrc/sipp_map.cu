@@ -102,7 +102,8 @@ __global__ void k_build_lowcost_view(const uint8_t* __restrict__ state, const ui
 __global__ void k_build_views(const uint8_t* __restrict__ state, const uint8_t* __restrict__ path,
                               const uint16_t* __restrict__ label, uint8_t* __restrict__ rec,
                               uint16_t* __restrict__ freelab, size_t pitch, size_t pitch16, int W, int H, int bv_kx_lo,
-                              int bv_kx_hi, int bv_ky_lo, int bv_ky_hi, int reach_x, int reach_y, int use_reach) {
+                              int bv_kx_hi, int bv_ky_lo, int bv_ky_hi, int reach_x, int reach_y, int use_reach,
+                              uint8_t* __restrict__ rec2_path, uint8_t* __restrict__ rec2_reach) {
   const int chunks_per_row = (int)(pitch / 16);
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)chunks_per_row * H) return;
@@ -117,6 +118,7 @@ __global__ void k_build_views(const uint8_t* __restrict__ state, const uint8_t* 
   const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
   uint32_t rw[4] = {0, 0, 0, 0};
   uint32_t fw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t w2p = 0, w2r = 0;     // 2 bits per cell: bit 0 = REC_UNK, bit 1 = REC_UNK_PATH / REC_UNK_REACH (the count evaluators' planes)
   const bool row_in_bv = (y >= bv_ky_lo && y <= bv_ky_hi);
   const bool row_reach = use_reach && (y >= reach_y - 1 && y <= reach_y + 1);
 #pragma unroll
@@ -139,8 +141,13 @@ __global__ void k_build_views(const uint8_t* __restrict__ state, const uint8_t* 
     if (inside && pm) r |= REC_PATH_RAW;
     if (r3) r |= REC_REACH_RAW;
     rw[b >> 2] |= r << ((b & 3) * 8);
+    w2p |= ((r & REC_UNK) | (r & REC_UNK_PATH)) << (2 * b);                 // REC_UNK = 1, REC_UNK_PATH = 2: already the two bits
+    w2r |= ((r & REC_UNK) | ((r & REC_UNK_REACH) >> 1)) << (2 * b);
     if (inbv && st == SIPP_STATE_FREE) fw[b >> 1] |= lb << ((b & 1) * 16);
   }
+  const size_t o2 = (size_t)y * (pitch / 4) + (size_t)(xc / 4);
+  *reinterpret_cast<uint32_t*>(rec2_path + o2) = w2p;
+  *reinterpret_cast<uint32_t*>(rec2_reach + o2) = w2r;
   *reinterpret_cast<uint4*>(rec + (size_t)y * pitch + xc) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
   *reinterpret_cast<uint4*>(freelab + (size_t)y * pitch16 + xc) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
   *reinterpret_cast<uint4*>(freelab + (size_t)y * pitch16 + xc + 8) = make_uint4(fw[4], fw[5], fw[6], fw[7]);
@@ -179,6 +186,8 @@ cudaError_t launch_clear_planes(sipp_ctx* ctx, cudaStream_t s) {
   if ((e = cudaMemsetAsync(ctx->d_path, 0, n8, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_mark, 0, n8, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_rec, 0, n8, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_rec2[0], 0, n8 / 4, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_rec2[1], 0, n8 / 4, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_freelab, 0, n16 * 2, s)) != cudaSuccess) return e;
   ctx->launches += 6;
   return cudaSuccess;
@@ -207,7 +216,7 @@ cudaError_t launch_build_views(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cu
   const int klo_y = use_bv ? g.bv_ky_lo : 0, khi_y = use_bv ? g.bv_ky_hi : ctx->H - 1;
   k_build_views<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_path, ctx->d_label, ctx->d_rec, ctx->d_freelab,
                                            ctx->pitch, ctx->pitch16, ctx->W, ctx->H, klo_x, khi_x, klo_y, khi_y,
-                                           ctx->start_loc[0], ctx->start_loc[1], ctx->desc.compute_reachability);
+                                           ctx->start_loc[0], ctx->start_loc[1], ctx->desc.compute_reachability, ctx->d_rec2[0], ctx->d_rec2[1]);
   ctx->launches += 1;
   return cudaGetLastError();
 }

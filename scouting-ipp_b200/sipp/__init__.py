@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libsipp.so")
+LIB_PATH = os.environ.get("SIPP_LIB_PATH") or os.path.join(_PKG, "libsipp.so")   # the override is for A/B runs of two builds
 
 MAX_IDS = 32
 COUNTS_PER_CANDIDATE = 4

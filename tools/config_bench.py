@@ -44,6 +44,7 @@ def eval_case(ctx, W, seed, T, npg, rep=1):
 
 
 def plan_case(ctx, reps=5):
+    ctx.set_incremental(False)      # from scratch
     ctx.plan()
     ts = []
     for _ in range(reps):

@@ -14,6 +14,7 @@ for cfg in cfgs:
     alpha, window = cfg.split(":")
     os.environ["SIPP_RELAX_ALPHA"] = alpha; os.environ["SIPP_RELAX_WINDOW"] = window
     ctx = sipp.Context(desc)
+    ctx.set_incremental(False)      # every plan below starts from scratch
     ctx.map_upload_full(lab, obs)
     ts = []
     for i in range(6):
