@@ -385,9 +385,10 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_gain<MODE_COUNT>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_gain<MODE_COUNT, packed>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": g_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * T,
-                "note": "the 16 MiB record plane is L2-resident by nature (126 MB L2): frac > 1 of the HBM copy peak is expected; see traffic"}
+                "note": "algorithmic bytes = one byte per window cell + pose + result (SURVEY 8(d)); the kernel reads a 2-bit-per-cell plane (4 MiB, L2 resident "
+                        "by nature: 126 MB L2), so frac > 1 of the HBM copy peak is expected; see traffic. It is bound by instruction issue and L2 latency, not by bytes"}
 
     # ---- end to end through the host-pointer C ABI (sipp_cycle): pinned host buffers, H2D + D2H inside the timed region
     h_xy = torch.from_numpy(xy).pin_memory()
@@ -524,7 +525,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 counts + f64 gain", "data": "synthetic",
         "config": {"workload": WORKLOAD, "candidates_per_gpu": T, "map": "%dx%d" % (W, H), "half_fov": HALF_FOV,
-                   "l2": "flushed between timed steps (256 MiB write, untimed); the 16 MiB record plane is smaller than L2",
+                   "l2": "flushed between timed steps (256 MiB write, untimed); the scanned planes (4 + 16 MiB) are smaller than L2",
                    "sharding": ("single GPU" if world == 1 else
                                 "candidates sharded, map replicated; the gain kernel's last CTA stores each shard's 16-byte winner into every peer's mailbox "
                                 "over NVLink (peer memory), waits for the peers' records of the same step and merges them: every step ends with the global "
