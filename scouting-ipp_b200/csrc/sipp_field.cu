@@ -892,10 +892,13 @@ k_pred(const PredArgs a) {
 // threads (re)load the window whenever the walk leaves it (>= 112 steps per load), then thread 0 chases the bytes.
 constexpr int PW = 256;
 constexpr int kBackThreads = 256;
+constexpr int kWalk = 112;      // steps per window load: the window is centred on the current node (x0 aligned down to 16)
+static_assert(PW == 256, "the walk packs a window cell as (ly << 8) | lx");
 __global__ void __launch_bounds__(kBackThreads)
 k_backtrack(const PathArgs a) {
   extern __shared__ __align__(16) uint8_t win[];     // [PW][PW]
-  __shared__ int s_x, s_y, s_len, s_fail;
+  __shared__ int s_x, s_y, s_len, s_fail, s_n;
+  __shared__ unsigned short s_buf[kWalk];
   const FieldGeom& g = a.g;
   const int tid = threadIdx.x;
   if (a.redo && *a.redo == 0) return;
@@ -931,16 +934,40 @@ k_backtrack(const PathArgs a) {
     }
     __syncthreads();
     if (tid == 0) {
-      int lx = x - x0, ly = y - y0;
-      while ((unsigned)lx < (unsigned)PW && (unsigned)ly < (unsigned)PW && !(x == g.start_x && y == g.start_y)) {
-        const int p = win[ly * PW + lx];
-        if (p > 7 || len >= a.cap || x < 0 || x >= g.W) { fail = true; break; }
-        const int dx = (p >= 5) - (p <= 2);                                   // NDX = {-1,-1,-1,0,0,1,1,1}
-        const int dy = (p == 2 || p == 4 || p == 7) - (p == 0 || p == 3 || p == 5);   // NDY = {-1,0,1,-1,1,-1,0,1}
-        x += dx; y += dy; lx += dx; ly += dy;
-        a.nodes[len++] = (x << 16) | y;
+      // kWalk steps cannot leave the window (the walk starts >= kWalk cells from every edge and moves one cell per step), so the
+      // chase is: byte load -> two shifts for (dx, dy) -> add, with no bounds tests; the visited cells go to a shared buffer and
+      // all threads turn them into node records afterwards.
+      int li = (y - y0) * PW + (x - x0);
+      const int sx = g.start_x - x0, sy = g.start_y - y0;
+      const int li_start = ((unsigned)sx < (unsigned)PW && (unsigned)sy < (unsigned)PW) ? sy * PW + sx : -1;
+      const int maxn = min(kWalk, a.cap - len);
+      int n = 0;
+      if (x < 0 || x >= g.W || y < 0 || y >= g.H || maxn <= 0) fail = true;
+      while (!fail && n < maxn) {
+        const int p = win[li];
+        if (p > 7) { fail = true; break; }
+        // NDX = {-1,-1,-1,0,0,1,1,1}, NDY = {-1,0,1,-1,1,-1,0,1} as 2-bit fields (value + 1)
+        li += (int)((0x9224u >> (2 * p)) & 3u) * PW + (int)((0xA940u >> (2 * p)) & 3u) - (PW + 1);
+        s_buf[n++] = (unsigned short)li;
+        if (li == li_start) break;
       }
-      s_x = x; s_y = y; s_len = len; s_fail = fail ? 1 : 0;
+      s_n = n;
+      s_fail = fail ? 1 : 0;
+    }
+    __syncthreads();
+    {
+      const int n = s_n, len0 = s_len;
+      for (int i = tid; i < n; i += kBackThreads) {
+        const int li = s_buf[i];
+        a.nodes[len0 + i] = ((x0 + (li & (PW - 1))) << 16) | (y0 + (li >> 8));
+      }
+      __syncthreads();
+      if (tid == 0 && n > 0) {
+        const int li = s_buf[n - 1];
+        s_x = x0 + (li & (PW - 1));
+        s_y = y0 + (li >> 8);
+        s_len = len0 + n;
+      }
     }
     __syncthreads();
   }
