@@ -487,7 +487,7 @@ def main():
 
     # ---- CPU baseline beside it: the oracle port of the reference evaluators on this box's host cores (bounded sample)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline belongs to the N = 1 line (the reference arm times it at every N)
         from oracle import oracle as orc
         odesc = orc.make_desc(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), min(ids), max(ids), max(ids))
         o = orc.Oracle(odesc)
