@@ -261,7 +261,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   const int pk_g = lane / pk_wpr, pk_k = lane - pk_g * pk_wpr;
   const int pk_nrows = (PACKED && pk_g < pk_rpp) ? (side - pk_g + pk_rpp - 1) / pk_rpp : 0;     // rows pk_g, pk_g + rpp, ... < side
   const int pk_span = pk_rpp * (pk_nrows > 0 ? pk_nrows - 1 : 0);                              // last row offset of this lane
-  const size_t pk_stride = (size_t)pk_rpp * a.rec2_pitch;
+  const uint32_t pk_pitch = (uint32_t)a.rec2_pitch;                    // the plane is far below 4 GiB: 32-bit offsets, one IMAD.WIDE per address
+  const uint32_t pk_stride = (uint32_t)pk_rpp * pk_pitch;
 
   // ---- per-batch lane state: the window of candidate (batch base + lane)
   Window cur, nxt;
@@ -340,8 +341,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
         uint32_t ones = 0, twos = 0, fours = 0, c8b = 0, c8a = 0, sb = 0, sa = 0;
         if (y >= 0 && y + pk_span < a.g.H) {
           // every row is on the plane (all candidates except those within half_fov of the top / bottom edge): no per-load tests
-          const uint8_t* ptr = a.rec2_plane + (size_t)y * a.rec2_pitch + colbyte;
-#define SIPP_LD(j) __ldg(reinterpret_cast<const uint32_t*>(ptr + (j) * pk_stride))
+          const uint8_t* ptr = a.rec2_plane + (size_t)((uint32_t)y * pk_pitch + (uint32_t)colbyte);
+#define SIPP_LD(j) __ldg(reinterpret_cast<const uint32_t*>(ptr + (size_t)((uint32_t)(j) * pk_stride)))
 #define SIPP_HS8(x0, x1, x2, x3, x4, x5, x6, x7)                                   \
   {                                                                                \
     uint32_t ta, tb, fa, fb, e8;                                                   \
@@ -359,20 +360,20 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           // every load of the window is issued before the first use (one L2 round trip per candidate, not one per block): an odd
           // last row first, then blocks of sixteen / eight rows
           uint32_t xl = 0;
-          if (nrows & 1) xl = __ldg(reinterpret_cast<const uint32_t*>(ptr + (size_t)(nrows - 1) * pk_stride)) & m;
+          if (nrows & 1) xl = __ldg(reinterpret_cast<const uint32_t*>(ptr + (size_t)((uint32_t)(nrows - 1) * pk_stride))) & m;
           nrows &= ~1;
           for (; nrows >= 16; nrows -= 16) {
             const uint32_t x0 = SIPP_LD(0), x1 = SIPP_LD(1), x2 = SIPP_LD(2), x3 = SIPP_LD(3), x4 = SIPP_LD(4), x5 = SIPP_LD(5), x6 = SIPP_LD(6),
                            x7 = SIPP_LD(7), x8 = SIPP_LD(8), x9 = SIPP_LD(9), xa = SIPP_LD(10), xb = SIPP_LD(11), xc = SIPP_LD(12), xd = SIPP_LD(13),
                            xe = SIPP_LD(14), xf = SIPP_LD(15);
-            ptr += 16 * pk_stride;
+            ptr += (size_t)(16u * pk_stride);
             SIPP_HS8(x0, x1, x2, x3, x4, x5, x6, x7)
             SIPP_HS8(x8, x9, xa, xb, xc, xd, xe, xf)
           }
           if (nrows >= 8) {
             const uint32_t x0 = SIPP_LD(0), x1 = SIPP_LD(1), x2 = SIPP_LD(2), x3 = SIPP_LD(3), x4 = SIPP_LD(4), x5 = SIPP_LD(5), x6 = SIPP_LD(6),
                            x7 = SIPP_LD(7);
-            ptr += 8 * pk_stride;
+            ptr += (size_t)(8u * pk_stride);
             nrows -= 8;
             SIPP_HS8(x0, x1, x2, x3, x4, x5, x6, x7)
           }
@@ -391,7 +392,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           const uint8_t* col = a.rec2_plane + colbyte;
           for (; nrows > 0; --nrows) {
             if (y >= 0 && y < a.g.H) {
-              const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)y * a.rec2_pitch)) & m;
+              const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)((uint32_t)y * pk_pitch))) & m;
               sb += __popc(x);
               sa += __popc(x & 0xAAAAAAAAu);
             }
