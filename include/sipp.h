@@ -308,6 +308,9 @@ int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params
  * in index order would select (largest value, lowest global index on ties; NaN / empty shards never win). No collective
  * library and no host round trip on the data path. All ranks must issue the same sequence of shard calls (lockstep); a rank
  * that waits longer than the timeout (SIPP_PEER_TIMEOUT_MS, default 20000) returns index -3 and sipp_peer_status != 0.
+ * The blocking host-pointer form (sipp_cycle_shard) needs one rank per device: ranks that share a device share its driver
+ * context, and a rank blocked in its call keeps the peer it waits for from launching — contexts that share a device use
+ * the asynchronous _dev forms, enqueued by one thread.
  * Replaces, for N GPUs, [upstream] SubsequentBest::selectNextBest over the whole candidate set. */
 #define SIPP_PEER_MAX_WORLD 16
 #define SIPP_PEER_HANDLE_BYTES 128

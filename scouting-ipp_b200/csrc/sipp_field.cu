@@ -1174,10 +1174,15 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   }
   const size_t relax_smem = kRelaxWarps * sizeof(TileSmem);
-  if (!occ) {   // once per process (per device would be the same answer: sm_100a only)
+  // function attributes belong to the device: once per device of this process (several contexts / devices per host process)
+  static bool attr_done[64] = {};
+  const int dev_slot = ctx->device & 63;
+  if (!attr_done[dev_slot] || !occ) {
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
     SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, relax_smem));
     if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
+    attr_done[dev_slot] = true;
   }
   RelaxArgs ra;
   ra.g = g;
@@ -1229,11 +1234,6 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_redo, 0, sizeof(int), s));
     k_path_check<<<(ctx->path_cap_nodes + 255) / 256, 256, 0, s>>>(ctx->d_path_nodes, ctx->d_plan_out, ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, d_redo);
     ctx->launches += 1;
-  }
-  static bool back_attr = false;
-  if (!back_attr) {
-    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
-    back_attr = true;
   }
   PredArgs pr;
   pr.g = g;

@@ -54,3 +54,17 @@ def test_cfg_files_mirror_reference_keys():
 def test_modules_parity_on_gpu(test_binary):
     out = _run(test_binary, "gpu")
     assert "gpu: 0 failure(s)" in out
+
+
+@pytest.mark.gpu
+def test_cpp_host_threads_drive_sharded_contexts(test_binary):
+    """tests/cpp/test_shard_threads.cpp: a C++ host with one std::thread per rank (contexts of one process, one per visible
+    device) scores shards with sipp_cycle_shard; the ranks meet in the kernels' peer-memory exchange; winners match the oracle."""
+    import torch
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "test_shard_threads"], stdout=subprocess.DEVNULL)
+    binary = os.path.join(ROOT, "tests", "cpp", "test_shard_threads")
+    ndev = max(1, torch.cuda.device_count())
+    for ranks in sorted({1, min(2, ndev), min(4, ndev)}):      # one rank per device (the blocking host-pointer calls need that)
+        p = subprocess.run([binary, str(ranks), str(ranks)], capture_output=True, text=True, timeout=300)
+        print(p.stdout[-2000:], p.stderr[-2000:])
+        assert p.returncode == 0 and "0 failure(s)" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
