@@ -110,11 +110,6 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
 // carry-save adder on 32 bit columns at once: h:l = a + b + c per bit (two LOP3)
 #define SIPP_CSA(h, l, a, b, c) { const uint32_t u_ = (a) ^ (b); h = ((a) & (b)) | (u_ & (c)); l = u_ ^ (c); }
 __device__ __forceinline__ uint32_t bytesum(uint32_t v) { return __dp4a(v, 0x01010101u, 0u); }
