@@ -566,9 +566,10 @@ struct InvalArgs {
   int start_x, start_y;
   int* flags; int* queue; int cap; int* ctl;
   uint8_t* tile_seed;       // [ntiles] out: tile holds invalidated cells
+  int* plan_out;            // [5] <- cells invalidated
   int spin_limit;
 };
-enum { CTL_MARKED = 7 };
+enum { CTL_MARKED = 7, CTL_EXITED = 8 };
 
 __global__ void __launch_bounds__(kInvalWarps * 32)
 k_inval(const InvalArgs a) {
@@ -722,21 +723,46 @@ k_inval(const InvalArgs a) {
     }
   }
   if (marked_local) atomicAdd(&a.ctl[CTL_MARKED], marked_local);
+  // the last warp to leave hands the queue over to the relaxation: every slot is back to -1 and every flag to 0 (whatever was
+  // pushed has been popped), only the counters have to be rewound — no separate reset kernel between the two phases
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    const int total = (int)gridDim.x * kInvalWarps;
+    if (atomicAdd(&a.ctl[CTL_EXITED], 1) == total - 1) {
+      __threadfence();
+      a.plan_out[5] = ld_volatile_i32(&a.ctl[CTL_MARKED]);
+      st_volatile_i32(&a.ctl[CTL_HEAD], 0);
+      st_volatile_i32(&a.ctl[CTL_TAIL], 0);
+      st_volatile_i32(&a.ctl[CTL_PENDING], 0);
+    }
+  }
 }
 
-// queue <- the listed tiles (the tiles the patches touched); also flags them as seeds of the relaxation
-__global__ void k_seed_from_list(const int* list, int n, int* flags, int* queue, int* ctl, uint8_t* tile_seed) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const int t = list[i];
-    flags[t] = ST_QUEUED;
-    queue[i] = t;
-    tile_seed[t] = 1;
+// First kernel of an incremental plan: resets the work queue and seeds it with the tiles the patches touched. `list` (nl tile
+// ids, the queue order) and `seedmap` (one byte per tile, the same set) come from the host in one copy; seedmap == nullptr: none.
+__global__ void k_inc_begin(const int* list, int nl, const uint8_t* seedmap, int ntiles, int qcap, int* flags, int* queue, int* ctl,
+                            uint8_t* tile_seed, int* plan_out) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int t = i0; t < ntiles; t += stride) {
+    const uint8_t sd = seedmap ? seedmap[t] : (uint8_t)0;
+    flags[t] = sd ? ST_QUEUED : 0;
+    tile_seed[t] = sd;
   }
-  if (i == 0) { ctl[CTL_TAIL] = n; ctl[CTL_PENDING] = n; }
+  for (int i = i0; i < qcap; i += stride) queue[i] = i < nl ? list[i] : -1;
+  if (i0 == 0) {
+    for (int k = 0; k < 32; ++k) ctl[k] = 0;
+    ctl[CTL_TAIL] = nl;
+    ctl[CTL_PENDING] = nl;
+    plan_out[5] = 0;      // cells invalidated
+    plan_out[6] = 0;      // tiles the relaxation starts from
+    plan_out[7] = 0;      // "redo the path" flag of k_path_check
+  }
 }
-// queue <- every tile that is a seed or touches one (the invalidated region and its rim, the patch tiles)
-__global__ void k_seed_relax(const uint8_t* tile_seed, int ntx, int nty, int* flags, int* queue, int* ctl) {
+// Between k_inval and k_relax: queue <- every tile that is a seed or touches one (the invalidated region and its rim, the patch
+// tiles); the marks of the seed tiles are cleared for the next plan (all marks live in seed tiles).
+__global__ void k_seed_relax(const uint8_t* tile_seed, int ntx, int nty, int* flags, int* queue, int* ctl, uint8_t* mark, size_t pitch, int H,
+                             int* plan_out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntx * nty) return;
   const int tx = t % ntx, ty = t / ntx;
@@ -746,10 +772,20 @@ __global__ void k_seed_relax(const uint8_t* tile_seed, int ntx, int nty, int* fl
       const int x = tx + dx, y = ty + dy;
       if (x >= 0 && x < ntx && y >= 0 && y < nty && tile_seed[y * ntx + x]) on = true;
     }
+  if (tile_seed[t]) {
+    for (int r = 0; r < TS; ++r) {
+      const int gy = ty * TS + r;
+      if (gy >= H) break;
+      uint4* row = reinterpret_cast<uint4*>(mark + (size_t)gy * pitch + (size_t)tx * TS);     // pitch is a multiple of 128: aligned, in the row
+      row[0] = make_uint4(0u, 0u, 0u, 0u);
+      row[1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   if (!on) return;
   flags[t] = ST_QUEUED;
   atomicAdd(&ctl[CTL_PENDING], 1);
   queue[atomicAdd(&ctl[CTL_TAIL], 1)] = t;
+  atomicAdd(&plan_out[6], 1);
 }
 
 // ---- canonical backtrack: one warp, lanes 0..7 = the 8 neighbours in ascending node-id order ------------
@@ -1141,13 +1177,21 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_plan_out + 5, 0, 2 * sizeof(int), s));
   } else {
     const int nl = (int)seed_tiles.size();
-    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_tile_seed, 0, (size_t)ntiles, s));
-    k_field_init<<<64, 256, 0, s>>>(ctx->d_field, 0, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
+    // one host->device copy: [seed map: one byte per tile, padded to 4][seed list: nl tile ids]
+    const size_t map_bytes = ((size_t)ntiles + 3) & ~(size_t)3;
+    uint8_t* d_seedmap = reinterpret_cast<uint8_t*>(ctx->d_seed_list);
+    int* d_list = reinterpret_cast<int*>(d_seedmap + map_bytes);
+    if (nl > 0) {
+      ctx->h_seed_stage.assign(map_bytes + (size_t)nl * sizeof(int), 0);
+      for (int t : seed_tiles) ctx->h_seed_stage[t] = 1;
+      memcpy(ctx->h_seed_stage.data() + map_bytes, seed_tiles.data(), (size_t)nl * sizeof(int));
+      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_seedmap, ctx->h_seed_stage.data(), ctx->h_seed_stage.size(), cudaMemcpyHostToDevice, s));
+    }
+    k_inc_begin<<<64, 256, 0, s>>>(d_list, nl, nl > 0 ? d_seedmap : nullptr, ntiles, qcap, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl,
+                                   ctx->d_tile_seed, ctx->d_plan_out);
     ctx->launches += 1;
     if (nl > 0) {
-      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_seed_list, seed_tiles.data(), (size_t)nl * sizeof(int), cudaMemcpyHostToDevice, s));
-      k_seed_from_list<<<(nl + 255) / 256, 256, 0, s>>>(ctx->d_seed_list, nl, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_tile_seed);
-      wa.tile_list = ctx->d_seed_list;
+      wa.tile_list = d_list;
       k_weights<<<nl, kWeightThreads, 0, s>>>(wa);
       InvalArgs ia;
       ia.W = ctx->W; ia.H = ctx->H; ia.ntx = ctx->n_tiles_x; ia.nty = ctx->n_tiles_y;
@@ -1155,21 +1199,15 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
       ia.start_x = g.start_x; ia.start_y = g.start_y;
       ia.flags = ctx->d_tile_flags; ia.queue = ctx->d_tile_list; ia.cap = qcap; ia.ctl = ctx->d_relax_ctl;
       ia.tile_seed = ctx->d_tile_seed;
+      ia.plan_out = ctx->d_plan_out;
       ia.spin_limit = 20 * 1000 * 1000;
       int igrid = (ntiles + 8 * kInvalWarps - 1) / (8 * kInvalWarps);
       if (igrid > 2 * num_sms) igrid = 2 * num_sms;
       if (igrid * kInvalWarps > qcap) igrid = qcap / kInvalWarps;
       k_inval<<<igrid, kInvalWarps * 32, 0, s>>>(ia);
+      k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl,
+                                                        ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
       ctx->launches += 3;
-      SIPP_CUDA_CHECK(ctx, cudaGetLastError());
-      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_plan_out + 5, ctx->d_relax_ctl + CTL_MARKED, sizeof(int), cudaMemcpyDeviceToDevice, s));
-      k_field_init<<<64, 256, 0, s>>>(ctx->d_field, 0, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
-      k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl);
-      ctx->launches += 2;
-      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_plan_out + 6, ctx->d_relax_ctl + CTL_TAIL, sizeof(int), cudaMemcpyDeviceToDevice, s));
-      SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_mark, 0, ctx->pitch * ctx->H, s));
-    } else {
-      SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_plan_out + 5, 0, 2 * sizeof(int), s));
     }
     SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   }
@@ -1231,7 +1269,6 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   ctx->path_mask_foreign = false;
   pa.redo = reuse ? d_redo : nullptr;
   if (reuse) {
-    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_redo, 0, sizeof(int), s));
     k_path_check<<<(ctx->path_cap_nodes + 255) / 256, 256, 0, s>>>(ctx->d_path_nodes, ctx->d_plan_out, ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, d_redo);
     ctx->launches += 1;
   }

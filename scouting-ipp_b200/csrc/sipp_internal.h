@@ -162,6 +162,7 @@ struct sipp_ctx {
   bool path_mask_foreign;      // d_path was written by sipp_set_path_mask since the last plan: the next plan must rasterise again
   bool warm_valid;             // d_field / d_pred hold the fixed point of the planner map as it was at the last plan
   double warm_init_cost;       // init cost the last plan used
+  std::vector<uint8_t> h_seed_stage;  // staging of the seed map + list of an incremental plan (one copy)
   std::vector<int> pending_rects;   // x0, y0, x1, y1 (cell ranges, inclusive) of the patches ingested since the last plan
   uint8_t* d_mark;             // [H][pitch] cells whose cost-to-go lost its support: 1 = first observed at a higher cost (k_ingest_patch), 2 = published
   uint8_t* d_tile_seed;        // [ntiles] tile holds invalidated cells / was touched by a patch
