@@ -215,6 +215,11 @@ static int testCpu() {
   if (planner.map) {
     auto ev = ModuleFactoryRegistry::createModule<TrajectoryEvaluator>(&bad, planner, &err);
     CHECK(!ev && err.find("NoSuchUpdater") != std::string::npos, "bad updater accepted");
+    // ... and so is an unknown cost computer (cost_computer/type: SegmentTime [upstream] or (Gpu)CostPlanExpMapIntegral)
+    Module::ParamMap badc = evalParams("GpuRRTStarEvaluator", "RRTStarUpdater", "UpdateAll");
+    badc["cost_computer/type"] = "NoSuchCost";
+    auto ev2 = ModuleFactoryRegistry::createModule<TrajectoryEvaluator>(&badc, planner, &err);
+    CHECK(!ev2 && err.find("NoSuchCost") != std::string::npos, "bad cost computer accepted");
   }
   // GpuPRMStarPlanner: INVALID + cost -1 when it has no context (prm_star_planner.cpp:39,66-68)
   planexp_base_planners::PlannerParams pp;
