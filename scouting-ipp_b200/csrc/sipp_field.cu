@@ -528,10 +528,10 @@ __global__ void k_field_init(double* field, size_t n, int* flags, int* queue, in
   for (size_t k = i; k < (size_t)qcap; k += stride) queue[k] = -1;
   if (i < 32) ctl[i] = 0;
 }
-__global__ void k_field_seed(double* field, int W, int H, int sx, int sy, int* flags, int* queue, int ntx, int* ctl) {
+__global__ void k_field_seed(double* field, int W, int H, int sx, int sy, int* flags, int* queue, int ntx, int* ctl, int unit) {
   if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
     field[(size_t)sy * W + sx] = 0.0;
-    const int t = (sy / TS) * ntx + (sx / TS);
+    const int t = (sy / unit) * ntx + (sx / unit);      // unit = edge of the scheduling unit: a 32 x 32 tile (k_relax) or a 128 x 128 block (k_relax_blk)
     flags[t] = 1;
     queue[0] = t;
     ctl[CTL_TAIL] = 1;
@@ -787,6 +787,8 @@ __global__ void k_seed_relax(const uint8_t* tile_seed, int ntx, int nty, int* fl
   queue[atomicAdd(&ctl[CTL_TAIL], 1)] = t;
   atomicAdd(&plan_out[6], 1);
 }
+
+#include "sipp_relax_blk.cuh"
 
 // ---- canonical backtrack: one warp, lanes 0..7 = the 8 neighbours in ascending node-id order ------------
 struct PathArgs {
@@ -1130,9 +1132,34 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
   // ring capacity: every tile can be queued at most once, and every waiting warp must own a distinct slot (ticket % cap)
   const int qcap = ntiles > 16384 ? ntiles : 16384;
-  static int num_sms = 0, occ = 0;
-  if (!num_sms) {
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  // function attributes and occupancy belong to the device: set up once per device of this process, under a process-wide lock
+  // (several contexts / devices / host threads per process)
+  int num_sms = 0, occ = 0;
+  {
+    static std::mutex dev_mu;
+    static struct { bool done; int num_sms, occ; } dev_info[64] = {};
+    std::lock_guard<std::mutex> lk(dev_mu);
+    auto& di = dev_info[ctx->device & 63];
+    if (!di.done) {
+      SIPP_CUDA_CHECK(ctx, cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
+      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
+      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
+      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
+      SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.occ, k_relax, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem)));
+      if (di.occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
+      di.done = true;
+    }
+    num_sms = di.num_sms;
+    occ = di.occ;
+  }
+  // SIPP_RELAX_KERNEL=0: the per-tile kernel (k_relax + edge-weight cache); default: the block-resident kernel (k_relax_blk)
+  static const int relax_kernel_env = getenv("SIPP_RELAX_KERNEL") ? atoi(getenv("SIPP_RELAX_KERNEL")) : 1;
+  const bool use_blk = relax_kernel_env != 0;
+  const int nbx = (ctx->W + BS - 1) / BS, nby = (ctx->H + BS - 1) / BS, nblocks = nbx * nby;
+  if (!use_blk && !ctx->d_tile_w) {      // the weight cache of the per-tile kernel is only allocated when that kernel is selected
+    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+    SIPP_CUDA_CHECK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tile_w), (size_t)ntiles * kTileWDoubles * sizeof(double)));
   }
   WeightArgs wa;
   wa.g = g;
@@ -1167,13 +1194,15 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     if (ctx->warm_valid || !ctx->pending_rects.empty())   // ingest marks of an abandoned warm start must not leak into a later one
       SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_mark, 0, ctx->pitch * ctx->H, s));
     k_field_init<<<592, 256, 0, s>>>(ctx->d_field, ncell, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
-    k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->n_tiles_x,
-                                 ctx->d_relax_ctl);
+    k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->d_tile_list, use_blk ? nbx : ctx->n_tiles_x,
+                                 ctx->d_relax_ctl, use_blk ? BS : TS);
     ctx->launches += 2;
     SIPP_CUDA_CHECK(ctx, cudaGetLastError());
-    // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
-    k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
-    ctx->launches += 1;
+    if (!use_blk) {
+      // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
+      k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
+      ctx->launches += 1;
+    }
     SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_plan_out + 5, 0, 2 * sizeof(int), s));
   } else {
     const int nl = (int)seed_tiles.size();
@@ -1192,7 +1221,10 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     ctx->launches += 1;
     if (nl > 0) {
       wa.tile_list = d_list;
-      k_weights<<<nl, kWeightThreads, 0, s>>>(wa);
+      if (!use_blk) {
+        k_weights<<<nl, kWeightThreads, 0, s>>>(wa);
+        ctx->launches += 1;
+      }
       InvalArgs ia;
       ia.W = ctx->W; ia.H = ctx->H; ia.ntx = ctx->n_tiles_x; ia.nty = ctx->n_tiles_y;
       ia.mark = ctx->d_mark; ia.pred = ctx->d_pred; ia.pitch = ctx->pitch; ia.field = ctx->d_field;
@@ -1205,49 +1237,68 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
       if (igrid > 2 * num_sms) igrid = 2 * num_sms;
       if (igrid * kInvalWarps > qcap) igrid = qcap / kInvalWarps;
       k_inval<<<igrid, kInvalWarps * 32, 0, s>>>(ia);
-      k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl,
-                                                        ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
-      ctx->launches += 3;
+      if (use_blk)
+        k_seed_relax_blk<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, nbx, nby, ctx->d_tile_flags, ctx->d_tile_list,
+                                                              ctx->d_relax_ctl, ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
+      else
+        k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl,
+                                                          ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
+      ctx->launches += 2;
     }
     SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   }
-  const size_t relax_smem = kRelaxWarps * sizeof(TileSmem);
-  // function attributes belong to the device: once per device of this process (several contexts / devices per host process)
-  static bool attr_done[64] = {};
-  const int dev_slot = ctx->device & 63;
-  if (!attr_done[dev_slot] || !occ) {
-    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem));
-    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
-    SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax, kRelaxWarps * 32, relax_smem));
-    if (occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
-    attr_done[dev_slot] = true;
-  }
-  RelaxArgs ra;
-  ra.g = g;
-  ra.field = ctx->d_field;
-  ra.pcode = ctx->d_pcode;
-  ra.pitch16 = ctx->pitch16;
-  ra.ntx = ctx->n_tiles_x; ra.nty = ctx->n_tiles_y;
-  ra.flags = ctx->d_tile_flags;
-  ra.queue = ctx->d_tile_list;
-  ra.cap = qcap;
-  ra.ctl = ctx->d_relax_ctl;
-  ra.tile_w = ctx->d_tile_w;
-  ra.spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
-  ra.mode = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
-  ra.touched = incremental ? ctx->d_tile_seed : nullptr;
-  // persistent workers: one CTA per SM for a large map; a small map (an ensemble of 640x480 maps runs many plans side by side on
-  // their contexts' streams) gets one warp per ~3 tiles so that several relaxations share the GPU instead of queueing for all SMs
+  const int spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
   static const int grid_env = getenv("SIPP_RELAX_GRID") ? atoi(getenv("SIPP_RELAX_GRID")) : 0;
-  int grid = num_sms * occ;
-  const int want = grid_env > 0 ? grid_env : (ntiles + 15) / 16;
-  if (want < grid) grid = want;
-  if (grid < 1) grid = 1;
-  if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
-  // a plain launch: the workers never wait for each other (no grid barrier; any one warp can drain the queue alone), so CTAs that
-  // only become resident later — e.g. while other contexts' kernels hold SMs — just join late. Cooperative launches of different
-  // streams do not overlap, which serialised the plans of an ensemble.
-  k_relax<<<grid, kRelaxWarps * 32, relax_smem, s>>>(ra);
+  if (use_blk) {
+    // block-resident kernel: one persistent CTA (16 warps, the whole 128 x 128 window in shared memory) per SM; a small map (an
+    // ensemble of 640x480 maps runs many plans side by side) gets at most one CTA per block
+    BlkArgs ba;
+    ba.g = g;
+    ba.field = ctx->d_field;
+    ba.pcode = ctx->d_pcode;
+    ba.pitch16 = ctx->pitch16;
+    ba.nbx = nbx; ba.nby = nby;
+    ba.ntx = ctx->n_tiles_x; ba.nty = ctx->n_tiles_y;
+    ba.flags = ctx->d_tile_flags;
+    ba.queue = ctx->d_tile_list;
+    ba.cap = qcap;
+    ba.ctl = ctx->d_relax_ctl;
+    ba.spin_limit = spin_limit;
+    ba.touched = incremental ? ctx->d_tile_seed : nullptr;
+    const float hf = (float)g.init_half_cost;
+    ba.init_inexact = ((double)hf != g.init_half_cost) ? 1 : 0;      // the shared-memory half costs are fp32
+    int grid = grid_env > 0 ? grid_env : num_sms;
+    if (grid > nblocks) grid = nblocks;
+    if (grid < 1) grid = 1;
+    if (ba.init_inexact) k_relax_blk<true><<<grid, kBlkThreads, sizeof(BlkSmem), s>>>(ba);
+    else k_relax_blk<false><<<grid, kBlkThreads, sizeof(BlkSmem), s>>>(ba);
+  } else {
+    RelaxArgs ra;
+    ra.g = g;
+    ra.field = ctx->d_field;
+    ra.pcode = ctx->d_pcode;
+    ra.pitch16 = ctx->pitch16;
+    ra.ntx = ctx->n_tiles_x; ra.nty = ctx->n_tiles_y;
+    ra.flags = ctx->d_tile_flags;
+    ra.queue = ctx->d_tile_list;
+    ra.cap = qcap;
+    ra.ctl = ctx->d_relax_ctl;
+    ra.tile_w = ctx->d_tile_w;
+    ra.spin_limit = spin_limit;
+    ra.mode = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
+    ra.touched = incremental ? ctx->d_tile_seed : nullptr;
+    // persistent workers: one CTA per SM for a large map; a small map gets one warp per ~3 tiles so that several relaxations share
+    // the GPU instead of queueing for all SMs
+    int grid = num_sms * occ;
+    const int want = grid_env > 0 ? grid_env : (ntiles + 15) / 16;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
+    // a plain launch: the workers never wait for each other (no grid barrier; any one warp can drain the queue alone), so CTAs that
+    // only become resident later — e.g. while other contexts' kernels hold SMs — just join late. Cooperative launches of different
+    // streams do not overlap, which serialised the plans of an ensemble.
+    k_relax<<<grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(ra);
+  }
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   ctx->launches += 1;
 

@@ -64,3 +64,39 @@ def world(W, H, seed, K, desc_fn, init_cost="min", **kw):
     init = min(ids) if init_cost == "min" else (max(ids) if init_cost == "max" else float(init_cost))
     desc = desc_fn(W, H, W * MPP, H * MPP, (0.5, 0.5), (W * MPP - 0.5, H * MPP - 0.5), min(ids), max(ids), init, **kw)
     return lab, obs, desc
+
+
+def make_tree(W, H, seed, T):
+    """RRT-like candidate tree for config 1: T nodes, node 0 = the root at the start pose, every other node hangs off
+    the nearest earlier node; renumbered in pre-order (children in creation order) as sipp_update_tree expects.
+    Returns parent[T] (int32, parent[0] = -1), end_xy[T,2], start_xy[T,2] (= the parent's end point), cost[T] (segment length at
+    v_max 1 m/s: SegmentTime, cfg/planners/example_config.yaml:28,45-46)."""
+    rng = np.random.default_rng(seed + 15485863)
+    pts = np.empty((T, 2), np.float64)
+    pts[0] = (0.5, 0.5)
+    pts[1:, 0] = rng.uniform(0.0, W * MPP, T - 1)
+    pts[1:, 1] = rng.uniform(0.0, H * MPP, T - 1)
+    par = np.full(T, -1, np.int64)
+    for i in range(1, T):
+        d2 = ((pts[:i] - pts[i]) ** 2).sum(axis=1)
+        par[i] = int(np.argmin(d2))
+    kids = [[] for _ in range(T)]
+    for i in range(1, T):
+        kids[par[i]].append(i)
+    order, stack = [], [0]
+    while stack:
+        v = stack.pop()
+        order.append(v)
+        stack.extend(reversed(kids[v]))
+    new = np.empty(T, np.int64)
+    new[np.array(order)] = np.arange(T)
+    parent = np.full(T, -1, np.int32)
+    end = np.empty((T, 2), np.float64)
+    for old in range(T):
+        end[new[old]] = pts[old]
+        if old:
+            parent[new[old]] = new[par[old]]
+    start = np.where(parent[:, None] >= 0, end[np.maximum(parent, 0)], end)
+    cost = np.sqrt(((end - start) ** 2).sum(axis=1))
+    cost[0] = 0.0
+    return parent, end, start, cost

@@ -234,6 +234,124 @@ def test_config4_field_properties_8192():
     assert cost2 == cost and n2 == n and np.array_equal(path2, path) and np.array_equal(g.field_download(), f)
 
 
+def test_config4_full_cycle_8192_against_oracle():
+    """BASELINE config 4 (full planning cycle, 65536 candidates on an 8192^2 map) compared cell by cell with the oracle: field,
+    path, status, mask, every count, terminal flag and the selected candidate (the oracle's Dijkstra takes ~12 s at this size)."""
+    W = H = 8192
+    lab, obs, dg = synth.world(W, H, 1004, 6000, sipp.make_desc, init_cost="max")
+    _, _, do = synth.world(W, H, 1004, 6000, orc.make_desc, init_cost="max")
+    g, o = sipp.Context(dg), orc.Oracle(do)
+    g.map_upload_full(lab, obs)
+    o.map_upload_full(lab, obs)
+    del lab, obs
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+    fg, fo = g.field_download(), o.field_download()
+    assert np.array_equal(fg, fo), "field differs in %d cells" % int((fg != fo).sum())
+    del fg, fo
+    assert np.array_equal(g.map_download()[3], o.map_download()[3])
+    xy, cost = synth.make_candidates(W, H, 1004, 65536)
+    for npg in (0.001, 0.0):
+        pgp = sipp.make_params(sipp.EVAL_RRT_STAR, non_path_voxel_gain=npg)
+        pop = orc.make_params(orc.EVAL_RRT_STAR, non_path_voxel_gain=npg)
+        gg, gc, gt = g.gain_batch(pgp, xy)
+        og, oc, ot = o.gain_batch(pop, xy, variant=1, threads=16)
+        assert np.array_equal(gc, oc) and np.array_equal(gt, ot)
+        gg2, gt2, gv, gi, gbv = g.cycle(pgp, xy, cost)
+        og2, ot2, ov, oi, obv = o.cycle(pop, xy, cost, variant=1, threads=16)
+        assert gi == oi, "selected candidate differs"
+        assert np.array_equal(gt2, ot2) and np.array_equal(gg2, gg)
+        assert np.allclose(gv, ov, rtol=RTOL, atol=0) and abs(gbv - obv) <= RTOL * abs(obv)
+        if npg == 0.0:
+            assert np.array_equal(gg, og) and np.array_equal(gv, ov) and gbv == obv
+
+
+FP_PARAM_SETS = [
+    dict(evaluator=sipp.EVAL_GOAL_DISTANCE, max_gain=100.0),
+    dict(evaluator=sipp.EVAL_RRT_STAR, use_distance_discount=True, non_path_voxel_gain=0.0),
+    dict(evaluator=sipp.EVAL_RRT_STAR, use_distance_discount=True, non_path_voxel_gain=0.005),
+    dict(evaluator=sipp.EVAL_AVERAGE_VIEW_COST),
+    dict(evaluator=sipp.EVAL_EXPAND_LOW_COST),
+    dict(evaluator=sipp.EVAL_EXPAND_LOW_COST, augment_unknown_with_mean=True),
+    dict(evaluator=sipp.EVAL_EXPAND_REACHABLE, discount_factor=0.1),
+    dict(evaluator=sipp.EVAL_NAIVE),
+]
+
+
+def test_selected_candidate_is_bit_exact_for_every_evaluator_config2():
+    """north_star: "bit-exact ... selected candidate". Config 2 (4096 poses, 1024^2 map): the candidate sipp_cycle selects equals the
+    oracle's for the floating-point evaluators too (their gains agree to ~1e-12 relative, so only an exact tie between the two best
+    values could flip the winner; the winner's index is asserted, not only its value)."""
+    W = H = 1024
+    kwm = dict(compute_closest_observed=True)
+    lab, obs, dg = synth.world(W, H, 1002, 100, sipp.make_desc, init_cost="max", **kwm)
+    _, _, do = synth.world(W, H, 1002, 100, orc.make_desc, init_cost="max", **kwm)
+    g, o = sipp.Context(dg), orc.Oracle(do)
+    # patches (not one masked upload) so that the closest-observed plane of ExpandLowCostArea is maintained
+    from sipp import episode
+    rng = np.random.default_rng(5)
+    for k in range(60):
+        x0, y0 = (0, 0) if k == 0 else (int(rng.integers(-20, W)), int(rng.integers(-20, H)))
+        rows = cols = 200 if k == 0 else 65
+        patch = episode.extract_patch(lab, x0, y0, rows, cols)
+        g.map_update_patch(x0, y0, patch)
+        o.map_update_patch(x0, y0, patch)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[3] == ro[3]
+    xy, cost = synth.make_candidates(W, H, 1002, 4096)
+    for kw in FP_PARAM_SETS:
+        pg, po = sipp.make_params(half_fov=32, **kw), orc.make_params(half_fov=32, **kw)
+        gg, gt, gv, gi, gbv = g.cycle(pg, xy, cost, start_xy=xy[::-1].copy())
+        og, ot, ov, oi, obv = o.cycle(po, xy, cost, start_xy=xy[::-1].copy(), variant=1, threads=8)
+        assert gi == oi, ("selected candidate differs", kw, gi, oi, gbv, obv)
+        assert np.array_equal(gt, ot)
+        assert np.allclose(gv, ov, rtol=RTOL, atol=0, equal_nan=True) and abs(gbv - obv) <= RTOL * abs(obv)
+        # the runner-up is not within rounding distance of the winner: the selection does not hang on the last bits of a sum
+        srt = np.sort(ov[np.isfinite(ov)])
+        if len(srt) > 1 and srt[-1] > 0:
+            assert (srt[-1] - srt[-2]) / srt[-1] > 1e-9 or srt[-1] == srt[-2], kw
+
+
+def test_config1_example_launch_tree_cycle(golden):
+    """BASELINE config 1 (example.launch defaults: map_212, GoalDistanceEvaluator max_gain 100, half_fov 32, prm_star follower,
+    unknown_init_cost min; launch/example.launch:33,38-39) on an RRT-like tree of 1024 nodes: one updater pass
+    (RRTStarUpdater -> UpdateAll) + value + next-best selection. Gains within RTOL, terminal flags / re-scored set / selected child
+    identical to the oracle's literal emulation of the reference pass."""
+    from sipp import episode
+    labels, cfg = golden["map_212"]
+    lab = labels.astype(np.int32)
+    W, H = cfg["W"], cfg["H"]
+    g = sipp.Context(inloop_desc(cfg, sipp.make_desc, "min"))
+    o = orc.Oracle(inloop_desc(cfg, orc.make_desc, "min"))
+    obs = synth.make_observed(W, H, 1001, 40)
+    ys, xs = np.nonzero(obs)
+    rng = np.random.default_rng(1001)
+    # the observed region arrives as patches (65 x 65 footprints + the initial square), like in the loop
+    cover = np.zeros_like(obs)
+    x0s = [(0, 0, 320)] + [(int(xs[j]) - 32, int(ys[j]) - 32, 65) for j in rng.integers(0, len(xs), 60)]
+    for x0, y0, sz in x0s:
+        patch = episode.extract_patch(lab, x0, y0, sz, sz)
+        g.map_update_patch(x0, y0, patch)
+        o.map_update_patch(x0, y0, patch)
+    rg, ro = g.plan(), o.plan()
+    assert rg[0] == ro[0] and rg[1] == ro[1] and rg[3] == ro[3] and np.array_equal(rg[2], ro[2])
+    T = 1024
+    parent, end, start, cost = synth.make_tree(W, H, 1001, T)
+    for kw in (dict(evaluator=sipp.EVAL_GOAL_DISTANCE, max_gain=100.0), dict(evaluator=sipp.EVAL_RRT_STAR, non_path_voxel_gain=0.001)):
+        pg, po = sipp.make_params(half_fov=32, **kw), orc.make_params(half_fov=32, **kw)
+        gain0, value0, term0 = np.zeros(T), np.zeros(T), np.zeros(T, np.uint8)
+        ug, uo = sipp.make_updater(sipp.UPD_RRT_STAR, sipp.FOLLOW_UPDATE_ALL, -1e9, 1e9, True, False, True), orc.make_updater(0, 0, -1e9, 1e9, True, False, True)
+        gg, gv, gt, nres = g.update_tree(pg, ug, parent, end, gain0, cost, value0, term0, (0.5, 0.5), True, start_xy=start)
+        og, ov, ot = o.update_tree(po, uo, parent, end, gain0, cost, value0, term0, (0.5, 0.5), True, start_xy=start)
+        assert np.array_equal(gt, ot) and nres >= T - 1
+        assert np.allclose(gg, og, rtol=RTOL, atol=0, equal_nan=True) and np.allclose(gv, ov, rtol=RTOL, atol=0, equal_nan=True)
+        # next-best selection over the updated tree ([upstream] SubsequentBest): the same child of the root
+        vg, bg, bvg = g.value_select(gg, cost, parent)
+        vo, bo, bvo = orc.value_select(og, cost, parent)
+        assert bg == bo, ("selected child differs", kw, bg, bo, bvg, bvo)
+        assert abs(bvg - bvo) <= RTOL * abs(bvo)
+
+
 def _random_tree(rng, n, W, H):
     """pre-order parent array of a random RRT-like tree (children in index order) + end / start points of the segments"""
     par = np.full(n, -1, np.int32)
