@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIPP_ABI_VERSION 1
+#define SIPP_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------------------- */
 #define SIPP_OK 0
@@ -175,6 +175,9 @@ int sipp_map_download(sipp_ctx* ctx, uint8_t* state, int32_t* cost, uint8_t* rea
  * nodes (may exceed path_cap; only path_cap are written). status: SIPP_PLAN_*. */
 int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap,
               int32_t* path_len);
+/* the path of the last sipp_plan again (start -> goal, x y metres): up to path_cap points are written, *path_len = its full length.
+ * For callers whose buffer was too small for a long, winding path (PRMStarPlanner::plan hands back every node, :54-62). */
+int sipp_path_download(sipp_ctx* ctx, double* path_xy, int32_t path_cap, int32_t* path_len);
 /* the converged field d[] of the last sipp_plan, W*H doubles row-major, +inf = unreachable */
 int sipp_field_download(sipp_ctx* ctx, double* field);
 /* MapServerPlanExp::getCurrentPathMapId (map_server_planexp.h:103) */
@@ -241,10 +244,20 @@ int sipp_value_preorder(sipp_ctx* ctx, int32_t n, const double* gain_new, const 
  * the eligible nodes are scored (one batched gain launch), values get the pre-order semantics of sipp_value_preorder.
  * end_xy / start_xy: n x 2 (last / first trajectory point of each segment; start_xy may be NULL unless RRTStar binary+discount).
  * gain, value, terminal: in/out (terminal is only ever set). cost: in. cur_xy: current robot position (2 doubles).
+ * The root (node 0) enters with gain = cost = 0 (it just became the current segment). The root-first call applies the chain to it:
+ * an RRTStarUpdater only compares path ids there (:21,30-38) and leaves the root alone; a ConstrainedUpdater / a following updater
+ * used directly re-score it like any node, and its new gain is part of every value below it (gain[0] / value[0] / terminal[0] are
+ * then written too).
+ * Costs are the caller's: the library never recomputes them inside the pass. With update_cost set ([upstream] UpdateAll /
+ * UpdateAllNonTerminal call computeCost before computeValue, update_all_non_terminal.cpp:20-22) the caller recomputes the costs of the
+ * nodes the chain follows first (sipp_cost_integral; SegmentTime costs do not depend on the map) and passes them in `cost`, and the
+ * costs as they were before the pass in `cost_below` (what computeValue(i) still finds on the nodes below i; cost[0] is then the
+ * root's cost of this pass: 0 unless the chain re-scores the root); cost_below == NULL: costs did not change.
  * path_changed: RRTStarUpdater's rrt_path_has_changed_ for this pass. n_rescored (optional out): nodes whose gain was recomputed. */
 int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n,
                      const int32_t* parent, const double* end_xy, const double* start_xy, double* gain, const double* cost,
-                     double* value, uint8_t* terminal, const double* cur_xy, int32_t path_changed, int32_t* n_rescored);
+                     double* value, uint8_t* terminal, const double* cur_xy, int32_t path_changed, int32_t* n_rescored,
+                     const double* cost_below);
 
 /* ---- fused evaluation cycle ------------------------------------------------------------------------ */
 /* gain for all n candidates (flat tree, candidate i is node i+1 under a virtual root) + value + argmax

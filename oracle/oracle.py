@@ -162,7 +162,7 @@ def lib():
         L.orc_value_select.argtypes = [i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64)]
         L.orc_cost_integral.argtypes = [vp, C.POINTER(CostParams), i32, vp, vp, vp, vp, vp]
         L.orc_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64), i32, i32]
-        L.orc_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
+        L.orc_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
         _lib = L
     return _lib
 
@@ -328,7 +328,8 @@ class Oracle:
         return gain, terminal, value, bi.value, bv.value
 
 
-    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, variant=1):
+    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, variant=1,
+                    cost_below=None):
         """literal pre-order emulation of one re-evaluation pass (orc_update_tree); returns (gain, value, terminal)"""
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         n = parent.shape[0]
@@ -339,8 +340,9 @@ class Oracle:
         t = np.array(terminal, dtype=np.uint8, copy=True)
         cost = np.ascontiguousarray(cost, dtype=np.float64)
         cur = np.ascontiguousarray(cur_xy, dtype=np.float64)
+        cb = None if cost_below is None else np.ascontiguousarray(cost_below, dtype=np.float64)
         self._L.orc_update_tree(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g), _ptr(cost),
-                                _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), int(variant))
+                                _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), int(variant), _ptr(cb))
         return g, v, t
 
 

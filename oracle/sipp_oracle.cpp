@@ -853,16 +853,20 @@ int orc_value_select(int32_t n, const double* gain_in, const double* cost_in, co
 //   RRTStarUpdater::updateSegment            advanced_planner_modules/src/evaluator_updater/rrt_star_updater.cpp:19-42
 //   [upstream] ConstrainedUpdater::updateSegment (same predicate without the terminal / path-changed terms)
 //   [upstream] UpdateAll::updateSegment / UpdateAllNonTerminal::updateSegment  (update_all_non_terminal.cpp:16-27)
-// Nodes are given in pre-order (parent[i] < i, children in index order), node 0 is the root (never updated).
+// Nodes are given in pre-order (parent[i] < i, children in index order), node 0 is the root (its gain / cost are zeroed on entry: it just
+// became the current segment; whether the root-first call of the patched planner re-scores it depends on the chain, see below).
 // gain / value / terminal are in-out; computeValue sees whatever gains the array holds at that moment.
 int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
                     const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
-                    const double* cur_xy, int path_changed, int variant) {
+                    const double* cur_xy, int path_changed, int variant, const double* cost_below) {
   Oracle& o = c->o;
   std::vector<std::vector<int>> children(n);
   for (int i = 1; i < n; ++i) children[parent[i]].push_back(i);
-  std::vector<double> g(gain, gain + n), cst(cost, cost + n);
+  // cost_below != NULL: update_cost — computeCost(i) runs before computeValue(i) (update_all_non_terminal.cpp:20-22): `cost` holds the
+  // costs the pass computes, cost_below the costs the tree carried before it; node i switches from the old to the new cost when visited
+  std::vector<double> g(gain, gain + n), cst(cost_below ? cost_below : cost, (cost_below ? cost_below : cost) + n);
   g[0] = 0.0; cst[0] = 0.0;
+  if (u->updater != SIPP_UPD_RRT_STAR) value[0] = 0.0;     // the new current segment enters with gain = cost = value = 0 [upstream requestNextTrajectory]
   const bool setsTerminal = p->evaluator == SIPP_EVAL_RRT_STAR || p->evaluator == SIPP_EVAL_EXPAND_REACHABLE;
   auto compute_gain = [&](int i) {
     double gi; uint8_t ti;
@@ -878,13 +882,21 @@ int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_pa
   auto following = [&](int i) {
     if (u->following == SIPP_FOLLOW_UPDATE_ALL) {
       if (u->update_gain) compute_gain(i);
+      if (u->update_cost && cost_below) cst[i] = cost[i];
       if (u->update_value) compute_value(i);
     } else {
       if (u->update_gain && !terminal[i]) compute_gain(i);
+      if (u->update_cost && cost_below) cst[i] = cost[i];
       if (u->update_value && !(terminal[i] && !u->update_cost)) compute_value(i);
     }
   };
-  for (int i = 1; i < n; ++i) {     // pre-order; the root segment cannot be updated (rrt_star_updater.cpp:21)
+  // The patched planner calls trajectory_evaluator_->updateSegment(root) first (mav_active_3d_planning.patch:56), then [upstream]
+  // updateEvaluatorStep visits every node BELOW the root in pre-order. RRTStarUpdater only inspects the path id on its root visit
+  // (rrt_star_updater.cpp:21,30-38: "cannot update the root segment"); a ConstrainedUpdater / a following updater used directly
+  // treats the root like any node, so the root's gain (zeroed when it became the current segment) is recomputed and enters every
+  // value below it. Pinned against the reference's own sources by tests/test_ref_pin.py.
+  for (int i = 0; i < n; ++i) {
+    if (i == 0 && u->updater == SIPP_UPD_RRT_STAR) continue;
     const double dx = cur_xy[0] - end_xy[2 * i], dy = cur_xy[1] - end_xy[2 * i + 1];
     const double dist = std::sqrt(dx * dx + dy * dy + 0.0 * 0.0);
     if (u->updater == SIPP_UPD_RRT_STAR) {
@@ -898,7 +910,7 @@ int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_pa
       following(i);                 // cfg/evaluators/expand_reachable_area.yaml:23-27: no gating updater in front
     }
   }
-  for (int i = 1; i < n; ++i) gain[i] = g[i];
+  for (int i = (u->updater == SIPP_UPD_RRT_STAR ? 1 : 0); i < n; ++i) gain[i] = g[i];
   return 0;
 }
 

@@ -625,6 +625,22 @@ int sipp_plan(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int
   return plan_impl(ctx, cost, status, path_xy, path_cap, path_len);
 }
 
+int sipp_path_download(sipp_ctx* ctx, double* path_xy, int32_t path_cap, int32_t* path_len) {
+  SIPP_ENTER(ctx);
+  if (!ctx->field_valid) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "no path: call sipp_plan first");
+  int* out = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->h_pinned) + 64);
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int len = out[2] != 0 ? out[0] : 0;
+  if (path_len) *path_len = len;
+  if (path_xy && len > 0 && path_cap > 0) {
+    const int m = len < path_cap ? len : path_cap;
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(path_xy, ctx->d_path_xy, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SIPP_OK;
+}
+
 int sipp_plan_info(const sipp_ctx* ctx, int64_t info[4]) {
   if (!ctx || !info) return SIPP_ERR_INVALID_ARG;
   for (int i = 0; i < 4; ++i) info[i] = ctx->plan_info[i];
@@ -1035,7 +1051,7 @@ int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params
 
 int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
                      const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
-                     const double* cur_xy, int32_t path_changed, int32_t* n_rescored) {
+                     const double* cur_xy, int32_t path_changed, int32_t* n_rescored, const double* cost_below) {
   SIPP_ENTER(ctx);
   int rc = check_params(ctx, params);
   if (rc != SIPP_OK) return rc;
@@ -1046,13 +1062,13 @@ int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_u
   for (int i = 1; i < n; ++i)
     if (parent[i] < 0 || parent[i] >= i) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "parent[%d] = %d violates 0 <= parent[i] < i", i, parent[i]);
   cudaStream_t s = ctx->stream;
-  // device staging: doubles end_xy[2n] start_xy[2n] gain_old gain_new gain_tmp cost value value_tmp | int32 parent sel n_sel | u8 flags x5
-  const size_t N = (size_t)n, need = N * (16 + 16 + 8 * 6) + N * 8 + 64 + N * 5 + 256;
+  // device staging: doubles end_xy[2n] start_xy[2n] gain_old gain_new gain_tmp cost value value_tmp cost_below | int32 parent sel n_sel | u8 flags x5
+  const size_t N = (size_t)n, need = N * (16 + 16 + 8 * 7) + N * 8 + 64 + N * 5 + 256;
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
   double* d_end = reinterpret_cast<double*>(ctx->d_stage);
   double *d_start = d_end + 2 * N, *d_gold = d_start + 2 * N, *d_gnew = d_gold + N, *d_gtmp = d_gnew + N, *d_cost = d_gtmp + N, *d_val = d_cost + N,
-         *d_vtmp = d_val + N;
-  int32_t* d_parent = reinterpret_cast<int32_t*>(d_vtmp + N);
+         *d_vtmp = d_val + N, *d_cbelow = d_vtmp + N;
+  int32_t* d_parent = reinterpret_cast<int32_t*>(d_cbelow + N);
   int* d_sel = d_parent + N;
   int* d_nsel = d_sel + N;                       // 16 ints reserved
   uint8_t* d_term = reinterpret_cast<uint8_t*>(d_nsel + 16);
@@ -1060,8 +1076,15 @@ int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_u
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_end, end_xy, N * 16, cudaMemcpyHostToDevice, s));
   if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_start, start_xy, N * 16, cudaMemcpyHostToDevice, s));
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_gold, gain, N * 8, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_gold, 0, 8, s));       // the root just became the current segment: gain = cost = 0 [upstream]
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cost, cost, N * 8, cudaMemcpyHostToDevice, s));
+  if (!cost_below) SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_cost, 0, 8, s));     // with cost_below the caller states the root's cost of this pass
+  if (cost_below) {     // update_cost: `cost` holds this pass's costs, cost_below last pass's (what computeValue still finds below the visited node)
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cbelow, cost_below, N * 8, cudaMemcpyHostToDevice, s));
+    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_cbelow, 0, 8, s));
+  }
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_val, value, N * 8, cudaMemcpyHostToDevice, s));
+  if (updater->updater != SIPP_UPD_RRT_STAR) SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(d_val, 0, 8, s));   // ... and value = 0
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_parent, parent, N * 4, cudaMemcpyHostToDevice, s));
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_term, terminal, N, cudaMemcpyHostToDevice, s));
   // 1. the updater predicate for every node + compaction of the nodes whose gain is recomputed
@@ -1075,16 +1098,20 @@ int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_u
   SIPP_CUDA_CHECK(ctx, launch_update_apply(ctx, *updater, n, sets_terminal, d_dog, d_fol, d_gold, d_gtmp, d_ttmp, d_gnew, d_term, d_dov, s));
   // 4. values with the pre-order semantics (new gains on the chain root..i, old gains below i)
   if ((rc = ensure_dev(ctx, &ctx->d_tree_ws, &ctx->d_tree_ws_bytes, N * 16 + 512)) != SIPP_OK) return rc;
-  SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_gnew, d_gold, d_cost, d_parent, d_vtmp, ctx->d_best, ctx->d_tree_ws, s));
+  // the root-first call of the patched planner re-scores the root unless the chain starts with an RRTStarUpdater; its new gain then
+  // enters every value below it (pinned against the reference's own updater sources: tests/test_ref_pin.py)
+  const int root_live = updater->updater != SIPP_UPD_RRT_STAR;
+  SIPP_CUDA_CHECK(ctx, launch_value_tree(ctx, n, d_gnew, d_gold, d_cost, d_parent, d_vtmp, ctx->d_best, ctx->d_tree_ws, s, root_live, cost_below ? d_cbelow : nullptr));
   SIPP_CUDA_CHECK(ctx, launch_update_value(ctx, n, d_dov, d_vtmp, d_val, s));
   BestRec* h_best = reinterpret_cast<BestRec*>(ctx->h_pinned);
   int* h_nsel = reinterpret_cast<int*>(h_best + 1);
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_best, ctx->d_best, sizeof(BestRec), cudaMemcpyDeviceToHost, s));
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_nsel, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
-  if (n > 1) {
-    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain + 1, d_gnew + 1, (N - 1) * 8, cudaMemcpyDeviceToHost, s));     // the root's gain is not ours to touch
-    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value + 1, d_val + 1, (N - 1) * 8, cudaMemcpyDeviceToHost, s));
-    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal + 1, d_term + 1, N - 1, cudaMemcpyDeviceToHost, s));
+  const size_t first = root_live ? 0 : 1;     // an RRTStarUpdater chain never touches the root's numbers
+  if (N > first) {
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain + first, d_gnew + first, (N - first) * 8, cudaMemcpyDeviceToHost, s));
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(value + first, d_val + first, (N - first) * 8, cudaMemcpyDeviceToHost, s));
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal + first, d_term + first, N - first, cudaMemcpyDeviceToHost, s));
   }
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
   if (h_best->index == -2) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "tree deeper than 512 levels");

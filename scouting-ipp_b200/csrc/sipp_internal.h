@@ -240,7 +240,8 @@ cudaError_t launch_peer_exchange(sipp_ctx* ctx, const BestRec* d_mine, BestRec* 
 void peer_release(sipp_ctx* ctx);
 cudaError_t launch_value_flat(sipp_ctx* ctx, int n, const double* d_gain, const double* d_cost, double* d_value, cudaStream_t s);
 cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_gain_below, const double* d_cost,
-                              const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s);
+                              const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s, int root_live = 0,
+                              const double* d_cost_below = nullptr);
 cudaError_t launch_merge_best(sipp_ctx* ctx, const BestRec* d_recs, int world, long long stride, BestRec* d_out, cudaStream_t s);
 size_t select_workspace_bytes();
 // sipp_cost.cu

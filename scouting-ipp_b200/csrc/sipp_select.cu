@@ -124,9 +124,12 @@ __global__ void k_tree_init(int n, unsigned long long* __restrict__ best, int* _
 // gain_below (optional): gains to use for the nodes strictly BELOW the evaluated node i. The reference re-evaluates the tree
 // in pre-order (OnlinePlanner::updateEvaluatorStep [upstream]): when computeValue(i) runs, i and its ancestors already carry
 // this cycle's gains while i's descendants still carry last cycle's. gain_below == nullptr: one consistent gain array.
+// root_live: the root's gain / cost are used as given (an updater pass that re-scored the root); otherwise they count as 0 (the
+// planner zeroes the segment that becomes the root [upstream OnlinePlanner::requestNextTrajectory]).
+// cost_below (optional): likewise for the costs — with update_cost the pass also recomputes the cost of every visited node.
 __global__ void k_tree_pairs(int n, const double* __restrict__ gain, const double* __restrict__ gain_below, const double* __restrict__ cost,
-                             const int32_t* __restrict__ parent, unsigned long long* __restrict__ best,
-                             uint8_t* __restrict__ own_nan, int* __restrict__ flags) {
+                             const double* __restrict__ cost_below, const int32_t* __restrict__ parent, unsigned long long* __restrict__ best,
+                             uint8_t* __restrict__ own_nan, int* __restrict__ flags, int root_live) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
   int chain[kMaxTreeDepth];   // chain[0] = m, chain[depth-1] = root
@@ -140,13 +143,13 @@ __global__ void k_tree_pairs(int n, const double* __restrict__ gain, const doubl
     double g = 0.0, c = 0.0;
     for (int b = a + 1; b < depth; ++b) {   // computeValue: ancestors of i = chain[a], nearest first
       const int k = chain[b];
-      g += (k == 0) ? 0.0 : gain[k];        // the root (current segment) has gain = cost = 0 [upstream OnlinePlanner]
-      c += (k == 0) ? 0.0 : cost[k];
+      g += (k == 0 && !root_live) ? 0.0 : gain[k];        // the root (current segment) has gain = cost = 0 [upstream OnlinePlanner]
+      c += (k == 0 && !root_live) ? 0.0 : cost[k];
     }
     for (int b = a; b >= 0; --b) {          // findBest: i itself, then down to m
       const int k = chain[b];
-      g += (k == 0) ? 0.0 : ((b == a || !gain_below) ? gain[k] : gain_below[k]);
-      c += (k == 0) ? 0.0 : cost[k];
+      g += (k == 0 && !root_live) ? 0.0 : ((b == a || !gain_below) ? gain[k] : gain_below[k]);
+      c += (k == 0 && !root_live) ? 0.0 : ((b == a || !cost_below) ? cost[k] : cost_below[k]);
     }
     const double v = c > 0 ? g / c : 0.0;
     if (v != v) {
@@ -222,13 +225,14 @@ cudaError_t launch_value_flat(sipp_ctx* ctx, int n, const double* d_gain, const 
 
 // ws: best[n] u64 + own_nan[n] bytes + flags (int) -> 9 n + 64 bytes
 cudaError_t launch_value_tree(sipp_ctx* ctx, int n, const double* d_gain, const double* d_gain_below, const double* d_cost,
-                              const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s) {
+                              const int32_t* d_parent, double* d_value, BestRec* d_best, void* ws, cudaStream_t s, int root_live,
+                              const double* d_cost_below) {
   unsigned long long* best = reinterpret_cast<unsigned long long*>(ws);
   uint8_t* own_nan = reinterpret_cast<uint8_t*>(best + n);
   int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + (((size_t)n * 9 + 15) & ~(size_t)15));
   const int threads = 128, blocks = (n + threads - 1) / threads;
   k_tree_init<<<blocks, threads, 0, s>>>(n, best, flags);
-  k_tree_pairs<<<blocks, threads, 0, s>>>(n, d_gain, d_gain_below, d_cost, d_parent, best, own_nan, flags);
+  k_tree_pairs<<<blocks, threads, 0, s>>>(n, d_gain, d_gain_below, d_cost, d_cost_below, d_parent, best, own_nan, flags, root_live);
   k_tree_final<<<blocks, threads, 0, s>>>(n, best, own_nan, d_value);
   k_select<<<sel_grid(n), kSelThreads, 0, s>>>(n, d_value, d_parent, 1, 0, reinterpret_cast<SelectWs*>(ctx->d_select_ws), d_best, nullptr, flags, PeerDev{}, -1);
   ctx->launches += 4;

@@ -16,7 +16,10 @@ __global__ void k_update_select(sipp_updater_params u, int n, const double* __re
                                 uint8_t* __restrict__ do_gain, uint8_t* __restrict__ follow_out, int* __restrict__ sel, int* __restrict__ n_sel) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool follow = false, dg = false;
-  if (i >= 1 && i < n) {                                       // the root segment cannot be updated (rrt_star_updater.cpp:21)
+  // Node 0 is the root: the patched planner visits it first (trajectory_evaluator_->updateSegment(current_segment),
+  // mav_active_3d_planning.patch:56). RRTStarUpdater only compares path ids there ("cannot update the root segment",
+  // rrt_star_updater.cpp:21,30-38); a ConstrainedUpdater / a following updater used directly treat it like any other node.
+  if (i < n && !(i == 0 && u.updater == SIPP_UPD_RRT_STAR)) {
     const double dx = cur_x - end_xy[2 * i], dy = cur_y - end_xy[2 * i + 1];
     // (current_position - trajectory.back().position_W).norm() with z = 0                                        :25
     const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.0));

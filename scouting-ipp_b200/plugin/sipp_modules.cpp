@@ -151,6 +151,13 @@ bool GpuMapPlanExp::computeCurrentPathEstimate() {
     planner_.printError(std::string("'GpuMapPlanExp': ") + sipp_last_error(ctx_));
     return false;
   }
+  if ((size_t)len > xy.size() / 2) {     // longer than 4 (W + H) nodes (a path winding through a maze): fetch all of it
+    xy.resize(2 * (size_t)len);
+    if (sipp_path_download(ctx_, xy.data(), len, &len) != SIPP_OK) {
+      planner_.printError(std::string("'GpuMapPlanExp': ") + sipp_last_error(ctx_));
+      return false;
+    }
+  }
   last_status_ = status;
   last_path_.clear();
   for (int i = 0; i < len && (size_t)i < xy.size() / 2; ++i) last_path_.push_back(Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]));
@@ -195,26 +202,30 @@ void FlatTree::build(TrajectorySegment* root) {
 }
 
 void updaterMasks(const sipp_updater_params& u, const FlatTree& t, const double cur_xy[2], bool path_changed, std::vector<uint8_t>* do_gain,
-                  std::vector<uint8_t>* maybe_value) {
+                  std::vector<uint8_t>* maybe_value, bool followed_instead_of_value) {
   const int n = (int)t.nodes.size();
   do_gain->assign(n, 0);
   maybe_value->assign(n, 0);
-  for (int i = 1; i < n; ++i) {                                           // the root segment cannot be updated (rrt_star_updater.cpp:21)
+  // node 0 is the root: the patched planner's root-first call (mav_active_3d_planning.patch:56) runs the chain on it as well. An
+  // RRTStarUpdater only compares path ids there (rrt_star_updater.cpp:21,30-38); the other chains treat it like any node, with the
+  // gain = 0 the planner gave it when it became the current segment.
+  for (int i = (u.updater == SIPP_UPD_RRT_STAR ? 1 : 0); i < n; ++i) {
     const double dx = cur_xy[0] - t.end_xy[2 * i], dy = cur_xy[1] - t.end_xy[2 * i + 1];
     const double dist = std::sqrt(dx * dx + dy * dy + 0.0 * 0.0);
+    const double gi = i == 0 ? 0.0 : t.gain[i];
     bool follow;
     if (u.updater == SIPP_UPD_RRT_STAR) {
       if (t.terminal[i]) continue;                                        // :22
-      follow = (t.gain[i] > u.minimum_gain || path_changed) && (dist <= u.update_range || path_changed);   // :24-28
+      follow = (gi > u.minimum_gain || path_changed) && (dist <= u.update_range || path_changed);   // :24-28
     } else if (u.updater == SIPP_UPD_CONSTRAINED) {
-      follow = t.gain[i] > u.minimum_gain && dist <= u.update_range;      // [upstream] ConstrainedUpdater
+      follow = gi > u.minimum_gain && dist <= u.update_range;             // [upstream] ConstrainedUpdater
     } else {
       follow = true;                                                      // following updater used directly
     }
     if (!follow) continue;
     if (u.following == SIPP_FOLLOW_UPDATE_ALL) (*do_gain)[i] = u.update_gain ? 1 : 0;
     else (*do_gain)[i] = (u.update_gain && !t.terminal[i]) ? 1 : 0;       // update_all_non_terminal.cpp:17-19
-    (*maybe_value)[i] = u.update_value ? 1 : 0;                           // NonTerminal re-checks gain_terminal after the gain update (:23)
+    (*maybe_value)[i] = (followed_instead_of_value || u.update_value) ? 1 : 0;   // NonTerminal re-checks gain_terminal after the gain update (:23)
   }
 }
 
@@ -241,6 +252,17 @@ void GpuGainEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
   int hf;
   setParam<int>(param_map, "sensor_model/half_fov", &hf, 10);
   params_.half_fov = hf;
+  setParam<double>(param_map, "sensor_model/sampling_time", &sampling_time_, 0.0);          // sensor_model_planexp.cpp:170
+  {
+    double m[7];
+    const char* keys[7] = {"mounting_translation_x", "mounting_translation_y", "mounting_translation_z", "mounting_rotation_x",
+                           "mounting_rotation_y", "mounting_rotation_z", "mounting_rotation_w"};   // [upstream] SensorModel::setupFromParamMap
+    mounting_nonzero_ = false;
+    for (int k = 0; k < 7; ++k) {
+      setParam<double>(param_map, std::string("sensor_model/") + keys[k], &m[k], k == 6 ? 1.0 : 0.0);
+      if (m[k] != (k == 6 ? 1.0 : 0.0)) mounting_nonzero_ = true;
+    }
+  }
   // [upstream] bounding volume of SimulatedSensorEvaluator (cfg/experiments/example.yaml:12-18)
   setParam<bool>(param_map, "bounding_volume/enabled", &b, false);
   params_.use_bounding_volume = b;
@@ -287,6 +309,11 @@ bool GpuGainEvaluator::checkParamsValid(std::string* error_message) {
   if (!map_ || !map_->ctx()) { *error_message = "map of type 'GpuMapPlanExp' with a live context expected"; return false; }
   if (!config_error_.empty()) { *error_message = config_error_; return false; }
   if (params_.half_fov < 0 || params_.half_fov > 112) { *error_message = "sensor_model/half_fov expected in [0, 112]"; return false; }
+  // one view per segment, taken at its last trajectory point (every shipped cfg: sampling_time 0, no mounting transform). A sensor
+  // model that samples several views along the segment (sensor_model_planexp.cpp:65-90) or is mounted off-centre (:30-31) would
+  // see other voxels than the batched kernels score: refuse the configuration instead of diverging silently.
+  if (sampling_time_ > 0.0) { *error_message = "sensor_model/sampling_time > 0 (several views per segment) is not supported by the Gpu*Evaluator"; return false; }
+  if (mounting_nonzero_) { *error_message = "sensor_model/mounting_translation_* / mounting_rotation_* must be the identity for the Gpu*Evaluator"; return false; }
   return true;
 }
 
@@ -380,16 +407,52 @@ bool GpuGainEvaluator::updateSegment(TrajectorySegment* segment) {
   std::vector<double> gain(t.gain), value(t.value);
   std::vector<uint8_t> terminal(t.terminal);
   int32_t rescored = 0;
-  if (sipp_update_tree(map_->ctx(), &params_, &updater_, n, t.parent.data(), t.end_xy.data(), t.start_xy.data(), gain.data(), t.cost.data(),
-                       value.data(), terminal.data(), cur_xy, (updater_.updater == SIPP_UPD_RRT_STAR && rrt_path_has_changed_) ? 1 : 0,
-                       &rescored) != SIPP_OK) {
+  const int path_changed = (updater_.updater == SIPP_UPD_RRT_STAR && rrt_path_has_changed_) ? 1 : 0;
+  // update_cost ([upstream] UpdateAll / UpdateAllNonTerminal: computeCost before computeValue, update_all_non_terminal.cpp:20-22).
+  // SegmentTime costs do not depend on the map, so recomputing them changes nothing; the map line integral does: the segments the
+  // chain follows are re-integrated in ONE batched call, parents first for the accumulate mode, and handed to the pass together with
+  // the costs the tree carried before it (what computeValue still finds below the node it visits).
+  std::vector<double> cost_new;
+  const bool recost = updater_.update_cost && cost_is_integral_;
+  if (recost) {
+    std::vector<uint8_t> do_gain, followed;
+    updaterMasks(updater_, t, cur_xy, path_changed != 0, &do_gain, &followed, true);
+    std::vector<int32_t> off(1, 0), ids;
+    std::vector<double> pts;
+    for (int i = 0; i < n; ++i) {
+      if (!followed[i]) continue;
+      ids.push_back(i);
+      for (const auto& p : t.nodes[i]->trajectory) { pts.push_back(p.position_W.x()); pts.push_back(p.position_W.y()); pts.push_back(p.position_W.z()); }
+      off.push_back((int32_t)(pts.size() / 3));
+    }
+    cost_new = t.cost;
+    cost_new[0] = 0.0;
+    if (!ids.empty()) {
+      std::vector<double> c(ids.size());
+      sipp_cost_params cp = cost_params_;
+      cp.accumulate = 0;
+      if (sipp_cost_integral(map_->ctx(), &cp, (int32_t)ids.size(), off.data(), pts.data(), nullptr, c.data(), nullptr) != SIPP_OK) {
+        planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
+        return false;
+      }
+      for (size_t k = 0; k < ids.size(); ++k) {       // pre-order: a parent's cost of this pass is final before its children are visited
+        const int i = ids[k];
+        cost_new[i] = c[k];
+        if (cost_params_.accumulate && t.parent[i] >= 0) cost_new[i] += cost_new[t.parent[i]];      // cost_planexp_map_integral.cpp:68-70
+      }
+    }
+  }
+  if (sipp_update_tree(map_->ctx(), &params_, &updater_, n, t.parent.data(), t.end_xy.data(), t.start_xy.data(), gain.data(),
+                       recost ? cost_new.data() : t.cost.data(), value.data(), terminal.data(), cur_xy, path_changed, &rescored,
+                       recost ? t.cost.data() : nullptr) != SIPP_OK) {
     planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
     return false;
   }
   last_batch_ = rescored;
-  for (int i = 1; i < n; ++i) {
+  for (int i = (updater_.updater == SIPP_UPD_RRT_STAR ? 1 : 0); i < n; ++i) {
     t.nodes[i]->gain = gain[i];
     t.nodes[i]->value = value[i];
+    if (recost) t.nodes[i]->cost = cost_new[i];
     if (terminal[i]) t.nodes[i]->gain_terminal = true;
   }
   return true;
@@ -442,6 +505,14 @@ ResultStatus GpuPRMStarPlanner::plan(std::vector<Eigen::Vector2d>* path, double&
     error_ = sipp_last_error(ctx_);
     cost = -1.0;
     return ResultStatus::INVALID;
+  }
+  if ((size_t)len > xy.size() / 2) {     // a path that winds through a maze can be longer than 4 (W + H) nodes: fetch all of it
+    xy.resize(2 * (size_t)len);
+    if (sipp_path_download(ctx_, xy.data(), len, &len) != SIPP_OK) {
+      error_ = sipp_last_error(ctx_);
+      cost = -1.0;
+      return ResultStatus::INVALID;
+    }
   }
   current_best_path_.clear();
   for (int i = 0; i < len && (size_t)i < xy.size() / 2; ++i) current_best_path_.push_back(Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]));

@@ -15,9 +15,11 @@
 // Each Gpu*Evaluator is a full TrajectoryEvaluator: computeGain (batch of one), computeCost ([upstream] SegmentTime),
 // computeValue / selectNextBest ([upstream] GlobalNormalizedGain / SubsequentBest) and — the batching point — updateSegment:
 // the patched planner calls trajectory_evaluator_->updateSegment(root) FIRST (mav_active_3d_planning.patch:56); on that call
-// the module walks the whole tree, applies the updater policy (RRTStarUpdater / ConstrainedUpdater + UpdateAll /
-// UpdateAllNonTerminal, rrt_star_updater.cpp:19-42, update_all_non_terminal.cpp:16-27) on the host, scores all selected nodes
-// with ONE sipp_gain_batch and all values with ONE sipp_value_preorder; the per-node updateSegment calls that follow return
+// the module flattens the whole tree and makes ONE sipp_update_tree call: the updater policy (RRTStarUpdater / ConstrainedUpdater +
+// UpdateAll / UpdateAllNonTerminal, rrt_star_updater.cpp:19-42, update_all_non_terminal.cpp:16-27) is evaluated on the DEVICE for
+// all nodes at once, the eligible nodes are compacted and scored by one batched gain launch, the values get the pre-order semantics
+// of the reference pass (updaterMasks() is the host statement of the same predicate, used for the batched re-costing when
+// update_cost is set with the map-integral cost computer and by the tests); the per-node updateSegment calls that follow return
 // true without work.
 //   GpuPRMStarPlanner : planexp_base_planners::PlannerBase  replaces PRMStarPlanner (prm_star_planner.cpp:11-186).
 // Error convention as in the reference: bool returns, configuration problems through checkParamsValid / printError,
@@ -98,7 +100,7 @@ struct FlatTree {
 
 // the host half of row A13: which nodes get computeGain / computeValue in this pass (pre-order semantics)
 void updaterMasks(const sipp_updater_params& u, const FlatTree& t, const double cur_xy[2], bool path_changed, std::vector<uint8_t>* do_gain,
-                  std::vector<uint8_t>* maybe_value);
+                  std::vector<uint8_t>* maybe_value, bool followed_instead_of_value = false);
 
 class GpuGainEvaluator : public TrajectoryEvaluator {
  public:
@@ -124,6 +126,8 @@ class GpuGainEvaluator : public TrajectoryEvaluator {
   int last_rrt_path_id_ = 0;          // rrt_star_updater.h:30-31
   bool rrt_path_has_changed_ = true;
   int last_batch_ = 0;
+  double sampling_time_ = 0.0;        // sensor_model/sampling_time (sensor_model_planexp.cpp:170): only <= 0 (last point) is supported
+  bool mounting_nonzero_ = false;     // sensor_model/mounting_*: only the identity is supported
   std::string config_error_;
 };
 

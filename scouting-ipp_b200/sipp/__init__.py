@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
     "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
+    "sipp_path_download",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -173,6 +174,7 @@ def lib():
         L.sipp_map_download.argtypes = [vp, vp, vp, vp, vp]
         L.sipp_plan.argtypes = [vp, pf64, pi32, vp, i32, pi32]
         L.sipp_field_download.argtypes = [vp, vp]
+        L.sipp_path_download.argtypes = [vp, vp, i32, pi32]
         L.sipp_path_mask_generation.argtypes = [vp]
         L.sipp_set_path_mask.argtypes = [vp, vp]
         L.sipp_plan_stats.argtypes = [vp, vp]
@@ -184,7 +186,7 @@ def lib():
         L.sipp_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, pi32, pf64]
         L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.sipp_merge_best_dev.argtypes = [vp, vp, i32, i64, vp, vp]
-        L.sipp_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, pi32]
+        L.sipp_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, pi32, vp]
         L.sipp_peer_export.argtypes = [vp, vp]
         L.sipp_peer_attach.argtypes = [vp, i32, i32, vp]
         L.sipp_peer_detach.argtypes = [vp]
@@ -297,6 +299,15 @@ class Context:
         self._check(self._L.sipp_plan(self._h, C.byref(cost), C.byref(status), _ptr(path), cap, C.byref(n)))
         return cost.value, status.value, path[: min(n.value, cap)].copy(), n.value
 
+    def path_download(self, cap=None):
+        """the path of the last plan again (all of it by default)"""
+        n = C.c_int32()
+        self._check(self._L.sipp_path_download(self._h, None, 0, C.byref(n)))
+        cap = n.value if cap is None else cap
+        path = np.zeros((max(cap, 1), 2), np.float64)
+        self._check(self._L.sipp_path_download(self._h, _ptr(path), cap, C.byref(n)))
+        return path[: min(n.value, cap)].copy(), n.value
+
     def plan_stats(self):
         st = np.zeros(4, np.int64)
         self._check(self._L.sipp_plan_stats(self._h, _ptr(st)))
@@ -381,7 +392,7 @@ class Context:
         self._check(self._L.sipp_cycle_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost),
                                            _ptr(d_gain), _ptr(d_terminal), _ptr(d_value), _ptr(d_best), _ptr(stream)))
 
-    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None):
+    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, cost_below=None):
         """one re-evaluation pass over a pre-order tree; returns (gain, value, terminal, n_rescored) — inputs are not modified"""
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         n = parent.shape[0]
@@ -392,9 +403,10 @@ class Context:
         t = np.array(terminal, dtype=np.uint8, copy=True)
         cost = np.ascontiguousarray(cost, dtype=np.float64)
         cur = np.ascontiguousarray(cur_xy, dtype=np.float64)
+        cb = None if cost_below is None else np.ascontiguousarray(cost_below, dtype=np.float64)
         nres = C.c_int32()
         self._check(self._L.sipp_update_tree(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g),
-                                             _ptr(cost), _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), C.byref(nres)))
+                                             _ptr(cost), _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), C.byref(nres), _ptr(cb)))
         return g, v, t, nres.value
 
     def merge_best_dev(self, d_recs, world, shard_stride, d_out, stream=None):

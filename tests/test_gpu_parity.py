@@ -352,6 +352,74 @@ def test_config1_example_launch_tree_cycle(golden):
         assert abs(bvg - bvo) <= RTOL * abs(bvo)
 
 
+def test_cuda_matches_committed_reference_vectors():
+    """CUDA against tests/golden/ref_evaluators.npz — vectors produced by the reference's OWN evaluator / updater / cost sources
+    (compiled unmodified into oracle/_ref, tests/golden/make_ref_golden.py): unknown-voxel counts, terminal flags, updater passes'
+    terminal flags and trajectory cost integrals bit for bit; gains / values exact where they are integer valued, else within RTOL."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_ref_golden as G
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_evaluators.npz"))
+    g = sipp.Context(G.make_desc(sipp.make_desc))
+    for x0, y0, patch in G.patches():
+        g.map_update_patch(x0, y0, patch)
+    g.plan()
+    state, cost, reach, path = g.map_download()
+    assert np.array_equal(state, vec["state"]) and np.array_equal(cost, vec["cost"]) and np.array_equal(reach, vec["reach"])
+    assert np.array_equal(path, vec["path"]) and g.map_stats()[:2] == tuple(vec["mean_max"])
+    xy, sxy = G.poses()
+    close = lambda a, b: np.allclose(a, b, rtol=RTOL, atol=0.0, equal_nan=True)
+    k = 0
+    for kw in G.EVAL_SETS:
+        for hf in G.HALF_FOVS:
+            for bv in G.BVS:
+                gg, gc, gt = g.gain_batch(sipp.make_params(half_fov=hf, bounding_volume=bv, **kw), xy, sxy)
+                assert np.array_equal(gc[:, 1], vec["unk_%03d" % k]) and np.array_equal(gt, vec["term_%03d" % k]), (kw, hf, bv)
+                if EXACT_GAIN(kw):
+                    assert np.array_equal(gg, vec["gain_%03d" % k], equal_nan=True), (kw, hf, bv)
+                else:
+                    assert close(gg, vec["gain_%03d" % k]), (kw, hf, bv)
+                k += 1
+    par, end, start, tcost, gain0, term0, value0 = G.tree()
+    k = 0
+    for upd, fol in G.UPDATER_SETS:
+        for kw in (G.EVAL_SETS[0], G.EVAL_SETS[3], G.EVAL_SETS[5], G.EVAL_SETS[6], G.EVAL_SETS[7]):
+            for pc in (False, True):
+                for flags in ((True, False, True), (False, False, True), (True, False, False)):
+                    u = sipp.make_updater(upd, fol, 0.001, 4.0, *flags)
+                    tg, tv, tt, _ = g.update_tree(sipp.make_params(half_fov=10, **kw), u, par, end, gain0, tcost, value0, term0, (3.1, 2.7), pc, start_xy=start)
+                    first = 1 if upd == 0 else 0
+                    assert np.array_equal(tt[first:], vec["tt_%03d" % k][first:]), (upd, fol, kw, pc, flags)
+                    assert close(tg[first:], vec["tg_%03d" % k][first:]) and close(tv[first:], vec["tv_%03d" % k][first:]), (upd, fol, kw, pc, flags)
+                    k += 1
+    # update_cost with the map-integral cost: re-integrate the followed segments (one batched sipp_cost_integral), pass old + new costs
+    n = len(par)
+    off = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    pts = np.zeros((2 * n, 3))
+    pts[0::2, :2], pts[1::2, :2] = start, end
+    integral, _ = g.cost_integral(sipp.make_cost_params(False, 0.05), off, pts)
+    for k, (upd, fol) in enumerate(G.UPDATER_SETS):
+        rc = vec["cc_%03d" % k]
+        base = np.where(np.arange(n) == 0, 0.0, tcost)
+        followed = rc != base
+        cost_new = base.copy()
+        cost_new[followed] = integral[followed]
+        assert np.array_equal(cost_new, rc), (upd, fol)            # the CUDA line integral IS the reference's, bit for bit
+        u = sipp.make_updater(upd, fol, 0.001, 4.0, True, True, True)
+        tg, tv, tt, _ = g.update_tree(sipp.make_params(half_fov=10, **G.EVAL_SETS[5]), u, par, end, gain0, cost_new, value0, term0, (3.1, 2.7), True,
+                                      start_xy=start, cost_below=tcost)
+        first = 1 if upd == 0 else 0
+        assert np.array_equal(tt[first:], vec["ct_%03d" % k][first:])
+        assert close(tg[first:], vec["cg_%03d" % k][first:]) and close(tv[first:], vec["cv_%03d" % k][first:]), (upd, fol)
+    off, pts, pcost = G.segments()
+    k = 0
+    for acc in (False, True):
+        for msd in (0.05, 0.3):
+            c, vd = g.cost_integral(sipp.make_cost_params(acc, msd), off, pts, pcost if acc else None)
+            assert np.array_equal(c, vec["ci_%d" % k], equal_nan=True) and np.array_equal(vd, vec["civ_%d" % k]), (acc, msd)
+            k += 1
+
+
 def _random_tree(rng, n, W, H):
     """pre-order parent array of a random RRT-like tree (children in index order) + end / start points of the segments"""
     par = np.full(n, -1, np.int32)
