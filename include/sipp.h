@@ -297,6 +297,30 @@ typedef struct sipp_cost_params {
 int sipp_cost_integral(sipp_ctx* ctx, const sipp_cost_params* params, int32_t n, const int32_t* point_offset,
                        const double* points_xyz, const double* parent_cost, double* cost, uint8_t* valid);
 
+/* ---- simulator travel cost (second half) -------------------------------------------------------------------- */
+/* MavSimulator::computeCost (mav_simulator/src/mav_simulator.cpp:785-821): the cost the simulator books for every flown segment,
+ * integrated over the GROUND-TRUTH label map (mav_simulator.h:112 map_), not the observed one. The truth map is uploaded once
+ * (sipp_truth_upload; W*H int32 row-major like every host plane here) and stays resident; the episode / ensemble runners cut the
+ * scout's observation patches out of it on the device as well.
+ * Per (start, goal) pair: distance = |goal - start|, n = ceil(distance / max_step_size) equal steps, each charged
+ *   MapCost:      mean of the two end cells' labels * step length   (:799,805)   pixel = (int)(p * cols / map_width) (:582-587)
+ *   DistanceCost: step length                                        (:808)
+ *   TimeCost:     step length / mav_speed                            (:811)
+ * accumulated sequentially in the reference's order (one thread per pair): bit-identical to the C++ loop. A sample outside the
+ * map (undefined behaviour in the reference: unchecked Eigen index) reads label 0. */
+#define SIPP_TRAVEL_MAP_COST 0
+#define SIPP_TRAVEL_DISTANCE_COST 1
+#define SIPP_TRAVEL_TIME_COST 2
+typedef struct sipp_travel_params {
+  int32_t formulation;      /* SIPP_TRAVEL_* (mav_simulator/include/mav_simulator/types.h:7-11, mav_simulator.cpp:33-43) */
+  int32_t pad_;
+  double max_step_size;     /* default 0.05 m (mav_simulator.h:104) */
+  double mav_speed;         /* default 1.0 m/s (mav_simulator.h:134) */
+} sipp_travel_params;
+int sipp_truth_upload(sipp_ctx* ctx, const int32_t* labels);
+int sipp_travel_cost(sipp_ctx* ctx, const sipp_travel_params* params, int32_t n, const double* start_xyz, const double* goal_xyz,
+                     double* cost);
+
 /* ---- episode replay (offline evaluation replay / ensembles of independent maps) ------------------ */
 /* The host loop of one exploration episode, run natively so that many episodes can be driven side by side from plain host
  * threads (one context each; contexts are independent and their kernels overlap on the GPU): per cycle c

@@ -75,6 +75,19 @@ class CostParams(C.Structure):  # sipp_cost_params
     _fields_ = [("accumulate", C.c_int32), ("pad_", C.c_int32), ("max_sample_distance", C.c_double)]
 
 
+TRAVEL_MAP_COST, TRAVEL_DISTANCE_COST, TRAVEL_TIME_COST = range(3)
+
+
+class TravelParams(C.Structure):  # sipp_travel_params
+    _fields_ = [("formulation", C.c_int32), ("pad_", C.c_int32), ("max_step_size", C.c_double), ("mav_speed", C.c_double)]
+
+
+def make_travel_params(formulation=TRAVEL_MAP_COST, max_step_size=0.05, mav_speed=1.0):
+    p = TravelParams()
+    p.formulation, p.max_step_size, p.mav_speed = int(formulation), float(max_step_size), float(mav_speed)
+    return p
+
+
 def make_cost_params(accumulate=False, max_sample_distance=0.05):
     p = CostParams()
     p.accumulate, p.max_sample_distance = int(bool(accumulate)), float(max_sample_distance)
@@ -161,6 +174,7 @@ def lib():
         L.orc_gain_batch.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, i32, i32]
         L.orc_value_select.argtypes = [i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64)]
         L.orc_cost_integral.argtypes = [vp, C.POINTER(CostParams), i32, vp, vp, vp, vp, vp]
+        L.orc_travel_cost.argtypes = [vp, vp, C.POINTER(TravelParams), i32, vp, vp, vp]
         L.orc_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64), i32, i32]
         L.orc_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
         _lib = L
@@ -312,6 +326,15 @@ class Oracle:
         cost, valid = np.zeros(n, np.float64), np.zeros(n, np.uint8)
         self._L.orc_cost_integral(self._h, C.byref(cparams), n, _ptr(off), _ptr(pts), _ptr(pc), _ptr(cost), _ptr(valid))
         return cost, valid
+
+    def travel_cost(self, truth, tparams, start_xyz, goal_xyz):
+        """MavSimulator::computeCost (mav_simulator.cpp:785-821) over the ground-truth label map `truth`"""
+        truth = np.ascontiguousarray(truth, dtype=np.int32)
+        a = np.ascontiguousarray(start_xyz, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(goal_xyz, dtype=np.float64).reshape(-1, 3)
+        cost = np.zeros(len(a), np.float64)
+        self._L.orc_travel_cost(self._h, _ptr(truth), C.byref(tparams), len(a), _ptr(a), _ptr(b), _ptr(cost))
+        return cost
 
     def cycle(self, params, xy, cost, start_xy=None, variant=0, threads=1):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

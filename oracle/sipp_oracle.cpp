@@ -968,6 +968,49 @@ int orc_cost_integral(orc_ctx* c, const sipp_cost_params* cp, int32_t n, const i
   return 0;
 }
 
+// MavSimulator::computeCost (mav_simulator/src/mav_simulator.cpp:785-821) on the simulator's ground-truth label map `truth`
+// (W x H int32 row-major; the reference's map_ is an Eigen::ArrayXXi indexed (row = y, col = x) through AM(), mav_simulator.h:15,112).
+// pixel = ((int)(x * cols / map_width), (int)(y * rows / map_height)) (:582-587). A pixel outside the array is undefined behaviour in
+// the reference (unchecked Eigen index): here it reads 0 and is counted in oob_events.
+int orc_travel_cost(orc_ctx* c, const int32_t* truth, const sipp_travel_params* tp, int32_t n, const double* start_xyz, const double* goal_xyz,
+                    double* cost_out) {
+  Oracle& o = c->o;
+  auto label_at = [&](double x, double y) -> int {
+    const double fx = x * (long)o.W / o.desc.width, fy = y * (long)o.H / o.desc.height;
+    if (!(fx > -2.0e9 && fx < 2.0e9 && fy > -2.0e9 && fy < 2.0e9)) { ++o.oob_events; return 0; }
+    const int ix = (int)fx, iy = (int)fy;
+    if (ix < 0 || ix >= o.W || iy < 0 || iy >= o.H) { ++o.oob_events; return 0; }
+    return truth[(size_t)iy * o.W + ix];
+  };
+  for (int s = 0; s < n; ++s) {
+    const double sx = start_xyz[3 * s], sy = start_xyz[3 * s + 1], sz = start_xyz[3 * s + 2];
+    const double dx = goal_xyz[3 * s] - sx, dy = goal_xyz[3 * s + 1] - sy, dz = goal_xyz[3 * s + 2] - sz;
+    double cost = 0.0;
+    const double distance = std::sqrt(dx * dx + dy * dy + dz * dz);                  // :788 (goal - start).norm()
+    const double q = distance / tp->max_step_size;
+    const int n_elements = (q < 2.0e9) ? (int)std::ceil(q) : 0;                       // :789
+    if (n_elements > 0) {
+      const double step_distance = distance / n_elements;                             // :791
+      const double stx = dx / n_elements, sty = dy / n_elements, stz = dz / n_elements;   // :792
+      double cx = sx, cy = sy, cz = sz;
+      for (int i = 0; i < n_elements; ++i) {
+        const double tx = cx + stx, ty = cy + sty, tz = cz + stz;                     // :796
+        const int ls = label_at(cx, cy), le = label_at(tx, ty);                       // :797-798
+        const double average_segment_cost = (ls + le) / 2.0;                          // :799
+        switch (tp->formulation) {
+          case SIPP_TRAVEL_MAP_COST: cost += average_segment_cost * step_distance; break;     // :805
+          case SIPP_TRAVEL_DISTANCE_COST: cost += step_distance; break;                       // :808
+          case SIPP_TRAVEL_TIME_COST: cost += (step_distance / tp->mav_speed); break;         // :811
+          default: break;
+        }
+        cx = tx; cy = ty; cz = tz;                                                    // :817
+      }
+    }
+    cost_out[s] = cost;
+  }
+  return 0;
+}
+
 int orc_cycle(orc_ctx* c, const sipp_eval_params* p, int32_t n, const double* xy, const double* start_xy, const double* cost,
               double* gain, uint8_t* terminal, double* value, int32_t* best_index, double* best_value, int variant, int threads) {
   orc_gain_batch(c, p, n, xy, start_xy, gain, nullptr, terminal, variant, threads);

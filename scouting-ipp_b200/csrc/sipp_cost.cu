@@ -79,7 +79,68 @@ __global__ void k_cost_integral(const CostArgs a) {
   if (a.valid) a.valid[s] = 1;
 }
 
+// ---- MavSimulator::computeCost (mav_simulator/src/mav_simulator.cpp:785-821) over the ground-truth label plane -----------------------
+struct TravelArgs {
+  int n;
+  const double* start;   // n x 3
+  const double* goal;    // n x 3
+  double* cost;
+  const uint16_t* truth;
+  size_t pitch16;
+  int W, H;
+  double map_width, map_height, max_step, speed;
+  int formulation;
+};
+
+// position2pixelLocation (:582-587): (int)(p * cols / width); a pixel outside the map reads label 0
+__device__ __forceinline__ int truth_at(const TravelArgs& a, double x, double y) {
+  const double fx = __ddiv_rn(__dmul_rn(x, (double)a.W), a.map_width), fy = __ddiv_rn(__dmul_rn(y, (double)a.H), a.map_height);
+  if (!(fx > -2.0e9 && fx < 2.0e9 && fy > -2.0e9 && fy < 2.0e9)) return 0;
+  const int ix = (int)fx, iy = (int)fy;
+  if (ix < 0 || ix >= a.W || iy < 0 || iy >= a.H) return 0;
+  return (int)a.truth[(size_t)iy * a.pitch16 + ix];
+}
+
+__global__ void k_travel_cost(const TravelArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.n) return;
+  const double sx = a.start[3 * s], sy = a.start[3 * s + 1], sz = a.start[3 * s + 2];
+  const double dx = __dadd_rn(a.goal[3 * s], -sx), dy = __dadd_rn(a.goal[3 * s + 1], -sy), dz = __dadd_rn(a.goal[3 * s + 2], -sz);
+  const double distance = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));      // :788
+  double cost = 0.0;
+  const double q = __ddiv_rn(distance, a.max_step);
+  const int n_elements = (q < 2.0e9) ? (int)ceil(q) : 0;                                                                   // :789 (NaN / absurd lengths: nothing)
+  if (n_elements > 0) {
+    const double step_distance = __ddiv_rn(distance, (double)n_elements);                                                  // :791
+    const double stx = __ddiv_rn(dx, (double)n_elements), sty = __ddiv_rn(dy, (double)n_elements), stz = __ddiv_rn(dz, (double)n_elements);   // :792
+    double cx = sx, cy = sy, cz = sz;
+    int ls = truth_at(a, cx, cy);
+    for (int i = 0; i < n_elements; ++i) {
+      const double tx = __dadd_rn(cx, stx), ty = __dadd_rn(cy, sty), tz = __dadd_rn(cz, stz);                              // :796
+      const int le = truth_at(a, tx, ty);
+      const double average_segment_cost = __ddiv_rn((double)(ls + le), 2.0);                                              // :799 (int + int, then / 2.0)
+      if (a.formulation == SIPP_TRAVEL_MAP_COST) cost = __dadd_rn(cost, __dmul_rn(average_segment_cost, step_distance));  // :805
+      else if (a.formulation == SIPP_TRAVEL_DISTANCE_COST) cost = __dadd_rn(cost, step_distance);                          // :808
+      else cost = __dadd_rn(cost, __ddiv_rn(step_distance, a.speed));                                                      // :811
+      cx = tx; cy = ty; cz = tz;
+      ls = le;                     // the next step starts where this one ended: same position, same lookup
+    }
+  }
+  a.cost[s] = cost;
+}
+
 }  // namespace
+
+cudaError_t launch_travel_cost(sipp_ctx* ctx, const sipp_travel_params& p, int n, const double* d_start, const double* d_goal, double* d_cost, cudaStream_t s) {
+  TravelArgs a;
+  a.n = n; a.start = d_start; a.goal = d_goal; a.cost = d_cost;
+  a.truth = ctx->d_truth; a.pitch16 = ctx->pitch16; a.W = ctx->W; a.H = ctx->H;
+  a.map_width = ctx->desc.width; a.map_height = ctx->desc.height; a.max_step = p.max_step_size; a.speed = p.mav_speed;
+  a.formulation = p.formulation;
+  k_travel_cost<<<(n + 127) / 128, 128, 0, s>>>(a);
+  ctx->launches += 1;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_cost_integral(sipp_ctx* ctx, const sipp_cost_params& p, int n, const int32_t* d_off, const double* d_pts, const double* d_parent_cost,
                                  double* d_cost, uint8_t* d_valid, cudaStream_t s) {

@@ -8,6 +8,7 @@
 #include <map>
 
 #include "sipp_internal.h"
+#include "sipp_peer.cuh"
 
 static thread_local std::string g_create_err;
 
@@ -205,7 +206,10 @@ bool same_bv(const sipp_eval_params& a, const sipp_eval_params& b) {
 // (re)build the evaluator view planes when the map, the path mask or the bounding volume changed
 int ensure_views(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, cudaStream_t s) {
   if (p->evaluator == SIPP_EVAL_EXPAND_LOW_COST) {
-    // ExpandLowCostAreaEvaluator: its own view plane + the reciprocal table recip[idx] (idx = closest cost + 1)
+    // ExpandLowCostAreaEvaluator: its own view plane + the reciprocal table recip[idx] (idx = closest cost + 1). The view packs idx
+    // into 15 bits next to the "counted" bit: a label above 32766 cannot be represented there — refuse instead of aliasing costs.
+    if (ctx->max_cost > (double)(kRecipEntries - 2))
+      return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "ExpandLowCostAreaEvaluator: labels up to %d only (a label of %.0f was ingested)", kRecipEntries - 2, ctx->max_cost);
     const bool bv_changed = !(ctx->view_params_valid && same_bv(ctx->view_params, *p));
     if (ctx->lowcost_view_dirty || bv_changed) {
       SIPP_CUDA_CHECK(ctx, launch_build_lowcost_view(ctx, g, p->use_bounding_volume != 0, s));
@@ -216,9 +220,9 @@ int ensure_views(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, cu
     }
     const int aug = p->augment_unknown_with_mean != 0;
     if (!ctx->recip_valid || ctx->recip_augment != aug || memcmp(&ctx->recip_mean, &ctx->mean_cost, sizeof(double)) != 0) {
-      std::vector<double> r(4097, 0.0);
+      std::vector<double> r(kRecipEntries, 0.0);
       r[1] = aug ? 1.0 / ctx->mean_cost : 0.0;                  // cost <= 0: expand_low_cost_area_evaluator.cpp:55-57,64-66
-      for (int k = 2; k <= 4096; ++k) r[k] = 1.0 / (double)(k - 1);   // :53,62
+      for (int k = 2; k < kRecipEntries; ++k) r[k] = 1.0 / (double)(k - 1);   // :53,62
       SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_recip, r.data(), r.size() * 8, cudaMemcpyHostToDevice, s));
       SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));         // r goes out of scope
       ctx->recip_valid = true; ctx->recip_augment = aug; ctx->recip_mean = ctx->mean_cost;
@@ -298,7 +302,7 @@ void sipp_destroy(sipp_ctx* ctx) {
   void* ptrs[] = {ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->d_path, ctx->d_rec, ctx->d_freelab, ctx->d_closest, ctx->d_cclab, ctx->d_closest_dist,
                   ctx->d_recip, ctx->d_field, ctx->d_pred, ctx->d_tile_w, ctx->d_xcls, ctx->d_ycls, ctx->d_hdist, ctx->d_vdist, ctx->d_ddist, ctx->d_tile_flags,
                   ctx->d_tile_list, ctx->d_relax_ctl, ctx->d_path_nodes, ctx->d_path_xy, ctx->d_plan_out, ctx->d_stage, ctx->d_tree_ws,
-                  ctx->d_best, ctx->d_select_ws, ctx->d_mark, ctx->d_tile_seed, ctx->d_seed_list, ctx->d_rec2[0], ctx->d_rec2[1]};
+                  ctx->d_best, ctx->d_select_ws, ctx->d_mark, ctx->d_tile_seed, ctx->d_seed_list, ctx->d_rec2[0], ctx->d_rec2[1], ctx->d_truth};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   peer_release(ctx);
@@ -362,7 +366,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   ctx->d_state = ctx->d_path = ctx->d_rec = nullptr;
   ctx->d_label = ctx->d_pcode = ctx->d_freelab = ctx->d_closest = ctx->d_cclab = nullptr;
   ctx->lowcost_view_dirty = true; ctx->recip_valid = false;
-  ctx->d_closest_dist = nullptr; ctx->d_recip = nullptr; ctx->d_field = nullptr; ctx->d_pred = nullptr; ctx->d_tile_w = nullptr;
+  ctx->d_closest_dist = nullptr; ctx->d_recip = nullptr; ctx->d_field = nullptr; ctx->d_pred = nullptr; ctx->d_tile_w = nullptr; ctx->d_truth = nullptr;
   ctx->d_xcls = ctx->d_ycls = nullptr; ctx->d_hdist = ctx->d_vdist = ctx->d_ddist = nullptr;
   ctx->d_tile_flags = nullptr; ctx->d_tile_list = nullptr; ctx->d_relax_ctl = nullptr;
   ctx->d_path_nodes = nullptr; ctx->d_path_xy = nullptr; ctx->d_plan_out = nullptr;
@@ -422,7 +426,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   rc |= dev_alloc(ctx, &ctx->d_pcode, n8);
   rc |= dev_alloc(ctx, &ctx->d_freelab, n8);
   rc |= dev_alloc(ctx, &ctx->d_closest, n8);
-  rc |= dev_alloc(ctx, &ctx->d_recip, (size_t)4097);
+  rc |= dev_alloc(ctx, &ctx->d_recip, (size_t)kRecipEntries);
   if (ctx->desc.compute_closest_observed) {
     rc |= dev_alloc(ctx, &ctx->d_cclab, n8);
     rc |= dev_alloc(ctx, &ctx->d_closest_dist, n8);
@@ -796,9 +800,17 @@ static int cycle_dev_impl(sipp_ctx* ctx, const sipp_eval_params* params, int32_t
                           int peer_mode = 0) {
   int rc = check_params(ctx, params);
   if (rc != SIPP_OK) return rc;
-  if (n < 1 || !d_xy || !d_cost || !d_gain || !d_value || !d_best) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
   if (shard && ctx->peer_world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "peers are not attached (sipp_peer_attach)");
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  if (shard && n == 0 && d_best) {
+    // an empty shard (fewer candidates than ranks, or everything pruned on this rank) still takes part in the lockstep exchange:
+    // it publishes {0.0, -1} — "never wins" — so the step counter advances on every rank and nobody waits for a record that never comes
+    const BestRec none = {0.0, -1};
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_best + 1, &none, sizeof(none), cudaMemcpyHostToDevice, s));
+    SIPP_CUDA_CHECK(ctx, launch_peer_exchange(ctx, ctx->d_best + 1, reinterpret_cast<BestRec*>(d_best), peer_mode == 1 ? PEER_PIPELINED : PEER_SYNC, s));
+    return SIPP_OK;
+  }
+  if (n < 1 || !d_xy || !d_cost || !d_gain || !d_value || !d_best) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
   const GainGeom g = make_gain_geom(ctx, params);
   if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
   // one launch: the argmax (and, sharded, the exchange of the shard winners) is the tail of the gain kernel
@@ -849,9 +861,21 @@ static int cycle_host_impl(sipp_ctx* ctx, const sipp_eval_params* params, int32_
                            double* gain, uint8_t* terminal, double* value, int64_t* best_index, double* best_value, bool shard, int64_t index_offset) {
   int rc = check_params(ctx, params);
   if (rc != SIPP_OK) return rc;
-  if (n < 1 || !xy || !cost) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
   if (shard && ctx->peer_world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "peers are not attached (sipp_peer_attach)");
   cudaStream_t s = ctx->stream;
+  if (shard && n == 0) {       // empty shard: exchange only (see cycle_dev_impl)
+    const BestRec none = {0.0, -1};
+    BestRec* h_best0 = reinterpret_cast<BestRec*>(ctx->h_pinned);
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_best + 1, &none, sizeof(none), cudaMemcpyHostToDevice, s));
+    SIPP_CUDA_CHECK(ctx, launch_peer_exchange(ctx, ctx->d_best + 1, ctx->d_best, PEER_SYNC, s));
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(h_best0, ctx->d_best, sizeof(BestRec), cudaMemcpyDeviceToHost, s));
+    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+    if (best_index) *best_index = h_best0->index;
+    if (best_value) *best_value = h_best0->value;
+    if (h_best0->index == -3) return sipp_set_err(ctx, SIPP_ERR_CUDA, "peer exchange timed out (a rank died or the ranks are not calling in lockstep)");
+    return SIPP_OK;
+  }
+  if (n < 1 || !xy || !cost) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad cycle arguments");
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, stage_bytes(n))) != SIPP_OK) return rc;
   const Stage st = carve(ctx->d_stage, n);
   const GainGeom g = make_gain_geom(ctx, params);
@@ -1001,6 +1025,47 @@ int sipp_cost_integral(sipp_ctx* ctx, const sipp_cost_params* params, int32_t n,
   SIPP_CUDA_CHECK(ctx, launch_cost_integral(ctx, *params, n, d_off, d_pts, acc ? d_parent : nullptr, d_cost, d_valid, s));
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(cost, d_cost, N * 8, cudaMemcpyDeviceToHost, s));
   if (valid) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(valid, d_valid, N, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  return SIPP_OK;
+}
+
+// ---- simulator travel cost --------------------------------------------------------------------------------
+int sipp_truth_upload(sipp_ctx* ctx, const int32_t* labels) {
+  SIPP_ENTER(ctx);
+  if (!labels) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "labels == NULL");
+  const size_t n = (size_t)ctx->W * ctx->H;
+  std::vector<uint16_t> packed(ctx->pitch16 * (size_t)ctx->H, 0);
+  for (int y = 0; y < ctx->H; ++y)
+    for (int x = 0; x < ctx->W; ++x) {
+      const int32_t v = labels[(size_t)y * ctx->W + x];
+      if (v < 0 || v > 65533) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "label %d outside [0,65533]", v);
+      packed[(size_t)y * ctx->pitch16 + x] = (uint16_t)v;
+    }
+  (void)n;
+  if (!ctx->d_truth) SIPP_CUDA_CHECK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_truth), packed.size() * sizeof(uint16_t)));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_truth, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return SIPP_OK;
+}
+
+int sipp_travel_cost(sipp_ctx* ctx, const sipp_travel_params* params, int32_t n, const double* start_xyz, const double* goal_xyz, double* cost) {
+  SIPP_ENTER(ctx);
+  if (!params || n < 0 || (n > 0 && (!start_xyz || !goal_xyz || !cost))) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad travel_cost arguments");
+  if (params->formulation < SIPP_TRAVEL_MAP_COST || params->formulation > SIPP_TRAVEL_TIME_COST)
+    return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "unknown cost formulation %d", params->formulation);      // mav_simulator.cpp:813-815
+  if (!(params->max_step_size > 0) || !(params->mav_speed > 0)) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "max_step_size and mav_speed must be positive");
+  if (!ctx->d_truth) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "no ground-truth map: call sipp_truth_upload first");
+  if (n == 0) return SIPP_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t N = (size_t)n;
+  int rc;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, N * 56 + 256)) != SIPP_OK) return rc;
+  double* d_start = reinterpret_cast<double*>(ctx->d_stage);
+  double *d_goal = d_start + 3 * N, *d_cost = d_goal + 3 * N;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_start, start_xyz, N * 24, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_goal, goal_xyz, N * 24, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, launch_travel_cost(ctx, *params, n, d_start, d_goal, d_cost, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(cost, d_cost, N * 8, cudaMemcpyDeviceToHost, s));
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
   return SIPP_OK;
 }

@@ -17,6 +17,7 @@
 // coordinates); lane 0 adds the duplicate with the reference's own double-precision index math.
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "sipp_argmax.cuh"
 #include "sipp_internal.h"
@@ -471,12 +472,12 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           if (MODE == MODE_AVG_VIEW_COST) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) sum_aux2 += (wds[q] & 0xFFFFu) + (wds[q] >> 16);
-          } else {  // MODE_LOW_COST: bit 15 = counted (UNKNOWN, inside the bounding volume), bits 0..11 = closest cost + 1
+          } else {  // MODE_LOW_COST: bit 15 = counted (UNKNOWN, inside the bounding volume), bits 0..14 = closest cost + 1
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t l0 = wds[q] & 0xFFFFu, l1 = wds[q] >> 16;
-              if (l0 & 0x8000u) { n_unk += 1; fsum += a.recip[l0 & 0x0FFFu]; }
-              if (l1 & 0x8000u) { n_unk += 1; fsum += a.recip[l1 & 0x0FFFu]; }
+              if (l0 & 0x8000u) { n_unk += 1; fsum += a.recip[l0 & 0x7FFFu]; }
+              if (l1 & 0x8000u) { n_unk += 1; fsum += a.recip[l1 & 0x7FFFu]; }
             }
           }
         }
@@ -529,7 +530,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
           const uint32_t crec = my_crec, caux16 = my_caux16;
           bool c_unk, c_free = false, c_path = false, c_reach = false;
           if (MODE == MODE_LOW_COST) {
-            c_unk = c_in_bounds ? ((caux16 & 0x0FFFu) != 0) : true;      // idx != 0 <=> the cell is UNKNOWN
+            c_unk = c_in_bounds ? ((caux16 & 0x7FFFu) != 0) : true;      // idx != 0 <=> the cell is UNKNOWN
           } else {
             c_unk = c_in_bounds ? ((crec & REC_RAW_UNK) != 0) : true;
             c_free = c_in_bounds && (crec & REC_RAW_FREE) != 0;
@@ -552,7 +553,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
               const double dist = sqrt(dx * dx + dy * dy);
               fsum += (dist > a.inv_max_gain) ? 1.0 / dist : a.max_gain;
             } else if (MODE == MODE_LOW_COST) {
-              fsum += a.recip[c_in_bounds ? (caux16 & 0x0FFFu) : 1u];   // outside the map server's bounds the lookup gives -1
+              fsum += a.recip[c_in_bounds ? (caux16 & 0x7FFFu) : 1u];   // outside the map server's bounds the lookup gives -1
             }
           } else if (MODE == MODE_AVG_VIEW_COST && c_free) {
             n_aux += 1;
@@ -707,19 +708,32 @@ const CUtensorMap* cached_tmap(sipp_ctx* ctx, int half_fov, int kind, int* rc) {
 
 template <int MODE, bool PACKED = false>
 int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_aux, const GainArgs& a, cudaStream_t s) {
-  static int num_sms = 0;
-  if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  // per device and per instantiation, once, under a process-wide lock (contexts are driven from several host threads): the SM count
+  // and the dynamic shared-memory opt-in — set to the maximum once instead of per launch, so that two threads launching this kernel
+  // with different tile shapes cannot interleave "set attribute" and "launch"
+  int num_sms = 0;
+  auto kern = k_gain<MODE, PACKED>;
+  {
+    static std::mutex mu;
+    static struct { bool done; int num_sms; } info[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    auto& di = info[ctx->device & 63];
+    if (!di.done) {
+      cudaError_t e0 = cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+      if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+      if (e0 != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_gain setup: %s", cudaGetErrorString(e0));
+      di.done = true;
+    }
+    num_sms = di.num_sms;
+  }
   // warps per CTA x tile slots per warp: as many slots as fit in ~220 KB of shared memory
   const int kStages = a.stages;
   int wpc = ctx->gain_warps > 0 ? ctx->gain_warps : kMaxWarpsPerCta;
   while (wpc > 1 && (size_t)wpc * kStages * a.slot_bytes > 220 * 1024) --wpc;
   const size_t smem = PACKED ? 0 : (size_t)wpc * kStages * a.slot_bytes;     // the packed form keeps no tiles
-  if (smem > 227 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %zu bytes of shared memory per CTA", a.half_fov, smem);
-  auto kern = k_gain<MODE, PACKED>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  if (smem > 221 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %zu bytes of shared memory per CTA", a.half_fov, smem);
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem);
   if (e != cudaSuccess || occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
   const int want = (a.n + wpc - 1) / wpc;
   int grid = want < num_sms * occ ? want : num_sms * occ;   // persistent: a multiple of the SM count when saturated

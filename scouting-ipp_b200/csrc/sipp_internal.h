@@ -32,6 +32,7 @@
 #define PCODE_UNEXPLORED 0xFFFFu  // cost = init_cost
 #define PCODE_REMOVED 0xFFFEu     // first observation was an obstacle id: all edges deleted
 
+constexpr int kRecipEntries = 32768;   // ExpandLowCost view: idx = closest-observed label + 1 in 15 bits (labels <= 32766)
 #define SIPP_MAX_CLASSES 64  // distinct |dX|^2 (or |dY|^2) values of the node lattice (9..14 in practice)
 
 struct FieldGeom {  // device-side view of the implicit per-pixel graph geometry
@@ -134,10 +135,11 @@ struct sipp_ctx {
   float* d_closest_dist; // map_distance_closest_ as squared pixel distance
   bool lowcost_view_dirty;
   double recip_mean; int recip_augment; bool recip_valid;   // what d_recip was filled for
-  double* d_recip;       // [65536] 1/label lookup for ExpandLowCost
+  double* d_recip;       // [kRecipEntries] 1/label lookup for ExpandLowCost, indexed by closest cost + 1
   double* d_field;       // W*H doubles
   double* d_tile_w;      // [ntiles][4][34][34] edge-weight cache of the relaxation tiles (k_weights)
   uint8_t* d_pred;       // canonical predecessor direction per cell (k_pred), [H][pitch]
+  uint16_t* d_truth;     // the simulator's ground-truth labels (sipp_truth_upload), [H][pitch16]; nullptr until uploaded
   // geometry tables on device
   uint8_t *d_xcls, *d_ycls;
   double *d_hdist, *d_vdist, *d_ddist;
@@ -247,6 +249,7 @@ size_t select_workspace_bytes();
 // sipp_cost.cu
 cudaError_t launch_cost_integral(sipp_ctx* ctx, const sipp_cost_params& p, int n, const int32_t* d_off, const double* d_pts, const double* d_parent_cost,
                                  double* d_cost, uint8_t* d_valid, cudaStream_t s);
+cudaError_t launch_travel_cost(sipp_ctx* ctx, const sipp_travel_params& p, int n, const double* d_start, const double* d_goal, double* d_cost, cudaStream_t s);
 // sipp_field.cu
 int field_plan(sipp_ctx* ctx, cudaStream_t s);
 

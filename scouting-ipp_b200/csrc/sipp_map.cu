@@ -79,7 +79,7 @@ __global__ void k_fill_f32(float* p, size_t n, float v) {
 }
 
 // ExpandLowCostAreaEvaluator view (expand_low_cost_area_evaluator.cpp:50-69): per cell a 16-bit entry
-//   bits 0..11  idx = closest-observed cost + 1 when the cell is UNKNOWN (1 when there is no closest cost: plane not computed
+//   bits 0..14  idx = closest-observed cost + 1 when the cell is UNKNOWN (labels up to 32766: ensure_views refuses larger ones) (1 when there is no closest cost: plane not computed
 //               -> the lookup returns -1, or never set -> 0), 0 when the cell is observed
 //   bit 15      the corner voxel of the cell is counted: UNKNOWN and inside the bounding volume
 // The kernel adds recip[idx] per counted cell: recip[1] = augment ? 1/mean : 0, recip[k] = 1/(k-1).

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
     "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
-    "sipp_path_download",
+    "sipp_path_download", "sipp_truth_upload", "sipp_travel_cost",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -84,6 +84,19 @@ class EvalParams(C.Structure):  # sipp_eval_params
 
 class CostParams(C.Structure):  # sipp_cost_params
     _fields_ = [("accumulate", C.c_int32), ("pad_", C.c_int32), ("max_sample_distance", C.c_double)]
+
+
+TRAVEL_MAP_COST, TRAVEL_DISTANCE_COST, TRAVEL_TIME_COST = range(3)
+
+
+class TravelParams(C.Structure):  # sipp_travel_params
+    _fields_ = [("formulation", C.c_int32), ("pad_", C.c_int32), ("max_step_size", C.c_double), ("mav_speed", C.c_double)]
+
+
+def make_travel_params(formulation=TRAVEL_MAP_COST, max_step_size=0.05, mav_speed=1.0):
+    p = TravelParams()
+    p.formulation, p.max_step_size, p.mav_speed = int(formulation), float(max_step_size), float(mav_speed)
+    return p
 
 
 def make_cost_params(accumulate=False, max_sample_distance=0.05):
@@ -175,6 +188,8 @@ def lib():
         L.sipp_plan.argtypes = [vp, pf64, pi32, vp, i32, pi32]
         L.sipp_field_download.argtypes = [vp, vp]
         L.sipp_path_download.argtypes = [vp, vp, i32, pi32]
+        L.sipp_truth_upload.argtypes = [vp, vp]
+        L.sipp_travel_cost.argtypes = [vp, C.POINTER(TravelParams), i32, vp, vp, vp]
         L.sipp_path_mask_generation.argtypes = [vp]
         L.sipp_set_path_mask.argtypes = [vp, vp]
         L.sipp_plan_stats.argtypes = [vp, vp]
@@ -421,6 +436,19 @@ class Context:
         cost, valid = np.zeros(n, np.float64), np.zeros(n, np.uint8)
         self._check(self._L.sipp_cost_integral(self._h, C.byref(cparams), n, _ptr(off), _ptr(pts), _ptr(pc), _ptr(cost), _ptr(valid)))
         return cost, valid
+
+    def truth_upload(self, labels):
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        assert labels.shape == (self.H, self.W)
+        self._check(self._L.sipp_truth_upload(self._h, _ptr(labels)))
+
+    def travel_cost(self, tparams, start_xyz, goal_xyz):
+        """MavSimulator::computeCost for n (start, goal) pairs over the uploaded ground-truth map"""
+        a = np.ascontiguousarray(start_xyz, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(goal_xyz, dtype=np.float64).reshape(-1, 3)
+        cost = np.zeros(len(a), np.float64)
+        self._check(self._L.sipp_travel_cost(self._h, C.byref(tparams), len(a), _ptr(a), _ptr(b), _ptr(cost)))
+        return cost
 
     def episode_run(self, truth, params, cand_xy, cand_cost, fov=65, init=320, start=(0.5, 0.5)):
         """sipp_episode_run: cand_xy [cycles][n][2], cand_cost [cycles][n]; returns the per-cycle trace as a list of

@@ -785,3 +785,31 @@ def test_incremental_replan_is_bit_identical_to_a_plan_from_scratch(init):
         b.update_unknown_cost(45.0)
     assert gi.plan()[0] == gf.plan()[0] == o.plan()[0] and not gi.plan_info()["incremental"]
     assert np.array_equal(gi.field_download(), o.field_download())
+
+
+def test_expand_low_cost_large_labels():
+    """closest-observed labels beyond 4095 (the view packs label + 1 into 15 bits next to the "counted" bit): parity with the oracle up
+    to the largest representable label, an explicit refusal above it instead of aliased costs."""
+    rng = np.random.default_rng(21)
+    W, H = 128, 96
+    mk = lambda f: f(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), 30, 120, 30, compute_closest_observed=True)
+    g, o = both(mk)
+    for k in range(10):
+        x0, y0 = int(rng.integers(-8, W - 10)), int(rng.integers(-8, H - 10))
+        patch = rng.choice([30, 4094, 4095, 4096, 8191, 20000, 32766], size=(25, 25)).astype(np.int32)
+        g.map_update_patch(x0, y0, patch)
+        o.map_update_patch(x0, y0, patch)
+    xy = rng.uniform(-0.2, W * 0.0625 + 0.2, (200, 2))
+    xy[:, 1] = rng.uniform(-0.2, H * 0.0625 + 0.2, 200)
+    for aug in (False, True):
+        pg = sipp.make_params(sipp.EVAL_EXPAND_LOW_COST, half_fov=12, augment_unknown_with_mean=aug)
+        po = orc.make_params(orc.EVAL_EXPAND_LOW_COST, half_fov=12, augment_unknown_with_mean=aug)
+        gg, gc, gt = g.gain_batch(pg, xy)
+        og, oc, ot = o.gain_batch(po, xy, variant=1)
+        assert np.array_equal(gc[:, :2], oc[:, :2]) and np.allclose(gg, og, rtol=RTOL, atol=0.0, equal_nan=True)
+        assert np.max(np.abs(gg - og)) <= 1e-9 * max(1.0, np.max(np.abs(og)))
+    g.map_update_patch(3, 3, np.full((4, 4), 40000, np.int32))
+    with pytest.raises(sipp.SippError) as e:
+        g.gain_batch(sipp.make_params(sipp.EVAL_EXPAND_LOW_COST, half_fov=12), xy)
+    assert e.value.code == sipp.ERR_UNSUPPORTED
+    g.gain_batch(sipp.make_params(sipp.EVAL_NAIVE, half_fov=12), xy)          # the other evaluators are not affected

@@ -193,3 +193,43 @@ def test_peer_argument_errors():
     with pytest.raises(sipp.SippError):
         g.peer_exchange_dev(1, 1)                                     # detached
     g.close()
+
+
+def test_empty_shards_take_part_in_the_exchange():
+    """fewer candidates than ranks: the ranks whose shard is empty publish {0, -1} ("never wins") so that the step counter advances
+    everywhere and nobody waits for a record that never comes; every rank ends with the winner of the non-empty shards."""
+    import torch
+    world, W, H, n_total = 4, 160, 128, 2
+    lab, obs, dg = synth.world(W, H, 42, 4, sipp.make_desc, init_cost="max")
+    _, _, do = synth.world(W, H, 42, 4, orc.make_desc, init_cost="max")
+    o = orc.Oracle(do)
+    o.map_upload_full(lab, obs)
+    o.plan()
+    ctxs = [sipp.Context(dg) for _ in range(world)]
+    for c in ctxs:
+        c.map_upload_full(lab, obs)
+        c.plan()
+    _attach_all(ctxs)
+    dev = torch.device("cuda", 0)
+    xy, cost = synth.make_candidates(W, H, 9, n_total)
+    pg, po = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=10), orc.make_params(orc.EVAL_RRT_STAR, half_fov=10)
+    bufs = []
+    for r in range(world):
+        lo, hi = shard.shard_range(n_total, r, world)
+        m = max(hi - lo, 1)
+        bufs.append((lo, hi, torch.from_numpy(np.ascontiguousarray(xy[lo:lo + m])).to(dev), torch.from_numpy(np.ascontiguousarray(cost[lo:lo + m])).to(dev),
+                     torch.empty(m, dtype=torch.float64, device=dev), torch.empty(m, dtype=torch.float64, device=dev),
+                     torch.empty(m, dtype=torch.uint8, device=dev), torch.zeros(2, dtype=torch.int64, device=dev)))
+    assert sum(1 for lo, hi, *_ in bufs if hi == lo) >= 2          # at least two ranks have nothing to score
+    torch.cuda.synchronize()
+    for r in range(world):
+        lo, hi, d_xy, d_cost, d_gain, d_val, d_term, d_best = bufs[r]
+        ctxs[r].cycle_shard_dev(pg, hi - lo, d_xy.data_ptr(), None, d_cost.data_ptr(), d_gain.data_ptr(), d_term.data_ptr(), d_val.data_ptr(), lo, d_best.data_ptr())
+    for c in ctxs:
+        assert c.peer_status() == (0, 1)
+    _, _, _, oi, obv = o.cycle(po, xy, cost, variant=1)
+    for r in range(world):
+        assert _rec(bufs[r][7]) == (obv, oi), (r, _rec(bufs[r][7]), oi, obv)
+    for c in ctxs:
+        c.peer_detach()
+        c.close()
