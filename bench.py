@@ -19,6 +19,13 @@ import sys
 import threading
 import time
 
+# The end-to-end leg is a tight host loop around the CUDA driver. torchrun (N > 1) exports OMP_NUM_THREADS=1; a plain `python bench.py`
+# (N = 1) would start numpy's / torch's OpenMP pools with one spinning worker per vCPU, which on the 16-vCPU GPU VMs competes with the
+# thread that feeds the GPU (measured: 175-192 us per call at N = 1 against 113-126 us for the same call under torchrun). Nothing in
+# this benchmark uses those pools (the CPU baseline runs its own std::threads), so both launch modes get the same setting.
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "scouting-ipp_b200"))
@@ -37,6 +44,15 @@ ALG_BYTES_PER_EVAL = 4257   # (2*32+1)^2 one-byte cell records +
 WORKLOAD = ("planning-cycle evaluation: %d candidate views per GPU (half_fov %d = 4226 voxels each), RRTStarEvaluator count mode "
             "(non_path_voxel_gain %g) + GlobalNormalizedGain value + argmax, %dx%d synthetic map (create_artificial_maps.py style, "
             "seed %d, %d observed footprints, unknown_init_cost max)" % (T_PER_GPU, HALF_FOV, NPG, W, H, SEED, K_OBS))
+
+
+def bench_config(n_gpus):
+    """the same dictionary in both arms (the driver compares them key by key)"""
+    return {"workload": WORKLOAD, "candidates_per_gpu": T_PER_GPU, "map": "%dx%d" % (W, H), "half_fov": HALF_FOV,
+            "evaluator": "RRTStarEvaluator (count mode, non_path_voxel_gain %g)" % NPG, "n_gpus": n_gpus,
+            "l2": "flushed between timed steps (256 MiB write, untimed); the scanned planes (4 + 16 MiB) are smaller than L2",
+            "sharding": ("single GPU" if n_gpus == 1 else "candidates sharded over %d GPUs (weak scaling: %d each), map replicated per GPU; the only "
+                         "cross-GPU traffic is each shard's 16-byte winner" % (n_gpus, T_PER_GPU))}
 
 
 def measured_peaks():
@@ -125,43 +141,64 @@ def build_inputs(n_gpus):
     return lab, obs, xy, cost, ids
 
 
-def run_reference(args):
-    """Reference arm: the reference's CPU evaluators (oracle port, faithful variant) on the box's host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+def cpu_reference(lab, obs, ids):
+    """The reference's CPU implementation of the path for the bench map: the reference's OWN evaluator sources (oracle/_ref, built from
+    /root/reference in the build container and shipped prebuilt) over the oracle's map state when that library is here, else the
+    oracle's restatement. Returns (cycle(params, xy, cost, threads) -> (gain, terminal, value, best_index, best_value), kind, note,
+    oracle context, seconds the oracle's follower plan took)."""
     from oracle import oracle as orc
-    lab, obs, xy, cost, ids = build_inputs(1)
     desc = orc.make_desc(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), min(ids), max(ids), max(ids))
     o = orc.Oracle(desc)
     o.map_upload_full(lab, obs)
     t0 = time.perf_counter()
     o.plan()
     plan_s = time.perf_counter() - t0
+    try:
+        from oracle import ref
+        if ref.available():
+            r = ref.Reference(desc).snapshot(o)
+            return (lambda p, xy, cost, threads: r.cycle(p, xy, cost, threads=threads)), "reference", (
+                "the reference's own sources (advanced_planner_modules: MapPlanExp::getVoxelArea, CameraModelPlanExp, RRTStarEvaluator incl. its "
+                "quadratic erase loop) compiled unmodified into oracle/_ref against stand-in headers; map planes from the oracle's map server "
+                "restatement"), o, plan_s
+    except Exception:
+        pass
+    return (lambda p, xy, cost, threads: o.cycle(p, xy, cost, variant=0, threads=threads)), "port", (
+        "oracle port of the reference evaluator path (voxel vector + quadratic erase loop); oracle/_ref is not available here"), o, plan_s
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU evaluators on the box's host cores, all threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    lab, obs, xy, cost, ids = build_inputs(1)
+    cycle, kind, note, o, plan_s = cpu_reference(lab, obs, ids)
     p = orc.make_params(orc.EVAL_RRT_STAR, half_fov=HALF_FOV, non_path_voxel_gain=NPG)
     cores = os.cpu_count() or 1
     # bounded sample per step, sized from a probe so the whole run stays within a couple of minutes
     probe = 64 * cores
     t0 = time.perf_counter()
-    o.cycle(p, xy[:probe], cost[:probe], variant=0, threads=cores)
+    cycle(p, xy[:probe], cost[:probe], cores)
     rate = probe / (time.perf_counter() - t0)
-    budget_s = 60.0 / max(1, args.steps + args.warmup)
-    sample = int(min(T_PER_GPU, max(probe, rate * budget_s)))
+    budget_s = 90.0 / max(1, args.steps + args.warmup)
+    sample = int(min(T_PER_GPU, max(8 * cores, rate * budget_s)))
     for _ in range(args.warmup):
-        o.cycle(p, xy[:sample], cost[:sample], variant=0, threads=cores)
+        cycle(p, xy[:sample], cost[:sample], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.cycle(p, xy[:sample], cost[:sample], variant=0, threads=cores)
+        cycle(p, xy[:sample], cost[:sample], cores)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": "candidate-view evals/sec on 4096^2 cost map", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 counts + f64 gain", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "sample": "%d of the %d candidates per step, faithful evaluator (voxel vector + quadratic erase loop), %d std::threads; "
-                                   "the reference itself is single-threaded and cannot be built here (ROS/Eigen/Boost/OMPL)" % (sample, T_PER_GPU, cores),
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind,
+                         "sample": "%d of the %d candidates per step, %d worker threads (the reference itself is single-threaded: one module "
+                                   "instance per thread); %s" % (sample, T_PER_GPU, cores, note),
                          "plan_s": plan_s},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -172,8 +209,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)      # 200 x ~41 us: long enough for the clock sampler to see the GPU under load
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
@@ -292,9 +329,16 @@ def main():
             stream.wait_event(g_done[1 - b])
         return d_glob[b]
 
-    def timed(step, overlapped_gather, flush_peers=False):
+    d_align = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_align[0][1] = -1                          # an "empty shard" record: never wins, only lines the ranks up
+
+    def timed(step, overlapped_gather, flush_peers=False, align=False):
         """W warm-up steps, then K timed ones: barrier + synchronize on both sides, CUDA events around every step on the
-        launching stream (the L2 flush between them is untimed), max over ranks of the summed step times."""
+        launching stream (the L2 flush between them is untimed), max over ranks of the summed step times.
+        align (N > 1, synchronous exchange): an untimed on-device exchange of an empty record sits between the flush and the start
+        event of every step. It completes on a rank only when every rank has reached it, so the GPUs enter each timed step within
+        the exchange's own latency of each other — without it the per-rank jitter of the untimed 256 MiB flush is charged to
+        whichever rank has to wait for the slowest one inside the timed exchange."""
         with torch.cuda.stream(stream):
             for k in range(args.warmup):
                 flush.fill_(1)
@@ -320,6 +364,8 @@ def main():
             k0 = args.warmup + 1 if world > 1 else 0        # keeps the double-buffer parity of the overlapped NCCL variant going
             for k in range(args.steps):
                 flush.fill_(k & 0xFF)          # L2 flush between timed iterations (untimed)
+                if align:
+                    ctx.peer_exchange_dev(d_align[0].data_ptr(), d_align[1].data_ptr(), sh)
                 ev[k][0].record(stream)
                 best_ = step(k0 + k)
                 ev[k][1].record(stream)
@@ -335,7 +381,7 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
             wall_ = time.perf_counter() - wall0
-            launches_ = ctx.launch_count() - launches0
+            launches_ = ctx.launch_count() - launches0 - (args.steps if align else 0)   # the aligning exchanges sit between the timed steps, not in them
             clocks_ = sampler.result()
         tail_ms = ev[-1][1].elapsed_time(ev_tail)
         total = float(sum(a.elapsed_time(b) for a, b in ev)) + float(tail_ms)
@@ -343,17 +389,32 @@ def main():
             print("[rank %d] %s step ms: %s tail %.4f gaps %s" % (rank, step.__name__, " ".join("%.3f" % a.elapsed_time(b) for a, b in ev), tail_ms,
                                                                   " ".join("%.3f" % ev[i][1].elapsed_time(ev[i + 1][0]) for i in range(len(ev) - 1))), file=sys.stderr)
         t = torch.tensor([total], dtype=torch.float64, device=dev)
+        timed.per_rank = [total / args.steps]
         if world > 1:
+            allt = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allt, t)
+            timed.per_rank = [float(x.item()) / args.steps for x in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), best_, wall_, launches_, clocks_
 
     other = None
     if exchange == "p2p":
-        total_ms, best, wall, launches, clocks = timed(step_p2p_sync, False)   # every step ends with its own global winner
+        total_ms, best, wall, launches, clocks = timed(step_p2p_sync, False, align=True)   # every step ends with its own global winner
+        sync_per_rank = list(timed.per_rank)
+        u_ms, u_best, _, _, _ = timed(step_p2p_sync, False)                     # the same without the alignment: what the flush jitter costs
+        # the same kernel without any exchange, per rank: step time minus this = what a rank spends waiting for the slowest shard
+        l_ms, _, _, _, _ = timed(lambda k: (ctx.cycle_dev(params, T, d_xy.data_ptr(), None, d_cost.data_ptr(), d_gain.data_ptr(), d_term.data_ptr(),
+                                                         d_value.data_ptr(), d_best[k & 1].data_ptr(), sh), d_best[k & 1])[1], False)
+        local_per_rank = list(timed.per_rank)
         s_ms, s_best, _, _, _ = timed(step_p2p, False, True)
         o_ms, o_best, _, _, _ = timed(step_nccl, True)      # the collective-library form of the same step, for comparison
         assert torch.equal(o_best.cpu(), best.cpu()) and torch.equal(s_best.cpu(), best.cpu())
-        other = [{"exchange": "p2p, pipelined (step k collects the records of step k-1; the ranks may drift up to one step apart and the final flush, "
+        other = [{"exchange": "p2p, synchronous, ranks NOT aligned before the timed steps (the untimed L2 flush's per-rank jitter lands in the timed exchange)",
+                  "ms_per_step": u_ms / args.steps, "value": world * T * args.steps / (u_ms * 1e-3)},
+                 {"exchange": "none (every rank scores its shard and selects locally): the kernel alone, per rank", "ms_per_step_per_rank": local_per_rank,
+                  "exchange_wait_us_per_rank": [1e3 * (a - b) for a, b in zip(sync_per_rank, local_per_rank)],
+                  "note": "step time with the exchange minus the same rank's step time without it = time spent waiting for the slowest shard + one NVLink store / poll"},
+                 {"exchange": "p2p, pipelined (step k collects the records of step k-1; the ranks may drift up to one step apart and the final flush, "
                               "timed in full, waits for the slowest)", "ms_per_step": s_ms / args.steps, "value": world * T * args.steps / (s_ms * 1e-3)},
                  {"exchange": "nccl all_gather + merge kernel (gather of step k under the gain kernel of step k+1)", "ms_per_step": o_ms / args.steps,
                   "value": world * T * args.steps / (o_ms * 1e-3)}]

@@ -187,6 +187,10 @@ int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask);
 /* relaxation statistics of the last sipp_plan: [0]=tile queue pushes, [1]=tile activations, [2]=tile sweeps, [3]=aborted */
 int sipp_plan_stats(const sipp_ctx* ctx, int64_t stats[4]);
 
+/* device-timed phases of the last sipp_plan (CUDA events on the context's stream): ms[0] = the relaxation kernel alone, ms[1] = the
+ * whole plan (field + predecessors + path + mask). Measurement aid for bench.py's cost-to-go roofline entry. */
+int sipp_plan_phases(sipp_ctx* ctx, double ms[2]);
+
 /* Incremental re-plan. Between two plans only ingested patches change the planner's map, so sipp_plan
  * reuses the previous fixed point: cells first observed at a HIGHER cost than the planner assumed (obstacles, labels above the
  * init cost) invalidate — along the predecessor plane of the last plan — exactly the cost-to-go values whose path ran through

@@ -43,6 +43,7 @@ def lib():
         L.ref_set_planes.argtypes = [vp, vp, vp, vp, vp, vp, f64, f64]
         L.ref_visible_voxels.argtypes = [vp, i32, f64, f64, vp, i32]
         L.ref_gain_batch.argtypes = [vp, C.POINTER(orc.EvalParams), i32, vp, vp, vp, vp, vp, f64, i32, vp, vp]
+        L.ref_gain_batch_mt.argtypes = [vp, C.POINTER(orc.EvalParams), i32, vp, vp, vp, vp, vp, i32]
         L.ref_update_tree.argtypes = [vp, C.POINTER(orc.EvalParams), C.POINTER(orc.UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(orc.CostParams)]
         L.ref_cost_integral.argtypes = [vp, C.POINTER(orc.CostParams), i32, vp, vp, vp, vp, vp]
         L.ref_has_module.argtypes = [C.c_char_p]
@@ -117,6 +118,22 @@ class Reference:
         if rc != 0:
             raise RuntimeError("ref_gain_batch: evaluator %d is not part of the reference tree" % params.evaluator)
         return gain, unk, term
+
+    def cycle(self, params, xy, cost, start_xy=None, threads=1):
+        """gain of every candidate through the reference's own evaluator (worker threads with one module instance each), then the flat-tree
+        value gain / cost and the first maximum — what the oracle's cycle() does; returns (gain, terminal, value, best_index, best_value)"""
+        xy = np.ascontiguousarray(xy, np.float64)
+        n = len(xy)
+        start_xy = None if start_xy is None else np.ascontiguousarray(start_xy, np.float64)
+        gain = np.zeros(n, np.float64)
+        term = np.zeros(n, np.uint8)
+        rc = self._L.ref_gain_batch_mt(self._h, C.byref(params), n, _ptr(xy), _ptr(start_xy), _ptr(gain), None, _ptr(term), int(threads))
+        if rc != 0:
+            raise RuntimeError("ref_gain_batch_mt failed (%d)" % rc)
+        cost = np.asarray(cost, np.float64)
+        value = np.where(cost > 0, (0.0 + gain) / np.where(cost > 0, cost, 1.0), 0.0)
+        best = int(np.argmax(value)) if n else -1
+        return gain, term, value, best, (float(value[best]) if n else 0.0)
 
     def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, cost_params=None):
         """one pass of the patched planner's tree re-evaluation; returns (gain, value, terminal, cost). cost_params: the cost computer

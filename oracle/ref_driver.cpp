@@ -13,6 +13,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/sipp.h"
@@ -282,11 +283,39 @@ int ref_visible_voxels(ref_ctx* c, int half_fov, double x, double y, double* out
 // first (trajectory[0], only read by RRTStarEvaluator binary + discount), then — when traj_xy is given — npts - 2 intermediate points,
 // then xy[i] (the view). times_ns (optional, npts entries, shared by all segments) feed sampleViewpoints when sampling_time > 0.
 // n_unknown[i] = voxels left after the evaluator erased the observed ones; terminal[i] = gain_terminal.
+static int gain_range(RefPlanner* pl, int lo, int hi, const double* xy, const double* start_xy, double* gain, uint32_t* n_unknown, uint8_t* terminal,
+                      int32_t npts, const double* traj_xy, const int64_t* times_ns);
+
+// threads > 1: the reference itself is single-threaded (one planner loop); for the "all host cores" baseline every worker thread gets
+// its own planner + map + evaluator instances (module state such as the local path-map copy is per instance) over the shared planes.
+int ref_gain_batch_mt(ref_ctx* c, const sipp_eval_params* p, int32_t n, const double* xy, const double* start_xy, double* gain, uint32_t* n_unknown,
+                      uint8_t* terminal, int threads) {
+  if (threads < 1) threads = 1;
+  std::vector<std::unique_ptr<RefPlanner>> pls;
+  for (int t = 0; t < threads; ++t) {           // module construction is not thread safe (factory tables, the map-spec hand-over): do it here
+    pls.push_back(make_planner(c, p, nullptr, nullptr, 0.0));
+    if (!pls.back()) return SIPP_ERR_UNSUPPORTED;
+  }
+  std::vector<std::thread> th;
+  const int per = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    const int lo = t * per, hi = std::min(n, lo + per);
+    if (lo < hi) th.emplace_back(gain_range, pls[t].get(), lo, hi, xy, start_xy, gain, n_unknown, terminal, 0, nullptr, nullptr);
+  }
+  for (auto& t : th) t.join();
+  return 0;
+}
+
 int ref_gain_batch(ref_ctx* c, const sipp_eval_params* p, int32_t n, const double* xy, const double* start_xy, double* gain, uint32_t* n_unknown,
                    uint8_t* terminal, double sampling_time, int32_t npts, const double* traj_xy, const int64_t* times_ns) {
   auto pl = make_planner(c, p, nullptr, nullptr, sampling_time);
   if (!pl) return SIPP_ERR_UNSUPPORTED;
-  for (int i = 0; i < n; ++i) {
+  return gain_range(pl.get(), 0, n, xy, start_xy, gain, n_unknown, terminal, npts, traj_xy, times_ns);
+}
+
+static int gain_range(RefPlanner* pl, int lo, int hi, const double* xy, const double* start_xy, double* gain, uint32_t* n_unknown, uint8_t* terminal,
+                      int32_t npts, const double* traj_xy, const int64_t* times_ns) {
+  for (int i = lo; i < hi; ++i) {
     TrajectorySegment seg;
     if (traj_xy && npts >= 2) {
       seg.trajectory.resize(npts);

@@ -316,6 +316,8 @@ void sipp_destroy(sipp_ctx* ctx) {
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
   }
+  for (int i = 0; i < 4; ++i)
+    if (ctx->ev_plan[i]) cudaEventDestroy(ctx->ev_plan[i]);
   delete ctx;
 }
 
@@ -377,6 +379,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   ctx->cycle_graph = nullptr;
   ctx->cycle_graph_launches = 0;
   for (int i = 0; i < 8; ++i) ctx->ev_in[i] = ctx->ev_k[i] = nullptr;
+  for (int i = 0; i < 4; ++i) ctx->ev_plan[i] = nullptr;
 
   auto fail = [&](int rc) {
     g_create_err = ctx->err;
@@ -395,6 +398,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
     e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev_plan[i]);
   if (e != cudaSuccess) { sipp_set_err(ctx, SIPP_ERR_CUDA, "copy streams / events: %s", cudaGetErrorString(e)); return fail(SIPP_ERR_CUDA); }
   ctx->cycle_chunks = getenv("SIPP_CYCLE_CHUNKS") ? atoi(getenv("SIPP_CYCLE_CHUNKS")) : 0;
   ctx->inc_enabled = !(getenv("SIPP_INCREMENTAL") && atoi(getenv("SIPP_INCREMENTAL")) == 0);
@@ -580,9 +584,9 @@ static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_
   if (rc != SIPP_OK) { ctx->warm_valid = false; return rc; }
   // results come back through the context's pinned block (a copy into pageable memory is staged by the driver under a global lock)
   int* out = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->h_pinned) + 64);   // [10]
-  int* ctl = out + 16;   // [8] CTL_* of sipp_field.cu: head, tail, pending, activations, sweeps, abort, pushes
+  int* ctl = out + 16;   // [24] CTL_* of sipp_field.cu: head, tail, pending, activations, sweeps, abort, pushes; [16..23] watchdog diagnostics
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, 10 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, 24 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->plan_stats[0] = ctl[6];
   ctx->plan_stats[1] = ctl[3];
@@ -593,7 +597,8 @@ static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_
   ctx->plan_info[3] = out[5];
   if (ctl[5]) {
     ctx->warm_valid = false;
-    return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation aborted by its watchdog (work queue starved)");
+    return sipp_set_err(ctx, SIPP_ERR_CUDA, "cost-to-go relaxation aborted by its watchdog (code %d: 1 = work queue starved, 2 = sub-tile sweeps, 3 = block drain; "
+                        "head %d tail %d pending %d; diag %d %d %d %d %d)", ctl[5], ctl[0], ctl[1], ctl[2], ctl[16], ctl[17], ctl[18], ctl[19], ctl[20]);
   }
   // the converged field + predecessor plane are the warm start of the next plan
   ctx->warm_valid = ctx->inc_enabled;
@@ -642,6 +647,19 @@ int sipp_path_download(sipp_ctx* ctx, double* path_xy, int32_t path_cap, int32_t
     SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(path_xy, ctx->d_path_xy, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
     SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  return SIPP_OK;
+}
+
+int sipp_plan_phases(sipp_ctx* ctx, double ms[2]) {
+  SIPP_ENTER(ctx);
+  if (!ms) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "ms == NULL");
+  if (!ctx->field_valid) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "no plan yet");
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  float relax = 0.f, total = 0.f;
+  SIPP_CUDA_CHECK(ctx, cudaEventElapsedTime(&relax, ctx->ev_plan[0], ctx->ev_plan[1]));
+  SIPP_CUDA_CHECK(ctx, cudaEventElapsedTime(&total, ctx->ev_plan[2], ctx->ev_plan[3]));
+  ms[0] = relax;
+  ms[1] = total;
   return SIPP_OK;
 }
 

@@ -1127,6 +1127,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (timing) for (auto& e : ev) cudaEventCreate(&e);
   if (timing) cudaEventRecord(ev[0], s);
+  if (ctx->ev_plan[2]) cudaEventRecord(ctx->ev_plan[2], s);
   const FieldGeom g = make_geom(ctx);
   const size_t ncell = (size_t)ctx->W * ctx->H;
   const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
@@ -1153,8 +1154,8 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     num_sms = di.num_sms;
     occ = di.occ;
   }
-  // SIPP_RELAX_KERNEL=0: the per-tile kernel (k_relax + edge-weight cache); default: the block-resident kernel (k_relax_blk)
-  static const int relax_kernel_env = getenv("SIPP_RELAX_KERNEL") ? atoi(getenv("SIPP_RELAX_KERNEL")) : 1;
+  // default: the per-tile kernel (k_relax + edge-weight cache); SIPP_RELAX_KERNEL=1: the block-resident kernel (k_relax_blk), experimental
+  static const int relax_kernel_env = getenv("SIPP_RELAX_KERNEL") ? atoi(getenv("SIPP_RELAX_KERNEL")) : 0;
   const bool use_blk = relax_kernel_env != 0;
   const int nbx = (ctx->W + BS - 1) / BS, nby = (ctx->H + BS - 1) / BS, nblocks = nbx * nby;
   if (!use_blk && !ctx->d_tile_w) {      // the weight cache of the per-tile kernel is only allocated when that kernel is selected
@@ -1248,6 +1249,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   }
   const int spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
+  if (ctx->ev_plan[0]) cudaEventRecord(ctx->ev_plan[0], s);      // sipp_plan_phases: the relaxation kernel alone
   static const int grid_env = getenv("SIPP_RELAX_GRID") ? atoi(getenv("SIPP_RELAX_GRID")) : 0;
   if (use_blk) {
     // block-resident kernel: one persistent CTA (16 warps, the whole 128 x 128 window in shared memory) per SM; a small map (an
@@ -1301,6 +1303,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   }
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   ctx->launches += 1;
+  if (ctx->ev_plan[1]) cudaEventRecord(ctx->ev_plan[1], s);
 
   if (timing) cudaEventRecord(ev[1], s);
   PathArgs pa;
@@ -1361,6 +1364,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   k_path_finish<<<blocks, 256, 0, s>>>(rs);
   ctx->launches += 2;
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+  if (ctx->ev_plan[3]) cudaEventRecord(ctx->ev_plan[3], s);
   if (timing) {
     cudaEventRecord(ev[3], s);
     cudaEventSynchronize(ev[3]);

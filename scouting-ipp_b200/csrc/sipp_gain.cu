@@ -58,6 +58,8 @@ struct GainArgs {
   size_t rec_pitch;
   const uint8_t* rec2_plane;  // packed scan: the 2-bit plane of the evaluator (path or reachability flavour)
   size_t rec2_pitch;
+  const uint16_t* label_plane;  // AverageViewCost: map_cost_ (raw labels) for the duplicated centre voxel — the tile holds labels masked by the
+  size_t label_pitch16;         // CORNER voxels' bounding-volume test, the centre voxel has its own test on centre coordinates
   double* value2;         // optional second copy of value (the caller's pinned host array, written over PCIe by the kernel)
   const double* recip;    // ExpandLowCost lookup
   const int* sel;         // optional: candidate k of this launch is node sel[k] of the caller's arrays (outputs are scattered)
@@ -273,6 +275,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
       w.crec = 0;
       if (PACKED && w.on_map && w.cx >= 0 && w.cx < a.g.W && w.cy >= 0 && w.cy < a.g.H)
         w.crec = __ldg(a.rec_plane + (size_t)w.cy * a.rec_pitch + w.cx);      // needed only in the epilogue, a batch later
+      if (MODE == MODE_AVG_VIEW_COST && w.on_map && w.cx >= 0 && w.cx < a.g.W && w.cy >= 0 && w.cy < a.g.H)
+        w.crec = __ldg(a.label_plane + (size_t)w.cy * a.label_pitch16 + w.cx);   // raw label of the centre cell (crec is otherwise unused on the tiled path)
     }
     return w;
   };
@@ -557,7 +561,7 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
             }
           } else if (MODE == MODE_AVG_VIEW_COST && c_free) {
             n_aux += 1;
-            sum_aux2 += caux16;
+            sum_aux2 += w.crec;       // getVoxelWeight of the centre voxel: the cell's label, whatever the corner voxel's bounding-volume test says
           }
         }
       }
@@ -782,6 +786,8 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.value = d_cost ? d_value : nullptr;
   a.value2 = d_cost ? d_value2 : nullptr;
   a.recip = ctx->d_recip;
+  a.label_plane = ctx->d_label;
+  a.label_pitch16 = ctx->pitch16;
   a.sel = d_sel;
   a.n_dev = d_n;
   if (fs) {

@@ -95,6 +95,7 @@ struct sipp_ctx {
   cudaStream_t stream;
   cudaStream_t s_in, s_out;          // copy streams of the chunked host-pointer pipeline (sipp_cycle)
   cudaEvent_t ev_in[8], ev_k[8];
+  cudaEvent_t ev_plan[4];            // device timestamps of the last plan: relaxation start / end, plan start / end (sipp_plan_phases)
   int cycle_chunks;                  // 0 = automatic; tuning knob SIPP_CYCLE_CHUNKS
   // sipp_cycle's pipeline captured as a CUDA graph, replayed while the call's pointers / parameters stay the same
   bool cycle_use_graph;

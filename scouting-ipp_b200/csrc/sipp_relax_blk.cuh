@@ -27,6 +27,7 @@ constexpr int BPD = BS + 2;        // with the one-cell halo
 constexpr int kBlkSub = BS / TS;   // 4 sub-tiles per block edge
 constexpr int kBlkWarps = kBlkSub * kBlkSub;
 constexpr int kBlkThreads = kBlkWarps * 32;
+constexpr int kBlkIdleLimit = 1 << 21;   // idle polls (>= 100 ns each) before the drain watchdog gives up: a fraction of a second
 
 struct BlkSmem {
   double d[BPD][BPD];        // tentative costs incl. halo
@@ -41,7 +42,15 @@ struct BlkSmem {
   int again;
   int ring_m;                // neighbour blocks (N S W E NW NE SW SE) whose side of our ring was lowered in this run
   int notify_m;              // neighbour blocks that have to look at it
+#ifdef SIPP_BLK_DEBUG
+  int wst[kBlkWarps], wit[kBlkWarps], wruns[kBlkWarps], wadd[kBlkWarps], wdec[kBlkWarps], init_n, reruns;
+#endif
 };
+#ifdef SIPP_BLK_DEBUG
+#define BLK_DBG(x) x
+#else
+#define BLK_DBG(x)
+#endif
 static_assert(sizeof(BlkSmem) <= 227 * 1024, "block window must fit the opt-in shared memory of one SM");
 
 struct BlkArgs {
@@ -158,13 +167,14 @@ k_relax_blk(const BlkArgs a) {
       int* slot = a.queue + (ticket % (unsigned)a.cap);
       int spins = 0;
       for (;;) {
+        if (ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) break;       // an aborted plan: do not start another block
         const int v = ld_volatile_i32(slot);
         if (v >= 0) {
           st_volatile_i32(slot, -1);
           bi = v;
           break;
         }
-        if (ld_volatile_i32(&a.ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) break;
+        if (ld_volatile_i32(&a.ctl[CTL_PENDING]) == 0) break;
         if (++spins > a.spin_limit) {
           atomicExch(&a.ctl[CTL_ABORT], 1);
           break;
@@ -227,12 +237,14 @@ k_relax_blk(const BlkArgs a) {
     if (tid < kBlkWarps) {
       const int tx_ = tid & (kBlkSub - 1), ty_ = tid / kBlkSub;
       s.dirty[tid] = (bx * BS + tx_ * TS < g.W && by * BS + ty_ * TS < g.H) ? 1 : 0;     // sub-tiles off the map have nothing to do
+      BLK_DBG(s.wst[tid] = 0; s.wit[tid] = 0; s.wruns[tid] = 0; s.wadd[tid] = 0; s.wdec[tid] = 0;)
     }
     __syncthreads();
     if (tid == 0) {
       int n = 0;
       for (int k = 0; k < kBlkWarps; ++k) n += s.dirty[k];
       s.pending = n;
+      BLK_DBG(s.init_n = n; s.reruns = 0;)
       s.ring_m = 0;
       s.notify_m = 0;
     }
@@ -249,7 +261,9 @@ k_relax_blk(const BlkArgs a) {
         mine = __shfl_sync(0xFFFFFFFFu, mine, 0);
         if (mine) {
           __threadfence_block();
+          BLK_DBG(if (lane == 0) { s.wst[warp] = 1; s.wruns[warp] += 1; })
           for (int it = 0;; ++it) {
+            BLK_DBG(if (lane == 0) s.wit[warp] = it;)
             uint32_t rows_changed = 0;
             const bool ch = (it & 1) ? blk_sweep<-1, PATCH>(s, ddp, init_half, r0, c0, lane, rows_changed)
                                      : blk_sweep<+1, PATCH>(s, ddp, init_half, r0, c0, lane, rows_changed);
@@ -268,7 +282,11 @@ k_relax_blk(const BlkArgs a) {
                 const int nsx = sx + ddx[lane], nsy = sy + ddy[lane];
                 const int ox = nsx < 0 ? -1 : (nsx >= kBlkSub ? 1 : 0), oy = nsy < 0 ? -1 : (nsy >= kBlkSub ? 1 : 0);
                 if (ox == 0 && oy == 0) {
-                  if (atomicExch(&s.dirty[nsy * kBlkSub + nsx], 1) == 0) atomicAdd(&s.pending, 1);
+                  // count FIRST, flag second: the neighbour may take the flag, run and decrement before we get to the counter, and a
+                  // counter that touches 0 on the way lets the other warps leave the loop while work is still being handed out
+                  atomicAdd(&s.pending, 1);
+                  BLK_DBG(atomicAdd(&s.wadd[warp], 1);)
+                  if (atomicExch(&s.dirty[nsy * kBlkSub + nsx], 1) != 0) { atomicSub(&s.pending, 1); BLK_DBG(atomicSub(&s.wadd[warp], 1);) }     // was flagged (and counted) already
                 } else {
                   // a cell on the block's ring: the neighbouring block in direction (ox, oy) reads it
                   const int nb = oy == 0 ? (ox < 0 ? 2 : 3) : (ox == 0 ? (oy < 0 ? 0 : 1) : ((oy < 0 ? 4 : 6) + (ox < 0 ? 0 : 1)));
@@ -278,15 +296,43 @@ k_relax_blk(const BlkArgs a) {
               __syncwarp();
             }
             if (!ch && it >= 1) break;
+            if (it > 100000) {                 // watchdog: a sub-tile cannot need this many sweeps (values only ever decrease)
+              if (lane == 0) { atomicExch(&a.ctl[CTL_ABORT], 2); a.ctl[16] = bi; a.ctl[17] = warp; }
+              break;
+            }
           }
           if (lane == 0) {
             __threadfence_block();
             atomicSub(&s.pending, 1);
+            BLK_DBG(s.wst[warp] = 0; s.wdec[warp] += 1;)
           }
           idle = 0;
         } else {
-          if (ldvi(&s.pending) == 0) break;
+          if (ldvi(&s.pending) == 0) { BLK_DBG(if (lane == 0) s.wst[warp] = 2;) break; }
           if (++idle > 4) __nanosleep(100);
+          if ((idle & 4095) == 0 && ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) {      // another CTA gave up: leave with it
+            atomicExch(&s.pending, 0);
+            break;
+          }
+          if (idle > kBlkIdleLimit) {          // watchdog (~ seconds): the block's sub-tiles never drained
+            if (lane == 0) {
+#ifdef SIPP_BLK_DEBUG
+              if (atomicCAS(&a.ctl[CTL_ABORT], 0, 3) == 0) {
+                printf("[blk] watchdog: block %d run %d warp %d pending %d ring %x init_n %d reruns %d\n", bi, act_local, warp, ldvi(&s.pending), s.ring_m, s.init_n, s.reruns);
+                for (int k = 0; k < kBlkWarps; ++k)
+                  printf("[blk]   warp %2d dirty %d state %d it %d runs %d add %d dec %d\n", k, ldvi(&s.dirty[k]), ldvi(&s.wst[k]), ldvi(&s.wit[k]), ldvi(&s.wruns[k]),
+                         ldvi(&s.wadd[k]), ldvi(&s.wdec[k]));
+              }
+#endif
+              atomicExch(&a.ctl[CTL_ABORT], 3);
+              a.ctl[18] = bi; a.ctl[19] = ldvi(&s.pending);
+              int dm = 0;
+              for (int k = 0; k < kBlkWarps; ++k) dm |= (ldvi(&s.dirty[k]) ? 1 : 0) << k;
+              a.ctl[20] = dm;
+            }
+            atomicExch(&s.pending, 0);         // let everybody out: the plan is reported as aborted
+            break;
+          }
         }
       }
       __syncthreads();     // every warp saw pending == 0: nobody is sweeping, all flags are clear
@@ -408,6 +454,7 @@ k_relax_blk(const BlkArgs a) {
         int n = 0;
         for (int k = 0; k < kBlkWarps; ++k) n += s.dirty[k];
         s.pending = n;
+        BLK_DBG(s.init_n = n; s.reruns += 1; for (int k = 0; k < kBlkWarps; ++k) { s.wadd[k] = 0; s.wdec[k] = 0; s.wruns[k] = 0; })
       }
       __syncthreads();
       // nothing came back lower (the request was an echo): the loop above falls straight through to the release protocol

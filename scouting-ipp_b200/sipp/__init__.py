@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "sipp_cycle", "sipp_cycle_dev", "sipp_merge_best_dev", "sipp_update_tree", "sipp_launch_count",
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
     "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
-    "sipp_path_download", "sipp_truth_upload", "sipp_travel_cost",
+    "sipp_path_download", "sipp_truth_upload", "sipp_travel_cost", "sipp_plan_phases",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -189,6 +189,7 @@ def lib():
         L.sipp_field_download.argtypes = [vp, vp]
         L.sipp_path_download.argtypes = [vp, vp, i32, pi32]
         L.sipp_truth_upload.argtypes = [vp, vp]
+        L.sipp_plan_phases.argtypes = [vp, vp]
         L.sipp_travel_cost.argtypes = [vp, C.POINTER(TravelParams), i32, vp, vp, vp]
         L.sipp_path_mask_generation.argtypes = [vp]
         L.sipp_set_path_mask.argtypes = [vp, vp]
@@ -327,6 +328,12 @@ class Context:
         st = np.zeros(4, np.int64)
         self._check(self._L.sipp_plan_stats(self._h, _ptr(st)))
         return dict(pushes=int(st[0]), tile_activations=int(st[1]), tile_sweeps=int(st[2]), aborted=int(st[3]))
+
+    def plan_phases(self):
+        """device-timed (relaxation kernel ms, whole plan ms) of the last plan"""
+        ms = np.zeros(2, np.float64)
+        self._check(self._L.sipp_plan_phases(self._h, _ptr(ms)))
+        return float(ms[0]), float(ms[1])
 
     def set_incremental(self, enable):
         self._check(self._L.sipp_set_incremental(self._h, int(bool(enable))))
