@@ -11,12 +11,19 @@
 //   * inside the block every warp OWNS one 32 x 32 sub-tile (4 x 4 of them). A warp runs Gauss-Seidel row sweeps over its sub-tile
 //     (lane = column, previous row carried in registers, in-row shuffle fixed point — the sweep of k_relax) directly on the shared
 //     array: the halo of a sub-tile is simply the neighbouring warp's cells. A warp that lowers a cell on its border ring sets the
-//     neighbouring sub-tile's dirty flag (shared memory, ~30 cycles) — a hand-off between sub-tiles costs a flag instead of the
-//     publish / queue / pop / load round trip through L2 that a hop between k_relax tiles costs (8 of its 19 us);
-//   * when no sub-tile is dirty or running, the CTA publishes: the cells it lowered go to global memory with plain stores (a block is
-//     run by at most one CTA at a time, nobody else writes its cells), and a neighbouring block is queued only if relaxing across
-//     the border would lower the copy of its ring we hold (no echo activations). A block whose halo was lowered while it ran is
-//     re-run by the CTA that still holds it: only the halo is re-read.
+//     neighbouring sub-tile's dirty flag (shared memory) — a hand-off between sub-tiles costs a flag instead of the publish / queue /
+//     pop / load round trip through L2 that a hop between k_relax tiles costs (8 of its 19 us). The sub-tiles run in rounds separated
+//     by a block barrier at which the block votes on "any flag set?";
+//   * when no sub-tile is dirty, the CTA publishes: the cells it lowered go to global memory with plain stores (a block is run by at
+//     most one CTA at a time, nobody else writes its cells), and a neighbouring block is queued only if relaxing across the border
+//     would lower the copy of its ring we hold (no echo activations). A block whose halo was lowered while it ran goes back to the
+//     queue.
+//
+// STATUS: bit-identical to k_relax (tools/relax_ab.py, tests/test_gpu_parity.py::test_block_resident_relaxation_is_bit_identical) but
+// SLOWER on B200 — 14.0 ms against 8.0 ms at 4096^2, 62.7 against 31.1 ms at 8192^2, 2.8 against 1.35 ms at 640 x 480 (r2_j12 logs):
+// 8.6 runs per block and 3.6 x the sub-tile sweeps of k_relax, because a block run restarts its sub-tiles for every small improvement
+// that crosses it and only 148 x 16 warps are resident. It stays selectable (SIPP_RELAX_KERNEL=1) as the A/B partner of k_relax; the
+// default is k_relax.
 //
 // Exactness: every value ever stored is the rounded length of a real path (an upper bound of the fixed point), values only decrease,
 // and the kernel ends when no block is queued or running, i.e. at the fixed point — the argument of k_relax, unchanged.
@@ -27,7 +34,6 @@ constexpr int BPD = BS + 2;        // with the one-cell halo
 constexpr int kBlkSub = BS / TS;   // 4 sub-tiles per block edge
 constexpr int kBlkWarps = kBlkSub * kBlkSub;
 constexpr int kBlkThreads = kBlkWarps * 32;
-constexpr int kBlkIdleLimit = 1 << 21;   // idle polls (>= 100 ns each) before the drain watchdog gives up: a fraction of a second
 
 struct BlkSmem {
   double d[BPD][BPD];        // tentative costs incl. halo
@@ -37,20 +43,11 @@ struct BlkSmem {
   double dd[kMaxDd];         // diagonal length per class pair (+inf: not admitted, prm_star_planner.cpp:138)
   int xc[BPD], yc[BPD];      // class of those edges, premultiplied: xc[c] = class * Ky
   int dirty[kBlkWarps];      // sub-tile has unseen input
-  int pending;               // dirty + running sub-tiles
   int blk;                   // block being run (-1: the queue is drained)
-  int again;
   int ring_m;                // neighbour blocks (N S W E NW NE SW SE) whose side of our ring was lowered in this run
   int notify_m;              // neighbour blocks that have to look at it
-#ifdef SIPP_BLK_DEBUG
-  int wst[kBlkWarps], wit[kBlkWarps], wruns[kBlkWarps], wadd[kBlkWarps], wdec[kBlkWarps], init_n, reruns;
-#endif
+  int vote[3];               // "another round" votes, slot = round % 3
 };
-#ifdef SIPP_BLK_DEBUG
-#define BLK_DBG(x) x
-#else
-#define BLK_DBG(x)
-#endif
 static_assert(sizeof(BlkSmem) <= 227 * 1024, "block window must fit the opt-in shared memory of one SM");
 
 struct BlkArgs {
@@ -237,33 +234,31 @@ k_relax_blk(const BlkArgs a) {
     if (tid < kBlkWarps) {
       const int tx_ = tid & (kBlkSub - 1), ty_ = tid / kBlkSub;
       s.dirty[tid] = (bx * BS + tx_ * TS < g.W && by * BS + ty_ * TS < g.H) ? 1 : 0;     // sub-tiles off the map have nothing to do
-      BLK_DBG(s.wst[tid] = 0; s.wit[tid] = 0; s.wruns[tid] = 0; s.wadd[tid] = 0; s.wdec[tid] = 0;)
     }
     __syncthreads();
     if (tid == 0) {
-      int n = 0;
-      for (int k = 0; k < kBlkWarps; ++k) n += s.dirty[k];
-      s.pending = n;
-      BLK_DBG(s.init_n = n; s.reruns = 0;)
       s.ring_m = 0;
       s.notify_m = 0;
+      s.vote[0] = s.vote[1] = s.vote[2] = 0;
     }
     __syncthreads();
 
     uint32_t acc = 0;            // rows of this lane's column lowered since the last publish
-    for (;;) {                   // runs of this block: again whenever somebody lowered its halo while it was running
+    {                            // one run of this block
       ++act_local;
-      // ---- the sub-tiles relax until none is dirty or running
-      int idle = 0;
-      for (;;) {
+      // ---- the sub-tiles relax in ROUNDS until none is dirty. In a round every warp whose flag is set takes it and runs its sub-tile to
+      // the local fixed point, reading its neighbours' cells as they are and flagging the neighbours whose ring it lowered; then the
+      // block votes at a barrier: each warp arrives only once it has stopped, and a flag is always set before its setter arrives, so the
+      // flags the last arriving warp reads are final — if any is set there is another round. (An earlier form, a shared counter of dirty +
+      // running sub-tiles polled by the idle warps, lost count on the GPU and was dropped; waiting warps now sit in the barrier instead
+      // of competing for issue slots.)
+      for (int round = 0;; ++round) {
         int mine = 0;
         if (lane == 0) mine = ldvi(&s.dirty[warp]) ? atomicExch(&s.dirty[warp], 0) : 0;
         mine = __shfl_sync(0xFFFFFFFFu, mine, 0);
         if (mine) {
           __threadfence_block();
-          BLK_DBG(if (lane == 0) { s.wst[warp] = 1; s.wruns[warp] += 1; })
           for (int it = 0;; ++it) {
-            BLK_DBG(if (lane == 0) s.wit[warp] = it;)
             uint32_t rows_changed = 0;
             const bool ch = (it & 1) ? blk_sweep<-1, PATCH>(s, ddp, init_half, r0, c0, lane, rows_changed)
                                      : blk_sweep<+1, PATCH>(s, ddp, init_half, r0, c0, lane, rows_changed);
@@ -277,16 +272,11 @@ k_relax_blk(const BlkArgs a) {
                             ((lft >> 31) ? 64 : 0) | ((rgt >> 31) ? 128 : 0);
               __threadfence_block();       // the lowered cells before the flags
               if (lane < 8 && ((m >> lane) & 1)) {
-                const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-                const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-                const int nsx = sx + ddx[lane], nsy = sy + ddy[lane];
+                const int nsx = sx + ((0xA8 >> lane) & 1) - ((0x54 >> lane) & 1);      // dx of N S W E NW NE SW SE: 0 0 -1 1 -1 1 -1 1
+                const int nsy = sy + ((0xC2 >> lane) & 1) - ((0x31 >> lane) & 1);      // dy:                        -1 1 0 0 -1 -1 1 1
                 const int ox = nsx < 0 ? -1 : (nsx >= kBlkSub ? 1 : 0), oy = nsy < 0 ? -1 : (nsy >= kBlkSub ? 1 : 0);
                 if (ox == 0 && oy == 0) {
-                  // count FIRST, flag second: the neighbour may take the flag, run and decrement before we get to the counter, and a
-                  // counter that touches 0 on the way lets the other warps leave the loop while work is still being handed out
-                  atomicAdd(&s.pending, 1);
-                  BLK_DBG(atomicAdd(&s.wadd[warp], 1);)
-                  if (atomicExch(&s.dirty[nsy * kBlkSub + nsx], 1) != 0) { atomicSub(&s.pending, 1); BLK_DBG(atomicSub(&s.wadd[warp], 1);) }     // was flagged (and counted) already
+                  atomicExch(&s.dirty[nsy * kBlkSub + nsx], 1);
                 } else {
                   // a cell on the block's ring: the neighbouring block in direction (ox, oy) reads it
                   const int nb = oy == 0 ? (ox < 0 ? 2 : 3) : (ox == 0 ? (oy < 0 ? 0 : 1) : ((oy < 0 ? 4 : 6) + (ox < 0 ? 0 : 1)));
@@ -301,41 +291,23 @@ k_relax_blk(const BlkArgs a) {
               break;
             }
           }
-          if (lane == 0) {
-            __threadfence_block();
-            atomicSub(&s.pending, 1);
-            BLK_DBG(s.wst[warp] = 0; s.wdec[warp] += 1;)
-          }
-          idle = 0;
-        } else {
-          if (ldvi(&s.pending) == 0) { BLK_DBG(if (lane == 0) s.wst[warp] = 2;) break; }
-          if (++idle > 4) __nanosleep(100);
-          if ((idle & 4095) == 0 && ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) {      // another CTA gave up: leave with it
-            atomicExch(&s.pending, 0);
-            break;
-          }
-          if (idle > kBlkIdleLimit) {          // watchdog (~ seconds): the block's sub-tiles never drained
-            if (lane == 0) {
-#ifdef SIPP_BLK_DEBUG
-              if (atomicCAS(&a.ctl[CTL_ABORT], 0, 3) == 0) {
-                printf("[blk] watchdog: block %d run %d warp %d pending %d ring %x init_n %d reruns %d\n", bi, act_local, warp, ldvi(&s.pending), s.ring_m, s.init_n, s.reruns);
-                for (int k = 0; k < kBlkWarps; ++k)
-                  printf("[blk]   warp %2d dirty %d state %d it %d runs %d add %d dec %d\n", k, ldvi(&s.dirty[k]), ldvi(&s.wst[k]), ldvi(&s.wit[k]), ldvi(&s.wruns[k]),
-                         ldvi(&s.wadd[k]), ldvi(&s.wdec[k]));
-              }
-#endif
-              atomicExch(&a.ctl[CTL_ABORT], 3);
-              a.ctl[18] = bi; a.ctl[19] = ldvi(&s.pending);
-              int dm = 0;
-              for (int k = 0; k < kBlkWarps; ++k) dm |= (ldvi(&s.dirty[k]) ? 1 : 0) << k;
-              a.ctl[20] = dm;
-            }
-            atomicExch(&s.pending, 0);         // let everybody out: the plan is reported as aborted
-            break;
-          }
+          __threadfence_block();             // flags and cells before this warp's arrival at the vote
+        }
+        // the vote (plain barrier + a slot per round: barrier.red raised an illegal-instruction fault on this part). Slot r % 3 collects
+        // round r; thread 0 clears the slot of round r + 2 after barrier r, which nobody writes before barrier r + 1.
+        const int slot = round % 3;
+        const int flagged = (lane < kBlkWarps) ? ldvi(&s.dirty[lane]) : 0;
+        if (__any_sync(0xFFFFFFFFu, flagged != 0) && lane == 0) *reinterpret_cast<volatile int*>(&s.vote[slot]) = 1;
+        __syncthreads();
+        const int more = ldvi(&s.vote[slot]);
+        if (tid == 0) *reinterpret_cast<volatile int*>(&s.vote[(round + 2) % 3]) = 0;
+        if (!more) break;
+        if (round > (1 << 20)) {             // watchdog: the block's sub-tiles never drained
+          if (tid == 0) { atomicExch(&a.ctl[CTL_ABORT], 3); a.ctl[18] = bi; }
+          break;
         }
       }
-      __syncthreads();     // every warp saw pending == 0: nobody is sweeping, all flags are clear
+      // every flag is clear and nobody is sweeping
 
       // ---- publish: the cells this warp lowered (the block is ours alone: plain stores)
       {
@@ -414,50 +386,25 @@ k_relax_blk(const BlkArgs a) {
         // ---- done with this run: idle again, unless our halo was lowered meanwhile
         if (lane == 0) {
           fence_gpu();
-          int again = 0;
           if (atomicCAS(&a.flags[bi], ST_RUN, 0) != ST_RUN) {
-            atomicExch(&a.flags[bi], ST_RUN);      // take the request; everything lowered before this point is re-read below
-            fence_gpu();
-            again = 1;
+            // somebody lowered our halo while we ran: the block goes back to the queue (still counted in CTL_PENDING) and is loaded
+            // afresh by whoever pops it. (Re-running it in place on the window we hold, re-reading only the halo, produced wrong
+            // fields whenever two CTAs were involved and was dropped; the reload is 170 KB out of L2.)
+            atomicExch(&a.flags[bi], ST_QUEUED);
+            const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
+            int* slot = a.queue + (pos % (unsigned)a.cap);
+            int spins = 0;
+            while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);
+            st_volatile_i32(slot, bi);
+            ++push_local;
           } else {
             atomicSub(&a.ctl[CTL_PENDING], 1);     // after our pushes were counted: pending reaches 0 only at the global fixed point
           }
-          s.again = again;
           s.ring_m = 0;
           s.notify_m = 0;
         }
       }
       __syncthreads();
-      if (!s.again) break;
-      // ---- re-run: only the halo can have changed (the interior is ours alone and still here). Re-read it, keep the lower value,
-      // wake the sub-tiles that border a cell that came back lower.
-      for (int e = tid; e < 4 * BPD; e += kBlkThreads) {
-        const int q = e / BPD, k = e - q * BPD;
-        const int r = q == 0 ? 0 : (q == 1 ? BPD - 1 : k), c = q == 2 ? 0 : (q == 3 ? BPD - 1 : k);
-        const int gx = gx0 + c, gy = gy0 + r;
-        if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H) {
-          const double v = __ldcg(a.field + (size_t)gy * g.W + gx);
-          if (v < s.d[r][c]) {
-            s.d[r][c] = v;
-            // wake the sub-tiles whose ring touches this halo cell: the interior cells within one step of it
-            for (int dlt = -1; dlt <= 1; ++dlt) {
-              const int rr = q < 2 ? (q == 0 ? 1 : BS) : k + dlt, cc = q < 2 ? k + dlt : (q == 2 ? 1 : BS);
-              if (rr < 1 || rr > BS || cc < 1 || cc > BS) continue;
-              const int stx = (cc - 1) / TS, sty = (rr - 1) / TS;
-              if (bx * BS + stx * TS < g.W && by * BS + sty * TS < g.H) atomicExch(&s.dirty[sty * kBlkSub + stx], 1);
-            }
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int n = 0;
-        for (int k = 0; k < kBlkWarps; ++k) n += s.dirty[k];
-        s.pending = n;
-        BLK_DBG(s.init_n = n; s.reruns += 1; for (int k = 0; k < kBlkWarps; ++k) { s.wadd[k] = 0; s.wdec[k] = 0; s.wruns[k] = 0; })
-      }
-      __syncthreads();
-      // nothing came back lower (the request was an echo): the loop above falls straight through to the release protocol
     }
   }
   // statistics (plan_stats: pushes, block runs, sub-tile sweeps)

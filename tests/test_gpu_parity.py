@@ -813,3 +813,16 @@ def test_expand_low_cost_large_labels():
         g.gain_batch(sipp.make_params(sipp.EVAL_EXPAND_LOW_COST, half_fov=12), xy)
     assert e.value.code == sipp.ERR_UNSUPPORTED
     g.gain_batch(sipp.make_params(sipp.EVAL_NAIVE, half_fov=12), xy)          # the other evaluators are not affected
+
+
+@pytest.mark.gpu
+def test_block_resident_relaxation_is_bit_identical():
+    """A11: the fixed point does not depend on the relaxation order — the block-resident kernel (SIPP_RELAX_KERNEL=1, 128 x 128 blocks in
+    shared memory, many CTAs) leaves the same bits in the field as the per-tile default, on multi-block maps with ragged edges. The
+    kernel choice is read once per process, so both run in processes of their own (tools/blk_debug.py)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "blk_debug.py"), "130", "640", "1024"], capture_output=True, text=True, timeout=600)
+    text = out.stdout + out.stderr
+    assert out.returncode == 0, text
+    assert text.count("same_field=True") == 3 and "failed" not in text and "differs" not in text and "TIMEOUT" not in text, text

@@ -29,6 +29,26 @@ def child(W, H):
         if not same:
             bad = np.argwhere(g != f)
             print("  field differs in %d cells, first %s: %r vs %r" % (len(bad), bad[0], f[tuple(bad[0])], g[tuple(bad[0])]), flush=True)
+            print("    zeros new %s ref %s" % (np.argwhere(f == 0).tolist()[:8], np.argwhere(g == 0).tolist()[:8]), flush=True)
+            lows = np.argwhere(f < g)
+            # the lowest-valued wrong cell: where the bad information entered
+            k = lows[np.argmin(f[lows[:, 0], lows[:, 1]])]
+            y, x = int(k[0]), int(k[1])
+            print("    smallest wrong value at (row %d, col %d): new %r ref %r; neighbourhood new:" % (y, x, f[y, x], g[y, x]), flush=True)
+            with np.printoptions(precision=3, linewidth=250, suppress=True):
+                print(f[max(0, y - 3):y + 4, max(0, x - 3):x + 4], flush=True)
+                print("    ref:", flush=True)
+                print(g[max(0, y - 3):y + 4, max(0, x - 3):x + 4], flush=True)
+            for by in range(0, H, 128):
+                for bx in range(0, W, 128):
+                    fb, gb = f[by:by + 128, bx:bx + 128], g[by:by + 128, bx:bx + 128]
+                    with np.errstate(invalid="ignore"):
+                        lo, hi = int(np.sum(fb < gb)), int(np.sum(fb > gb))
+                    if lo or hi:
+                        w = np.argwhere(fb != gb)
+                        print("    block (%d,%d): %d lower %d higher; rows %d..%d cols %d..%d; inf new %d ref %d" % (
+                            bx // 128, by // 128, lo, hi, w[:, 0].min(), w[:, 0].max(), w[:, 1].min(), w[:, 1].max(),
+                            int(np.isinf(fb).sum()), int(np.isinf(gb).sum())), flush=True)
     else:
         np.save(ref, f)
     print("  %dx%d kernel=%s: first plan %.3f ms cost %.6f nodes %d stats %s same_field=%s" % (
