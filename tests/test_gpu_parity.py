@@ -1,6 +1,8 @@
 """GPU parity: libsipp.so (CUDA, through the C ABI) against the CPU oracle on the same inputs.
 Bit-exact for counts, terminal flags, cost fields, paths, masks and selected candidates; floating-point gains
 within 1e-5 relative (north_star tolerance) — exact where the reference's arithmetic is integer valued."""
+import os
+
 import numpy as np
 import pytest
 
