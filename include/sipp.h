@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIPP_ABI_VERSION 2
+#define SIPP_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------------------------------- */
 #define SIPP_OK 0
@@ -339,6 +339,37 @@ int sipp_travel_cost(sipp_ctx* ctx, const sipp_travel_params* params, int32_t n,
 int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params* params, int32_t cycles, int32_t n,
                      const double* cand_xy, const double* cand_cost, int32_t fov, int32_t init, double start_x, double start_y,
                      double* path_cost, int32_t* plan_status, int32_t* path_len, int32_t* best_index, double* best_value);
+
+/* ---- batched ensembles: m maps of one size on one device advance together ---------------------------------------------------
+ * Every kernel of a step (patch ingest, re-plan, view planes, gain + value + argmax) is launched ONCE for all maps (gridDim.y = m,
+ * per-map argument blocks in device memory), with one host->device copy of the inputs, one device->host copy of the results and
+ * one synchronisation per map-cycle — instead of m contexts x ~20 stream operations fed by m host threads. The contexts keep all
+ * state (sipp_map_download, sipp_field_download, sipp_path_download ... work between batch calls); they must be idle when a batch
+ * call starts and must not be driven from other threads while it runs. Results are bit-identical to the same calls made map by
+ * map (tests/test_gpu_batch.py).
+ * Limits: maps without compute_closest_observed; sipp_batch_cycle serves the count-type evaluators on the 2-bit plane
+ * (RRTStarEvaluator without distance discount, ExpandReachableArea, Naive; half_fov <= 96) and refuses the others.
+ * Replaces, for evaluation runs over many maps, the one-planner-process-per-saved-map loop of data_analysis/evaluation.py:39-62,
+ * 139-144 + planexp_base_planners/src/planexp_eval_planner.cpp:201-303 and the one-experiment-per-map loop of
+ * advanced_planner_ros/scripts/run_experiment.sh:190-212. */
+typedef struct sipp_batch sipp_batch;
+int sipp_batch_create(sipp_ctx* const* ctxs, int32_t m, sipp_batch** out);   /* on failure the message is in sipp_last_error(ctxs[i]) */
+void sipp_batch_destroy(sipp_batch* batch);                                   /* the contexts stay alive */
+const char* sipp_batch_last_error(const sipp_batch* batch);
+int64_t sipp_batch_launch_count(const sipp_batch* batch);
+/* sipp_map_update_patch for every map: map i ingests the rows x cols patch labels[i] at (x0[i], y0[i]) */
+int sipp_batch_ingest(sipp_batch* batch, const int32_t* x0, const int32_t* y0, int32_t rows, int32_t cols, const int32_t* const* labels);
+/* sipp_plan for every map (from scratch or incremental, decided per map): cost / status / path_len are m entries (any may be NULL) */
+int sipp_batch_plan(sipp_batch* batch, double* cost, int32_t* status, int32_t* path_len);
+/* sipp_cycle for every map: xy[i] = n x 2, cost[i] = n candidates of map i; best_index / best_value: m entries; gain: optional m
+ * pointers to n doubles each (entries may be NULL) */
+int sipp_batch_cycle(sipp_batch* batch, const sipp_eval_params* params, int32_t n, const double* const* xy, const double* const* cost,
+                     int64_t* best_index, double* best_value, double* const* gain);
+/* sipp_episode_run for every map, in lockstep. truth[i]: W x H labels; cand_xy[i] / cand_cost[i]: cycles x n candidates of map i.
+ * Outputs (any may be NULL): m x cycles, map-major. */
+int sipp_batch_episode_run(sipp_batch* batch, const int32_t* const* truth, const sipp_eval_params* params, int32_t cycles, int32_t n,
+                           const double* const* cand_xy, const double* const* cand_cost, int32_t fov, int32_t init, double start_x,
+                           double start_y, double* path_cost, int32_t* plan_status, int32_t* path_len, int32_t* best_index, double* best_value);
 
 /* ---- multi-GPU: exchange of the shard winners through peer memory (NVLink / NVSwitch), fused into the argmax kernel ----- */
 /* One process per GPU (or several contexts in one process). Every rank exports a handle to its mailbox, the host program

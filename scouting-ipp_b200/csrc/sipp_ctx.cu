@@ -7,6 +7,11 @@
 #include <cstring>
 #include <map>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
+
 #include "sipp_internal.h"
 #include "sipp_peer.cuh"
 
@@ -489,7 +494,8 @@ int sipp_patch_origin(const sipp_ctx* ctx, double px, double py, int32_t rows, i
   return SIPP_OK;
 }
 
-static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* labels, const uint8_t* observed) {
+// host half of a patch ingest: the sequential scalars + the bookkeeping of the incremental re-plan; the caller launches k_ingest_patch
+static int ingest_host_part(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* labels, const uint8_t* observed) {
   if (!labels || rows <= 0 || cols <= 0) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad patch %d x %d", rows, cols);
   int rc = host_ingest(ctx, x0, y0, rows, cols, labels, observed);
   if (rc != SIPP_OK) return rc;
@@ -504,6 +510,15 @@ static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, cons
       else { ctx->pending_rects.push_back(xa); ctx->pending_rects.push_back(ya); ctx->pending_rects.push_back(xb); ctx->pending_rects.push_back(yb); }
     }
   }
+  ctx->lowcost_view_dirty = true;
+  ctx->views_dirty = true;
+  ctx->field_valid = false;
+  return SIPP_OK;
+}
+
+static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* labels, const uint8_t* observed) {
+  int rc = ingest_host_part(ctx, x0, y0, rows, cols, labels, observed);
+  if (rc != SIPP_OK) return rc;
   const size_t n = (size_t)rows * cols;
   const size_t need = n * 4 + (observed ? n : 0) + 256;
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
@@ -514,9 +529,6 @@ static int ingest_common(sipp_ctx* ctx, int x0, int y0, int rows, int cols, cons
   SIPP_CUDA_CHECK(ctx, launch_ingest_patch(ctx, x0, y0, rows, cols, d_lab, d_obs, ctx->stream));
   // setClosestObservedMaps runs per MapData patch (map_server_planexp.cpp:264); the masked whole-map upload is not one
   if (ctx->desc.compute_closest_observed && !observed) SIPP_CUDA_CHECK(ctx, launch_closest_update(ctx, x0, y0, rows, cols, ctx->stream));
-  ctx->lowcost_view_dirty = true;
-  ctx->views_dirty = true;
-  ctx->field_valid = false;
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return SIPP_OK;
 }
@@ -579,6 +591,8 @@ int sipp_set_path_mask(sipp_ctx* ctx, const uint8_t* mask) {
 
 int sipp_path_mask_generation(const sipp_ctx* ctx) { return ctx ? ctx->path_generation : -1; }
 
+static int plan_collect(sipp_ctx* ctx, const int* out, const int* ctl, double* cost, int32_t* status, int* len_out, bool* found_out);
+
 static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_xy, int32_t path_cap, int32_t* path_len) {
   int rc = field_plan(ctx, ctx->stream);
   if (rc != SIPP_OK) { ctx->warm_valid = false; return rc; }
@@ -588,6 +602,20 @@ static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_plan_out, 10 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctl, ctx->d_relax_ctl, 24 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  int len = 0;
+  bool found = false;
+  if ((rc = plan_collect(ctx, out, ctl, cost, status, &len, &found)) != SIPP_OK) return rc;
+  if (path_len) *path_len = found ? len : 0;
+  if (path_xy && found && path_cap > 0) {
+    const int m = len < path_cap ? len : path_cap;
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(path_xy, ctx->d_path_xy, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SIPP_OK;
+}
+
+// host half of a plan's end: out = plan_out[0..9], ctl = the relaxation control block [0..23] as the kernels left them
+static int plan_collect(sipp_ctx* ctx, const int* out, const int* ctl, double* cost, int32_t* status, int* len_out, bool* found_out) {
   ctx->plan_stats[0] = ctl[6];
   ctx->plan_stats[1] = ctl[3];
   ctx->plan_stats[2] = ctl[4];
@@ -616,12 +644,8 @@ static int plan_impl(sipp_ctx* ctx, double* cost, int32_t* status, double* path_
   else if (out[4]) st = SIPP_PLAN_INVALID;
   if (cost) *cost = found ? c : -1.0;
   if (status) *status = st;
-  if (path_len) *path_len = found ? len : 0;
-  if (path_xy && found && path_cap > 0) {
-    const int m = len < path_cap ? len : path_cap;
-    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(path_xy, ctx->d_path_xy, (size_t)m * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  }
+  *len_out = len;
+  *found_out = found;
   ctx->path_generation += 1;     // path_counter_ map_server_planexp.cpp:896
   ctx->path_valid = true;
   ctx->field_valid = true;
@@ -1207,6 +1231,403 @@ int sipp_merge_best_dev(sipp_ctx* ctx, const void* d_recs, int32_t world, int64_
   if (!d_recs || !d_out || world < 1) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad merge_best arguments");
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   SIPP_CUDA_CHECK(ctx, launch_merge_best(ctx, reinterpret_cast<const BestRec*>(d_recs), world, (long long)shard_stride, reinterpret_cast<BestRec*>(d_out), s));
+  return SIPP_OK;
+}
+
+// =====================================================================================================
+// Batched ensembles (BASELINE config 5): m maps of one size on one device advance TOGETHER — every kernel of a
+// step (patch ingest, re-plan, view planes, gain + value + argmax) is launched once with gridDim.y = m and reads its per-map argument
+// block from device memory, instead of m contexts x ~20 stream operations per map-cycle fed by m host threads. One host->device
+// copy per step carries all argument blocks and inputs, one device->host copy all results, one synchronisation per map-cycle.
+// The contexts keep all state (sipp_map_download, sipp_field_download, ... keep working between batch calls); they must be idle
+// when a batch call starts and must not be driven from other threads while it runs.
+// Replaces, for evaluation runs over many maps, data_analysis/evaluation.py:39-62,139-144 + planexp_eval_planner.cpp:201-303
+// (one planner process per saved map) and advanced_planner_ros/scripts/run_experiment.sh:190-212 (one experiment per map).
+// host work of a batch step is a loop over maps with no dependence between them (the sequential scalars of an ingest, the seed
+// tiles of a plan, argument blocks): a few helper threads share it with the calling thread. No CUDA calls are made from the helpers.
+struct BatchPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  const std::function<void(int)>* fn = nullptr;
+  int n = 0, active = 0;
+  std::atomic<int> next{0};
+  uint64_t gen = 0;
+  bool stop = false;
+  void start(int helpers) {
+    for (int t = 0; t < helpers; ++t)
+      th.emplace_back([this] {
+        uint64_t seen = 0;
+        for (;;) {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return stop || gen != seen; });
+          if (stop) return;
+          seen = gen;
+          lk.unlock();
+          for (int i; (i = next.fetch_add(1)) < n;) (*fn)(i);
+          lk.lock();
+          if (--active == 0) cv_done.notify_one();
+        }
+      });
+  }
+  void run(int count, const std::function<void(int)>& f) {
+    if (th.empty() || count < 8) {
+      for (int i = 0; i < count; ++i) f(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      fn = &f; n = count; next.store(0); active = (int)th.size(); ++gen;
+    }
+    cv.notify_all();
+    for (int i; (i = next.fetch_add(1)) < count;) f(i);
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return active == 0; });
+  }
+  ~BatchPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+
+struct sipp_batch {
+  int m, device;
+  BatchPool pool;
+  std::vector<sipp_ctx*> ctx;
+  cudaStream_t stream;
+  std::mutex mu;
+  size_t plan_args, seed_stride;      // bytes per map
+  // pinned host / device staging; one region per step of a map-cycle so that no step overwrites what an earlier one still copies
+  uint8_t *h_plan, *d_plan;           // m x PlanArgsAll
+  uint8_t *h_seed, *d_seed;           // m x seed_stride
+  int *h_out, *d_out;                 // m x 40: plan_out[0..9], relaxation control block at [16..39]
+  uint8_t *h_ing, *d_ing;  size_t ing_bytes;     // ingest: m argument blocks + m patches
+  uint8_t *h_cyc, *d_cyc;  size_t cyc_bytes;     // cycle: m view blocks + m gain blocks + candidates (xy, cost)
+  uint8_t *d_res;  size_t res_bytes;  // cycle scratch: gain, value, terminal per candidate; best records at the front
+  BestRec* h_best;                    // m records
+  int64_t launches;
+  char err[320];
+};
+
+static int batch_err(sipp_batch* b, int rc, sipp_ctx* from) {
+  if (from) snprintf(b->err, sizeof(b->err), "%s", from->err.c_str());
+  return rc;
+}
+static int batch_fail(sipp_batch* b, int rc, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(b->err, sizeof(b->err), fmt, ap);
+  va_end(ap);
+  return rc;
+}
+#define SIPP_BATCH_CUDA(b, expr)                                                                                          \
+  do {                                                                                                                    \
+    cudaError_t e__ = (expr);                                                                                             \
+    if (e__ != cudaSuccess) return batch_fail((b), SIPP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static int batch_grow(sipp_batch* b, uint8_t** h, uint8_t** d, size_t* cur, size_t need) {
+  if (*cur >= need) return SIPP_OK;
+  SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  if (h && *h) cudaFreeHost(*h);
+  if (*d) cudaFree(*d);
+  if (h) *h = nullptr;
+  *d = nullptr; *cur = 0;
+  need = (need + (need >> 2) + 4095) & ~(size_t)4095;
+  if (h) SIPP_BATCH_CUDA(b, cudaMallocHost(reinterpret_cast<void**>(h), need));
+  SIPP_BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void**>(d), need));
+  *cur = need;
+  return SIPP_OK;
+}
+
+const char* sipp_batch_last_error(const sipp_batch* b) { return b ? b->err : "batch == NULL"; }
+int64_t sipp_batch_launch_count(const sipp_batch* b) { return b ? b->launches : 0; }
+
+void sipp_batch_destroy(sipp_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
+  void* hp[] = {b->h_plan, b->h_seed, b->h_out, b->h_ing, b->h_cyc, b->h_best};
+  void* dp[] = {b->d_plan, b->d_seed, b->d_out, b->d_ing, b->d_cyc, b->d_res};
+  for (void* p : hp) if (p) cudaFreeHost(p);
+  for (void* p : dp) if (p) cudaFree(p);
+  delete b;
+}
+
+int sipp_batch_create(sipp_ctx* const* ctxs, int32_t m, sipp_batch** out) {
+  if (!ctxs || m < 1 || !out) return SIPP_ERR_INVALID_ARG;
+  *out = nullptr;
+  for (int i = 0; i < m; ++i) {
+    if (!ctxs[i]) return SIPP_ERR_INVALID_ARG;
+    if (ctxs[i]->device != ctxs[0]->device || ctxs[i]->W != ctxs[0]->W || ctxs[i]->H != ctxs[0]->H)
+      return sipp_set_err(ctxs[i], SIPP_ERR_INVALID_ARG, "a batch takes maps of one size on one device (map %d differs from map 0)", i);
+    if (ctxs[i]->desc.compute_closest_observed)
+      return sipp_set_err(ctxs[i], SIPP_ERR_UNSUPPORTED, "batched ingest does not maintain the closest-observed planes (compute_closest_observed)");
+    for (int j = 0; j < i; ++j)
+      if (ctxs[j] == ctxs[i]) return sipp_set_err(ctxs[i], SIPP_ERR_INVALID_ARG, "context %d appears twice in the batch", i);
+  }
+  sipp_batch* b = new sipp_batch();
+  b->m = m;
+  b->device = ctxs[0]->device;
+  b->ctx.assign(ctxs, ctxs + m);
+  b->stream = nullptr;
+  b->h_plan = b->d_plan = b->h_seed = b->d_seed = b->h_ing = b->d_ing = b->h_cyc = b->d_cyc = b->d_res = nullptr;
+  b->h_out = b->d_out = nullptr;
+  b->h_best = nullptr;
+  b->ing_bytes = b->cyc_bytes = b->res_bytes = 0;
+  b->launches = 0;
+  b->err[0] = 0;
+  auto fail = [&](int rc) { sipp_set_err(ctxs[0], rc, "%s", b->err); sipp_batch_destroy(b); return rc; };
+  if (cudaSetDevice(b->device) != cudaSuccess) return fail(batch_fail(b, SIPP_ERR_CUDA, "cudaSetDevice(%d) failed", b->device));
+  const int ntiles = ctxs[0]->n_tiles_x * ctxs[0]->n_tiles_y;
+  b->plan_args = field_plan_batch_args_bytes();
+  b->seed_stride = ((((size_t)ntiles + 3) & ~(size_t)3) + (size_t)ntiles * sizeof(int) + 15) & ~(size_t)15;
+  cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_plan), b->plan_args * m);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->d_plan), b->plan_args * m);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_seed), b->seed_stride * m);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->d_seed), b->seed_stride * m);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_out), sizeof(int) * 40 * m);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->d_out), sizeof(int) * 40 * m);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_best), sizeof(BestRec) * m);
+  if (e != cudaSuccess) return fail(batch_fail(b, SIPP_ERR_CUDA, "batch staging: %s", cudaGetErrorString(e)));
+  // helper threads for the per-map host loops: SIPP_BATCH_THREADS (total, including the caller), default 4
+  int threads = getenv("SIPP_BATCH_THREADS") ? atoi(getenv("SIPP_BATCH_THREADS")) : 4;
+  if (threads > 64) threads = 64;
+  if (threads > 1 && m >= 8) b->pool.start(threads - 1);
+  *out = b;
+  return SIPP_OK;
+}
+
+#define SIPP_BATCH_ENTER(b)                                                                                       \
+  if (!(b)) return SIPP_ERR_INVALID_ARG;                                                                          \
+  std::lock_guard<std::mutex> lock__((b)->mu);                                                                    \
+  if (cudaSetDevice((b)->device) != cudaSuccess) return batch_fail((b), SIPP_ERR_CUDA, "cudaSetDevice failed")
+
+// ---- steps: enqueue on the batch stream; nothing here synchronises ------------------------------------------------------------
+// patches: labels + (size_t)i * label_stride = the rows x cols patch of map i (host memory)
+static int batch_ingest_enqueue(sipp_batch* b, const int32_t* x0, const int32_t* y0, int rows, int cols, const int32_t* const* labels) {
+  const int m = b->m;
+  if (!x0 || !y0 || !labels || rows <= 0 || cols <= 0) return batch_fail(b, SIPP_ERR_INVALID_ARG, "bad batch patch %d x %d", rows, cols);
+  // [m argument blocks, packed][pad to 256][m patches, 16-byte aligned each]
+  const size_t ab = ingest_args_bytes(), pb = ((size_t)rows * cols * sizeof(int32_t) + 15) & ~(size_t)15;
+  const size_t poff = (ab * m + 255) & ~(size_t)255;
+  int rc = batch_grow(b, &b->h_ing, &b->d_ing, &b->ing_bytes, poff + pb * m);
+  if (rc != SIPP_OK) return rc;
+  for (int i = 0; i < m; ++i)
+    if (!labels[i]) return batch_fail(b, SIPP_ERR_INVALID_ARG, "patch %d == NULL", i);
+  std::vector<int> rcs((size_t)m, SIPP_OK);
+  b->pool.run(m, [&](int i) {
+    sipp_ctx* ctx = b->ctx[i];
+    if ((rcs[i] = ingest_host_part(ctx, x0[i], y0[i], rows, cols, labels[i], nullptr)) != SIPP_OK) return;
+    memcpy(b->h_ing + poff + pb * i, labels[i], (size_t)rows * cols * sizeof(int32_t));
+    fill_ingest_args(ctx, x0[i], y0[i], rows, cols, reinterpret_cast<const int32_t*>(b->d_ing + poff + pb * i), b->h_ing + ab * i);
+  });
+  for (int i = 0; i < m; ++i)
+    if (rcs[i] != SIPP_OK) return batch_err(b, rcs[i], b->ctx[i]);
+  SIPP_BATCH_CUDA(b, cudaMemcpyAsync(b->d_ing, b->h_ing, poff + pb * m, cudaMemcpyHostToDevice, b->stream));
+  SIPP_BATCH_CUDA(b, launch_ingest_patch_batch(b->d_ing, m, rows, cols, b->stream));
+  b->launches += 1;
+  return SIPP_OK;
+}
+
+static int batch_plan_enqueue(sipp_batch* b) {
+  int n = 0;
+  const std::function<void(int, const std::function<void(int)>&)> runner = [b](int count, const std::function<void(int)>& f) { b->pool.run(count, f); };
+  int rc = field_plan_batch(b->ctx.data(), b->m, b->h_plan, b->d_plan, b->h_seed, b->d_seed, b->seed_stride, b->d_out, b->stream, &n, &runner);
+  if (rc != SIPP_OK) {
+    for (sipp_ctx* c : b->ctx) c->warm_valid = false;
+    return batch_err(b, rc, b->ctx[0]);
+  }
+  b->launches += n;
+  SIPP_BATCH_CUDA(b, cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int) * 40 * b->m, cudaMemcpyDeviceToHost, b->stream));
+  for (sipp_ctx* c : b->ctx) c->path_valid = true;      // the masks exist in stream order; plan_collect confirms after the synchronisation
+  return SIPP_OK;
+}
+// after the stream was synchronised
+static int batch_plan_collect(sipp_batch* b, double* cost, int32_t* status, int32_t* path_len, size_t stride) {
+  int first_rc = SIPP_OK;
+  for (int i = 0; i < b->m; ++i) {
+    int len = 0;
+    bool found = false;
+    double c = -1.0;
+    int32_t st = 0;
+    const int rc = plan_collect(b->ctx[i], b->h_out + 40 * i, b->h_out + 40 * i + 16, &c, &st, &len, &found);
+    if (rc != SIPP_OK && first_rc == SIPP_OK) first_rc = batch_err(b, rc, b->ctx[i]);
+    if (cost) cost[i * stride] = c;
+    if (status) status[i * stride] = st;
+    if (path_len) path_len[i * stride] = found ? len : 0;
+  }
+  return first_rc;
+}
+
+// candidates of map i: xy[i] (n x 2 doubles), cost[i] (n doubles), host memory
+static int batch_cycle_enqueue(sipp_batch* b, const sipp_eval_params* params, int n, const double* const* xy, const double* const* cost) {
+  const int m = b->m;
+  if (!params || n < 1 || !xy || !cost) return batch_fail(b, SIPP_ERR_INVALID_ARG, "bad batch cycle arguments");
+  // [m view blocks, packed][pad][m gain blocks, packed][pad][m x (xy, cost)]
+  const size_t vb = build_views_args_bytes(), gb = gain_args_bytes();
+  const size_t goff = (vb * m + 255) & ~(size_t)255, coff = (goff + gb * m + 255) & ~(size_t)255;
+  const size_t cb = ((size_t)n * 24 + 15) & ~(size_t)15;      // xy + cost of one map (the kernel reads xy as 16-byte pairs)
+  int rc = batch_grow(b, &b->h_cyc, &b->d_cyc, &b->cyc_bytes, coff + cb * m);
+  if (rc != SIPP_OK) return rc;
+  // scratch per map: gain, value (doubles), terminal (bytes, padded); the m best records sit at the front
+  const size_t rb = ((size_t)n * 17 + 15) & ~(size_t)15, best_bytes = ((size_t)m * sizeof(BestRec) + 255) & ~(size_t)255;
+  if ((rc = batch_grow(b, nullptr, &b->d_res, &b->res_bytes, best_bytes + rb * m)) != SIPP_OK) return rc;
+  uint8_t* h_views = b->h_cyc;
+  uint8_t* h_gain = b->h_cyc + goff;
+  uint8_t* h_cand = b->h_cyc + coff;
+  uint8_t* d_cand = b->d_cyc + coff;
+  BestRec* d_best = reinterpret_cast<BestRec*>(b->d_res);
+  bool any_views = false;
+  std::vector<uint8_t> stale_views((size_t)m, 0);
+  if (params->evaluator == SIPP_EVAL_EXPAND_LOW_COST) return batch_fail(b, SIPP_ERR_UNSUPPORTED, "batched evaluation does not serve ExpandLowCostAreaEvaluator");
+  for (int i = 0; i < m; ++i)
+    if (!xy[i] || !cost[i]) return batch_fail(b, SIPP_ERR_INVALID_ARG, "candidates of map %d == NULL", i);
+  std::vector<int> rcs((size_t)m, SIPP_OK);
+  b->pool.run(m, [&](int i) {
+    sipp_ctx* ctx = b->ctx[i];
+    if ((rcs[i] = check_params(ctx, params)) != SIPP_OK) return;
+    const GainGeom g = make_gain_geom(ctx, params);
+    const bool stale = !(!ctx->views_dirty && ctx->view_params_valid && same_bv(ctx->view_params, *params));
+    stale_views[i] = stale ? 1 : 0;
+    fill_build_views_args(ctx, g, params->use_bounding_volume != 0, stale ? 1 : 0, h_views + vb * i);
+    memcpy(h_cand + cb * i, xy[i], (size_t)n * 16);
+    memcpy(h_cand + cb * i + (size_t)n * 16, cost[i], (size_t)n * 8);
+    const double* d_xy = reinterpret_cast<const double*>(d_cand + cb * i);
+    const double* d_cost = d_xy + (size_t)n * 2;
+    double* d_gain = reinterpret_cast<double*>(b->d_res + best_bytes + rb * i);
+    double* d_value = d_gain + n;
+    uint8_t* d_term = reinterpret_cast<uint8_t*>(d_value + n);
+    FusedSelect fs;
+    fs.best_out = d_best + i;
+    fs.index_offset = 0;
+    fs.peer = nullptr;
+    fs.peer_mode = 0;
+    rcs[i] = gain_fill_batch_args(ctx, params, g, n, d_xy, d_cost, d_gain, d_term, d_value, &fs, h_gain + gb * i);
+  });
+  for (int i = 0; i < m; ++i) {
+    if (rcs[i] != SIPP_OK) return batch_err(b, rcs[i], b->ctx[i]);
+    any_views |= stale_views[i] != 0;
+  }
+  SIPP_BATCH_CUDA(b, cudaMemcpyAsync(b->d_cyc, b->h_cyc, coff + cb * m, cudaMemcpyHostToDevice, b->stream));
+  for (int i = 0; i < m; ++i)          // every argument block is in place: only now do the contexts learn that their views get rebuilt
+    if (stale_views[i]) {
+      sipp_ctx* ctx = b->ctx[i];
+      if (!(ctx->view_params_valid && same_bv(ctx->view_params, *params))) ctx->lowcost_view_dirty = true;
+      ctx->views_dirty = false;
+      ctx->view_params = *params;
+      ctx->view_params_valid = true;
+    }
+  if (any_views) {
+    SIPP_BATCH_CUDA(b, launch_build_views_batch(b->d_cyc, m, b->ctx[0]->pitch, b->ctx[0]->H, b->stream));
+    b->launches += 1;
+  }
+  if ((rc = gain_launch_batch(b->ctx[0], b->d_cyc + goff, m, n, b->stream)) != SIPP_OK) return batch_err(b, rc, b->ctx[0]);
+  b->launches += 1;
+  SIPP_BATCH_CUDA(b, cudaMemcpyAsync(b->h_best, d_best, sizeof(BestRec) * m, cudaMemcpyDeviceToHost, b->stream));
+  return SIPP_OK;
+}
+
+// ---- public calls --------------------------------------------------------------------------------------------------------------
+int sipp_batch_ingest(sipp_batch* b, const int32_t* x0, const int32_t* y0, int32_t rows, int32_t cols, const int32_t* const* labels) {
+  SIPP_BATCH_ENTER(b);
+  int rc = batch_ingest_enqueue(b, x0, y0, rows, cols, labels);
+  if (rc != SIPP_OK) return rc;
+  SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  return SIPP_OK;
+}
+
+int sipp_batch_plan(sipp_batch* b, double* cost, int32_t* status, int32_t* path_len) {
+  SIPP_BATCH_ENTER(b);
+  int rc = batch_plan_enqueue(b);
+  if (rc != SIPP_OK) return rc;
+  SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  return batch_plan_collect(b, cost, status, path_len, 1);
+}
+
+int sipp_batch_cycle(sipp_batch* b, const sipp_eval_params* params, int32_t n, const double* const* xy, const double* const* cost, int64_t* best_index,
+                     double* best_value, double* const* gain) {
+  SIPP_BATCH_ENTER(b);
+  int rc = batch_cycle_enqueue(b, params, n, xy, cost);
+  if (rc != SIPP_OK) return rc;
+  if (gain) {
+    const size_t rb = ((size_t)n * 17 + 15) & ~(size_t)15, best_bytes = ((size_t)b->m * sizeof(BestRec) + 255) & ~(size_t)255;
+    for (int i = 0; i < b->m; ++i)
+      if (gain[i]) SIPP_BATCH_CUDA(b, cudaMemcpyAsync(gain[i], b->d_res + best_bytes + rb * i, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream));
+  }
+  SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < b->m; ++i) {
+    if (best_index) best_index[i] = b->h_best[i].index;
+    if (best_value) best_value[i] = b->h_best[i].value;
+  }
+  return SIPP_OK;
+}
+
+// m episodes in lockstep (sipp_episode_run for every map of the batch): per cycle ONE ingest launch, one plan sequence, one scoring
+// launch and one synchronisation for all maps. truth[i]: W x H labels of map i; cand_xy[i] / cand_cost[i]: cycles x n candidates of map i.
+// Outputs (any may be NULL): m x cycles, map-major.
+int sipp_batch_episode_run(sipp_batch* b, const int32_t* const* truth, const sipp_eval_params* params, int32_t cycles, int32_t n,
+                           const double* const* cand_xy, const double* const* cand_cost, int32_t fov, int32_t init, double start_x, double start_y,
+                           double* path_cost, int32_t* plan_status, int32_t* path_len, int32_t* best_index, double* best_value) {
+  SIPP_BATCH_ENTER(b);
+  if (!truth || !params || cycles < 0 || n < 1 || !cand_xy || !cand_cost || fov < 1 || fov > 4096 || init < 0)
+    return batch_fail(b, SIPP_ERR_INVALID_ARG, "bad episode arguments");
+  const int m = b->m, W = b->ctx[0]->W, H = b->ctx[0]->H;
+  for (int i = 0; i < m; ++i)
+    if (!truth[i] || !cand_xy[i] || !cand_cost[i]) return batch_fail(b, SIPP_ERR_INVALID_ARG, "inputs of map %d == NULL", i);
+  std::vector<std::vector<int32_t>> patch((size_t)m);
+  std::vector<const int32_t*> pp((size_t)m);
+  std::vector<int32_t> x0((size_t)m), y0((size_t)m);
+  std::vector<double> px((size_t)m, start_x), py((size_t)m, start_y);
+  std::vector<const double*> xy((size_t)m), cc((size_t)m);
+  auto cut = [&](int rows, int cols) {       // the simulator's MapData patches: truth labels, 0 off the image
+    b->pool.run(m, [&](int k) {
+      patch[k].assign((size_t)rows * cols, 0);
+      for (int i = 0; i < rows; ++i) {
+        const int y = y0[k] + i;
+        if (y < 0 || y >= H) continue;
+        for (int j = 0; j < cols; ++j) {
+          const int x = x0[k] + j;
+          if (x >= 0 && x < W) patch[k][(size_t)i * cols + j] = truth[k][(size_t)y * W + x];
+        }
+      }
+      pp[k] = patch[k].data();
+    });
+  };
+  int rc;
+  if (init > 0) {       // mav_simulator.cpp:156-159
+    for (int k = 0; k < m; ++k) x0[k] = y0[k] = 0;
+    const int rows = init < H ? init : H, cols = init < W ? init : W;
+    cut(rows, cols);
+    if ((rc = batch_ingest_enqueue(b, x0.data(), y0.data(), rows, cols, pp.data())) != SIPP_OK) return rc;
+    SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  }
+  for (int c = 0; c < cycles; ++c) {
+    for (int k = 0; k < m; ++k) {
+      const sipp_ctx* ctx = b->ctx[k];
+      const int ix = (int)(px[k] * (long)W / ctx->desc.width), iy = (int)(py[k] * (long)H / ctx->desc.height);   // sipp_patch_origin
+      x0[k] = ix - fov / 2;
+      y0[k] = iy - fov / 2;
+      xy[k] = cand_xy[k] + (size_t)c * n * 2;
+      cc[k] = cand_cost[k] + (size_t)c * n;
+    }
+    cut(fov, fov);
+    if ((rc = batch_ingest_enqueue(b, x0.data(), y0.data(), fov, fov, pp.data())) != SIPP_OK) return rc;
+    if ((rc = batch_plan_enqueue(b)) != SIPP_OK) return rc;
+    if ((rc = batch_cycle_enqueue(b, params, n, xy.data(), cc.data())) != SIPP_OK) return rc;
+    SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+    if ((rc = batch_plan_collect(b, path_cost ? path_cost + c : nullptr, plan_status ? plan_status + c : nullptr, path_len ? path_len + c : nullptr,
+                                 (size_t)cycles)) != SIPP_OK)
+      return rc;
+    for (int k = 0; k < m; ++k) {
+      const int64_t bi = b->h_best[k].index;
+      if (best_index) best_index[(size_t)k * cycles + c] = (int32_t)bi;
+      if (best_value) best_value[(size_t)k * cycles + c] = b->h_best[k].value;
+      if (bi >= 0) { px[k] = xy[k][2 * bi]; py[k] = xy[k][2 * bi + 1]; }
+    }
+  }
   return SIPP_OK;
 }
 

@@ -20,6 +20,7 @@
 #include <math_constants.h>
 
 #include <cmath>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -236,10 +237,11 @@ struct WeightArgs {
   double* tile_w;    // [ntiles][4][TP][TP]
   int ntx;
   const int* tile_list;   // optional: block b rebuilds tile tile_list[b] (incremental re-plan: only the tiles a patch touched)
+  int n_items;            // blocks with work (a batched launch is as wide as the widest map's list)
 };
 constexpr int kWeightThreads = 256;
-__global__ void __launch_bounds__(kWeightThreads)
-k_weights(const WeightArgs a) {
+__device__ __forceinline__ void weights_body(const WeightArgs& a) {
+  if ((int)blockIdx.x >= a.n_items) return;
   __shared__ float hcf[TP][TP + 1];        // half costs (multiples of 0.5 <= 1799.5 or +inf: exact in fp32)
   __shared__ int xc[TP], yc[TP];           // class of the edge between tile columns c, c+1 / rows r, r+1 (-1: off map)
   __shared__ double hd[TP], vd[TP];
@@ -298,8 +300,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 //  (3) the kernel ends when the number of queued + running tiles drops to zero, i.e. at a global fixed point, which is unique.
 constexpr int ST_QUEUED = 1, ST_RUN = 2;
 
-__global__ void __launch_bounds__(kRelaxWarps * 32)
-k_relax(const RelaxArgs a) {
+__device__ __forceinline__ void relax_body(const RelaxArgs& a) {
   extern __shared__ __align__(16) uint8_t relax_smem[];
   __shared__ __align__(8) uint64_t s_bar[kRelaxWarps];
 
@@ -520,22 +521,39 @@ k_relax(const RelaxArgs a) {
   }
 }
 
-__global__ void k_field_init(double* field, size_t n, int* flags, int* queue, int ntiles, int qcap, int* ctl) {
+// Plan from scratch, first kernel: field <- +inf, empty work queue, zeroed control block and counters; the ingest marks of an abandoned
+// warm start are cleared as well (mark16 != nullptr)
+struct FieldInitArgs {
+  double* field; size_t n;
+  int* flags; int* queue; int ntiles, qcap; int* ctl;
+  uint4* mark16; size_t n_mark16;     // optional
+  int* plan_out;                      // [5], [6] <- 0
+};
+__device__ __forceinline__ void field_init_body(const FieldInitArgs& a) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = i; k < n; k += stride) field[k] = CUDART_INF;   // n == 0: queue reset only (incremental re-plan keeps the field)
-  for (size_t k = i; k < (size_t)ntiles; k += stride) flags[k] = 0;
-  for (size_t k = i; k < (size_t)qcap; k += stride) queue[k] = -1;
-  if (i < 32) ctl[i] = 0;
+  for (size_t k = i; k < a.n; k += stride) a.field[k] = CUDART_INF;
+  for (size_t k = i; k < (size_t)a.ntiles; k += stride) a.flags[k] = 0;
+  for (size_t k = i; k < (size_t)a.qcap; k += stride) a.queue[k] = -1;
+  if (a.mark16)
+    for (size_t k = i; k < a.n_mark16; k += stride) a.mark16[k] = make_uint4(0u, 0u, 0u, 0u);
+  if (i < 32) a.ctl[i] = 0;
+  if (i == 0) { a.plan_out[5] = 0; a.plan_out[6] = 0; }
 }
-__global__ void k_field_seed(double* field, int W, int H, int sx, int sy, int* flags, int* queue, int ntx, int* ctl, int unit) {
-  if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
-    field[(size_t)sy * W + sx] = 0.0;
-    const int t = (sy / unit) * ntx + (sx / unit);      // unit = edge of the scheduling unit: a 32 x 32 tile (k_relax) or a 128 x 128 block (k_relax_blk)
-    flags[t] = 1;
-    queue[0] = t;
-    ctl[CTL_TAIL] = 1;
-    ctl[CTL_PENDING] = 1;
+struct FieldSeedArgs {
+  double* field; int W, H, sx, sy;
+  int* flags; int* queue; int ntx; int* ctl;
+  int unit;      // edge of the scheduling unit: a 32 x 32 tile (k_relax) or a 128 x 128 block (k_relax_blk)
+};
+__device__ __forceinline__ void field_seed_body(const FieldSeedArgs& a) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (a.sx >= 0 && a.sx < a.W && a.sy >= 0 && a.sy < a.H) {
+    a.field[(size_t)a.sy * a.W + a.sx] = 0.0;
+    const int t = (a.sy / a.unit) * a.ntx + (a.sx / a.unit);
+    a.flags[t] = 1;
+    a.queue[0] = t;
+    a.ctl[CTL_TAIL] = 1;
+    a.ctl[CTL_PENDING] = 1;
   }
 }
 
@@ -571,8 +589,7 @@ struct InvalArgs {
 };
 enum { CTL_MARKED = 7, CTL_EXITED = 8 };
 
-__global__ void __launch_bounds__(kInvalWarps * 32)
-k_inval(const InvalArgs a) {
+__device__ __forceinline__ void inval_body(const InvalArgs& a) {
   __shared__ InvalSmem sm[kInvalWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   InvalSmem& t = sm[warp];
@@ -741,28 +758,42 @@ k_inval(const InvalArgs a) {
 
 // First kernel of an incremental plan: resets the work queue and seeds it with the tiles the patches touched. `list` (nl tile
 // ids, the queue order) and `seedmap` (one byte per tile, the same set) come from the host in one copy; seedmap == nullptr: none.
-__global__ void k_inc_begin(const int* list, int nl, const uint8_t* seedmap, int ntiles, int qcap, int* flags, int* queue, int* ctl,
-                            uint8_t* tile_seed, int* plan_out) {
+struct IncBeginArgs {
+  const int* list; int nl; const uint8_t* seedmap;
+  int ntiles, qcap; int* flags; int* queue; int* ctl;
+  uint8_t* tile_seed; int* plan_out;
+};
+__device__ __forceinline__ void inc_begin_body(const IncBeginArgs& a) {
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-  for (int t = i0; t < ntiles; t += stride) {
-    const uint8_t sd = seedmap ? seedmap[t] : (uint8_t)0;
-    flags[t] = sd ? ST_QUEUED : 0;
-    tile_seed[t] = sd;
+  for (int t = i0; t < a.ntiles; t += stride) {
+    const uint8_t sd = a.seedmap ? a.seedmap[t] : (uint8_t)0;
+    a.flags[t] = sd ? ST_QUEUED : 0;
+    a.tile_seed[t] = sd;
   }
-  for (int i = i0; i < qcap; i += stride) queue[i] = i < nl ? list[i] : -1;
+  for (int i = i0; i < a.qcap; i += stride) a.queue[i] = i < a.nl ? a.list[i] : -1;
   if (i0 == 0) {
-    for (int k = 0; k < 32; ++k) ctl[k] = 0;
-    ctl[CTL_TAIL] = nl;
-    ctl[CTL_PENDING] = nl;
-    plan_out[5] = 0;      // cells invalidated
-    plan_out[6] = 0;      // tiles the relaxation starts from
-    plan_out[7] = 0;      // "redo the path" flag of k_path_check
+    for (int k = 0; k < 32; ++k) a.ctl[k] = 0;
+    a.ctl[CTL_TAIL] = a.nl;
+    a.ctl[CTL_PENDING] = a.nl;
+    a.plan_out[5] = 0;      // cells invalidated
+    a.plan_out[6] = 0;      // tiles the relaxation starts from
+    a.plan_out[7] = 0;      // "redo the path" flag of k_path_check
   }
 }
 // Between k_inval and k_relax: queue <- every tile that is a seed or touches one (the invalidated region and its rim, the patch
 // tiles); the marks of the seed tiles are cleared for the next plan (all marks live in seed tiles).
-__global__ void k_seed_relax(const uint8_t* tile_seed, int ntx, int nty, int* flags, int* queue, int* ctl, uint8_t* mark, size_t pitch, int H,
-                             int* plan_out) {
+struct SeedRelaxArgs {
+  const uint8_t* tile_seed; int ntx, nty, nbx, nby;
+  int* flags; int* queue; int* ctl;
+  uint8_t* mark; size_t pitch; int H;
+  int* plan_out;
+};
+__device__ __forceinline__ void seed_relax_body(const SeedRelaxArgs& a) {
+  const uint8_t* tile_seed = a.tile_seed;
+  const int ntx = a.ntx, nty = a.nty, H = a.H;
+  int *flags = a.flags, *queue = a.queue, *ctl = a.ctl, *plan_out = a.plan_out;
+  uint8_t* mark = a.mark;
+  const size_t pitch = a.pitch;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntx * nty) return;
   const int tx = t % ntx, ty = t / ntx;
@@ -830,8 +861,7 @@ struct PredSmem {
   int xc[TP], yc[TP];
 };
 
-__global__ void __launch_bounds__(kPredThreads)
-k_pred(const PredArgs a) {
+__device__ __forceinline__ void pred_body(const PredArgs& a) {
   __shared__ PredSmem t;
   const FieldGeom& g = a.g;
   const int tid = threadIdx.x;
@@ -932,8 +962,7 @@ constexpr int PW = 256;
 constexpr int kBackThreads = 256;
 constexpr int kWalk = 112;      // steps per window load: the window is centred on the current node (x0 aligned down to 16)
 static_assert(PW == 256, "the walk packs a window cell as (ly << 8) | lx");
-__global__ void __launch_bounds__(kBackThreads)
-k_backtrack(const PathArgs a) {
+__device__ __forceinline__ void backtrack_body(const PathArgs& a) {
   extern __shared__ __align__(16) uint8_t win[];     // [PW][PW]
   __shared__ int s_x, s_y, s_len, s_fail, s_n;
   __shared__ unsigned short s_buf[kWalk];
@@ -1050,31 +1079,38 @@ __device__ __forceinline__ void node_pose(const FieldGeom& g, int packed, double
 
 // Incremental re-plan: does the previous plan's path touch a tile whose predecessor bytes were recomputed (the tile or a neighbour
 // was relaxed / invalidated / hit by a patch)? If not, the walk from the goal would read exactly the bytes it read last time.
-__global__ void k_path_check(const int* nodes, const int* out, const uint8_t* touched, int ntx, int nty, int* redo) {
+struct PathCheckArgs {
+  const int* nodes; const int* out; const uint8_t* touched; int ntx, nty; int* redo;
+};
+__device__ __forceinline__ void path_check_body(const PathCheckArgs& a) {
+  const int* nodes = a.nodes; const int* out = a.out; const uint8_t* touched = a.touched;
+  const int ntx = a.ntx, nty = a.nty;
+  int* redo = a.redo;
   const int len = out[0];
   if (blockIdx.x == 0 && threadIdx.x == 0 && (out[2] == 0 || len <= 0)) *redo = 1;     // no path last time: look again
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= len) return;
-  const int nj = nodes[j];
-  const int tx = (nj >> 16) / TS, ty = (nj & 0xFFFF) / TS;
-  for (int dy = -1; dy <= 1; ++dy)
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int x = tx + dx, y = ty + dy;
-      if (x >= 0 && x < ntx && y >= 0 && y < nty && touched[y * ntx + x]) { *redo = 1; return; }
-    }
+  // grid-stride over the path nodes: a single plan's grid covers the node buffer, a batched one brings a few blocks per map
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+    const int nj = nodes[j];
+    const int tx = (nj >> 16) / TS, ty = (nj & 0xFFFF) / TS;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = tx + dx, y = ty + dy;
+        if (x >= 0 && x < ntx && y >= 0 && y < nty && touched[y * ntx + x]) { *redo = 1; return; }
+      }
+  }
 }
-__global__ void k_mask_clear(uint8_t* path, size_t n16, const int* redo) {
-  if (redo && *redo == 0) return;
-  uint4* p = reinterpret_cast<uint4*>(path);
+struct MaskClearArgs {
+  uint8_t* path; size_t n16; const int* redo;
+};
+__device__ __forceinline__ void mask_clear_body(const MaskClearArgs& a) {
+  if (a.redo && *a.redo == 0) return;
+  uint4* p = reinterpret_cast<uint4*>(a.path);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += stride) p[k] = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.n16; k += stride) p[k] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-__global__ void k_path_finish(const RasterArgs a) {
-  if (a.redo && *a.redo == 0) return;
-  const int len = a.out[0];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;   // path point index, start -> goal
-  if (j >= len) return;
+// one path point: j = index start -> goal
+__device__ __forceinline__ void path_finish_at(const RasterArgs& a, const int len, const int j) {
   const int nj = a.nodes[len - 1 - j];
   double px, py;
   node_pose(a.g, nj, &px, &py);
@@ -1103,6 +1139,77 @@ __global__ void k_path_finish(const RasterArgs a) {
     mark(a, ix, iy);
   }
 }
+__device__ __forceinline__ void path_finish_body(const RasterArgs& a) {
+  if (a.redo && *a.redo == 0) return;
+  const int len = a.out[0];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) path_finish_at(a, len, j);
+}
+
+
+// ---- kernels: one map per launch (argument block by value) and batched (gridDim.y = maps, argument blocks in device memory) ----------
+// Everything one sipp_plan launches for one map, as one block: the host fills it (plan_prepare), a single plan launches the kernels
+// with the members by value, a batched plan (sipp_batch_plan: an ensemble of maps that advance together) uploads one block per map
+// and launches every kernel ONCE with gridDim.y = number of maps. `on_*` = this plan runs that step.
+struct PlanArgsAll {
+  int on_init, on_weights, on_inc, on_inval, on_check;
+  int relax_grid, inval_grid;
+  FieldInitArgs fi;
+  FieldSeedArgs fs;
+  WeightArgs wa;
+  IncBeginArgs ib;
+  InvalArgs ia;
+  SeedRelaxArgs sr;
+  RelaxArgs ra;
+  PathCheckArgs pc;
+  PredArgs pr;
+  PathArgs pa;
+  MaskClearArgs mc;
+  RasterArgs rs;
+};
+
+__global__ void k_field_init(const FieldInitArgs a) { field_init_body(a); }
+__global__ void k_field_seed(const FieldSeedArgs a) { field_seed_body(a); }
+__global__ void __launch_bounds__(kWeightThreads) k_weights(const WeightArgs a) { weights_body(a); }
+__global__ void k_inc_begin(const IncBeginArgs a) { inc_begin_body(a); }
+__global__ void __launch_bounds__(kInvalWarps * 32) k_inval(const InvalArgs a) { inval_body(a); }
+__global__ void k_seed_relax(const SeedRelaxArgs a) { seed_relax_body(a); }
+__global__ void __launch_bounds__(kRelaxWarps * 32) k_relax(const RelaxArgs a) { relax_body(a); }
+__global__ void k_path_check(const PathCheckArgs a) { path_check_body(a); }
+__global__ void __launch_bounds__(kPredThreads) k_pred(const PredArgs a) { pred_body(a); }
+__global__ void __launch_bounds__(kBackThreads) k_backtrack(const PathArgs a) { backtrack_body(a); }
+__global__ void k_mask_clear(const MaskClearArgs a) { mask_clear_body(a); }
+__global__ void k_path_finish(const RasterArgs a) { path_finish_body(a); }
+
+// batched forms: block (x, y) works for map y. The argument block is copied out of global memory first (the bodies then read
+// registers / local memory, as they read the parameter space in the single form).
+#define SIPP_BATCH_KERNEL(name, bounds, member, cond, body)                                  \
+  __global__ void bounds name(const PlanArgsAll* __restrict__ all) {                         \
+    const PlanArgsAll& m = all[blockIdx.y];                                                  \
+    if (!(cond)) return;                                                                     \
+    const auto a = m.member;                                                                 \
+    body(a);                                                                                 \
+  }
+SIPP_BATCH_KERNEL(k_field_init_b, , fi, m.on_init, field_init_body)
+SIPP_BATCH_KERNEL(k_field_seed_b, , fs, m.on_init, field_seed_body)
+SIPP_BATCH_KERNEL(k_weights_b, __launch_bounds__(kWeightThreads), wa, m.on_weights, weights_body)
+SIPP_BATCH_KERNEL(k_inc_begin_b, , ib, m.on_inc, inc_begin_body)
+SIPP_BATCH_KERNEL(k_inval_b, __launch_bounds__(kInvalWarps * 32), ia, m.on_inval && (int)blockIdx.x < m.inval_grid, inval_body)
+SIPP_BATCH_KERNEL(k_seed_relax_b, , sr, m.on_inval, seed_relax_body)
+SIPP_BATCH_KERNEL(k_relax_b, __launch_bounds__(kRelaxWarps * 32), ra, (int)blockIdx.x < m.relax_grid, relax_body)
+SIPP_BATCH_KERNEL(k_path_check_b, , pc, m.on_check, path_check_body)
+SIPP_BATCH_KERNEL(k_pred_b, __launch_bounds__(kPredThreads), pr, true, pred_body)
+SIPP_BATCH_KERNEL(k_backtrack_b, __launch_bounds__(kBackThreads), pa, true, backtrack_body)
+SIPP_BATCH_KERNEL(k_mask_clear_b, , mc, true, mask_clear_body)
+SIPP_BATCH_KERNEL(k_path_finish_b, , rs, true, path_finish_body)
+#undef SIPP_BATCH_KERNEL
+
+// results of a batched plan: every map's plan_out[0..9] and relaxation control block [0..23] gathered into one array (one copy back)
+__global__ void k_gather_plan_out(const PlanArgsAll* __restrict__ all, int* __restrict__ out) {
+  const PlanArgsAll& m = all[blockIdx.x];
+  const int t = threadIdx.x;
+  if (t < 10) out[blockIdx.x * 40 + t] = m.pa.out[t];
+  else if (t >= 16 && t < 40) out[blockIdx.x * 40 + t] = m.ra.ctl[t - 16];
+}
 
 }  // namespace
 
@@ -1121,54 +1228,54 @@ static FieldGeom make_geom(const sipp_ctx* ctx) {
   return g;
 }
 
-int field_plan(sipp_ctx* ctx, cudaStream_t s) {
-  // SIPP_PLAN_TIMING=1: per-phase device times of every plan on stderr (tuning aid)
-  static const bool timing = getenv("SIPP_PLAN_TIMING") != nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (timing) for (auto& e : ev) cudaEventCreate(&e);
-  if (timing) cudaEventRecord(ev[0], s);
-  if (ctx->ev_plan[2]) cudaEventRecord(ctx->ev_plan[2], s);
+namespace {
+
+constexpr int kSpinLimit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
+
+struct DevInfo { int num_sms, occ; };
+// function attributes and occupancy belong to the device: set up once per device of this process, under a process-wide lock
+// (several contexts / devices / host threads per process)
+int device_setup(sipp_ctx* ctx, DevInfo* out) {
+  static std::mutex dev_mu;
+  static struct { bool done; int num_sms, occ; } dev_info[64] = {};
+  std::lock_guard<std::mutex> lk(dev_mu);
+  auto& di = dev_info[ctx->device & 63];
+  if (!di.done) {
+    SIPP_CUDA_CHECK(ctx, cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack_b, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
+    SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.occ, k_relax, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem)));
+    if (di.occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
+    di.done = true;
+  }
+  out->num_sms = di.num_sms;
+  out->occ = di.occ;
+  return SIPP_OK;
+}
+
+// Host half of a plan: decides how this plan starts (from scratch / incrementally from the patch rectangles since the last plan) and
+// fills the argument blocks of every kernel. The seed block of an incremental start ([seed map: one byte per tile, padded to 4][seed
+// list: nl tile ids]) is left in ctx->h_seed_stage for the caller to copy to `d_seed` (the map's own buffer, or its slice of a
+// batch's staging area). blk: the block-resident relaxation kernel was selected (single plans only).
+int plan_prepare(sipp_ctx* ctx, PlanArgsAll& A, uint8_t* d_seed, bool blk, const DevInfo& dev, bool* incremental_out, int* nl_out, int batch_m = 0) {
+  memset(&A, 0, sizeof(A));
   const FieldGeom g = make_geom(ctx);
   const size_t ncell = (size_t)ctx->W * ctx->H;
   const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
   // ring capacity: every tile can be queued at most once, and every waiting warp must own a distinct slot (ticket % cap)
   const int qcap = ntiles > 16384 ? ntiles : 16384;
-  // function attributes and occupancy belong to the device: set up once per device of this process, under a process-wide lock
-  // (several contexts / devices / host threads per process)
-  int num_sms = 0, occ = 0;
-  {
-    static std::mutex dev_mu;
-    static struct { bool done; int num_sms, occ; } dev_info[64] = {};
-    std::lock_guard<std::mutex> lk(dev_mu);
-    auto& di = dev_info[ctx->device & 63];
-    if (!di.done) {
-      SIPP_CUDA_CHECK(ctx, cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
-      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
-      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
-      SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
-      SIPP_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.occ, k_relax, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem)));
-      if (di.occ < 1) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_relax does not fit on an SM");
-      di.done = true;
-    }
-    num_sms = di.num_sms;
-    occ = di.occ;
-  }
-  // default: the per-tile kernel (k_relax + edge-weight cache); SIPP_RELAX_KERNEL=1: the block-resident kernel (k_relax_blk), experimental
-  static const int relax_kernel_env = getenv("SIPP_RELAX_KERNEL") ? atoi(getenv("SIPP_RELAX_KERNEL")) : 0;
-  const bool use_blk = relax_kernel_env != 0;
-  const int nbx = (ctx->W + BS - 1) / BS, nby = (ctx->H + BS - 1) / BS, nblocks = nbx * nby;
-  if (!use_blk && !ctx->d_tile_w) {      // the weight cache of the per-tile kernel is only allocated when that kernel is selected
-    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
-    SIPP_CUDA_CHECK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tile_w), (size_t)ntiles * kTileWDoubles * sizeof(double)));
-  }
-  WeightArgs wa;
-  wa.g = g;
-  wa.pcode = ctx->d_pcode;
-  wa.pitch16 = ctx->pitch16;
-  wa.tile_w = ctx->d_tile_w;
-  wa.ntx = ctx->n_tiles_x;
-  wa.tile_list = nullptr;
+  const int nbx = (ctx->W + BS - 1) / BS, nby = (ctx->H + BS - 1) / BS;
+  A.wa.g = g;
+  A.wa.pcode = ctx->d_pcode;
+  A.wa.pitch16 = ctx->pitch16;
+  A.wa.tile_w = ctx->d_tile_w;
+  A.wa.ntx = ctx->n_tiles_x;
+  A.wa.tile_list = nullptr;
+  A.wa.n_items = ntiles;
 
   // ---- incremental start? the tiles the patches since the last plan touched (one cell of margin: a tile's weight block and
   // halo reach one cell into its neighbours)
@@ -1188,94 +1295,70 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     }
     if ((int)seed_tiles.size() * 2 > ntiles) incremental = false;     // most of the map changed: start over
   }
+  const int nl = incremental ? (int)seed_tiles.size() : 0;
   ctx->plan_info[0] = incremental ? 1 : 0;
   ctx->plan_info[1] = (int64_t)seed_tiles.size();
+  *incremental_out = incremental;
+  *nl_out = nl;
+  ctx->h_seed_stage.clear();
 
   if (!incremental) {
-    if (ctx->warm_valid || !ctx->pending_rects.empty())   // ingest marks of an abandoned warm start must not leak into a later one
-      SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_mark, 0, ctx->pitch * ctx->H, s));
-    k_field_init<<<592, 256, 0, s>>>(ctx->d_field, ncell, ctx->d_tile_flags, ctx->d_tile_list, ntiles, qcap, ctx->d_relax_ctl);
-    k_field_seed<<<1, 1, 0, s>>>(ctx->d_field, ctx->W, ctx->H, g.start_x, g.start_y, ctx->d_tile_flags, ctx->d_tile_list, use_blk ? nbx : ctx->n_tiles_x,
-                                 ctx->d_relax_ctl, use_blk ? BS : TS);
-    ctx->launches += 2;
-    SIPP_CUDA_CHECK(ctx, cudaGetLastError());
-    if (!use_blk) {
-      // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
-      k_weights<<<ntiles, kWeightThreads, 0, s>>>(wa);
-      ctx->launches += 1;
-    }
-    SIPP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_plan_out + 5, 0, 2 * sizeof(int), s));
+    A.on_init = 1;
+    A.fi.field = ctx->d_field; A.fi.n = ncell;
+    A.fi.flags = ctx->d_tile_flags; A.fi.queue = ctx->d_tile_list; A.fi.ntiles = ntiles; A.fi.qcap = qcap; A.fi.ctl = ctx->d_relax_ctl;
+    // ingest marks of an abandoned warm start must not leak into a later one
+    const bool clear_marks = ctx->warm_valid || !ctx->pending_rects.empty();
+    A.fi.mark16 = clear_marks ? reinterpret_cast<uint4*>(ctx->d_mark) : nullptr;
+    A.fi.n_mark16 = ctx->pitch * ctx->H / 16;
+    A.fi.plan_out = ctx->d_plan_out;
+    A.fs.field = ctx->d_field; A.fs.W = ctx->W; A.fs.H = ctx->H; A.fs.sx = g.start_x; A.fs.sy = g.start_y;
+    A.fs.flags = ctx->d_tile_flags; A.fs.queue = ctx->d_tile_list; A.fs.ntx = blk ? nbx : ctx->n_tiles_x; A.fs.ctl = ctx->d_relax_ctl;
+    A.fs.unit = blk ? BS : TS;
+    A.on_weights = blk ? 0 : 1;      // edge weights of every tile (they depend on the planner's map and the init cost, not on d)
   } else {
-    const int nl = (int)seed_tiles.size();
     // one host->device copy: [seed map: one byte per tile, padded to 4][seed list: nl tile ids]
     const size_t map_bytes = ((size_t)ntiles + 3) & ~(size_t)3;
-    uint8_t* d_seedmap = reinterpret_cast<uint8_t*>(ctx->d_seed_list);
+    uint8_t* d_seedmap = d_seed;
     int* d_list = reinterpret_cast<int*>(d_seedmap + map_bytes);
     if (nl > 0) {
       ctx->h_seed_stage.assign(map_bytes + (size_t)nl * sizeof(int), 0);
       for (int t : seed_tiles) ctx->h_seed_stage[t] = 1;
       memcpy(ctx->h_seed_stage.data() + map_bytes, seed_tiles.data(), (size_t)nl * sizeof(int));
-      SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(d_seedmap, ctx->h_seed_stage.data(), ctx->h_seed_stage.size(), cudaMemcpyHostToDevice, s));
     }
-    k_inc_begin<<<64, 256, 0, s>>>(d_list, nl, nl > 0 ? d_seedmap : nullptr, ntiles, qcap, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl,
-                                   ctx->d_tile_seed, ctx->d_plan_out);
-    ctx->launches += 1;
+    A.on_inc = 1;
+    A.ib.list = d_list; A.ib.nl = nl; A.ib.seedmap = nl > 0 ? d_seedmap : nullptr;
+    A.ib.ntiles = ntiles; A.ib.qcap = qcap; A.ib.flags = ctx->d_tile_flags; A.ib.queue = ctx->d_tile_list; A.ib.ctl = ctx->d_relax_ctl;
+    A.ib.tile_seed = ctx->d_tile_seed; A.ib.plan_out = ctx->d_plan_out;
     if (nl > 0) {
-      wa.tile_list = d_list;
-      if (!use_blk) {
-        k_weights<<<nl, kWeightThreads, 0, s>>>(wa);
-        ctx->launches += 1;
-      }
-      InvalArgs ia;
+      A.wa.tile_list = d_list;
+      A.wa.n_items = nl;
+      A.on_weights = blk ? 0 : 1;
+      A.on_inval = 1;
+      InvalArgs& ia = A.ia;
       ia.W = ctx->W; ia.H = ctx->H; ia.ntx = ctx->n_tiles_x; ia.nty = ctx->n_tiles_y;
       ia.mark = ctx->d_mark; ia.pred = ctx->d_pred; ia.pitch = ctx->pitch; ia.field = ctx->d_field;
       ia.start_x = g.start_x; ia.start_y = g.start_y;
       ia.flags = ctx->d_tile_flags; ia.queue = ctx->d_tile_list; ia.cap = qcap; ia.ctl = ctx->d_relax_ctl;
       ia.tile_seed = ctx->d_tile_seed;
       ia.plan_out = ctx->d_plan_out;
-      ia.spin_limit = 20 * 1000 * 1000;
+      ia.spin_limit = kSpinLimit;
       int igrid = (ntiles + 8 * kInvalWarps - 1) / (8 * kInvalWarps);
-      if (igrid > 2 * num_sms) igrid = 2 * num_sms;
+      if (igrid > 2 * dev.num_sms) igrid = 2 * dev.num_sms;
       if (igrid * kInvalWarps > qcap) igrid = qcap / kInvalWarps;
-      k_inval<<<igrid, kInvalWarps * 32, 0, s>>>(ia);
-      if (use_blk)
-        k_seed_relax_blk<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, nbx, nby, ctx->d_tile_flags, ctx->d_tile_list,
-                                                              ctx->d_relax_ctl, ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
-      else
-        k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, ctx->d_tile_flags, ctx->d_tile_list, ctx->d_relax_ctl,
-                                                          ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
-      ctx->launches += 2;
+      if (batch_m > 0) {      // batched: the maps share the SMs — about two CTAs of workers per SM in total, at least one per map
+        const int share = 2 * dev.num_sms / batch_m;
+        if (igrid > share) igrid = share < 1 ? 1 : share;
+      }
+      A.inval_grid = igrid;
+      SeedRelaxArgs& sr = A.sr;
+      sr.tile_seed = ctx->d_tile_seed; sr.ntx = ctx->n_tiles_x; sr.nty = ctx->n_tiles_y; sr.nbx = nbx; sr.nby = nby;
+      sr.flags = ctx->d_tile_flags; sr.queue = ctx->d_tile_list; sr.ctl = ctx->d_relax_ctl;
+      sr.mark = ctx->d_mark; sr.pitch = ctx->pitch; sr.H = ctx->H; sr.plan_out = ctx->d_plan_out;
     }
-    SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   }
-  const int spin_limit = 20 * 1000 * 1000;   // ~ seconds of polling an empty queue: only a bug can get there
-  if (ctx->ev_plan[0]) cudaEventRecord(ctx->ev_plan[0], s);      // sipp_plan_phases: the relaxation kernel alone
   static const int grid_env = getenv("SIPP_RELAX_GRID") ? atoi(getenv("SIPP_RELAX_GRID")) : 0;
-  if (use_blk) {
-    // block-resident kernel: one persistent CTA (16 warps, the whole 128 x 128 window in shared memory) per SM; a small map (an
-    // ensemble of 640x480 maps runs many plans side by side) gets at most one CTA per block
-    BlkArgs ba;
-    ba.g = g;
-    ba.field = ctx->d_field;
-    ba.pcode = ctx->d_pcode;
-    ba.pitch16 = ctx->pitch16;
-    ba.nbx = nbx; ba.nby = nby;
-    ba.ntx = ctx->n_tiles_x; ba.nty = ctx->n_tiles_y;
-    ba.flags = ctx->d_tile_flags;
-    ba.queue = ctx->d_tile_list;
-    ba.cap = qcap;
-    ba.ctl = ctx->d_relax_ctl;
-    ba.spin_limit = spin_limit;
-    ba.touched = incremental ? ctx->d_tile_seed : nullptr;
-    const float hf = (float)g.init_half_cost;
-    ba.init_inexact = ((double)hf != g.init_half_cost) ? 1 : 0;      // the shared-memory half costs are fp32
-    int grid = grid_env > 0 ? grid_env : num_sms;
-    if (grid > nblocks) grid = nblocks;
-    if (grid < 1) grid = 1;
-    if (ba.init_inexact) k_relax_blk<true><<<grid, kBlkThreads, sizeof(BlkSmem), s>>>(ba);
-    else k_relax_blk<false><<<grid, kBlkThreads, sizeof(BlkSmem), s>>>(ba);
-  } else {
-    RelaxArgs ra;
+  if (!blk) {
+    RelaxArgs& ra = A.ra;
     ra.g = g;
     ra.field = ctx->d_field;
     ra.pcode = ctx->d_pcode;
@@ -1286,27 +1369,26 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     ra.cap = qcap;
     ra.ctl = ctx->d_relax_ctl;
     ra.tile_w = ctx->d_tile_w;
-    ra.spin_limit = spin_limit;
-    ra.mode = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
+    ra.spin_limit = kSpinLimit;
+    static const int mode_env = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
+    ra.mode = mode_env;
     ra.touched = incremental ? ctx->d_tile_seed : nullptr;
     // persistent workers: one CTA per SM for a large map; a small map gets one warp per ~3 tiles so that several relaxations share
     // the GPU instead of queueing for all SMs
-    int grid = num_sms * occ;
+    int grid = dev.num_sms * dev.occ;
     const int want = grid_env > 0 ? grid_env : (ntiles + 15) / 16;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
-    // a plain launch: the workers never wait for each other (no grid barrier; any one warp can drain the queue alone), so CTAs that
-    // only become resident later — e.g. while other contexts' kernels hold SMs — just join late. Cooperative launches of different
-    // streams do not overlap, which serialised the plans of an ensemble.
-    k_relax<<<grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(ra);
+    if (batch_m > 0) {
+      // batched: a persistent CTA holds its SM until its map's queue is drained, so the maps' CTAs should all be resident at once —
+      // one wave in total, at least one CTA (any one worker can drain a queue alone) per map
+      const int share = dev.num_sms * dev.occ / batch_m;
+      if (grid > share) grid = share < 1 ? 1 : share;
+    }
+    A.relax_grid = grid;
   }
-  SIPP_CUDA_CHECK(ctx, cudaGetLastError());
-  ctx->launches += 1;
-  if (ctx->ev_plan[1]) cudaEventRecord(ctx->ev_plan[1], s);
-
-  if (timing) cudaEventRecord(ev[1], s);
-  PathArgs pa;
+  PathArgs& pa = A.pa;
   pa.g = g;
   pa.field = ctx->d_field;
   pa.pcode = ctx->d_pcode;
@@ -1315,6 +1397,8 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   pa.cap = ctx->path_cap_nodes;
   pa.out = ctx->d_plan_out;
   pa.cost_out = reinterpret_cast<double*>(ctx->d_plan_out + 8);
+  pa.pred = ctx->d_pred;
+  pa.pitch = ctx->pitch;
   // incremental: predecessor bytes are recomputed around the touched tiles only, and the walk / mask are skipped when the previous
   // path runs nowhere near them (d_plan_out[7] = "redo")
   int* d_redo = ctx->d_plan_out + 7;
@@ -1322,11 +1406,10 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   const bool reuse = incremental && reuse_env && !ctx->path_mask_foreign;
   ctx->path_mask_foreign = false;
   pa.redo = reuse ? d_redo : nullptr;
-  if (reuse) {
-    k_path_check<<<(ctx->path_cap_nodes + 255) / 256, 256, 0, s>>>(ctx->d_path_nodes, ctx->d_plan_out, ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, d_redo);
-    ctx->launches += 1;
-  }
-  PredArgs pr;
+  A.on_check = reuse ? 1 : 0;
+  A.pc.nodes = ctx->d_path_nodes; A.pc.out = ctx->d_plan_out; A.pc.touched = ctx->d_tile_seed;
+  A.pc.ntx = ctx->n_tiles_x; A.pc.nty = ctx->n_tiles_y; A.pc.redo = d_redo;
+  PredArgs& pr = A.pr;
   pr.g = g;
   pr.field = ctx->d_field;
   pr.pcode = ctx->d_pcode;
@@ -1335,18 +1418,9 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   pr.pitch = ctx->pitch;
   pr.ntx = ctx->n_tiles_x; pr.nty = ctx->n_tiles_y;
   pr.sel = incremental ? ctx->d_tile_seed : nullptr;
-  k_pred<<<ntiles, kPredThreads, 0, s>>>(pr);
-  pa.pred = ctx->d_pred;
-  pa.pitch = ctx->pitch;
-  k_backtrack<<<1, kBackThreads, PW * PW, s>>>(pa);
-  ctx->launches += 1;
-  ctx->launches += 1;
-  SIPP_CUDA_CHECK(ctx, cudaGetLastError());
-
-  if (timing) cudaEventRecord(ev[2], s);
   // new mask: computeCurrentPathEstimate swaps in a freshly zeroed map (map_server_planexp.cpp:894-899,904)
-  k_mask_clear<<<592, 256, 0, s>>>(ctx->d_path, ctx->pitch * ctx->H / 16, pa.redo);
-  RasterArgs rs;
+  A.mc.path = ctx->d_path; A.mc.n16 = ctx->pitch * ctx->H / 16; A.mc.redo = pa.redo;
+  RasterArgs& rs = A.rs;
   rs.redo = pa.redo;
   rs.g = g;
   rs.nodes = ctx->d_path_nodes;
@@ -1360,8 +1434,111 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
   rs.map_width = ctx->desc.width;
   rs.map_height = ctx->desc.height;
   rs.mpp_third = ctx->mpp / 3.0;
-  const int blocks = (ctx->path_cap_nodes + 255) / 256;
-  k_path_finish<<<blocks, 256, 0, s>>>(rs);
+  return SIPP_OK;
+}
+
+}  // namespace
+
+int field_plan(sipp_ctx* ctx, cudaStream_t s) {
+  // SIPP_PLAN_TIMING=1: per-phase device times of every plan on stderr (tuning aid)
+  static const bool timing = getenv("SIPP_PLAN_TIMING") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(ev[0], s);
+  if (ctx->ev_plan[2]) cudaEventRecord(ctx->ev_plan[2], s);
+  DevInfo dev;
+  int rc = device_setup(ctx, &dev);
+  if (rc != SIPP_OK) return rc;
+  const int ntiles = ctx->n_tiles_x * ctx->n_tiles_y;
+  // default: the per-tile kernel (k_relax + edge-weight cache); SIPP_RELAX_KERNEL=1: the block-resident kernel (k_relax_blk), experimental
+  static const int relax_kernel_env = getenv("SIPP_RELAX_KERNEL") ? atoi(getenv("SIPP_RELAX_KERNEL")) : 0;
+  const bool use_blk = relax_kernel_env != 0;
+  const int nbx = (ctx->W + BS - 1) / BS, nby = (ctx->H + BS - 1) / BS, nblocks = nbx * nby;
+  if (!use_blk && !ctx->d_tile_w) {      // the weight cache of the per-tile kernel is only allocated when that kernel is selected
+    SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+    SIPP_CUDA_CHECK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tile_w), (size_t)ntiles * kTileWDoubles * sizeof(double)));
+  }
+  PlanArgsAll A;
+  bool incremental = false;
+  int nl = 0;
+  if ((rc = plan_prepare(ctx, A, reinterpret_cast<uint8_t*>(ctx->d_seed_list), use_blk, dev, &incremental, &nl)) != SIPP_OK) return rc;
+
+  if (!incremental) {
+    k_field_init<<<592, 256, 0, s>>>(A.fi);
+    k_field_seed<<<1, 32, 0, s>>>(A.fs);
+    ctx->launches += 2;
+    if (A.on_weights) {
+      k_weights<<<ntiles, kWeightThreads, 0, s>>>(A.wa);
+      ctx->launches += 1;
+    }
+    SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+  } else {
+    if (nl > 0) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_seed_list, ctx->h_seed_stage.data(), ctx->h_seed_stage.size(), cudaMemcpyHostToDevice, s));
+    k_inc_begin<<<64, 256, 0, s>>>(A.ib);
+    ctx->launches += 1;
+    if (nl > 0) {
+      if (A.on_weights) {
+        k_weights<<<nl, kWeightThreads, 0, s>>>(A.wa);
+        ctx->launches += 1;
+      }
+      k_inval<<<A.inval_grid, kInvalWarps * 32, 0, s>>>(A.ia);
+      if (use_blk)
+        k_seed_relax_blk<<<(ntiles + 255) / 256, 256, 0, s>>>(ctx->d_tile_seed, ctx->n_tiles_x, ctx->n_tiles_y, nbx, nby, ctx->d_tile_flags, ctx->d_tile_list,
+                                                              ctx->d_relax_ctl, ctx->d_mark, ctx->pitch, ctx->H, ctx->d_plan_out);
+      else
+        k_seed_relax<<<(ntiles + 255) / 256, 256, 0, s>>>(A.sr);
+      ctx->launches += 2;
+    }
+    SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+  }
+  if (ctx->ev_plan[0]) cudaEventRecord(ctx->ev_plan[0], s);      // sipp_plan_phases: the relaxation kernel alone
+  if (use_blk) {
+    // block-resident kernel: one persistent CTA (16 warps, the whole 128 x 128 window in shared memory) per SM; a small map (an
+    // ensemble of 640x480 maps runs many plans side by side) gets at most one CTA per block
+    static const int grid_env = getenv("SIPP_RELAX_GRID") ? atoi(getenv("SIPP_RELAX_GRID")) : 0;
+    BlkArgs ba;
+    ba.g = A.pa.g;
+    ba.field = ctx->d_field;
+    ba.pcode = ctx->d_pcode;
+    ba.pitch16 = ctx->pitch16;
+    ba.nbx = nbx; ba.nby = nby;
+    ba.ntx = ctx->n_tiles_x; ba.nty = ctx->n_tiles_y;
+    ba.flags = ctx->d_tile_flags;
+    ba.queue = ctx->d_tile_list;
+    ba.cap = A.fi.qcap ? A.fi.qcap : A.ib.qcap;
+    ba.ctl = ctx->d_relax_ctl;
+    ba.spin_limit = kSpinLimit;
+    ba.touched = incremental ? ctx->d_tile_seed : nullptr;
+    const float hf = (float)ba.g.init_half_cost;
+    ba.init_inexact = ((double)hf != ba.g.init_half_cost) ? 1 : 0;      // the shared-memory half costs are fp32
+    int grid = grid_env > 0 ? grid_env : dev.num_sms;
+    if (grid > nblocks) grid = nblocks;
+    if (grid < 1) grid = 1;
+    if (ba.init_inexact) k_relax_blk<true><<<grid, kBlkThreads, sizeof(BlkSmem), s>>>(ba);
+    else k_relax_blk<false><<<grid, kBlkThreads, sizeof(BlkSmem), s>>>(ba);
+  } else {
+    // a plain launch: the workers never wait for each other (no grid barrier; any one warp can drain the queue alone), so CTAs that
+    // only become resident later — e.g. while other contexts' kernels hold SMs — just join late. Cooperative launches of different
+    // streams do not overlap, which serialised the plans of an ensemble.
+    k_relax<<<A.relax_grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(A.ra);
+  }
+  SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  if (ctx->ev_plan[1]) cudaEventRecord(ctx->ev_plan[1], s);
+
+  if (timing) cudaEventRecord(ev[1], s);
+  if (A.on_check) {
+    k_path_check<<<(ctx->path_cap_nodes + 255) / 256, 256, 0, s>>>(A.pc);
+    ctx->launches += 1;
+  }
+  k_pred<<<ntiles, kPredThreads, 0, s>>>(A.pr);
+  k_backtrack<<<1, kBackThreads, PW * PW, s>>>(A.pa);
+  ctx->launches += 2;
+  SIPP_CUDA_CHECK(ctx, cudaGetLastError());
+
+  if (timing) cudaEventRecord(ev[2], s);
+  k_mask_clear<<<592, 256, 0, s>>>(A.mc);
+  k_path_finish<<<(ctx->path_cap_nodes + 255) / 256, 256, 0, s>>>(A.rs);
   ctx->launches += 2;
   SIPP_CUDA_CHECK(ctx, cudaGetLastError());
   if (ctx->ev_plan[3]) cudaEventRecord(ctx->ev_plan[3], s);
@@ -1373,18 +1550,85 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     cudaEventElapsedTime(&t12, ev[1], ev[2]);
     cudaEventElapsedTime(&t23, ev[2], ev[3]);
     fprintf(stderr, "[sipp] plan phases: init+relax %.3f ms, backtrack %.3f ms, mask %.3f ms\n", t01, t12, t23);
-#ifdef SIPP_RELAX_PROFILE
-    {
-      int ctl[32];
-      cudaMemcpy(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
-      unsigned long long tp[6];
-      memcpy(tp, ctl + 16, sizeof(tp));
-      const double act = ctl[CTL_ACTIVATIONS] > 0 ? ctl[CTL_ACTIVATIONS] : 1;
-      fprintf(stderr, "[sipp] relax cycles per activation: pop %.0f  load %.0f  sweeps %.0f  merge+cross %.0f  push %.0f  weights %.0f  (activations %d, sweeps %d)\n",
-              tp[0] / act, tp[1] / act, tp[2] / act, tp[3] / act, tp[4] / act, tp[5] / act, ctl[CTL_ACTIVATIONS], ctl[CTL_SWEEPS]);
-    }
-#endif
     for (auto& e : ev) cudaEventDestroy(e);
   }
+  return SIPP_OK;
+}
+
+// Batched plan: the maps of `ctxs` (same device, same grid size; every context idle) are planned by ONE sequence of launches, every
+// kernel with gridDim.y = m. d_args: m PlanArgsAll blocks; d_seed: m slices of seed_stride bytes; d_out: m x 40 ints (plan_out[0..9] at
+// 0, the relaxation control block at 16). The host copies of the argument / seed blocks are built in h_args / h_seed (pinned, at
+// least as large). Returns after enqueueing on `s` (the caller synchronises and reads d_out).
+size_t field_plan_batch_args_bytes() { return sizeof(PlanArgsAll); }
+
+int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, uint8_t* h_seed, uint8_t* d_seed, size_t seed_stride, int* d_out,
+                     cudaStream_t s, int* launches, const std::function<void(int, const std::function<void(int)>&)>* runner) {
+  if (m <= 0) return SIPP_OK;
+  sipp_ctx* c0 = ctxs[0];
+  DevInfo dev;
+  int rc = device_setup(c0, &dev);
+  if (rc != SIPP_OK) return rc;
+  PlanArgsAll* A = reinterpret_cast<PlanArgsAll*>(h_args);
+  const int ntiles = c0->n_tiles_x * c0->n_tiles_y;
+  int any_init = 0, any_inc = 0, any_inval = 0, any_weights_all = 0, max_nl = 0, any_check = 0, max_relax = 1, max_inval = 1;
+  for (int i = 0; i < m; ++i) {
+    sipp_ctx* ctx = ctxs[i];
+    if (!ctx->d_tile_w) {
+      SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+      SIPP_CUDA_CHECK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tile_w), (size_t)ntiles * kTileWDoubles * sizeof(double)));
+    }
+  }
+  std::vector<int> rcs((size_t)m, SIPP_OK);
+  const std::function<void(int)> prep = [&](int i) {      // pure host work, no dependence between maps: shared with the batch's helper threads
+    sipp_ctx* ctx = ctxs[i];
+    bool inc = false;
+    int nl = 0;
+    if ((rcs[i] = plan_prepare(ctx, A[i], d_seed + (size_t)i * seed_stride, false, dev, &inc, &nl, m)) != SIPP_OK) return;
+    if (ctx->h_seed_stage.size() > seed_stride) { rcs[i] = sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "seed block larger than the batch slice"); return; }
+    if (!ctx->h_seed_stage.empty()) memcpy(h_seed + (size_t)i * seed_stride, ctx->h_seed_stage.data(), ctx->h_seed_stage.size());
+  };
+  if (runner) (*runner)(m, prep);
+  else for (int i = 0; i < m; ++i) prep(i);
+  for (int i = 0; i < m; ++i) {
+    if (rcs[i] != SIPP_OK) { if (i) sipp_set_err(c0, rcs[i], "%s", ctxs[i]->err.c_str()); return rcs[i]; }
+    any_init |= A[i].on_init;
+    any_inc |= A[i].on_inc;
+    any_inval |= A[i].on_inval;
+    any_check |= A[i].on_check;
+    if (A[i].on_weights) {
+      if (A[i].on_init) any_weights_all = 1;
+      else if (A[i].wa.n_items > max_nl) max_nl = A[i].wa.n_items;
+    }
+    if (A[i].relax_grid > max_relax) max_relax = A[i].relax_grid;
+    if (A[i].inval_grid > max_inval) max_inval = A[i].inval_grid;
+  }
+  SIPP_CUDA_CHECK(c0, cudaMemcpyAsync(d_args, h_args, (size_t)m * sizeof(PlanArgsAll), cudaMemcpyHostToDevice, s));
+  if (any_inval) SIPP_CUDA_CHECK(c0, cudaMemcpyAsync(d_seed, h_seed, (size_t)m * seed_stride, cudaMemcpyHostToDevice, s));
+  const PlanArgsAll* dA = reinterpret_cast<const PlanArgsAll*>(d_args);
+  const unsigned M = (unsigned)m;
+  int n = 0;
+  if (any_init) {
+    k_field_init_b<<<dim3(64, M), 256, 0, s>>>(dA);
+    k_field_seed_b<<<dim3(1, M), 32, 0, s>>>(dA);
+    n += 2;
+  }
+  if (any_inc) { k_inc_begin_b<<<dim3(16, M), 256, 0, s>>>(dA); n += 1; }
+  const int wgrid = any_weights_all ? ntiles : max_nl;
+  if (wgrid > 0) { k_weights_b<<<dim3(wgrid, M), kWeightThreads, 0, s>>>(dA); n += 1; }
+  if (any_inval) {
+    k_inval_b<<<dim3(max_inval, M), kInvalWarps * 32, 0, s>>>(dA);
+    k_seed_relax_b<<<dim3((ntiles + 255) / 256, M), 256, 0, s>>>(dA);
+    n += 2;
+  }
+  k_relax_b<<<dim3(max_relax, M), kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA);
+  if (any_check) { k_path_check_b<<<dim3(4, M), 256, 0, s>>>(dA); n += 1; }
+  k_pred_b<<<dim3(ntiles, M), kPredThreads, 0, s>>>(dA);
+  k_backtrack_b<<<dim3(1, M), kBackThreads, PW * PW, s>>>(dA);
+  k_mask_clear_b<<<dim3(32, M), 256, 0, s>>>(dA);
+  k_path_finish_b<<<dim3(4, M), 256, 0, s>>>(dA);
+  k_gather_plan_out<<<M, 64, 0, s>>>(dA, d_out);
+  n += 6;
+  SIPP_CUDA_CHECK(c0, cudaGetLastError());
+  if (launches) *launches = n;
   return SIPP_OK;
 }

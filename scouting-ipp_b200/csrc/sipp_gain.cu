@@ -188,9 +188,8 @@ __device__ __forceinline__ int clipped_extent(int c, int h, int lo, int hi) {
 // box (tools/gain_rows_probe.py: 30 us for 65536 candidates at 17 rows, 45 us at 65), which bounds the tiled form at one
 // candidate per ~200 cycles per SM; the direct form has no per-candidate fixed cost beyond its own instructions and runs two
 // CTAs per SM (no dynamic shared memory).
-template <int MODE, bool PACKED = false>
-__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, PACKED ? 2 : 1)
-k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_aux, const GainArgs a) {
+template <int MODE, bool PACKED>
+__device__ __forceinline__ void gain_body(const CUtensorMap* tm_rec_p, const CUtensorMap* tm_aux_p, const GainArgs& a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[kMaxWarpsPerCta * kMaxStages];
   __shared__ uint4 mask_tbl[16 * 16];
@@ -286,8 +285,8 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
     mbar_expect_tx(bar, tx_bytes);
     // TMA needs the box start 16-byte aligned in the contiguous dimension: start at the aligned column at or before
     // the window's first column; the box is wide enough to still cover the window (see gain_launch)
-    if (kNeedRec) tma_load_2d(dst, &tm_rec, bar, (w.cx - h) & ~15, w.cy - h);
-    if (kNeedAux) tma_load_2d(dst + (uint32_t)a.aux_off, &tm_aux, bar, (w.cx - h) & ~7, w.cy - h);
+    if (kNeedRec) tma_load_2d(dst, tm_rec_p, bar, (w.cx - h) & ~15, w.cy - h);
+    if (kNeedAux) tma_load_2d(dst + (uint32_t)a.aux_off, tm_aux_p, bar, (w.cx - h) & ~7, w.cy - h);
   };
 
   const bool fused = a.best_out != nullptr;     // every warp takes part in the CTA reduction of the fused argmax
@@ -659,6 +658,20 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
   }
 }
 
+// one map per launch: the tensor maps and the argument block travel in the kernel's parameter space
+template <int MODE, bool PACKED = false>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, PACKED ? 2 : 1)
+k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_aux, const GainArgs a) {
+  gain_body<MODE, PACKED>(&tm_rec, &tm_aux, a);
+}
+// batched (sipp_batch_cycle: an ensemble of maps scored by one launch): block (x, y) scores candidates of map y with the argument
+// block as[y]. Count-type evaluators on the 2-bit plane only — that form takes no tensor map.
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 2)
+k_gain_count_b(const GainArgs* __restrict__ as) {
+  const GainArgs a = as[blockIdx.y];
+  gain_body<MODE_COUNT, true>(nullptr, nullptr, a);
+}
+
 // ---- host side: tensor maps -----------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -751,14 +764,14 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
 
 }  // namespace
 
-int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
-                const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
-                cudaStream_t s, const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs) {
-  if (n <= 0) return SIPP_OK;
+// fills the argument block of a gain launch; *mode_out = kernel flavour, *packed_out = the 2-bit-plane form serves it
+static int gain_prepare(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
+                        const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
+                        const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs, GainArgs& a, int* mode_out, bool* packed_out,
+                        bool* need_aux_out) {
   const int h = p->half_fov;
   if (h < 0 || h > 112) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d outside [0,112] (TMA box limit 256 columns)", h);
   const int side = 2 * h + 1;
-  GainArgs a;
   memset(&a, 0, sizeof(a));
   a.g = g;
   a.evaluator = p->evaluator;
@@ -827,7 +840,22 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
   a.stages = ctx->gain_stages > 0 ? ctx->gain_stages : (packed ? 4 : 2);
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   while (a.stages > 2 && (size_t)a.stages * a.slot_bytes > 220 * 1024) --a.stages;
-  int rc = SIPP_OK;
+  *mode_out = mode;
+  *packed_out = packed;
+  *need_aux_out = need_aux;
+  return SIPP_OK;
+}
+
+int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
+                const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
+                cudaStream_t s, const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs) {
+  if (n <= 0) return SIPP_OK;
+  GainArgs a;
+  int mode = 0;
+  bool packed = false, need_aux = false;
+  int rc = gain_prepare(ctx, p, g, n, d_xy, d_start_xy, d_cost, d_gain, d_counts, d_terminal, d_value, d_sel, d_n, d_value2, fs, a, &mode, &packed, &need_aux);
+  if (rc != SIPP_OK) return rc;
+  const int h = p->half_fov;
   const CUtensorMap* tm_rec = cached_tmap(ctx, h, 0, &rc);      // the packed form does not use it (plain loads)
   if (!tm_rec) return rc;
   const CUtensorMap* tm_aux = tm_rec;
@@ -842,5 +870,51 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
     case MODE_AVG_VIEW_COST: return launch_mode<MODE_AVG_VIEW_COST>(ctx, tm_rec, tm_aux, a, s);
     case MODE_LOW_COST: return launch_mode<MODE_LOW_COST>(ctx, tm_rec, tm_aux, a, s);
   }
+  return SIPP_OK;
+}
+
+// ---- batched gain + value + argmax (sipp_batch_cycle) ---------------------------------------------------------------------------
+size_t gain_args_bytes() { return sizeof(GainArgs); }
+
+// argument block of map `ctx` for a batched launch (count-type evaluator on the 2-bit plane, fused value + argmax into fs->best_out)
+int gain_fill_batch_args(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_cost, double* d_gain,
+                         uint8_t* d_terminal, double* d_value, const FusedSelect* fs, void* dst) {
+  GainArgs a;
+  int mode = 0;
+  bool packed = false, need_aux = false;
+  int rc = gain_prepare(ctx, p, g, n, d_xy, nullptr, d_cost, d_gain, nullptr, d_terminal, d_value, nullptr, nullptr, nullptr, fs, a, &mode, &packed, &need_aux);
+  if (rc != SIPP_OK) return rc;
+  if (mode != MODE_COUNT || !packed)
+    return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "batched evaluation serves the count-type evaluators on the 2-bit plane (RRTStarEvaluator without distance "
+                        "discount, ExpandReachableArea, Naive; half_fov <= 96); evaluator %d / half_fov %d is not one of them", p->evaluator, p->half_fov);
+  memcpy(dst, &a, sizeof(a));
+  return SIPP_OK;
+}
+
+int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return SIPP_OK;
+  int num_sms = 0;
+  {
+    static std::mutex mu;
+    static struct { bool done; int num_sms; } info[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    auto& di = info[c0->device & 63];
+    if (!di.done) {
+      cudaError_t e0 = cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, c0->device);
+      if (e0 != cudaSuccess) return sipp_set_err(c0, SIPP_ERR_CUDA, "k_gain_count_b setup: %s", cudaGetErrorString(e0));
+      di.done = true;
+    }
+    num_sms = di.num_sms;
+  }
+  const int wpc = c0->gain_warps > 0 ? c0->gain_warps : kMaxWarpsPerCta;
+  const int want = (n + wpc - 1) / wpc;
+  // every map gets the same grid; together they should fill the GPU about twice (2 CTAs per SM)
+  int per_map = (2 * num_sms + m - 1) / m;
+  if (per_map < 1) per_map = 1;
+  int grid = want < per_map ? want : per_map;
+  if (grid > kSelMaxBlocks) grid = kSelMaxBlocks;
+  k_gain_count_b<<<dim3((unsigned)grid, (unsigned)m), wpc * 32, 0, s>>>(reinterpret_cast<const GainArgs*>(d_args));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return sipp_set_err(c0, SIPP_ERR_CUDA, "k_gain_count_b launch: %s", cudaGetErrorString(e));
   return SIPP_OK;
 }

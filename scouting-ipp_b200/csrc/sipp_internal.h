@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <list>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -253,5 +254,20 @@ cudaError_t launch_cost_integral(sipp_ctx* ctx, const sipp_cost_params& p, int n
 cudaError_t launch_travel_cost(sipp_ctx* ctx, const sipp_travel_params& p, int n, const double* d_start, const double* d_goal, double* d_cost, cudaStream_t s);
 // sipp_field.cu
 int field_plan(sipp_ctx* ctx, cudaStream_t s);
+
+// ---- batched forms (sipp_batch_*: an ensemble of maps advanced by one launch per kernel, gridDim.y = maps) ------------------------
+size_t field_plan_batch_args_bytes();
+int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, uint8_t* h_seed, uint8_t* d_seed, size_t seed_stride, int* d_out,
+                     cudaStream_t s, int* launches, const std::function<void(int, const std::function<void(int)>&)>* runner = nullptr);
+size_t ingest_args_bytes();
+size_t build_views_args_bytes();
+void fill_ingest_args(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* d_labels, void* dst);
+void fill_build_views_args(sipp_ctx* ctx, const GainGeom& g, bool use_bv, int on, void* dst);
+cudaError_t launch_ingest_patch_batch(const void* d_args, int m, int rows, int cols, cudaStream_t s);
+cudaError_t launch_build_views_batch(const void* d_args, int m, size_t pitch, int H, cudaStream_t s);
+size_t gain_args_bytes();
+int gain_fill_batch_args(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_cost, double* d_gain,
+                         uint8_t* d_terminal, double* d_value, const FusedSelect* fs, void* dst);
+int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, cudaStream_t s);
 
 #endif  // SIPP_INTERNAL_H_

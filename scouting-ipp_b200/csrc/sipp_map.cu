@@ -24,10 +24,21 @@ __device__ __forceinline__ bool in_ids(const IdList& l, int v) {
 }
 
 // One thread per patch cell. labels: rows x cols int32 row-major (MapData.data); observed: optional mask.
-__global__ void k_ingest_patch(uint8_t* __restrict__ state, uint16_t* __restrict__ label, uint16_t* __restrict__ pcode,
-                               size_t pitch, size_t pitch16, int W, int H, int x0, int y0, int rows, int cols,
-                               const int32_t* __restrict__ labels, const uint8_t* __restrict__ observed, IdList mav,
-                               IdList rov, uint8_t* __restrict__ mark, int init_cost_ceil) {
+struct IngestArgs {
+  uint8_t* state; uint16_t* label; uint16_t* pcode;
+  size_t pitch, pitch16;
+  int W, H, x0, y0, rows, cols;
+  const int32_t* labels; const uint8_t* observed;
+  IdList mav, rov;
+  uint8_t* mark; int init_cost_ceil;
+};
+__device__ __forceinline__ void ingest_patch_body(const IngestArgs& a) {
+  uint8_t* __restrict__ state = a.state; uint16_t* __restrict__ label = a.label; uint16_t* __restrict__ pcode = a.pcode;
+  const size_t pitch = a.pitch, pitch16 = a.pitch16;
+  const int W = a.W, H = a.H, x0 = a.x0, y0 = a.y0, rows = a.rows, cols = a.cols;
+  const int32_t* __restrict__ labels = a.labels; const uint8_t* __restrict__ observed = a.observed;
+  const IdList& mav = a.mav; const IdList& rov = a.rov;
+  uint8_t* __restrict__ mark = a.mark; const int init_cost_ceil = a.init_cost_ceil;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * cols) return;
   const int i = (int)(t / cols), j = (int)(t % cols);
@@ -99,11 +110,21 @@ __global__ void k_build_lowcost_view(const uint8_t* __restrict__ state, const ui
 // Builds the evaluator view planes. 16 cells per thread, 128-bit loads/stores.
 //   rec     : packed gain record (REC_* bits)
 //   freelab : label where the cell is observed FREE and inside the bounding volume, else 0
-__global__ void k_build_views(const uint8_t* __restrict__ state, const uint8_t* __restrict__ path,
-                              const uint16_t* __restrict__ label, uint8_t* __restrict__ rec,
-                              uint16_t* __restrict__ freelab, size_t pitch, size_t pitch16, int W, int H, int bv_kx_lo,
-                              int bv_kx_hi, int bv_ky_lo, int bv_ky_hi, int reach_x, int reach_y, int use_reach,
-                              uint8_t* __restrict__ rec2_path, uint8_t* __restrict__ rec2_reach) {
+struct BuildViewsArgs {
+  const uint8_t* state; const uint8_t* path; const uint16_t* label;
+  uint8_t* rec; uint16_t* freelab;
+  size_t pitch, pitch16;
+  int W, H, bv_kx_lo, bv_kx_hi, bv_ky_lo, bv_ky_hi, reach_x, reach_y, use_reach;
+  uint8_t* rec2_path; uint8_t* rec2_reach;
+  int on;       // batched launch: this map's views are stale
+};
+__device__ __forceinline__ void build_views_body(const BuildViewsArgs& a) {
+  const uint8_t* __restrict__ state = a.state; const uint8_t* __restrict__ path = a.path; const uint16_t* __restrict__ label = a.label;
+  uint8_t* __restrict__ rec = a.rec; uint16_t* __restrict__ freelab = a.freelab;
+  const size_t pitch = a.pitch, pitch16 = a.pitch16;
+  const int W = a.W, H = a.H, bv_kx_lo = a.bv_kx_lo, bv_kx_hi = a.bv_kx_hi, bv_ky_lo = a.bv_ky_lo, bv_ky_hi = a.bv_ky_hi;
+  const int reach_x = a.reach_x, reach_y = a.reach_y, use_reach = a.use_reach;
+  uint8_t* __restrict__ rec2_path = a.rec2_path; uint8_t* __restrict__ rec2_reach = a.rec2_reach;
   const int chunks_per_row = (int)(pitch / 16);
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)chunks_per_row * H) return;
@@ -174,7 +195,67 @@ IdList make_ids(const int32_t* ids, int n) {
   return l;
 }
 
+// one map per launch (arguments by value) / batched (gridDim.y = maps, argument blocks in device memory: sipp_batch_*)
+__global__ void k_ingest_patch(const IngestArgs a) { ingest_patch_body(a); }
+__global__ void k_build_views(const BuildViewsArgs a) { build_views_body(a); }
+__global__ void k_ingest_patch_b(const IngestArgs* __restrict__ as) {
+  const IngestArgs a = as[blockIdx.y];
+  ingest_patch_body(a);
+}
+__global__ void k_build_views_b(const BuildViewsArgs* __restrict__ as) {
+  if (!as[blockIdx.y].on) return;
+  const BuildViewsArgs a = as[blockIdx.y];
+  build_views_body(a);
+}
+
+IngestArgs make_ingest_args(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* d_labels, const uint8_t* d_observed) {
+  IngestArgs a;
+  a.state = ctx->d_state; a.label = ctx->d_label; a.pcode = ctx->d_pcode;
+  a.pitch = ctx->pitch; a.pitch16 = ctx->pitch16;
+  a.W = ctx->W; a.H = ctx->H; a.x0 = x0; a.y0 = y0; a.rows = rows; a.cols = cols;
+  a.labels = d_labels; a.observed = d_observed;
+  a.mav = make_ids(ctx->desc.obstacle_ids_mav, ctx->desc.n_obstacle_ids_mav);
+  a.rov = make_ids(ctx->desc.obstacle_ids_rov, ctx->desc.n_obstacle_ids_rov);
+  a.mark = ctx->warm_valid ? ctx->d_mark : nullptr;
+  a.init_cost_ceil = (int)floor(ctx->warm_init_cost);
+  return a;
+}
+BuildViewsArgs make_build_views_args(sipp_ctx* ctx, const GainGeom& g, bool use_bv, int on) {
+  BuildViewsArgs a;
+  a.state = ctx->d_state; a.path = ctx->d_path; a.label = ctx->d_label; a.rec = ctx->d_rec; a.freelab = ctx->d_freelab;
+  a.pitch = ctx->pitch; a.pitch16 = ctx->pitch16; a.W = ctx->W; a.H = ctx->H;
+  a.bv_kx_lo = use_bv ? g.bv_kx_lo : 0; a.bv_kx_hi = use_bv ? g.bv_kx_hi : ctx->W - 1;
+  a.bv_ky_lo = use_bv ? g.bv_ky_lo : 0; a.bv_ky_hi = use_bv ? g.bv_ky_hi : ctx->H - 1;
+  a.reach_x = ctx->start_loc[0]; a.reach_y = ctx->start_loc[1]; a.use_reach = ctx->desc.compute_reachability;
+  a.rec2_path = ctx->d_rec2[0]; a.rec2_reach = ctx->d_rec2[1];
+  a.on = on;
+  return a;
+}
+
 }  // namespace
+
+size_t ingest_args_bytes() { return sizeof(IngestArgs); }
+size_t build_views_args_bytes() { return sizeof(BuildViewsArgs); }
+void fill_ingest_args(sipp_ctx* ctx, int x0, int y0, int rows, int cols, const int32_t* d_labels, void* dst) {
+  const IngestArgs a = make_ingest_args(ctx, x0, y0, rows, cols, d_labels, nullptr);
+  memcpy(dst, &a, sizeof(a));
+}
+void fill_build_views_args(sipp_ctx* ctx, const GainGeom& g, bool use_bv, int on, void* dst) {
+  const BuildViewsArgs a = make_build_views_args(ctx, g, use_bv, on);
+  memcpy(dst, &a, sizeof(a));
+}
+cudaError_t launch_ingest_patch_batch(const void* d_args, int m, int rows, int cols, cudaStream_t s) {
+  const long long n = (long long)rows * cols;
+  if (n <= 0 || m <= 0) return cudaSuccess;
+  k_ingest_patch_b<<<dim3((unsigned)((n + 255) / 256), (unsigned)m), 256, 0, s>>>(reinterpret_cast<const IngestArgs*>(d_args));
+  return cudaGetLastError();
+}
+cudaError_t launch_build_views_batch(const void* d_args, int m, size_t pitch, int H, cudaStream_t s) {
+  const long long n = (long long)(pitch / 16) * H;
+  if (n <= 0 || m <= 0) return cudaSuccess;
+  k_build_views_b<<<dim3((unsigned)((n + 255) / 256), (unsigned)m), 256, 0, s>>>(reinterpret_cast<const BuildViewsArgs*>(d_args));
+  return cudaGetLastError();
+}
 
 cudaError_t launch_clear_planes(sipp_ctx* ctx, cudaStream_t s) {
   // MapServerPlanExp::clearMap (map_server_planexp.cpp:461-487) + PRMStarPlanner::set_derived_params (:24-27)
@@ -199,11 +280,7 @@ cudaError_t launch_ingest_patch(sipp_ctx* ctx, int x0, int y0, int rows, int col
   if (n <= 0) return cudaSuccess;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  k_ingest_patch<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_label, ctx->d_pcode, ctx->pitch, ctx->pitch16, ctx->W,
-                                            ctx->H, x0, y0, rows, cols, d_labels, d_observed,
-                                            make_ids(ctx->desc.obstacle_ids_mav, ctx->desc.n_obstacle_ids_mav),
-                                            make_ids(ctx->desc.obstacle_ids_rov, ctx->desc.n_obstacle_ids_rov),
-                                            ctx->warm_valid ? ctx->d_mark : nullptr, (int)floor(ctx->warm_init_cost));
+  k_ingest_patch<<<blocks, threads, 0, s>>>(make_ingest_args(ctx, x0, y0, rows, cols, d_labels, d_observed));
   ctx->launches += 1;
   return cudaGetLastError();
 }
@@ -212,11 +289,7 @@ cudaError_t launch_build_views(sipp_ctx* ctx, const GainGeom& g, bool use_bv, cu
   const long long n = (long long)(ctx->pitch / 16) * ctx->H;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  const int klo_x = use_bv ? g.bv_kx_lo : 0, khi_x = use_bv ? g.bv_kx_hi : ctx->W - 1;
-  const int klo_y = use_bv ? g.bv_ky_lo : 0, khi_y = use_bv ? g.bv_ky_hi : ctx->H - 1;
-  k_build_views<<<blocks, threads, 0, s>>>(ctx->d_state, ctx->d_path, ctx->d_label, ctx->d_rec, ctx->d_freelab,
-                                           ctx->pitch, ctx->pitch16, ctx->W, ctx->H, klo_x, khi_x, klo_y, khi_y,
-                                           ctx->start_loc[0], ctx->start_loc[1], ctx->desc.compute_reachability, ctx->d_rec2[0], ctx->d_rec2[1]);
+  k_build_views<<<blocks, threads, 0, s>>>(make_build_views_args(ctx, g, use_bv, 1));
   ctx->launches += 1;
   return cudaGetLastError();
 }

@@ -30,6 +30,8 @@ ABI_SYMBOLS = [
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
     "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
     "sipp_path_download", "sipp_truth_upload", "sipp_travel_cost", "sipp_plan_phases",
+    "sipp_batch_create", "sipp_batch_destroy", "sipp_batch_last_error", "sipp_batch_launch_count", "sipp_batch_ingest", "sipp_batch_plan",
+    "sipp_batch_cycle", "sipp_batch_episode_run",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -214,6 +216,17 @@ def lib():
         L.sipp_peer_flush_dev.argtypes = [vp, vp, vp]
         L.sipp_episode_run.argtypes = [vp, vp, C.POINTER(EvalParams), i32, i32, vp, vp, i32, i32, f64, f64, vp, vp, vp, vp, vp]
         L.sipp_cost_integral.argtypes = [vp, C.POINTER(CostParams), i32, vp, vp, vp, vp, vp]
+        L.sipp_batch_create.argtypes = [vp, i32, C.POINTER(vp)]
+        L.sipp_batch_destroy.argtypes = [vp]
+        L.sipp_batch_destroy.restype = None
+        L.sipp_batch_last_error.argtypes = [vp]
+        L.sipp_batch_last_error.restype = C.c_char_p
+        L.sipp_batch_launch_count.argtypes = [vp]
+        L.sipp_batch_launch_count.restype = C.c_int64
+        L.sipp_batch_ingest.argtypes = [vp, vp, vp, i32, i32, vp]
+        L.sipp_batch_plan.argtypes = [vp, vp, vp, vp]
+        L.sipp_batch_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp]
+        L.sipp_batch_episode_run.argtypes = [vp, vp, C.POINTER(EvalParams), i32, i32, vp, vp, i32, i32, f64, f64, vp, vp, vp, vp, vp]
         L.sipp_set_incremental.argtypes = [vp, i32]
         L.sipp_plan_info.argtypes = [vp, vp]
         L.sipp_launch_count.argtypes = [vp]
@@ -518,3 +531,73 @@ class Context:
         self._check(self._L.sipp_cycle(self._h, C.byref(params), int(n), _ptr(xy), _ptr(start_xy), _ptr(cost), _ptr(gain),
                                        _ptr(terminal), _ptr(value), C.byref(bi), C.byref(bv)))
         return bi.value, bv.value
+
+
+class Batch:
+    """m maps of one size on one device that advance together (sipp_batch): one launch per kernel for all maps."""
+
+    def __init__(self, contexts):
+        self._L = lib()
+        self.ctx = list(contexts)
+        self.m = len(self.ctx)
+        arr = (C.c_void_p * self.m)(*[c._h for c in self.ctx])
+        h = C.c_void_p()
+        rc = self._L.sipp_batch_create(arr, self.m, C.byref(h))
+        if rc != 0:
+            raise SippError(rc, self._L.sipp_last_error(self.ctx[0]._h).decode() if self.ctx else "empty batch")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sipp_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SippError(rc, self._L.sipp_batch_last_error(self._h).decode())
+
+    def _ptrs(self, arrays):
+        return (C.c_void_p * self.m)(*[a.ctypes.data for a in arrays])
+
+    def launch_count(self):
+        return int(self._L.sipp_batch_launch_count(self._h))
+
+    def ingest(self, x0, y0, patches):
+        """patches: m arrays [rows][cols] int32 (one shape)"""
+        ps = [np.ascontiguousarray(p, dtype=np.int32) for p in patches]
+        rows, cols = ps[0].shape
+        x0 = np.ascontiguousarray(x0, dtype=np.int32)
+        y0 = np.ascontiguousarray(y0, dtype=np.int32)
+        self._check(self._L.sipp_batch_ingest(self._h, _ptr(x0), _ptr(y0), rows, cols, self._ptrs(ps)))
+
+    def plan(self):
+        """returns m tuples (cost, status, path nodes)"""
+        cost, st, ln = np.zeros(self.m), np.zeros(self.m, np.int32), np.zeros(self.m, np.int32)
+        self._check(self._L.sipp_batch_plan(self._h, _ptr(cost), _ptr(st), _ptr(ln)))
+        return [(float(cost[i]), int(st[i]), int(ln[i])) for i in range(self.m)]
+
+    def cycle(self, params, xy, cost, want_gain=False):
+        """xy: m arrays [n][2], cost: m arrays [n]; returns (best_index[m], best_value[m][, gain m x n])"""
+        xs = [np.ascontiguousarray(a, dtype=np.float64) for a in xy]
+        cs = [np.ascontiguousarray(a, dtype=np.float64) for a in cost]
+        n = len(cs[0])
+        bi, bv = np.zeros(self.m, np.int64), np.zeros(self.m)
+        gains = [np.zeros(n) for _ in range(self.m)] if want_gain else None
+        self._check(self._L.sipp_batch_cycle(self._h, C.byref(params), n, self._ptrs(xs), self._ptrs(cs), _ptr(bi), _ptr(bv),
+                                             self._ptrs(gains) if want_gain else None))
+        return (bi, bv, gains) if want_gain else (bi, bv)
+
+    def episode_run(self, truths, params, cand_xy, cand_cost, fov=65, init=320, start=(0.5, 0.5)):
+        """sipp_batch_episode_run: truths m x [H][W]; cand_xy m x [cycles][n][2]; cand_cost m x [cycles][n]; returns m traces in the
+        format of Context.episode_run"""
+        ts = [np.ascontiguousarray(t, dtype=np.int32) for t in truths]
+        xs = [np.ascontiguousarray(a, dtype=np.float64) for a in cand_xy]
+        cs = [np.ascontiguousarray(a, dtype=np.float64) for a in cand_cost]
+        cycles, n = cs[0].shape
+        pc, bv = np.zeros((self.m, cycles)), np.zeros((self.m, cycles))
+        st, ln, bi = (np.zeros((self.m, cycles), np.int32) for _ in range(3))
+        self._check(self._L.sipp_batch_episode_run(self._h, self._ptrs(ts), C.byref(params), cycles, n, self._ptrs(xs), self._ptrs(cs), int(fov), int(init),
+                                                   float(start[0]), float(start[1]), _ptr(pc), _ptr(st), _ptr(ln), _ptr(bi), _ptr(bv)))
+        return [[(float(pc[k, c]), int(st[k, c]), int(ln[k, c]), int(bi[k, c]), float(bv[k, c])) for c in range(cycles)] for k in range(self.m)]

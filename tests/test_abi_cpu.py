@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(L):
     assert sorted(sipp.ABI_SYMBOLS) == declared
     for name in declared:
         assert hasattr(L, name), name
-    assert L.sipp_abi_version() == 2
+    assert L.sipp_abi_version() == 3
 
 
 def test_struct_layouts_match_between_product_and_oracle_bindings():

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--cycles", type=int, default=40)
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--check", type=int, default=2, help="episodes re-run on the CPU oracle and compared (rank 0)")
+    ap.add_argument("--mode", default="batch", choices=["batch", "threads"],
+                    help="batch: sipp_batch_episode_run, every kernel launched once for all maps (one host thread); threads: one sipp_episode_run per map from a pool of host threads")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     seeds = [2000 + i for i in range(args.maps * world)][rank::world]
@@ -43,13 +45,27 @@ def main():
         sd, lab, ctx = item
         return ctx.episode_run(lab, params, cands[sd][0], cands[sd][1])
 
-    with ThreadPoolExecutor(args.threads) as pool:
-        list(pool.map(lambda it: it[2].episode_run(it[1], params, cands[it[0]][0][:2], cands[it[0]][1][:2]), worlds))   # warm-up (allocations)
+    launches = None
+    if args.mode == "batch":
+        batch = sipp.Batch([w[2] for w in worlds])
+        labs = [w[1] for w in worlds]
+        batch.episode_run(labs, params, [cands[w[0]][0][:2] for w in worlds], [cands[w[0]][1][:2] for w in worlds])     # warm-up (allocations)
         for _, _, ctx in worlds:
             ctx.map_clear()
+        l0 = batch.launch_count()
         t0 = time.perf_counter()
-        traces = list(pool.map(run, worlds))
+        traces = batch.episode_run(labs, params, [cands[w[0]][0] for w in worlds], [cands[w[0]][1] for w in worlds])
         dt = time.perf_counter() - t0
+        launches = batch.launch_count() - l0
+        batch.close()
+    else:
+        with ThreadPoolExecutor(args.threads) as pool:
+            list(pool.map(lambda it: it[2].episode_run(it[1], params, cands[it[0]][0][:2], cands[it[0]][1][:2]), worlds))   # warm-up (allocations)
+            for _, _, ctx in worlds:
+                ctx.map_clear()
+            t0 = time.perf_counter()
+            traces = list(pool.map(run, worlds))
+            dt = time.perf_counter() - t0
     class Timed:          # per-call wall time of one episode running alone
         def __init__(self, ctx):
             self.ctx, self.t = ctx, {}
@@ -75,7 +91,10 @@ def main():
             assert episode.traces_match(traces[k][:len(want)], want), (k, traces[k][:len(want)], want)
             checked += 1
     line = {"metric": "ensemble map-cycles/s (640x480 maps, 1024 candidates per cycle)", "value": len(worlds) * args.cycles / dt, "unit": "map-cycles/s",
-            "rank": rank, "world": world, "maps_on_this_gpu": len(worlds), "cycles": args.cycles, "host_threads": args.threads, "driver": "sipp_episode_run (native host loop), one call per episode from a pool of host threads",
+            "rank": rank, "world": world, "maps_on_this_gpu": len(worlds), "cycles": args.cycles, "host_threads": 1 if args.mode == "batch" else args.threads,
+            "driver": ("sipp_batch_episode_run: every kernel launched once for all maps of the GPU (gridDim.y = maps), one host thread, one synchronisation per map-cycle"
+                       if args.mode == "batch" else "sipp_episode_run (native host loop), one call per episode from a pool of host threads"),
+            "kernel_launches_per_batch_cycle": (launches / args.cycles) if launches is not None else None,
             "ms_per_map_cycle_alone": dt_one / args.cycles * 1e3, "ms_per_map_cycle_in_ensemble": dt / (len(worlds) * args.cycles) * 1e3,
             "alone_ms_per_cycle_by_call": {k: v / args.cycles * 1e3 for k, v in tm.t.items()}, "episodes_checked_against_oracle": checked, "final_costs": [t[-1][0] for t in traces[:4]]}
     print(json.dumps(line), flush=True)
