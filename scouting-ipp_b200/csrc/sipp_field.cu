@@ -1345,9 +1345,9 @@ int plan_prepare(sipp_ctx* ctx, PlanArgsAll& A, uint8_t* d_seed, bool blk, const
       int igrid = (ntiles + 8 * kInvalWarps - 1) / (8 * kInvalWarps);
       if (igrid > 2 * dev.num_sms) igrid = 2 * dev.num_sms;
       if (igrid * kInvalWarps > qcap) igrid = qcap / kInvalWarps;
-      if (batch_m > 0) {      // batched: the maps share the SMs — about two CTAs of workers per SM in total, at least one per map
-        const int share = 2 * dev.num_sms / batch_m;
-        if (igrid > share) igrid = share < 1 ? 1 : share;
+      if (batch_m > 0) {      // batched: the maps share the SMs (several of these small CTAs fit on one) — about four CTAs per SM in total
+        const int share = 4 * dev.num_sms / batch_m < 4 ? 4 : 4 * dev.num_sms / batch_m;
+        if (igrid > share) igrid = share;
       }
       A.inval_grid = igrid;
       SeedRelaxArgs& sr = A.sr;
@@ -1380,11 +1380,12 @@ int plan_prepare(sipp_ctx* ctx, PlanArgsAll& A, uint8_t* d_seed, bool blk, const
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     if (grid * kRelaxWarps > qcap) grid = qcap / kRelaxWarps;
-    if (batch_m > 0) {
-      // batched: a persistent CTA holds its SM until its map's queue is drained, so the maps' CTAs should all be resident at once —
-      // one wave in total, at least one CTA (any one worker can drain a queue alone) per map
-      const int share = dev.num_sms * dev.occ / batch_m;
-      if (grid > share) grid = share < 1 ? 1 : share;
+    if (batch_m > 0 && incremental) {
+      // batched: a persistent CTA holds its SM until its map's queue is drained, so the CTAs of the maps that re-plan incrementally
+      // (a handful of tiles each) should all be resident at once — about one wave in total, two CTAs per map at least. A map that
+      // starts from scratch keeps the full set of workers: the step lasts as long as its slowest map.
+      const int share = dev.num_sms * dev.occ / batch_m < 2 ? 2 : dev.num_sms * dev.occ / batch_m;
+      if (grid > share) grid = share;
     }
     A.relax_grid = grid;
   }

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--cycles", type=int, default=40)
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--check", type=int, default=2, help="episodes re-run on the CPU oracle and compared (rank 0)")
+    ap.add_argument("--batches", type=int, default=2, help="batch mode: the maps are split into this many batches, driven side by side from one host thread each "
+                    "(the host preparation of one batch overlaps the kernels of another)")
     ap.add_argument("--mode", default="batch", choices=["batch", "threads"],
                     help="batch: sipp_batch_episode_run, every kernel launched once for all maps (one host thread); threads: one sipp_episode_run per map from a pool of host threads")
     args = ap.parse_args()
@@ -47,17 +49,29 @@ def main():
 
     launches = None
     if args.mode == "batch":
-        batch = sipp.Batch([w[2] for w in worlds])
-        labs = [w[1] for w in worlds]
-        batch.episode_run(labs, params, [cands[w[0]][0][:2] for w in worlds], [cands[w[0]][1][:2] for w in worlds])     # warm-up (allocations)
-        for _, _, ctx in worlds:
-            ctx.map_clear()
-        l0 = batch.launch_count()
-        t0 = time.perf_counter()
-        traces = batch.episode_run(labs, params, [cands[w[0]][0] for w in worlds], [cands[w[0]][1] for w in worlds])
-        dt = time.perf_counter() - t0
-        launches = batch.launch_count() - l0
-        batch.close()
+        nb = max(1, min(args.batches, len(worlds) // 8 or 1))
+        groups = [worlds[k::nb] for k in range(nb)]
+        batches = [sipp.Batch([w[2] for w in g]) for g in groups]
+
+        def run_group(k, ncyc=None):
+            g = groups[k]
+            return batches[k].episode_run([w[1] for w in g], params, [cands[w[0]][0][:ncyc] for w in g], [cands[w[0]][1][:ncyc] for w in g])
+
+        with ThreadPoolExecutor(nb) as pool:
+            list(pool.map(lambda k: run_group(k, 2), range(nb)))     # warm-up (allocations)
+            for _, _, ctx in worlds:
+                ctx.map_clear()
+            l0 = sum(b.launch_count() for b in batches)
+            t0 = time.perf_counter()
+            parts = list(pool.map(run_group, range(nb)))
+            dt = time.perf_counter() - t0
+        launches = (sum(b.launch_count() for b in batches) - l0) / nb
+        traces = [None] * len(worlds)
+        for k in range(nb):
+            for j, tr in enumerate(parts[k]):
+                traces[k + j * nb] = tr
+        for b in batches:
+            b.close()
     else:
         with ThreadPoolExecutor(args.threads) as pool:
             list(pool.map(lambda it: it[2].episode_run(it[1], params, cands[it[0]][0][:2], cands[it[0]][1][:2]), worlds))   # warm-up (allocations)
@@ -94,7 +108,7 @@ def main():
             "rank": rank, "world": world, "maps_on_this_gpu": len(worlds), "cycles": args.cycles, "host_threads": 1 if args.mode == "batch" else args.threads,
             "driver": ("sipp_batch_episode_run: every kernel launched once for all maps of the GPU (gridDim.y = maps), one host thread, one synchronisation per map-cycle"
                        if args.mode == "batch" else "sipp_episode_run (native host loop), one call per episode from a pool of host threads"),
-            "kernel_launches_per_batch_cycle": (launches / args.cycles) if launches is not None else None,
+            "kernel_launches_per_batch_cycle": (launches / args.cycles) if launches is not None else None, "batches": (args.batches if args.mode == "batch" else None),
             "ms_per_map_cycle_alone": dt_one / args.cycles * 1e3, "ms_per_map_cycle_in_ensemble": dt / (len(worlds) * args.cycles) * 1e3,
             "alone_ms_per_cycle_by_call": {k: v / args.cycles * 1e3 for k, v in tm.t.items()}, "episodes_checked_against_oracle": checked, "final_costs": [t[-1][0] for t in traces[:4]]}
     print(json.dumps(line), flush=True)
