@@ -206,6 +206,75 @@ def run_reference(args):
     return 0
 
 
+def config1_cycle():
+    """BASELINE config 1 — example.launch defaults (launch/example.launch:33,38-39) on the reference's own map_212: GoalDistanceEvaluator
+    (max_gain 100, half_fov 32), prm_star follower, one planning cycle = ingest of a 65 x 65 patch + follower plan + the updater pass over a
+    1024-node tree (what updateSegment(root) does) + next-best selection, timed through the ABI; beside it the CPU checker's literal
+    emulation of the reference pass on one host core (the reference's planner loop is single-threaded)."""
+    import sipp
+    from sipp import synth
+    res = {}
+    # map ingest of the observed region, follower plan, updater pass over a 1024-node tree (what updateSegment(root) does), selection;
+    # the CPU datapoint is the oracle's literal emulation of the reference pass on one host core (the reference is single-threaded)
+    from sipp import episode
+    from oracle import oracle as orc
+    maps = np.load(os.path.join(ROOT, "tests", "golden", "ref_maps.npz"))
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_maps.json")))["map_212"]
+    lab = maps["map_212"].astype(np.int32)
+    W, H = cfg["W"], cfg["H"]
+    ids = [i for i in cfg["present_ids"] if i not in cfg["obstacle_ids_rov"]]
+    mk = lambda f: f(W, H, cfg["width"], cfg["height"], cfg["start"], cfg["goal"], min(ids), max(ids), min(ids), obstacle_ids_mav=cfg["obstacle_ids_mav"],
+                     obstacle_ids_rov=cfg["obstacle_ids_rov"], unknown_id=cfg["unknown_id"])
+    g, o = sipp.Context(mk(sipp.make_desc)), orc.Oracle(mk(orc.make_desc))
+    obs = synth.make_observed(W, H, 1001, 40)
+    ys, xs = np.nonzero(obs)
+    rng = np.random.default_rng(1001)
+    patches = [(0, 0, 320)] + [(int(xs[j]) - 32, int(ys[j]) - 32, 65) for j in rng.integers(0, len(xs), 60)]
+    for x0, y0, sz in patches:
+        pt = episode.extract_patch(lab, x0, y0, sz, sz)
+        g.map_update_patch(x0, y0, pt); o.map_update_patch(x0, y0, pt)
+    T = 1024
+    parent, end, start, cost = synth.make_tree(W, H, 1001, T)
+    kw = dict(evaluator=sipp.EVAL_GOAL_DISTANCE, max_gain=100.0)
+    pg, po = sipp.make_params(half_fov=32, **kw), orc.make_params(half_fov=32, **kw)
+    ug = sipp.make_updater(sipp.UPD_RRT_STAR, sipp.FOLLOW_UPDATE_ALL, -1e9, 1e9, True, False, True)
+    uo = orc.make_updater(0, 0, -1e9, 1e9, True, False, True)
+    z, zt = np.zeros(T), np.zeros(T, np.uint8)
+
+    def gpu_cycle():
+        x0, y0, sz = patches[-1]
+        g.map_update_patch(x0, y0, episode.extract_patch(lab, x0, y0, sz, sz))
+        r = g.plan(path_cap=1)
+        gg, gv, gt, _ = g.update_tree(pg, ug, parent, end, z, cost, z, zt, (0.5, 0.5), True, start_xy=start)
+        return r, g.value_select(gg, cost, parent)
+
+    def cpu_cycle():
+        x0, y0, sz = patches[-1]
+        o.map_update_patch(x0, y0, episode.extract_patch(lab, x0, y0, sz, sz))
+        r = o.plan(path_cap=1)
+        og, ov, ot = o.update_tree(po, uo, parent, end, z, cost, z, zt, (0.5, 0.5), True, start_xy=start)
+        return r, orc.value_select(og, cost, parent)
+
+    def wall(fn, reps):
+        out = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); r = fn(); out.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(out)), min(out), r
+
+    gpu_cycle(); g_med, g_min, rg = wall(gpu_cycle, 15)
+    c_med, c_min, rc = wall(cpu_cycle, 3)
+    tg = wall(lambda: g.update_tree(pg, ug, parent, end, z, cost, z, zt, (0.5, 0.5), True, start_xy=start), 15)
+    tc = wall(lambda: o.update_tree(po, uo, parent, end, z, cost, z, zt, (0.5, 0.5), True, start_xy=start), 3)
+    res["config1_example_launch_map_212"] = {
+        "tree_nodes": T, "gpu_cycle_ms_median": g_med, "gpu_cycle_ms_min": g_min, "cpu_cycle_ms_median": c_med, "cpu_cores": 1, "cycle_speedup": c_med / g_med,
+        "gpu_update_tree_ms": tg[0], "cpu_update_tree_ms": tc[0], "same_plan": bool(rg[0][0] == rc[0][0] and rg[0][3] == rc[0][3]),
+        "same_selected_child": bool(rg[1][1] == rc[1][1]),
+        "note": "cycle = ingest of one 65x65 patch + follower plan (incremental on the GPU; the reference re-plans from scratch) + RRTStarUpdater/UpdateAll pass "
+                "over the tree + SubsequentBest selection, host-timed through the ABI with pageable host arrays; cpu = oracle emulation of the reference pass, 1 core"}
+    g.close()
+    return res["config1_example_launch_map_212"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -548,6 +617,7 @@ def main():
 
     # ---- CPU baseline beside it: the oracle port of the reference evaluators on this box's host cores (bounded sample)
     cpu = None
+    config1 = None
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline belongs to the N = 1 line (the reference arm times it at every N)
         from oracle import oracle as orc
         odesc = orc.make_desc(W, H, W * 0.0625, H * 0.0625, (0.5, 0.5), (W * 0.0625 - 0.5, H * 0.0625 - 0.5), min(ids), max(ids), max(ids))
@@ -575,25 +645,27 @@ def main():
         b3 = nb3 / (time.perf_counter() - t0)
         # parity spot-check of the timed GPU result against the oracle on the sample (the full check lives in tests/)
         hg = h_gain.numpy()[:ns]
-        parity = bool(np.allclose(hg, og, rtol=1e-5, atol=0) and (pcost == ocost) and (plen == olen))
+        hv = h_value.numpy()[:ns]
+        gi = int(np.argmax(hv))                # first maximum = the candidate the GPU's argmax selects among the sample
+        parity = bool(np.allclose(hg, og, rtol=1e-5, atol=0) and (pcost == ocost) and (plen == olen) and gi == oi)
         cpu = {"value": b1, "unit": "evals/s", "cores": 1, "kind": "port",
                "sample": "first %d of the %d candidates, 1 thread, faithful port of the reference evaluator path (voxel vector + quadratic erase loop)" % (ns, T),
                "linear_filter_1core": b2, "linear_filter_all_cores": b3, "host_cores": cores,
-               "plan_s": oplan_s, "parity_on_sample": parity}
+               "plan_s": oplan_s, "parity_on_sample": parity, "selected_on_sample": {"gpu": gi, "cpu": int(oi)}}
+        config1 = config1_cycle()
 
     line = {
         "metric": "candidate-view evals/sec on 4096^2 cost map", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 counts + f64 gain", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "candidates_per_gpu": T, "map": "%dx%d" % (W, H), "half_fov": HALF_FOV,
-                   "l2": "flushed between timed steps (256 MiB write, untimed); the scanned planes (4 + 16 MiB) are smaller than L2",
-                   "sharding": ("single GPU" if world == 1 else
-                                "candidates sharded, map replicated; the gain kernel's last CTA stores each shard's 16-byte winner into every peer's mailbox "
-                                "over NVLink (peer memory), waits for the peers' records of the same step and merges them: every step ends with the global "
-                                "winner on every rank, one launch per step, no collective call on the data path" if exchange == "p2p" else
-                                "candidates sharded, map replicated, NCCL all_gather of one 16-byte record per rank per step + one merge kernel; "
-                                "the gather of step k overlaps the gain kernel of step k+1, the last gather is timed in full"),
-                   "exchange": exchange, "exchange_note": p2p_note, "exchange_other": other},
+        "config": bench_config(world),
+        "exchange": {"kind": exchange, "note": p2p_note, "other": other,
+                     "how": ("single GPU" if world == 1 else
+                             "the gain kernel's last CTA stores each shard's 16-byte winner into every peer's mailbox over NVLink (peer memory), waits for the "
+                             "peers' records of the same step and merges them: every step ends with the global winner on every rank, one launch per step, "
+                             "no collective call on the data path" if exchange == "p2p" else
+                             "NCCL all_gather of one 16-byte record per rank per step + one merge kernel; the gather of step k overlaps the gain kernel of "
+                             "step k+1, the last gather is timed in full")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "cycle": {"plan_ms": float(np.median(plan_ms)), "plan_cost": pcost, "plan_path_nodes": plen, "plan_stats": pstats,
                   "eval_ms": total_ms / args.steps, "ms_per_full_cycle": float(np.median(plan_ms)) + total_ms / args.steps,
@@ -602,6 +674,7 @@ def main():
                   "note": "plan = fp64 cost-to-go field + canonical path + mask through sipp_plan FROM SCRATCH (host call, wall clock); "
                           "incremental = the same call after a patch ingest, warm-started from the previous field"},
         "selected": {"index": best_index, "value": best_value}, "wall_s_timed_region": wall,
+        "config1": config1,
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -1,9 +1,13 @@
 mkdir -p gpurun_out
-J=gpurun_out/r2_j20
-( timeout 600 python -m pytest tests/test_gpu_batch.py -m gpu -x -q --timeout 300 --timeout-method thread ) > ${J}_batch.log 2>&1
-tail -n 3 ${J}_batch.log | cut -c1-400
-for cfg in "128 1 8" "128 2 4" "128 4 4" "512 2 8" "512 4 4" "1024 4 4"; do
-  set -- $cfg
-  ( SIPP_BATCH_THREADS=$3 timeout 300 python tools/ensemble_bench.py --maps $1 --cycles 16 --mode batch --batches $2 --check 1 ) > ${J}_ens_m$1_b$2.json 2> ${J}_ens_m$1_b$2.err
-  python -c "import json,sys; d=json.loads(open('${J}_ens_m$1_b$2.json').read().strip().splitlines()[-1]); print('maps $1 batches $2 threads $3:', round(d['value']), d['ms_per_map_cycle_in_ensemble'])" || tail -n 3 ${J}_ens_m$1_b$2.err
-done
+J=gpurun_out/r2_j21
+( timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread ) > ${J}_pytest.log 2>&1
+tail -n 12 ${J}_pytest.log | cut -c1-300
+( timeout 900 python bench.py > ${J}_bench.json 2> ${J}_bench.err ) ; echo "bench rc $?"; tail -c 1200 ${J}_bench.json; tail -n 3 ${J}_bench.err
+( timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${J}_bench_ref.json 2> ${J}_bench_ref.err ); echo "ref rc $?"; tail -c 400 ${J}_bench_ref.json
+( timeout 900 python tools/config_bench.py > ${J}_configs.json 2> ${J}_configs.err ); echo "configs rc $?"; tail -c 600 ${J}_configs.json
+# launch list of the same bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
+( timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${J}_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline ) > ${J}_ncu_l.log 2>&1
+python tools/launch_summary.py ${J}_launches.csv > ${J}_launches.txt 2>&1; head -n 30 ${J}_launches.txt | cut -c1-200
+# one full-set capture of the top kernels on the short fixed workload
+( timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_gain|k_relax|k_backtrack|k_pred|k_inval|k_weights" -c 12 -o ${J}_full python tools/prof_run.py 4096 65536 3 ) > ${J}_ncu_f.log 2>&1
+python tools/ncu_summary.py ${J}_full.ncu-rep > ${J}_full.txt 2>&1; head -n 40 ${J}_full.txt | cut -c1-160
