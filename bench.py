@@ -38,6 +38,15 @@ W = H = 4096
 SEED = 1003
 K_OBS = 1500
 T_PER_GPU = 65536
+SCALING = "weak"
+if os.environ.get("SIPP_BENCH_WORKLOAD") == "config4":
+    # BASELINE config 4 (not the default line): full planning cycle with 65536 candidates IN TOTAL on the 8192^2 map at 1/2/4/8 GPUs —
+    # strong scaling of the evaluation (the candidates are split), the follower plan is replicated on every GPU (one dependent front)
+    W = H = 8192
+    SEED = 1004
+    K_OBS = 6000
+    T_PER_GPU = 65536 // max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    SCALING = "strong"
 HALF_FOV = 32
 NPG = 0.001
 ALG_BYTES_PER_EVAL = 4257   # (2*32+1)^2 one-byte cell records + 16 B pose in + 16 B result out
@@ -51,8 +60,8 @@ def bench_config(n_gpus):
     return {"workload": WORKLOAD, "candidates_per_gpu": T_PER_GPU, "map": "%dx%d" % (W, H), "half_fov": HALF_FOV,
             "evaluator": "RRTStarEvaluator (count mode, non_path_voxel_gain %g)" % NPG, "n_gpus": n_gpus,
             "l2": "flushed between timed steps (256 MiB write, untimed); the scanned planes (4 + 16 MiB) are smaller than L2",
-            "sharding": ("single GPU" if n_gpus == 1 else "candidates sharded over %d GPUs (weak scaling: %d each), map replicated per GPU; the only "
-                         "cross-GPU traffic is each shard's 16-byte winner" % (n_gpus, T_PER_GPU))}
+            "sharding": ("single GPU" if n_gpus == 1 else "candidates sharded over %d GPUs (%s scaling: %d each), map replicated per GPU; the only "
+                         "cross-GPU traffic is each shard's 16-byte winner" % (n_gpus, SCALING, T_PER_GPU))}
 
 
 def measured_peaks():
@@ -194,7 +203,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "candidate-view evals/sec on 4096^2 cost map", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 counts + f64 gain", "data": "synthetic",
+        "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "u8 counts + f64 gain", "data": "synthetic",
         "config": bench_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind,
                          "sample": "%d of the %d candidates per step, %d worker threads (the reference itself is single-threaded: one module "
@@ -656,7 +665,7 @@ def main():
 
     line = {
         "metric": "candidate-view evals/sec on 4096^2 cost map", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
         "dtype": "u8 counts + f64 gain", "data": "synthetic",
         "config": bench_config(world),
         "exchange": {"kind": exchange, "note": p2p_note, "other": other,
