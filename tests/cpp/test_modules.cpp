@@ -5,6 +5,7 @@
 //
 //   test_modules cpu   registry / param parsing / tree flattening / updater predicate / error path without a device
 //   test_modules gpu   full parity on cuda:0 (map ingest, plan, per-node gain, batched update pass, selection)
+#include <chrono>
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -378,8 +379,17 @@ static int testGpu() {
       orc_update_tree(orc, &P, &U, N, t.parent.data(), t.end_xy.data(), t.start_xy.data(), g2.data(), oc.data(), v2.data(), t2.data(),
                       cur_xy, path_changed, 0, nullptr);
       // the planner calls updateSegment(root) first (mav_active_3d_planning.patch:56), then once per node
+      const auto tm0 = std::chrono::steady_clock::now();
       CHECK(gev->updateSegment(&root), "updateSegment(root)");
+      const auto tm1 = std::chrono::steady_clock::now();
       for (int i = 1; i < N; ++i) CHECK(gev->updateSegment(t.nodes[i]), "updateSegment(node)");
+      const auto tm2 = std::chrono::steady_clock::now();
+      // what the planner pays per re-evaluation of the tree through the module interface: the root call flattens the tree, runs
+      // the whole pass on the device (sipp_update_tree: copies in, predicate + compaction, gain, values, copies out) and writes
+      // the nodes back; the per-node calls that follow find their results already there
+      std::printf("    timing %s pass %d: updateSegment(root) %.3f ms for %d nodes (%d re-scored), the %d per-node calls after it %.3f ms\n", cfg.type, pass,
+                  std::chrono::duration<double, std::milli>(tm1 - tm0).count(), N, gev->lastBatchSize(), N - 1,
+                  std::chrono::duration<double, std::milli>(tm2 - tm1).count());
       int dg = 0, dv = 0, dt = 0;
       // the root-first call re-scores the root too unless the chain starts with an RRTStarUpdater (pinned by tests/test_ref_pin.py)
       for (int i = (U.updater == SIPP_UPD_RRT_STAR ? 1 : 0); i < N; ++i) {
