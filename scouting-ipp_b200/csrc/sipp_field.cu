@@ -48,6 +48,7 @@ struct RelaxArgs {
   const double* tile_w;     // [ntiles][4][TP][TP] edge-weight cache (k_weights)
   int spin_limit;           // watchdog: a warp that polls an empty queue this many times aborts the kernel
   int mode;                 // bit0: publish after every sweep (else once per run); bit1: exclusive tile ownership (owner re-runs)
+  int check;                // 1 (needs mode bit0): test whether the opposite sweep has anything to do before running it (sweep_needed)
   uint8_t* touched;         // optional [ntiles]: set for every tile that was activated (incremental re-plan: where d may have changed)
 };
 enum { CTL_HEAD = 0, CTL_TAIL = 1, CTL_PENDING = 2, CTL_ACTIVATIONS = 3, CTL_SWEEPS = 4, CTL_ABORT = 5, CTL_PUSHES = 6 };
@@ -149,6 +150,28 @@ __device__ __forceinline__ bool sweep_rows(TileSmem& t, int lane, uint32_t& rows
   }
   __syncwarp();                                    // the sweep's stores are visible to the whole warp
   return __any_sync(0xFFFFFFFFu, chg);
+}
+
+// Would a sweep in direction DIR lower anything? After a sweep in the OPPOSITE direction every cell satisfies the inequalities towards
+// that sweep's previous row and towards its row neighbours (rows are final once processed), so the tile is at its local fixed point
+// iff no cell can be lowered from the three cells of the row a DIR sweep would come from — exactly the first thing such a sweep
+// tests for every row, here without the in-row shuffle loop and without any dependence between rows (the loads and adds of all
+// rows overlap). One sweep + this test replaces the "confirming" second sweep of a run whose front came from one side.
+template <int DIR>
+__device__ __forceinline__ bool sweep_needed(const TileSmem& t, int lane) {
+  const int lx = lane + 1;
+  bool need = false;
+#pragma unroll 8
+  for (int r = 1; r <= TS; ++r) {
+    const int p = r - DIR;                                  // the row a DIR sweep relaxes row r against
+    const double wn = (DIR > 0) ? t.ws[r - 1][lx] : t.ws[r][lx];
+    const double wnl = (DIR > 0) ? t.wse[r - 1][lx - 1] : t.wsw[r][lx];
+    const double wnr = (DIR > 0) ? t.wsw[r - 1][lx + 1] : t.wse[r][lx];
+    double ca = __dadd_rn(t.d[p][lx], wn);
+    { const double c1 = __dadd_rn(t.d[p][lx - 1], wnl), c2 = __dadd_rn(t.d[p][lx + 1], wnr); const double c3 = c1 < c2 ? c1 : c2; ca = c3 < ca ? c3 : ca; }
+    need |= ca < t.d[r][lx];
+  }
+  return __any_sync(0xFFFFFFFFu, need);
 }
 
 // Loads d of the 34x34 window whose interior starts at (x0, y0) into shared memory. Loads are issued in batches (plain
@@ -394,7 +417,10 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
         SIPP_TICK(2)
         const bool last = !c && it >= 1;
         if (c) any_change = true;
-        if ((a.mode & 1) ? (c || (last && !published)) : last) {
+        // with the one-sided test below a run may end after its first sweep: the publish every run owes (offers of values that were
+        // pushed into this tile to its other neighbours) then happens here instead of after a second sweep
+        const bool owe = !published && (last || (a.check && it == 0));
+        if ((a.mode & 1) ? (c || owe) : last) {
           if (!(a.mode & 1)) rows_changed = any_change ? 0xFFFFFFFFu : 0u;   // one publish per run: store every row
           published = true;
           // ---- store what this lane lowered in this sweep
@@ -490,6 +516,8 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
           SIPP_TICK(4)
         }
         if (last) break;
+        // the opposite sweep only if it has something to do (tested on the halo as the publish above left it)
+        if (a.check && !((it & 1) ? sweep_needed<+1>(t, lane) : sweep_needed<-1>(t, lane))) break;
       }
       // ---- done with this run: idle again, unless one of our cells was lowered meanwhile
       int again = 0;
@@ -1372,6 +1400,8 @@ int plan_prepare(sipp_ctx* ctx, PlanArgsAll& A, uint8_t* d_seed, bool blk, const
     ra.spin_limit = kSpinLimit;
     static const int mode_env = getenv("SIPP_RELAX_MODE") ? atoi(getenv("SIPP_RELAX_MODE")) : 1;   // measured best at 4096^2 (tools/plan_bench.py)
     ra.mode = mode_env;
+    static const int check_env = getenv("SIPP_RELAX_CHECK") ? atoi(getenv("SIPP_RELAX_CHECK")) : 1;
+    ra.check = (check_env != 0 && (mode_env & 1)) ? 1 : 0;
     ra.touched = incremental ? ctx->d_tile_seed : nullptr;
     // persistent workers: one CTA per SM for a large map; a small map gets one warp per ~3 tiles so that several relaxations share
     // the GPU instead of queueing for all SMs

@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-J=gpurun_out/r2_j22
-( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > ${J}_smoke.log 2>&1; tail -n 3 ${J}_smoke.log | cut -c1-300
-( timeout 300 ./tests/cpp/test_modules gpu ) > ${J}_modules.log 2>&1; grep -n "timing\|failure" ${J}_modules.log | cut -c1-250
+J=gpurun_out/r2_j23
+for W in 4096 8192 1024 640; do
+  ( timeout 400 python tools/relax_ab.py $W "0,SIPP_RELAX_CHECK=0" "0,SIPP_RELAX_CHECK=1" ) > ${J}_ab$W.log 2>&1
+  cut -c1-330 ${J}_ab$W.log
+done
+( SIPP_RELAX_CHECK=1 timeout 200 python tools/replan_bench.py 4096 ) > ${J}_replan4096.log 2>&1; tail -n 3 ${J}_replan4096.log | cut -c1-300
