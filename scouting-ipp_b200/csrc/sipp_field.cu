@@ -423,11 +423,13 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
         if ((a.mode & 1) ? (c || owe) : last) {
           if (!(a.mode & 1)) rows_changed = any_change ? 0xFFFFFFFFu : 0u;   // one publish per run: store every row
           published = true;
-          // ---- store what this lane lowered in this sweep
-          {
+          // ---- store what this lane lowered in this sweep. The border ring first: it is what the neighbours read as their halo, and it
+          // has to be visible before they are told to look; the interior (nobody else reads it) follows AFTER the pushes below, off the
+          // chain of dependent activations that bounds the plan
+          const bool edge_col = lane == 0 || lane == 31;
+          const uint32_t ring_rows = edge_col ? 0xFFFFFFFFu : 0x80000001u;
+          auto store_rows = [&](uint32_t rc) {
             const int gx = x0 + lane;
-            const bool edge_col = lane == 0 || lane == 31;
-            uint32_t rc = rows_changed;
             while (rc) {
               const int r = __ffs(rc) - 1;
               rc &= rc - 1;
@@ -439,7 +441,8 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
               else
                 *dst = v;                                 // interior: this warp is the only writer
             }
-          }
+          };
+          store_rows(rows_changed & ring_rows);
           // ---- relax ACROSS the tile border: every halo cell n (it belongs to a neighbour tile) against its up to three
           // neighbours c on our side, cand = d[c] + w(c,n) — bit for bit what the neighbour would compute from its own halo.
           // A neighbour is queued only if cand beats the value we hold for n (then our copy is updated too), so a tile is
@@ -513,6 +516,7 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
             }
             __syncwarp();
           }
+          store_rows(rows_changed & ~ring_rows);         // the interior (ordered before this run's release by the fence there)
           SIPP_TICK(4)
         }
         if (last) break;

@@ -40,7 +40,7 @@ if __name__ == "__main__":
     W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     kernels = sys.argv[2:] or ["0", "1"]
     ref = "/tmp/relax_ab_ref_%d.npy" % W
-    if os.path.exists(ref):
+    if os.path.exists(ref) and not os.environ.get("AB_KEEP_REF"):      # AB_KEEP_REF=1: compare with the field a previous invocation saved
         os.remove(ref)
     for k in kernels:
         env = dict(os.environ)
