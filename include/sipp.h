@@ -347,8 +347,8 @@ int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params
  * state (sipp_map_download, sipp_field_download, sipp_path_download ... work between batch calls); they must be idle when a batch
  * call starts and must not be driven from other threads while it runs. Results are bit-identical to the same calls made map by
  * map (tests/test_gpu_batch.py).
- * Limits: maps without compute_closest_observed; sipp_batch_cycle serves the count-type evaluators on the 2-bit plane
- * (RRTStarEvaluator without distance discount, ExpandReachableArea, Naive; half_fov <= 96) and refuses the others.
+ * Limits: maps without compute_closest_observed; sipp_batch_cycle serves every evaluator except ExpandLowCostArea (its
+ * closest-observed planes) and RRTStarEvaluator's binary + discount mode (per-candidate start points) and refuses those two.
  * Replaces, for evaluation runs over many maps, the one-planner-process-per-saved-map loop of data_analysis/evaluation.py:39-62,
  * 139-144 + planexp_base_planners/src/planexp_eval_planner.cpp:201-303 and the one-experiment-per-map loop of
  * advanced_planner_ros/scripts/run_experiment.sh:190-212. */

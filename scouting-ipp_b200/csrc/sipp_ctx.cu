@@ -1483,6 +1483,7 @@ static int batch_cycle_enqueue(sipp_batch* b, const sipp_eval_params* params, in
   bool any_views = false;
   std::vector<uint8_t> stale_views((size_t)m, 0);
   if (params->evaluator == SIPP_EVAL_EXPAND_LOW_COST) return batch_fail(b, SIPP_ERR_UNSUPPORTED, "batched evaluation does not serve ExpandLowCostAreaEvaluator");
+  std::vector<int> kinds((size_t)m, 0), smems((size_t)m, 0), wpcs((size_t)m, 0);
   for (int i = 0; i < m; ++i)
     if (!xy[i] || !cost[i]) return batch_fail(b, SIPP_ERR_INVALID_ARG, "candidates of map %d == NULL", i);
   std::vector<int> rcs((size_t)m, SIPP_OK);
@@ -1505,11 +1506,12 @@ static int batch_cycle_enqueue(sipp_batch* b, const sipp_eval_params* params, in
     fs.index_offset = 0;
     fs.peer = nullptr;
     fs.peer_mode = 0;
-    rcs[i] = gain_fill_batch_args(ctx, params, g, n, d_xy, d_cost, d_gain, d_term, d_value, &fs, h_gain + gb * i);
+    rcs[i] = gain_fill_batch_args(ctx, params, g, n, d_xy, d_cost, d_gain, d_term, d_value, &fs, h_gain + gb * i, &kinds[i], &smems[i], &wpcs[i]);
   });
   for (int i = 0; i < m; ++i) {
     if (rcs[i] != SIPP_OK) return batch_err(b, rcs[i], b->ctx[i]);
     any_views |= stale_views[i] != 0;
+    if (kinds[i] != kinds[0] || smems[i] != smems[0] || wpcs[i] != wpcs[0]) return batch_fail(b, SIPP_ERR_INVALID_ARG, "map %d needs another kernel shape than map 0", i);
   }
   SIPP_BATCH_CUDA(b, cudaMemcpyAsync(b->d_cyc, b->h_cyc, coff + cb * m, cudaMemcpyHostToDevice, b->stream));
   for (int i = 0; i < m; ++i)          // every argument block is in place: only now do the contexts learn that their views get rebuilt
@@ -1524,7 +1526,7 @@ static int batch_cycle_enqueue(sipp_batch* b, const sipp_eval_params* params, in
     SIPP_BATCH_CUDA(b, launch_build_views_batch(b->d_cyc, m, b->ctx[0]->pitch, b->ctx[0]->H, b->stream));
     b->launches += 1;
   }
-  if ((rc = gain_launch_batch(b->ctx[0], b->d_cyc + goff, m, n, b->stream)) != SIPP_OK) return batch_err(b, rc, b->ctx[0]);
+  if ((rc = gain_launch_batch(b->ctx[0], b->d_cyc + goff, m, n, kinds[0], smems[0], wpcs[0], b->stream)) != SIPP_OK) return batch_err(b, rc, b->ctx[0]);
   b->launches += 1;
   SIPP_BATCH_CUDA(b, cudaMemcpyAsync(b->h_best, d_best, sizeof(BestRec) * m, cudaMemcpyDeviceToHost, b->stream));
   return SIPP_OK;

@@ -666,10 +666,28 @@ k_gain(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUten
 }
 // batched (sipp_batch_cycle: an ensemble of maps scored by one launch): block (x, y) scores candidates of map y with the argument
 // block as[y]. Count-type evaluators on the 2-bit plane only — that form takes no tensor map.
+// One item per map: the argument block and, for the tiled forms, the map's two tensor maps IN DEVICE MEMORY (written by the host before
+// the launch, 128-byte aligned; cp.async.bulk.tensor takes a tensor map from global memory as well as from the parameter space).
+struct GainBatchItem {
+  alignas(128) CUtensorMap tm_rec;
+  alignas(128) CUtensorMap tm_aux;
+  alignas(16) GainArgs a;
+};
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 2)
-k_gain_count_b(const GainArgs* __restrict__ as) {
-  const GainArgs a = as[blockIdx.y];
+k_gain_count_b(const GainBatchItem* __restrict__ items) {
+  const GainArgs a = items[blockIdx.y].a;
   gain_body<MODE_COUNT, true>(nullptr, nullptr, a);
+}
+// the tiled byte path for the floating-point evaluators (and the count modes when the 2-bit plane is switched off)
+template <int MODE>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
+k_gain_tiled_b(const GainBatchItem* __restrict__ items) {
+  const GainBatchItem& it = items[blockIdx.y];
+  const GainArgs a = it.a;
+  // the tensor maps were written into global memory by a host copy: the tensor-map proxy has to acquire them before its first use
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(&it.tm_rec)) : "memory");
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(&it.tm_aux)) : "memory");
+  gain_body<MODE, false>(&it.tm_rec, &it.tm_aux, a);
 }
 
 // ---- host side: tensor maps -----------------------------------------------------------------------------
@@ -874,24 +892,62 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
 }
 
 // ---- batched gain + value + argmax (sipp_batch_cycle) ---------------------------------------------------------------------------
-size_t gain_args_bytes() { return sizeof(GainArgs); }
+size_t gain_args_bytes() { return sizeof(GainBatchItem); }
 
-// argument block of map `ctx` for a batched launch (count-type evaluator on the 2-bit plane, fused value + argmax into fs->best_out)
+// item of map `ctx` for a batched launch (fused value + argmax into fs->best_out). *kind_out: 0 = count-type evaluator on the 2-bit
+// plane, 1 + MODE = tiled byte path of that mode; every map of a batch must come out with the same kind (same parameters: it does)
 int gain_fill_batch_args(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_cost, double* d_gain,
-                         uint8_t* d_terminal, double* d_value, const FusedSelect* fs, void* dst) {
-  GainArgs a;
+                         uint8_t* d_terminal, double* d_value, const FusedSelect* fs, void* dst, int* kind_out, int* smem_out, int* wpc_out) {
+  GainBatchItem it;
+  memset(&it, 0, sizeof(it));
   int mode = 0;
   bool packed = false, need_aux = false;
-  int rc = gain_prepare(ctx, p, g, n, d_xy, nullptr, d_cost, d_gain, nullptr, d_terminal, d_value, nullptr, nullptr, nullptr, fs, a, &mode, &packed, &need_aux);
+  int rc = gain_prepare(ctx, p, g, n, d_xy, nullptr, d_cost, d_gain, nullptr, d_terminal, d_value, nullptr, nullptr, nullptr, fs, it.a, &mode, &packed, &need_aux);
   if (rc != SIPP_OK) return rc;
-  if (mode != MODE_COUNT || !packed)
-    return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "batched evaluation serves the count-type evaluators on the 2-bit plane (RRTStarEvaluator without distance "
-                        "discount, ExpandReachableArea, Naive; half_fov <= 96); evaluator %d / half_fov %d is not one of them", p->evaluator, p->half_fov);
-  memcpy(dst, &a, sizeof(a));
+  if (mode == MODE_LOW_COST)
+    return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "batched evaluation does not serve ExpandLowCostAreaEvaluator (its closest-observed planes are not maintained by the batched ingest)");
+  if (mode == MODE_COUNT && p->evaluator == SIPP_EVAL_RRT_STAR && p->do_binary_check && p->use_distance_discount)
+    return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "batched evaluation does not serve RRTStarEvaluator's binary + discount mode (it needs per-candidate start points)");
+  *kind_out = packed ? 0 : 1 + mode;
+  *smem_out = 0;
+  *wpc_out = ctx->gain_warps > 0 ? ctx->gain_warps : kMaxWarpsPerCta;
+  if (!packed) {
+    const CUtensorMap* tm_rec = cached_tmap(ctx, p->half_fov, 0, &rc);
+    if (!tm_rec) return rc;
+    const CUtensorMap* tm_aux = tm_rec;
+    if (need_aux) {
+      tm_aux = cached_tmap(ctx, p->half_fov, 1, &rc);
+      if (!tm_aux) return rc;
+    }
+    memcpy(&it.tm_rec, tm_rec, sizeof(CUtensorMap));
+    memcpy(&it.tm_aux, tm_aux, sizeof(CUtensorMap));
+    int wpc = ctx->gain_warps > 0 ? ctx->gain_warps : kMaxWarpsPerCta;
+    while (wpc > 1 && (size_t)wpc * it.a.stages * it.a.slot_bytes > 220 * 1024) --wpc;
+    *smem_out = wpc * it.a.stages * it.a.slot_bytes;
+    *wpc_out = wpc;
+    if (*smem_out > 221 * 1024) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d needs %d bytes of shared memory per CTA", p->half_fov, *smem_out);
+  }
+  memcpy(dst, &it, sizeof(it));
   return SIPP_OK;
 }
 
-int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, cudaStream_t s) {
+template <int MODE>
+static cudaError_t launch_tiled_b(sipp_ctx* c0, const GainBatchItem* items, int grid, int m, int threads, int smem, cudaStream_t s) {
+  static std::mutex mu;
+  static bool done[64] = {};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[c0->device & 63]) {
+      cudaError_t e0 = cudaFuncSetAttribute(k_gain_tiled_b<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+      if (e0 != cudaSuccess) return e0;
+      done[c0->device & 63] = true;
+    }
+  }
+  k_gain_tiled_b<MODE><<<dim3((unsigned)grid, (unsigned)m), threads, smem, s>>>(items);
+  return cudaGetLastError();
+}
+
+int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, int kind, int smem, int wpc, cudaStream_t s) {
   if (m <= 0 || n <= 0) return SIPP_OK;
   int num_sms = 0;
   {
@@ -901,20 +957,37 @@ int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, cudaStream
     auto& di = info[c0->device & 63];
     if (!di.done) {
       cudaError_t e0 = cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, c0->device);
-      if (e0 != cudaSuccess) return sipp_set_err(c0, SIPP_ERR_CUDA, "k_gain_count_b setup: %s", cudaGetErrorString(e0));
+      if (e0 != cudaSuccess) return sipp_set_err(c0, SIPP_ERR_CUDA, "batched gain setup: %s", cudaGetErrorString(e0));
       di.done = true;
     }
     num_sms = di.num_sms;
   }
-  const int wpc = c0->gain_warps > 0 ? c0->gain_warps : kMaxWarpsPerCta;
-  const int want = (n + wpc - 1) / wpc;
-  // every map gets the same grid; together they should fill the GPU about twice (2 CTAs per SM)
-  int per_map = (2 * num_sms + m - 1) / m;
-  if (per_map < 1) per_map = 1;
-  int grid = want < per_map ? want : per_map;
-  if (grid > kSelMaxBlocks) grid = kSelMaxBlocks;
-  k_gain_count_b<<<dim3((unsigned)grid, (unsigned)m), wpc * 32, 0, s>>>(reinterpret_cast<const GainArgs*>(d_args));
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return sipp_set_err(c0, SIPP_ERR_CUDA, "k_gain_count_b launch: %s", cudaGetErrorString(e));
+  const GainBatchItem* items = reinterpret_cast<const GainBatchItem*>(d_args);
+  cudaError_t e = cudaSuccess;
+  if (kind == 0) {
+    const int want = (n + wpc - 1) / wpc;
+    // every map gets the same grid; together they should fill the GPU about twice (2 CTAs per SM)
+    int per_map = (2 * num_sms + m - 1) / m;
+    if (per_map < 1) per_map = 1;
+    int grid = want < per_map ? want : per_map;
+    if (grid > kSelMaxBlocks) grid = kSelMaxBlocks;
+    k_gain_count_b<<<dim3((unsigned)grid, (unsigned)m), wpc * 32, 0, s>>>(items);
+    e = cudaGetLastError();
+  } else {
+    // tiled form: one CTA per SM (its tile slots fill the shared memory); the maps share the SMs
+    const int want = (n + wpc - 1) / wpc;
+    int per_map = (num_sms + m - 1) / m;
+    if (per_map < 1) per_map = 1;
+    int grid = want < per_map ? want : per_map;
+    if (grid > kSelMaxBlocks) grid = kSelMaxBlocks;
+    switch (kind - 1) {
+      case MODE_COUNT: e = launch_tiled_b<MODE_COUNT>(c0, items, grid, m, wpc * 32, smem, s); break;
+      case MODE_RRT_DISCOUNT: e = launch_tiled_b<MODE_RRT_DISCOUNT>(c0, items, grid, m, wpc * 32, smem, s); break;
+      case MODE_GOAL_DISTANCE: e = launch_tiled_b<MODE_GOAL_DISTANCE>(c0, items, grid, m, wpc * 32, smem, s); break;
+      case MODE_AVG_VIEW_COST: e = launch_tiled_b<MODE_AVG_VIEW_COST>(c0, items, grid, m, wpc * 32, smem, s); break;
+      default: return sipp_set_err(c0, SIPP_ERR_UNSUPPORTED, "batched evaluation: no kernel for mode %d", kind - 1);
+    }
+  }
+  if (e != cudaSuccess) return sipp_set_err(c0, SIPP_ERR_CUDA, "batched gain launch: %s", cudaGetErrorString(e));
   return SIPP_OK;
 }

@@ -267,7 +267,7 @@ cudaError_t launch_ingest_patch_batch(const void* d_args, int m, int rows, int c
 cudaError_t launch_build_views_batch(const void* d_args, int m, size_t pitch, int H, cudaStream_t s);
 size_t gain_args_bytes();
 int gain_fill_batch_args(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_cost, double* d_gain,
-                         uint8_t* d_terminal, double* d_value, const FusedSelect* fs, void* dst);
-int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, cudaStream_t s);
+                         uint8_t* d_terminal, double* d_value, const FusedSelect* fs, void* dst, int* kind_out, int* smem_out, int* wpc_out);
+int gain_launch_batch(sipp_ctx* c0, const void* d_args, int m, int n, int kind, int smem, int wpc, cudaStream_t s);
 
 #endif  // SIPP_INTERNAL_H_

@@ -90,6 +90,39 @@ def test_batch_episode_matches_native_episode_and_oracle():
     b.close()
 
 
+@pytest.mark.parametrize("kw", [dict(evaluator=sipp.EVAL_GOAL_DISTANCE, max_gain=100.0), dict(evaluator=sipp.EVAL_AVERAGE_VIEW_COST),
+                                dict(evaluator=sipp.EVAL_RRT_STAR, use_distance_discount=True, non_path_voxel_gain=0.005),
+                                dict(evaluator=sipp.EVAL_EXPAND_REACHABLE, discount_factor=0.1), dict(evaluator=sipp.EVAL_NAIVE),
+                                dict(evaluator=sipp.EVAL_RRT_STAR, do_binary_check=True),
+                                dict(evaluator=sipp.EVAL_GOAL_DISTANCE, max_gain=100.0, bounding_volume=(1.0, 30.0, 2.0, 25.0))])
+def test_batch_cycle_serves_every_evaluator_family(kw):
+    """the tiled floating-point evaluators (tensor maps per map in device memory) and the count-type ones through one batched launch:
+    gains bit-identical to the same evaluator called map by map, the same selected candidate"""
+    m, T = 4, 1500
+    params = sipp.make_params(half_fov=32, **kw)
+    labs, single, batched = [], [], []
+    for k in range(m):
+        lab, desc = make_map(3400 + k, sipp.make_desc)
+        obs = synth.make_observed(W, H, 3400 + k, 10 + 2 * k)
+        for group in (single, batched):
+            c = sipp.Context(desc)
+            c.map_upload_full(lab, obs)
+            group.append(c)
+    b = sipp.Batch(batched)
+    plans = b.plan()
+    rng = np.random.default_rng(11)
+    xy = [np.ascontiguousarray(rng.uniform([-0.5, -0.5], [W * synth.MPP + 0.5, H * synth.MPP + 0.5], (T, 2))) for _ in range(m)]     # some views hang over the map edge
+    cost = [rng.uniform(0.5, 3.0, T) for _ in range(m)]
+    bi, bv, gains = b.cycle(params, xy, cost, want_gain=True)
+    for k in range(m):
+        c, st, _, n = single[k].plan(path_cap=1)
+        assert plans[k] == (c, st, n)
+        g, _, v, i, val = single[k].cycle(params, xy[k], cost[k])
+        assert np.array_equal(g, gains[k], equal_nan=True), (kw, k, np.flatnonzero(g != gains[k])[:5])
+        assert i == bi[k] and (val == bv[k] or (np.isnan(val) and np.isnan(bv[k]))), (kw, k, i, bi[k], val, bv[k])
+    b.close()
+
+
 def test_batch_refuses_what_it_does_not_serve():
     lab, desc = make_map(3300, sipp.make_desc)
     a, c = sipp.Context(desc), sipp.Context(desc)
@@ -101,8 +134,8 @@ def test_batch_refuses_what_it_does_not_serve():
     b.ingest([0, 0], [0, 0], [lab[:320, :320], lab[:320, :320]])
     b.plan()
     xy, cost = synth.make_candidates(W, H, 1, 64)
-    with pytest.raises(sipp.SippError) as e:                    # a floating-point evaluator: not on the 2-bit plane
-        b.cycle(sipp.make_params(sipp.EVAL_GOAL_DISTANCE, half_fov=32), [xy, xy], [cost, cost])
+    with pytest.raises(sipp.SippError) as e:                    # its closest-observed planes are not maintained by the batched ingest
+        b.cycle(sipp.make_params(sipp.EVAL_EXPAND_LOW_COST, half_fov=32), [xy, xy], [cost, cost])
     assert e.value.code == sipp.ERR_UNSUPPORTED
     bi, bv = b.cycle(sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001), [xy, xy], [cost, cost])
     assert bi[0] == bi[1] and bv[0] == bv[1]

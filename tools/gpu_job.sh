@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-J=gpurun_out/r2_j25
-for W in 4096 8192 640; do
-  ( SIPP_LIB_PATH=$PWD/scouting-ipp_b200/libsipp_prev.so timeout 400 python tools/relax_ab.py $W 0 ) > ${J}_prev$W.log 2>&1
-  ( AB_KEEP_REF=1 timeout 400 python tools/relax_ab.py $W 0 ) > ${J}_new$W.log 2>&1
-  cut -c1-200 ${J}_prev$W.log ${J}_new$W.log
-done
+J=gpurun_out/r2_j26
+( timeout 600 python -m pytest tests/test_gpu_batch.py -m gpu -q --timeout 300 --timeout-method thread ) > ${J}_batch.log 2>&1
+tail -n 30 ${J}_batch.log | cut -c1-300
