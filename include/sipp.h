@@ -340,6 +340,21 @@ int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params
                      const double* cand_xy, const double* cand_cost, int32_t fov, int32_t init, double start_x, double start_y,
                      double* path_cost, int32_t* plan_status, int32_t* path_len, int32_t* best_index, double* best_value);
 
+/* ---- segments viewed from several sampled viewpoints (sensor_model/sampling_time > 0) ---------------------------------------
+ * SensorModelPlanExp::getVisibleVoxelsFromTrajectory (sensor_model_planexp.cpp:18-63) views a segment from every trajectory point
+ * sampleViewpoints (:65-90) selects — with the mounting translation applied (:28-31) — concatenates the views' voxel lists and
+ * removes only adjacent duplicates; the evaluators then count the whole list. The host selects the viewpoints (the rule is host
+ * logic over time stamps: plugin/sipp_modules.cpp), these calls score them: segment i has the views
+ * view_xy[view_offset[i] .. view_offset[i+1]) (view_offset: n + 1 entries starting at 0; a segment without views scores 0 and,
+ * for the evaluators that set it, is terminal — an empty voxel list). start_xy: trajectory[0] per segment (RRTStarEvaluator binary
+ * + discount; may be NULL otherwise). One view per segment gives exactly sipp_gain_batch / sipp_update_tree. */
+int sipp_gain_batch_views(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const int32_t* view_offset, const double* view_xy,
+                          const double* start_xy, double* gain, uint32_t* counts, uint8_t* terminal);
+int sipp_update_tree_views(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
+                           const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                           const double* cur_xy, int32_t path_changed, int32_t* n_rescored, const double* cost_below, const int32_t* view_offset,
+                           const double* view_xy);
+
 /* ---- batched ensembles: m maps of one size on one device advance together ---------------------------------------------------
  * Every kernel of a step (patch ingest, re-plan, view planes, gain + value + argmax) is launched ONCE for all maps (gridDim.y = m,
  * per-map argument blocks in device memory), with one host->device copy of the inputs, one device->host copy of the results and

@@ -177,6 +177,9 @@ def lib():
         L.orc_travel_cost.argtypes = [vp, vp, C.POINTER(TravelParams), i32, vp, vp, vp]
         L.orc_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(f64), i32, i32]
         L.orc_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+        L.orc_update_tree_views.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+        L.orc_gain_batch_views.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_sample_viewpoints.argtypes = [vp, i32, f64, vp, i32]
         _lib = L
     return _lib
 
@@ -318,6 +321,19 @@ class Oracle:
                                _ptr(terminal), int(variant), int(threads))
         return gain, counts, terminal
 
+    def gain_batch_views(self, params, view_off, view_xy, start_xy=None, variant=1):
+        """segments scored from several sampled viewpoints each (sensor_model/sampling_time > 0): segment i has the views
+        view_xy[view_off[i]:view_off[i+1]]"""
+        off = np.ascontiguousarray(view_off, dtype=np.int32)
+        n = off.shape[0] - 1
+        vxy = np.ascontiguousarray(view_xy, dtype=np.float64).reshape(-1, 2)
+        sxy = None if start_xy is None else np.ascontiguousarray(start_xy, dtype=np.float64).reshape(n, 2)
+        gain = np.zeros(n, np.float64)
+        counts = np.zeros((n, COUNTS_PER_CANDIDATE), np.uint32)
+        terminal = np.zeros(n, np.uint8)
+        self._L.orc_gain_batch_views(self._h, C.byref(params), n, _ptr(off), _ptr(vxy), _ptr(sxy), _ptr(gain), _ptr(counts), _ptr(terminal), int(variant))
+        return gain, counts, terminal
+
     def cost_integral(self, cparams, point_offset, points_xyz, parent_cost=None):
         off = np.ascontiguousarray(point_offset, dtype=np.int32)
         n = off.shape[0] - 1
@@ -352,7 +368,7 @@ class Oracle:
 
 
     def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, variant=1,
-                    cost_below=None):
+                    cost_below=None, view_off=None, view_xy=None):
         """literal pre-order emulation of one re-evaluation pass (orc_update_tree); returns (gain, value, terminal)"""
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         n = parent.shape[0]
@@ -364,9 +380,19 @@ class Oracle:
         cost = np.ascontiguousarray(cost, dtype=np.float64)
         cur = np.ascontiguousarray(cur_xy, dtype=np.float64)
         cb = None if cost_below is None else np.ascontiguousarray(cost_below, dtype=np.float64)
-        self._L.orc_update_tree(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g), _ptr(cost),
-                                _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), int(variant), _ptr(cb))
+        off = None if view_off is None else np.ascontiguousarray(view_off, dtype=np.int32)
+        vxy = None if view_xy is None else np.ascontiguousarray(view_xy, dtype=np.float64).reshape(-1, 2)
+        self._L.orc_update_tree_views(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g), _ptr(cost),
+                                      _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), int(variant), _ptr(cb), _ptr(off), _ptr(vxy))
         return g, v, t
+
+
+def sample_viewpoints(times_ns, sampling_time):
+    """SensorModelPlanExp::sampleViewpoints (sensor_model_planexp.cpp:65-90): indices of the trajectory points a segment is viewed from"""
+    t = np.ascontiguousarray(times_ns, dtype=np.int64)
+    out = np.zeros(max(1, len(t)), np.int32)
+    k = lib().orc_sample_viewpoints(_ptr(t), len(t), float(sampling_time), _ptr(out), len(out))
+    return out[:k].copy()
 
 
 def value_select(gain, cost, parent=None):

@@ -488,11 +488,13 @@ inline void erase_observed(std::vector<Vec3>& v, bool faithful, Pred observed) {
 // One candidate: [upstream] SimulatedSensorEvaluator::computeGain -> SensorModelPlanExp::getVisibleVoxelsFromTrajectory
 // (sensor_model_planexp.cpp:18-63) -> CameraModelPlanExp::getVisibleVoxels (camera_model_planexp.cpp:23-28) ->
 // bounding-volume filter -> <Evaluator>::computeGainFromVisibleVoxels.
-void eval_one(Oracle& o, const sipp_eval_params& p, double px, double py, const double* start_xy, bool faithful,
-              double* gain_out, uint32_t* cnt, uint8_t* terminal_out) {
+// `views`: the nv sampled viewpoints of the segment (sampleViewpoints, sensor_model_planexp.cpp:65-90, with the mounting translation
+// applied, :28-31) in trajectory order; their voxel lists are concatenated (:34) and only ADJACENT duplicates are removed (:61).
+void eval_views(Oracle& o, const sipp_eval_params& p, const double* views, int nv, const double* start_xy, bool faithful,
+                double* gain_out, uint32_t* cnt, uint8_t* terminal_out) {
   std::vector<Vec3> raw;
-  raw.reserve((size_t)(2 * p.half_fov + 1) * (2 * p.half_fov + 1) + 1);
-  get_voxel_area(o, &raw, Vec3{px, py, 0.0}, p.half_fov);
+  raw.reserve(((size_t)(2 * p.half_fov + 1) * (2 * p.half_fov + 1) + 1) * (size_t)(nv > 0 ? nv : 1));
+  for (int k = 0; k < nv; ++k) get_voxel_area(o, &raw, Vec3{views[2 * k], views[2 * k + 1], 0.0}, p.half_fov);
   raw.erase(std::unique(raw.begin(), raw.end()), raw.end());         // sensor_model_planexp.cpp:61
   std::vector<Vec3> vox;
   vox.reserve(raw.size());
@@ -615,6 +617,12 @@ void eval_one(Oracle& o, const sipp_eval_params& p, double px, double py, const 
   *gain_out = gain;
   if (cnt) { cnt[SIPP_CNT_VISIBLE] = c_vis; cnt[SIPP_CNT_UNKNOWN] = c_unk; cnt[SIPP_CNT_AUX] = c_aux; cnt[SIPP_CNT_AUX2] = c_aux2; }
   if (terminal_out) *terminal_out = terminal ? 1 : 0;
+}
+// one view at the segment's last trajectory point: sampling_time <= 0, every shipped cfg (sensor_model_planexp.cpp:72-75)
+void eval_one(Oracle& o, const sipp_eval_params& p, double px, double py, const double* start_xy, bool faithful,
+              double* gain_out, uint32_t* cnt, uint8_t* terminal_out) {
+  const double v[2] = {px, py};
+  eval_views(o, p, v, 1, start_xy, faithful, gain_out, cnt, terminal_out);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -817,6 +825,43 @@ int orc_gain_batch(orc_ctx* c, const sipp_eval_params* p, int32_t n, const doubl
   return 0;
 }
 
+// SensorModelPlanExp::sampleViewpoints (sensor_model_planexp.cpp:65-90): indices of the trajectory points a segment is viewed from.
+// times_ns = time_from_start_ns of its npts points. Returns the number of indices (0 for an empty trajectory).
+int orc_sample_viewpoints(const int64_t* times_ns, int32_t npts, double sampling_time, int32_t* out_idx, int32_t cap) {
+  if (npts < 1) return 0;                                            // :67-70
+  int k = 0;
+  auto push = [&](int i) { if (k < cap) out_idx[k] = i; ++k; };
+  if (sampling_time <= 0.0) {                                        // :71-73: only the last point
+    push(npts - 1);
+  } else {
+    const int64_t sampling_time_ns = static_cast<int64_t>(sampling_time * 1.0e9);      // :75
+    if (sampling_time_ns >= times_ns[npts - 1]) {                    // :76-78: no point within one interval: the last point
+      push(npts - 1);
+    } else {
+      int64_t current_time = sampling_time_ns;                       // :81-87
+      for (int i = 0; i < npts; ++i)
+        if (times_ns[i] >= current_time) {
+          current_time += sampling_time_ns;
+          push(i);
+        }
+    }
+  }
+  return k;
+}
+
+// Segments with several sampled viewpoints (sensor_model/sampling_time > 0): segment i has the views view_xy[view_off[i] .. view_off[i+1]).
+int orc_gain_batch_views(orc_ctx* c, const sipp_eval_params* p, int32_t n, const int32_t* view_off, const double* view_xy, const double* start_xy,
+                         double* gain, uint32_t* counts, uint8_t* terminal, int variant) {
+  Oracle& o = c->o;
+  for (int i = 0; i < n; ++i) {
+    const int a = view_off[i], nv = view_off[i + 1] - view_off[i];
+    const double none[2] = {0.0, 0.0};
+    eval_views(o, *p, view_xy + 2 * (size_t)a, nv, start_xy ? start_xy + 2 * i : (nv > 0 ? view_xy + 2 * (size_t)a : none), variant == 0, gain + i,
+               counts ? counts + (size_t)SIPP_COUNTS_PER_CANDIDATE * i : nullptr, terminal ? terminal + i : nullptr);
+  }
+  return 0;
+}
+
 // [upstream] GlobalNormalizedGain + SubsequentBest on a parent-index tree (node 0 = root, parent[i] < i).
 int orc_value_select(int32_t n, const double* gain_in, const double* cost_in, const int32_t* parent, double* value,
                      int32_t* best_child, double* best_value) {
@@ -856,9 +901,18 @@ int orc_value_select(int32_t n, const double* gain_in, const double* cost_in, co
 // Nodes are given in pre-order (parent[i] < i, children in index order), node 0 is the root (its gain / cost are zeroed on entry: it just
 // became the current segment; whether the root-first call of the patched planner re-scores it depends on the chain, see below).
 // gain / value / terminal are in-out; computeValue sees whatever gains the array holds at that moment.
+int orc_update_tree_views(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
+                          const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                          const double* cur_xy, int path_changed, int variant, const double* cost_below, const int32_t* view_off, const double* view_xy);
 int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
                     const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
                     const double* cur_xy, int path_changed, int variant, const double* cost_below) {
+  return orc_update_tree_views(c, p, u, n, parent, end_xy, start_xy, gain, cost, value, terminal, cur_xy, path_changed, variant, cost_below, nullptr, nullptr);
+}
+// view_off / view_xy (optional): node i is scored from its sampled viewpoints instead of its end point alone
+int orc_update_tree_views(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
+                          const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                          const double* cur_xy, int path_changed, int variant, const double* cost_below, const int32_t* view_off, const double* view_xy) {
   Oracle& o = c->o;
   std::vector<std::vector<int>> children(n);
   for (int i = 1; i < n; ++i) children[parent[i]].push_back(i);
@@ -870,7 +924,10 @@ int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_pa
   const bool setsTerminal = p->evaluator == SIPP_EVAL_RRT_STAR || p->evaluator == SIPP_EVAL_EXPAND_REACHABLE;
   auto compute_gain = [&](int i) {
     double gi; uint8_t ti;
-    eval_one(o, *p, end_xy[2 * i], end_xy[2 * i + 1], start_xy ? start_xy + 2 * i : end_xy + 2 * i, variant == 0, &gi, nullptr, &ti);
+    if (view_off)
+      eval_views(o, *p, view_xy + 2 * (size_t)view_off[i], view_off[i + 1] - view_off[i], start_xy ? start_xy + 2 * i : end_xy + 2 * i, variant == 0, &gi, nullptr, &ti);
+    else
+      eval_one(o, *p, end_xy[2 * i], end_xy[2 * i + 1], start_xy ? start_xy + 2 * i : end_xy + 2 * i, variant == 0, &gi, nullptr, &ti);
     g[i] = gi;
     if (setsTerminal && ti) terminal[i] = 1;      // the evaluators only ever set gain_terminal, never clear it
   };

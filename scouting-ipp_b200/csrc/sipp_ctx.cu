@@ -753,6 +753,65 @@ int sipp_gain_batch(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, co
 }
 
 // ---- value + selection -----------------------------------------------------------------------------------
+// device carve-up for segments with several views: [view_xy nv x 16][vcounts nv x 16][vgain nv x 8][vfsum nv x 8][counts n x 16][start n x 16][gain n x 8]
+// [view_off (n + 1) x 4, padded][terminal n]
+struct ViewStage {
+  double *view_xy, *vgain, *vfsum, *start_xy, *gain;
+  uint32_t *vcounts, *counts;
+  int* view_off;
+  uint8_t* terminal;
+};
+static size_t view_stage_bytes(size_t n, size_t nv) { return nv * 48 + n * 41 + 4 * (n + 1) + 256; }
+static ViewStage carve_views(void* base, size_t n, size_t nv) {
+  ViewStage v;
+  char* p = reinterpret_cast<char*>(base);
+  v.view_xy = reinterpret_cast<double*>(p); p += 16 * nv;
+  v.vcounts = reinterpret_cast<uint32_t*>(p); p += 16 * nv;
+  v.counts = reinterpret_cast<uint32_t*>(p); p += 16 * n;
+  v.start_xy = reinterpret_cast<double*>(p); p += 16 * n;
+  v.vgain = reinterpret_cast<double*>(p); p += 8 * nv;
+  v.vfsum = reinterpret_cast<double*>(p); p += 8 * nv;
+  v.gain = reinterpret_cast<double*>(p); p += 8 * n;
+  v.view_off = reinterpret_cast<int*>(p); p += 4 * ((n + 1 + 3) & ~(size_t)3);
+  v.terminal = reinterpret_cast<uint8_t*>(p);
+  return v;
+}
+static int check_views(sipp_ctx* ctx, int32_t n, const int32_t* view_offset, const double* view_xy, int64_t* nv_out) {
+  if (!view_offset || view_offset[0] != 0) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "view_offset must start at 0");
+  for (int i = 0; i < n; ++i)
+    if (view_offset[i + 1] < view_offset[i]) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "view_offset decreases at segment %d", i);
+  *nv_out = view_offset[n];
+  if (*nv_out > 0 && !view_xy) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "view_xy == NULL");
+  return SIPP_OK;
+}
+
+int sipp_gain_batch_views(sipp_ctx* ctx, const sipp_eval_params* params, int32_t n, const int32_t* view_offset, const double* view_xy,
+                          const double* start_xy, double* gain, uint32_t* counts, uint8_t* terminal) {
+  SIPP_ENTER(ctx);
+  int rc = check_params(ctx, params);
+  if (rc != SIPP_OK) return rc;
+  if (n < 0 || (n > 0 && !gain)) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "bad batch arguments");
+  if (n == 0) return SIPP_OK;
+  int64_t nv = 0;
+  if ((rc = check_views(ctx, n, view_offset, view_xy, &nv)) != SIPP_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, view_stage_bytes((size_t)n, (size_t)nv))) != SIPP_OK) return rc;
+  const ViewStage st = carve_views(ctx->d_stage, (size_t)n, (size_t)nv);
+  if (nv > 0) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.view_xy, view_xy, (size_t)nv * 16, cudaMemcpyHostToDevice, s));
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.view_off, view_offset, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (start_xy) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(st.start_xy, start_xy, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  const GainGeom g = make_gain_geom(ctx, params);
+  if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
+  if ((rc = gain_launch_views(ctx, params, g, n, st.view_off, (int)nv, st.view_xy, start_xy ? st.start_xy : nullptr, st.vgain, st.vcounts, st.vfsum, st.gain,
+                              counts ? st.counts : nullptr, terminal ? st.terminal : nullptr, s)) != SIPP_OK)
+    return rc;
+  SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(gain, st.gain, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (counts) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, st.counts, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+  if (terminal) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(terminal, st.terminal, (size_t)n, cudaMemcpyDeviceToHost, s));
+  SIPP_CUDA_CHECK(ctx, cudaStreamSynchronize(s));
+  return SIPP_OK;
+}
+
 int sipp_value_select_dev(sipp_ctx* ctx, int32_t n, const double* d_gain, const double* d_cost, const int32_t* d_parent, double* d_value,
                           int32_t* d_best_child, double* d_best_value, void* stream) {
   SIPP_ENTER(ctx);
@@ -1156,10 +1215,33 @@ int sipp_episode_run(sipp_ctx* ctx, const int32_t* truth, const sipp_eval_params
   return SIPP_OK;
 }
 
+static int update_tree_impl(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
+                            const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                            const double* cur_xy, int32_t path_changed, int32_t* n_rescored, const double* cost_below, const int32_t* view_offset,
+                            const double* view_xy);
+
 int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
                      const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
                      const double* cur_xy, int32_t path_changed, int32_t* n_rescored, const double* cost_below) {
   SIPP_ENTER(ctx);
+  return update_tree_impl(ctx, params, updater, n, parent, end_xy, start_xy, gain, cost, value, terminal, cur_xy, path_changed, n_rescored, cost_below, nullptr,
+                          nullptr);
+}
+
+int sipp_update_tree_views(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
+                           const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                           const double* cur_xy, int32_t path_changed, int32_t* n_rescored, const double* cost_below, const int32_t* view_offset,
+                           const double* view_xy) {
+  SIPP_ENTER(ctx);
+  if (!view_offset) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "view_offset == NULL");
+  return update_tree_impl(ctx, params, updater, n, parent, end_xy, start_xy, gain, cost, value, terminal, cur_xy, path_changed, n_rescored, cost_below,
+                          view_offset, view_xy);
+}
+
+static int update_tree_impl(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_updater_params* updater, int32_t n, const int32_t* parent,
+                            const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                            const double* cur_xy, int32_t path_changed, int32_t* n_rescored, const double* cost_below, const int32_t* view_offset,
+                            const double* view_xy) {
   int rc = check_params(ctx, params);
   if (rc != SIPP_OK) return rc;
   if (!updater || n < 1 || !parent || !end_xy || !gain || !cost || !value || !terminal || !cur_xy)
@@ -1169,8 +1251,12 @@ int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_u
   for (int i = 1; i < n; ++i)
     if (parent[i] < 0 || parent[i] >= i) return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "parent[%d] = %d violates 0 <= parent[i] < i", i, parent[i]);
   cudaStream_t s = ctx->stream;
+  int64_t nv = 0;
+  if (view_offset && (rc = check_views(ctx, n, view_offset, view_xy, &nv)) != SIPP_OK) return rc;
   // device staging: doubles end_xy[2n] start_xy[2n] gain_old gain_new gain_tmp cost value value_tmp cost_below | int32 parent sel n_sel | u8 flags x5
-  const size_t N = (size_t)n, need = N * (16 + 16 + 8 * 7) + N * 8 + 64 + N * 5 + 256;
+  // | with views: a ViewStage behind it (256-byte aligned)
+  const size_t N = (size_t)n, need0 = (N * (16 + 16 + 8 * 7) + N * 8 + 64 + N * 5 + 256 + 255) & ~(size_t)255;
+  const size_t need = need0 + (view_offset ? view_stage_bytes(N, (size_t)nv) : 0);
   if ((rc = ensure_dev(ctx, &ctx->d_stage, &ctx->d_stage_bytes, need)) != SIPP_OK) return rc;
   double* d_end = reinterpret_cast<double*>(ctx->d_stage);
   double *d_start = d_end + 2 * N, *d_gold = d_start + 2 * N, *d_gnew = d_gold + N, *d_gtmp = d_gnew + N, *d_cost = d_gtmp + N, *d_val = d_cost + N,
@@ -1199,7 +1285,16 @@ int sipp_update_tree(sipp_ctx* ctx, const sipp_eval_params* params, const sipp_u
   // 2. one batched gain launch over the compacted list (count read on the device), results scattered by node index
   const GainGeom g = make_gain_geom(ctx, params);
   if ((rc = ensure_views(ctx, params, g, s)) != SIPP_OK) return rc;
-  if ((rc = gain_launch(ctx, params, g, n, d_end, start_xy ? d_start : nullptr, nullptr, d_gtmp, nullptr, d_ttmp, nullptr, s, d_sel, d_nsel)) != SIPP_OK) return rc;
+  if (view_offset) {
+    // several sampled viewpoints per node: every view of every node is scored (the trees are small next to the GPU), the per-node sums
+    // land in gain_tmp / terminal_tmp and k_update_apply takes them for the selected nodes only
+    const ViewStage vs = carve_views(reinterpret_cast<char*>(ctx->d_stage) + need0, N, (size_t)nv);
+    if (nv > 0) SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(vs.view_xy, view_xy, (size_t)nv * 16, cudaMemcpyHostToDevice, s));
+    SIPP_CUDA_CHECK(ctx, cudaMemcpyAsync(vs.view_off, view_offset, (N + 1) * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = gain_launch_views(ctx, params, g, n, vs.view_off, (int)nv, vs.view_xy, start_xy ? d_start : d_end, vs.vgain, vs.vcounts, vs.vfsum, d_gtmp, nullptr,
+                                d_ttmp, s)) != SIPP_OK)
+      return rc;
+  } else if ((rc = gain_launch(ctx, params, g, n, d_end, start_xy ? d_start : nullptr, nullptr, d_gtmp, nullptr, d_ttmp, nullptr, s, d_sel, d_nsel)) != SIPP_OK) return rc;
   // 3. new gains / terminal flags, which nodes get a new value
   const int sets_terminal = params->evaluator == SIPP_EVAL_RRT_STAR || params->evaluator == SIPP_EVAL_EXPAND_REACHABLE;
   SIPP_CUDA_CHECK(ctx, launch_update_apply(ctx, *updater, n, sets_terminal, d_dog, d_fol, d_gold, d_gtmp, d_ttmp, d_gnew, d_term, d_dov, s));

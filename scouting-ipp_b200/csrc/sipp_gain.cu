@@ -61,6 +61,7 @@ struct GainArgs {
   const uint16_t* label_plane;  // AverageViewCost: map_cost_ (raw labels) for the duplicated centre voxel — the tile holds labels masked by the
   size_t label_pitch16;         // CORNER voxels' bounding-volume test, the centre voxel has its own test on centre coordinates
   double* value2;         // optional second copy of value (the caller's pinned host array, written over PCIe by the kernel)
+  double* fsum_out;       // optional: the candidate's floating-point accumulator before the epilogue (several views per segment: k_gain_combine)
   const double* recip;    // ExpandLowCost lookup
   const int* sel;         // optional: candidate k of this launch is node sel[k] of the caller's arrays (outputs are scattered)
   const int* n_dev;       // optional: number of candidates, read on the device (a.n is then only the upper bound for the grid)
@@ -601,6 +602,7 @@ __device__ __forceinline__ void gain_body(const CUtensorMap* tm_rec_p, const CUt
       }
       a.gain[cand] = gain;
       if (a.counts) *reinterpret_cast<uint4*>(a.counts + 4 * (size_t)cand) = make_uint4(n_vis, n_unk, n_aux, sum_aux2);
+      if (a.fsum_out) a.fsum_out[cand] = fsum;
       if (a.terminal) a.terminal[cand] = (uint8_t)terminal;
       if (a.value) {
         // flat tree: GlobalNormalizedGain with a zeroed root: value = gain / cost when cost > 0
@@ -786,7 +788,7 @@ int launch_mode(sipp_ctx* ctx, const CUtensorMap* tm_rec, const CUtensorMap* tm_
 static int gain_prepare(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
                         const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
                         const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs, GainArgs& a, int* mode_out, bool* packed_out,
-                        bool* need_aux_out) {
+                        bool* need_aux_out, double* d_fsum = nullptr) {
   const int h = p->half_fov;
   if (h < 0 || h > 112) return sipp_set_err(ctx, SIPP_ERR_UNSUPPORTED, "half_fov %d outside [0,112] (TMA box limit 256 columns)", h);
   const int side = 2 * h + 1;
@@ -816,6 +818,7 @@ static int gain_prepare(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom
   a.terminal = d_terminal;
   a.value = d_cost ? d_value : nullptr;
   a.value2 = d_cost ? d_value2 : nullptr;
+  a.fsum_out = d_fsum;
   a.recip = ctx->d_recip;
   a.label_plane = ctx->d_label;
   a.label_pitch16 = ctx->pitch16;
@@ -866,12 +869,12 @@ static int gain_prepare(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom
 
 int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy, const double* d_start_xy,
                 const double* d_cost, double* d_gain, uint32_t* d_counts, uint8_t* d_terminal, double* d_value,
-                cudaStream_t s, const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs) {
+                cudaStream_t s, const int* d_sel, const int* d_n, double* d_value2, const FusedSelect* fs, double* d_fsum) {
   if (n <= 0) return SIPP_OK;
   GainArgs a;
   int mode = 0;
   bool packed = false, need_aux = false;
-  int rc = gain_prepare(ctx, p, g, n, d_xy, d_start_xy, d_cost, d_gain, d_counts, d_terminal, d_value, d_sel, d_n, d_value2, fs, a, &mode, &packed, &need_aux);
+  int rc = gain_prepare(ctx, p, g, n, d_xy, d_start_xy, d_cost, d_gain, d_counts, d_terminal, d_value, d_sel, d_n, d_value2, fs, a, &mode, &packed, &need_aux, d_fsum);
   if (rc != SIPP_OK) return rc;
   const int h = p->half_fov;
   const CUtensorMap* tm_rec = cached_tmap(ctx, h, 0, &rc);      // the packed form does not use it (plain loads)
@@ -889,6 +892,122 @@ int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int
     case MODE_LOW_COST: return launch_mode<MODE_LOW_COST>(ctx, tm_rec, tm_aux, a, s);
   }
   return SIPP_OK;
+}
+
+// ---- segments viewed from several sampled viewpoints (sensor_model/sampling_time > 0, sensor_model_planexp.cpp:18-90) -----------------
+// The reference concatenates the voxel lists of a segment's views and removes only ADJACENT duplicates (:34,:61). A view's list is
+// [centre voxel (half-integer cell coordinates), corner voxels (integer cell coordinates) ...] (map_planexp.cpp:81-101), so a seam
+// between two lists never joins equal elements and the evaluator sees every view's voxels: its counts are the sums of the per-view
+// counts and its running floating-point sum continues from view to view. k_gain scores every view as a candidate of its own and
+// leaves the accumulators (counts + fsum_out); this kernel adds them up per segment, in view order, and applies the evaluator's
+// closing formulas — the ones at the end of k_gain, restated over the sums.
+namespace {
+struct CombineArgs {
+  int n, mode, evaluator, do_binary, use_discount;
+  double npg, discount_factor, discount_offset, goal_x, goal_y, mean_cost;
+  const int* view_off;          // [n + 1]
+  const uint32_t* vcounts;      // [views][4]
+  const double* vfsum;          // [views]
+  const double* start_xy;       // [n][2] (RRTStar binary + discount: trajectory[0])
+  double* gain;                 // [n]
+  uint32_t* counts;             // optional [n][4]
+  uint8_t* terminal;            // optional [n]
+};
+__global__ void k_gain_combine(const CombineArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  uint32_t n_vis = 0, n_unk = 0, n_aux = 0, sum2 = 0;
+  double fsum = 0.0;
+  for (int v = a.view_off[i]; v < a.view_off[i + 1]; ++v) {
+    const uint4 c = *reinterpret_cast<const uint4*>(a.vcounts + 4 * (size_t)v);
+    n_vis += c.x; n_unk += c.y; n_aux += c.z; sum2 += c.w;
+    fsum = __dadd_rn(fsum, a.vfsum[v]);
+  }
+  double gain = 0.0;
+  uint32_t terminal = 0;
+  if (a.mode == MODE_COUNT) {
+    if (a.evaluator == SIPP_EVAL_RRT_STAR) {
+      if (n_unk == 0) terminal = 1;                                               // rrt_star_evaluator.cpp:53-57
+      else if (a.do_binary) {
+        if (n_aux > 0) {
+          if (a.use_discount) {                                                   // :61-68
+            const double dx = a.goal_x - a.start_xy[2 * i], dy = a.goal_y - a.start_xy[2 * i + 1];
+            const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            gain = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(nrm, a.discount_offset)));
+          } else gain = 1.0;                                                      // :69-75
+        }
+      } else gain = __dadd_rn((double)n_aux, __dmul_rn((double)(n_unk - n_aux), a.npg));      // :85-89
+    } else if (a.evaluator == SIPP_EVAL_EXPAND_REACHABLE) {
+      if (n_unk == 0) terminal = 1;                                               // expand_reachable_area_evaluator.cpp:50-54
+      else gain = __dadd_rn((double)n_aux, __dmul_rn((double)(n_unk - n_aux), a.discount_factor));
+    } else {                                                                      // NaiveEvaluator [upstream]
+      gain = (double)n_unk;
+      n_aux = 0;
+    }
+  } else if (a.mode == MODE_RRT_DISCOUNT) {
+    if (n_unk == 0) terminal = 1;
+    else gain = __dadd_rn(fsum, __dmul_rn((double)(n_unk - n_aux), a.npg));       // :78-84
+  } else if (a.mode == MODE_GOAL_DISTANCE) {
+    gain = fsum;
+    n_aux = 0;
+  } else if (a.mode == MODE_AVG_VIEW_COST) {
+    if (n_aux > 0) {                                                              // average_view_cost_evaluator.cpp:54-56
+      const double mean_view_cost = __ddiv_rn((double)sum2, (double)n_aux);
+      gain = __dmul_rn((double)n_unk, __ddiv_rn(1.0, mean_view_cost));
+    } else gain = __dmul_rn((double)n_unk, __ddiv_rn(1.0, a.mean_cost));          // :57-59
+  } else if (a.mode == MODE_LOW_COST) {
+    gain = fsum;
+  }
+  a.gain[i] = gain;
+  if (a.counts) *reinterpret_cast<uint4*>(a.counts + 4 * (size_t)i) = make_uint4(n_vis, n_unk, n_aux, sum2);
+  if (a.terminal) a.terminal[i] = (uint8_t)terminal;
+}
+}  // namespace
+
+// n segments, segment i viewed from the views d_view_off[i] .. d_view_off[i + 1]) of d_view_xy (n_views in total). Scratch (device):
+// d_vgain [n_views] doubles, d_vcounts [n_views][4] uint32, d_vfsum [n_views] doubles. d_start_xy: [n][2] (needed by RRTStar binary + discount).
+int gain_launch_views(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const int* d_view_off, int n_views, const double* d_view_xy,
+                      const double* d_start_xy, double* d_vgain, uint32_t* d_vcounts, double* d_vfsum, double* d_gain, uint32_t* d_counts,
+                      uint8_t* d_terminal, cudaStream_t s) {
+  if (n <= 0) return SIPP_OK;
+  int rc;
+  // every view as a candidate of its own; the per-view gains are not used (binary + discount reads a start point per candidate: the view itself)
+  if (n_views > 0 && (rc = gain_launch(ctx, p, g, n_views, d_view_xy, d_view_xy, nullptr, d_vgain, d_vcounts, nullptr, nullptr, s, nullptr, nullptr, nullptr,
+                                       nullptr, d_vfsum)) != SIPP_OK)
+    return rc;
+  CombineArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n;
+  switch (p->evaluator) {
+    case SIPP_EVAL_RRT_STAR: a.mode = (p->use_distance_discount && !p->do_binary_check) ? MODE_RRT_DISCOUNT : MODE_COUNT; break;
+    case SIPP_EVAL_EXPAND_REACHABLE:
+    case SIPP_EVAL_NAIVE: a.mode = MODE_COUNT; break;
+    case SIPP_EVAL_GOAL_DISTANCE: a.mode = MODE_GOAL_DISTANCE; break;
+    case SIPP_EVAL_AVERAGE_VIEW_COST: a.mode = MODE_AVG_VIEW_COST; break;
+    case SIPP_EVAL_EXPAND_LOW_COST: a.mode = MODE_LOW_COST; break;
+    default: return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "unknown evaluator %d", p->evaluator);
+  }
+  if (a.mode == MODE_COUNT && p->evaluator == SIPP_EVAL_RRT_STAR && p->do_binary_check && p->use_distance_discount && !d_start_xy)
+    return sipp_set_err(ctx, SIPP_ERR_INVALID_ARG, "RRTStarEvaluator binary+discount mode needs start_xy (trajectory[0])");
+  a.evaluator = p->evaluator;
+  a.do_binary = p->do_binary_check;
+  a.use_discount = p->use_distance_discount;
+  a.npg = p->non_path_voxel_gain;
+  a.discount_factor = p->discount_factor;
+  a.discount_offset = p->discount_offset;
+  a.goal_x = g.goal_x; a.goal_y = g.goal_y; a.mean_cost = g.mean_cost;
+  a.view_off = d_view_off;
+  a.vcounts = d_vcounts;
+  a.vfsum = d_vfsum;
+  a.start_xy = d_start_xy;
+  a.gain = d_gain;
+  a.counts = d_counts;
+  a.terminal = d_terminal;
+  k_gain_combine<<<(n + 255) / 256, 256, 0, s>>>(a);
+  ctx->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return sipp_set_err(ctx, SIPP_ERR_CUDA, "k_gain_combine launch: %s", cudaGetErrorString(e));
+  return sipp_debug_sync(ctx, s, "k_gain_combine");
 }
 
 // ---- batched gain + value + argmax (sipp_batch_cycle) ---------------------------------------------------------------------------

@@ -227,7 +227,10 @@ struct FusedSelect {       // argmax over value fused into the tail of k_gain (f
 int gain_launch(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const double* d_xy,
                 const double* d_start_xy, const double* d_cost, double* d_gain, uint32_t* d_counts,
                 uint8_t* d_terminal, double* d_value, cudaStream_t s, const int* d_sel = nullptr, const int* d_n = nullptr,
-                double* d_value2 = nullptr, const FusedSelect* fs = nullptr);
+                double* d_value2 = nullptr, const FusedSelect* fs = nullptr, double* d_fsum = nullptr);
+int gain_launch_views(sipp_ctx* ctx, const sipp_eval_params* p, const GainGeom& g, int n, const int* d_view_off, int n_views, const double* d_view_xy,
+                      const double* d_start_xy, double* d_vgain, uint32_t* d_vcounts, double* d_vfsum, double* d_gain, uint32_t* d_counts,
+                      uint8_t* d_terminal, cudaStream_t s);
 // sipp_update.cu: evaluator-updater policy on the device (row A13)
 cudaError_t launch_update_select(sipp_ctx* ctx, const sipp_updater_params& u, int n, const double* d_end_xy, const double* d_gain,
                                  const uint8_t* d_terminal, double cur_x, double cur_y, int path_changed, uint8_t* d_do_gain, uint8_t* d_follow,

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
     "sipp_path_download", "sipp_truth_upload", "sipp_travel_cost", "sipp_plan_phases",
     "sipp_batch_create", "sipp_batch_destroy", "sipp_batch_last_error", "sipp_batch_launch_count", "sipp_batch_ingest", "sipp_batch_plan",
-    "sipp_batch_cycle", "sipp_batch_episode_run",
+    "sipp_batch_cycle", "sipp_batch_episode_run", "sipp_gain_batch_views", "sipp_update_tree_views",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
 
@@ -205,6 +205,8 @@ def lib():
         L.sipp_cycle_dev.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.sipp_merge_best_dev.argtypes = [vp, vp, i32, i64, vp, vp]
         L.sipp_update_tree.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, pi32, vp]
+        L.sipp_update_tree_views.argtypes = [vp, C.POINTER(EvalParams), C.POINTER(UpdaterParams), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, pi32, vp, vp, vp]
+        L.sipp_gain_batch_views.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp, vp]
         L.sipp_peer_export.argtypes = [vp, vp]
         L.sipp_peer_attach.argtypes = [vp, i32, i32, vp]
         L.sipp_peer_detach.argtypes = [vp]
@@ -382,6 +384,18 @@ class Context:
                                             _ptr(terminal)))
         return gain, counts, terminal
 
+    def gain_batch_views(self, params, view_off, view_xy, start_xy=None):
+        """segments scored from several sampled viewpoints each: segment i has the views view_xy[view_off[i]:view_off[i+1]]"""
+        off = np.ascontiguousarray(view_off, dtype=np.int32)
+        n = off.shape[0] - 1
+        vxy = np.ascontiguousarray(view_xy, dtype=np.float64).reshape(-1, 2)
+        sxy = None if start_xy is None else np.ascontiguousarray(start_xy, dtype=np.float64).reshape(n, 2)
+        gain = np.zeros(n, np.float64)
+        counts = np.zeros((n, COUNTS_PER_CANDIDATE), np.uint32)
+        terminal = np.zeros(n, np.uint8)
+        self._check(self._L.sipp_gain_batch_views(self._h, C.byref(params), n, _ptr(off), _ptr(vxy), _ptr(sxy), _ptr(gain), _ptr(counts), _ptr(terminal)))
+        return gain, counts, terminal
+
     def value_select(self, gain, cost, parent=None):
         gain = np.ascontiguousarray(gain, dtype=np.float64)
         cost = np.ascontiguousarray(cost, dtype=np.float64)
@@ -427,7 +441,8 @@ class Context:
         self._check(self._L.sipp_cycle_dev(self._h, C.byref(params), int(n), _ptr(d_xy), _ptr(d_start_xy), _ptr(d_cost),
                                            _ptr(d_gain), _ptr(d_terminal), _ptr(d_value), _ptr(d_best), _ptr(stream)))
 
-    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, cost_below=None):
+    def update_tree(self, params, updater, parent, end_xy, gain, cost, value, terminal, cur_xy, path_changed, start_xy=None, cost_below=None,
+                    view_off=None, view_xy=None):
         """one re-evaluation pass over a pre-order tree; returns (gain, value, terminal, n_rescored) — inputs are not modified"""
         parent = np.ascontiguousarray(parent, dtype=np.int32)
         n = parent.shape[0]
@@ -440,6 +455,13 @@ class Context:
         cur = np.ascontiguousarray(cur_xy, dtype=np.float64)
         cb = None if cost_below is None else np.ascontiguousarray(cost_below, dtype=np.float64)
         nres = C.c_int32()
+        if view_off is not None:        # node i is scored from its sampled viewpoints (sensor_model/sampling_time > 0)
+            off = np.ascontiguousarray(view_off, dtype=np.int32)
+            vxy = np.ascontiguousarray(view_xy, dtype=np.float64).reshape(-1, 2)
+            self._check(self._L.sipp_update_tree_views(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g),
+                                                       _ptr(cost), _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), C.byref(nres), _ptr(cb),
+                                                       _ptr(off), _ptr(vxy)))
+            return g, v, t, nres.value
         self._check(self._L.sipp_update_tree(self._h, C.byref(params), C.byref(updater), n, _ptr(parent), _ptr(end_xy), _ptr(sxy), _ptr(g),
                                              _ptr(cost), _ptr(v), _ptr(t), _ptr(cur), int(bool(path_changed)), C.byref(nres), _ptr(cb)))
         return g, v, t, nres.value

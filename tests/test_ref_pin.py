@@ -171,3 +171,58 @@ def test_oracle_matches_reference_on_random_scenarios(seed):
                 rg, ru, rt = r.gain_batch(p, xy, sxy)
                 assert same(og, rg), (kw, hf, bv, np.argwhere(~((og == rg) | (np.isnan(og) & np.isnan(rg)))).ravel()[:5])
                 assert same(oc[:, 1], ru) and same(ot, rt), (kw, hf, bv)
+
+
+# ---- segments viewed from several sampled viewpoints (sensor_model/sampling_time > 0) ----------------------------------------------------
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_ref_views_golden as GV  # noqa: E402
+
+
+def views_of(traj, times, sampling_time):
+    """what the host side of the product does: the reference's sampleViewpoints rule picks trajectory points, their positions are the views"""
+    idx = orc.sample_viewpoints(times, sampling_time)
+    off = np.arange(0, (len(traj) + 1) * len(idx), len(idx), dtype=np.int32)
+    return off, np.ascontiguousarray(traj[:, idx, :]).reshape(-1, 2), idx
+
+
+def test_sample_viewpoints_rule():
+    t = (np.arange(9) * 0.4e9).astype(np.int64)
+    assert orc.sample_viewpoints(t, 0.0).tolist() == [8] and orc.sample_viewpoints(t, -1.0).tolist() == [8]
+    assert orc.sample_viewpoints(t, 10.0).tolist() == [8] and orc.sample_viewpoints(t, 3.2).tolist() == [8]       # interval >= the segment's duration
+    assert orc.sample_viewpoints(t, 0.5).tolist() == [2, 3, 4, 5, 7, 8]          # first point at or after 0.5, 1.0, 1.5, ... (one per point at most)
+    assert orc.sample_viewpoints(t, 1.0).tolist() == [3, 5, 8]
+    assert orc.sample_viewpoints(t, 0.1).tolist() == [1, 2, 3, 4, 5, 6, 7, 8]    # a denser rate than the trajectory: every point but the first
+    assert orc.sample_viewpoints(np.zeros(0, np.int64), 0.5).tolist() == []
+
+
+def test_multi_view_oracle_matches_committed_reference_vectors(scenario):
+    vec = np.load(os.path.join(ROOT, "tests", "golden", "ref_views.npz"))
+    traj, times = GV.trajectories()
+    assert same(traj, vec["traj"]) and same(times, vec["times"])
+    k = 0
+    for st in GV.SAMPLING:
+        off, vxy, idx = views_of(traj, times, st)
+        for kw in G.EVAL_SETS:
+            for hf in GV.HALF_FOVS:
+                for bv in GV.BVS:
+                    og, oc, ot = scenario.gain_batch_views(orc.make_params(half_fov=hf, bounding_volume=bv, **kw), off, vxy, traj[:, 0, :], variant=0)
+                    assert same(og, vec["gain_%03d" % k]), (st, kw, hf, bv, idx)
+                    assert same(oc[:, 1], vec["unk_%03d" % k]) and same(ot, vec["term_%03d" % k]), (st, kw, hf, bv)
+                    k += 1
+
+
+@needs_ref
+def test_multi_view_vectors_are_what_the_reference_library_produces(scenario):
+    vec = np.load(os.path.join(ROOT, "tests", "golden", "ref_views.npz"))
+    r = ref.Reference(G.make_desc(orc.make_desc)).snapshot(scenario)
+    traj, times = GV.trajectories()
+    k = 0
+    for st in GV.SAMPLING:
+        for kw in G.EVAL_SETS:
+            for hf in GV.HALF_FOVS:
+                for bv in GV.BVS:
+                    if k % 7 == 0:      # a sample of the sets: the generator runs all of them
+                        g, u, t = r.gain_batch(orc.make_params(half_fov=hf, bounding_volume=bv, **kw), traj[:, -1, :], traj[:, 0, :], sampling_time=st,
+                                               traj_xy=traj, times_ns=times)
+                        assert same(g, vec["gain_%03d" % k]) and same(u, vec["unk_%03d" % k]) and same(t, vec["term_%03d" % k]), (st, kw, hf, bv)
+                    k += 1
