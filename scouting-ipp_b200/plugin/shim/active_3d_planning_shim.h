@@ -38,6 +38,22 @@ struct Vector3d {
   Vector3d operator-(const Vector3d& o) const { return Vector3d(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
   double norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 };
+// unit quaternion (w, x, y, z): the orientation of a trajectory point; operator* rotates a vector like Eigen::Quaterniond does
+struct Quaterniond {
+  double qw, qx, qy, qz;
+  Quaterniond() : qw(1), qx(0), qy(0), qz(0) {}
+  Quaterniond(double w, double x, double y, double z) : qw(w), qx(x), qy(y), qz(z) {}
+  double w() const { return qw; }
+  double x() const { return qx; }
+  double y() const { return qy; }
+  double z() const { return qz; }
+  Vector3d operator*(const Vector3d& p) const {     // v + 2 w (u x v) + 2 u x (u x v), u = (x, y, z)
+    const double ux = qx, uy = qy, uz = qz;
+    const double cx = uy * p.v[2] - uz * p.v[1], cy = uz * p.v[0] - ux * p.v[2], cz = ux * p.v[1] - uy * p.v[0];
+    const double dx = uy * cz - uz * cy, dy = uz * cx - ux * cz, dz = ux * cy - uy * cx;
+    return Vector3d(p.v[0] + 2.0 * (qw * cx + dx), p.v[1] + 2.0 * (qw * cy + dy), p.v[2] + 2.0 * (qw * cz + dz));
+  }
+};
 struct Vector2d {
   double v[2];
   Vector2d() : v{0, 0} {}
@@ -71,6 +87,7 @@ namespace active_3d_planning {
 
 struct EigenTrajectoryPoint {           // mav_msgs::EigenTrajectoryPoint subset
   Eigen::Vector3d position_W;
+  Eigen::Quaterniond orientation_W_B;
   int64_t time_from_start_ns = 0;
 };
 typedef std::vector<EigenTrajectoryPoint> EigenTrajectoryPointVector;

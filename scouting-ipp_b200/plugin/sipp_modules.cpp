@@ -176,8 +176,38 @@ double GpuMapPlanExp::getMeanWeight() const {
 
 namespace trajectory_evaluator {
 
-void FlatTree::build(TrajectorySegment* root) {
+void ViewSampler::indices(const EigenTrajectoryPointVector& trajectory, std::vector<int>* out) const {
+  out->clear();
+  if (trajectory.empty()) return;                                            // sensor_model_planexp.cpp:67-70
+  const int n = (int)trajectory.size();
+  if (sampling_time <= 0.0) { out->push_back(n - 1); return; }               // :71-73: rate 0 means the last point only
+  const int64_t sampling_time_ns = static_cast<int64_t>(sampling_time * 1.0e9);      // :75
+  if (sampling_time_ns >= trajectory.back().time_from_start_ns) { out->push_back(n - 1); return; }   // :76-78
+  int64_t current_time = sampling_time_ns;                                   // :81-87
+  for (int i = 0; i < n; ++i)
+    if (trajectory[i].time_from_start_ns >= current_time) {
+      current_time += sampling_time_ns;
+      out->push_back(i);
+    }
+}
+
+void ViewSampler::appendViews(const EigenTrajectoryPointVector& trajectory, std::vector<double>* view_xy) const {
+  std::vector<int> idx;
+  indices(trajectory, &idx);
+  for (int i : idx) {
+    const auto& p = trajectory[i];
+    // position = position + orientation * mounting_translation (:28-30); the mounting rotation only turns the sensor, and the planar
+    // footprint of CameraModelPlanExp (camera_model_planexp.cpp:23-28) does not depend on where it looks
+    const Eigen::Vector3d t = p.orientation_W_B * mounting_translation;
+    view_xy->push_back(p.position_W[0] + t[0]);
+    view_xy->push_back(p.position_W[1] + t[1]);
+  }
+}
+
+void FlatTree::build(TrajectorySegment* root, const ViewSampler* sampler) {
   nodes.clear(); parent.clear(); end_xy.clear(); start_xy.clear(); gain.clear(); cost.clear(); value.clear(); terminal.clear();
+  view_off.clear(); view_xy.clear();
+  if (sampler) view_off.push_back(0);
   // pre-order, children in vector order — the order of [upstream] OnlinePlanner::updateEvaluatorStep
   std::vector<std::pair<TrajectorySegment*, int>> stack;
   stack.push_back({root, -1});
@@ -197,6 +227,10 @@ void FlatTree::build(TrajectorySegment* root) {
     cost.push_back(s->cost);
     value.push_back(s->value);
     terminal.push_back(s->gain_terminal ? 1 : 0);
+    if (sampler) {
+      sampler->appendViews(s->trajectory, &view_xy);
+      view_off.push_back((int32_t)(view_xy.size() / 2));
+    }
     for (int k = (int)s->children.size() - 1; k >= 0; --k) stack.push_back({s->children[k].get(), id});
   }
 }
@@ -252,16 +286,13 @@ void GpuGainEvaluator::setupFromParamMap(Module::ParamMap* param_map) {
   int hf;
   setParam<int>(param_map, "sensor_model/half_fov", &hf, 10);
   params_.half_fov = hf;
-  setParam<double>(param_map, "sensor_model/sampling_time", &sampling_time_, 0.0);          // sensor_model_planexp.cpp:170
+  setParam<double>(param_map, "sensor_model/sampling_time", &sampler_.sampling_time, 0.0);          // sensor_model_planexp.cpp:170
   {
-    double m[7];
-    const char* keys[7] = {"mounting_translation_x", "mounting_translation_y", "mounting_translation_z", "mounting_rotation_x",
-                           "mounting_rotation_y", "mounting_rotation_z", "mounting_rotation_w"};   // [upstream] SensorModel::setupFromParamMap
-    mounting_nonzero_ = false;
-    for (int k = 0; k < 7; ++k) {
-      setParam<double>(param_map, std::string("sensor_model/") + keys[k], &m[k], k == 6 ? 1.0 : 0.0);
-      if (m[k] != (k == 6 ? 1.0 : 0.0)) mounting_nonzero_ = true;
-    }
+    double m[3];
+    const char* keys[3] = {"mounting_translation_x", "mounting_translation_y", "mounting_translation_z"};   // [upstream] SensorModel::setupFromParamMap
+    for (int k = 0; k < 3; ++k) setParam<double>(param_map, std::string("sensor_model/") + keys[k], &m[k], 0.0);
+    sampler_.mounting_translation = Eigen::Vector3d(m[0], m[1], m[2]);
+    // sensor_model/mounting_rotation_*: turns the sensor about its own position; the planar footprint does not depend on it
   }
   // [upstream] bounding volume of SimulatedSensorEvaluator (cfg/experiments/example.yaml:12-18)
   setParam<bool>(param_map, "bounding_volume/enabled", &b, false);
@@ -309,11 +340,8 @@ bool GpuGainEvaluator::checkParamsValid(std::string* error_message) {
   if (!map_ || !map_->ctx()) { *error_message = "map of type 'GpuMapPlanExp' with a live context expected"; return false; }
   if (!config_error_.empty()) { *error_message = config_error_; return false; }
   if (params_.half_fov < 0 || params_.half_fov > 112) { *error_message = "sensor_model/half_fov expected in [0, 112]"; return false; }
-  // one view per segment, taken at its last trajectory point (every shipped cfg: sampling_time 0, no mounting transform). A sensor
-  // model that samples several views along the segment (sensor_model_planexp.cpp:65-90) or is mounted off-centre (:30-31) would
-  // see other voxels than the batched kernels score: refuse the configuration instead of diverging silently.
-  if (sampling_time_ > 0.0) { *error_message = "sensor_model/sampling_time > 0 (several views per segment) is not supported by the Gpu*Evaluator"; return false; }
-  if (mounting_nonzero_) { *error_message = "sensor_model/mounting_translation_* / mounting_rotation_* must be the identity for the Gpu*Evaluator"; return false; }
+  // sensor_model/sampling_time > 0 (several views per segment, sensor_model_planexp.cpp:65-90) and a mounting translation (:28-31) are
+  // served: the host samples the viewpoints, sipp_gain_batch_views / sipp_update_tree_views score them
   return true;
 }
 
@@ -323,7 +351,16 @@ bool GpuGainEvaluator::computeGain(TrajectorySegment* traj_in) {
   const double sxy[2] = {traj_in->trajectory.front().position_W[0], traj_in->trajectory.front().position_W[1]};
   double gain = 0.0;
   uint8_t term = 0;
-  if (sipp_gain_batch(map_->ctx(), &params_, 1, xy, sxy, &gain, nullptr, &term) != SIPP_OK) {
+  int rc;
+  if (multi_view()) {
+    std::vector<double> views;
+    sampler_.appendViews(traj_in->trajectory, &views);
+    const int32_t off[2] = {0, (int32_t)(views.size() / 2)};
+    rc = sipp_gain_batch_views(map_->ctx(), &params_, 1, off, views.data(), sxy, &gain, nullptr, &term);
+  } else {
+    rc = sipp_gain_batch(map_->ctx(), &params_, 1, xy, sxy, &gain, nullptr, &term);
+  }
+  if (rc != SIPP_OK) {
     planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
     traj_in->gain = 0.0;
     return false;
@@ -398,7 +435,7 @@ bool GpuGainEvaluator::updateSegment(TrajectorySegment* segment) {
   last_rrt_path_id_ = map_->getPathMapId();
 
   FlatTree t;
-  t.build(segment);
+  t.build(segment, multi_view() ? &sampler_ : nullptr);
   const int n = (int)t.nodes.size();
   const Eigen::Vector3d cur = planner_.getCurrentPosition();
   const double cur_xy[2] = {cur[0], cur[1]};
@@ -442,9 +479,14 @@ bool GpuGainEvaluator::updateSegment(TrajectorySegment* segment) {
       }
     }
   }
-  if (sipp_update_tree(map_->ctx(), &params_, &updater_, n, t.parent.data(), t.end_xy.data(), t.start_xy.data(), gain.data(),
-                       recost ? cost_new.data() : t.cost.data(), value.data(), terminal.data(), cur_xy, path_changed, &rescored,
-                       recost ? t.cost.data() : nullptr) != SIPP_OK) {
+  const int urc = multi_view()
+      ? sipp_update_tree_views(map_->ctx(), &params_, &updater_, n, t.parent.data(), t.end_xy.data(), t.start_xy.data(), gain.data(),
+                               recost ? cost_new.data() : t.cost.data(), value.data(), terminal.data(), cur_xy, path_changed, &rescored,
+                               recost ? t.cost.data() : nullptr, t.view_off.data(), t.view_xy.data())
+      : sipp_update_tree(map_->ctx(), &params_, &updater_, n, t.parent.data(), t.end_xy.data(), t.start_xy.data(), gain.data(),
+                         recost ? cost_new.data() : t.cost.data(), value.data(), terminal.data(), cur_xy, path_changed, &rescored,
+                         recost ? t.cost.data() : nullptr);
+  if (urc != SIPP_OK) {
     planner_.printError(std::string("'Gpu*Evaluator': ") + sipp_last_error(map_->ctx()));
     return false;
   }

@@ -95,7 +95,22 @@ struct FlatTree {
   std::vector<int32_t> parent;
   std::vector<double> end_xy, start_xy, gain, cost, value;
   std::vector<uint8_t> terminal;
-  void build(TrajectorySegment* root);
+  // the viewpoints every node is scored from (SensorModelPlanExp::sampleViewpoints + mounting translation): node i has
+  // view_xy[view_off[i] .. view_off[i+1]); filled when the sensor model samples along the segment, empty otherwise
+  std::vector<int32_t> view_off;
+  std::vector<double> view_xy;
+  void build(TrajectorySegment* root, const struct ViewSampler* sampler = nullptr);
+};
+
+// SensorModelPlanExp::sampleViewpoints (sensor_model_planexp.cpp:65-90) + the mounting translation (:28-31) on the host: which
+// trajectory points a segment is viewed from, and where the sensor is then
+struct ViewSampler {
+  double sampling_time = 0.0;                       // sensor_model/sampling_time; <= 0: the last point only
+  Eigen::Vector3d mounting_translation;             // sensor_model/mounting_translation_{x,y,z}, rotated by the point's orientation
+  bool single_view() const { return sampling_time <= 0.0; }
+  bool identity_mount() const { return mounting_translation[0] == 0.0 && mounting_translation[1] == 0.0 && mounting_translation[2] == 0.0; }
+  void indices(const EigenTrajectoryPointVector& trajectory, std::vector<int>* out) const;
+  void appendViews(const EigenTrajectoryPointVector& trajectory, std::vector<double>* view_xy) const;     // x, y per sampled viewpoint
 };
 
 // the host half of row A13: which nodes get computeGain / computeValue in this pass (pre-order semantics)
@@ -126,8 +141,8 @@ class GpuGainEvaluator : public TrajectoryEvaluator {
   int last_rrt_path_id_ = 0;          // rrt_star_updater.h:30-31
   bool rrt_path_has_changed_ = true;
   int last_batch_ = 0;
-  double sampling_time_ = 0.0;        // sensor_model/sampling_time (sensor_model_planexp.cpp:170): only <= 0 (last point) is supported
-  bool mounting_nonzero_ = false;     // sensor_model/mounting_*: only the identity is supported
+  ViewSampler sampler_;               // sensor_model/sampling_time (sensor_model_planexp.cpp:170) + sensor_model/mounting_translation_*
+  bool multi_view() const { return !sampler_.single_view() || !sampler_.identity_mount(); }
   std::string config_error_;
 };
 

@@ -32,6 +32,12 @@ int orc_value_select(int32_t n, const double* gain_in, const double* cost_in, co
 int orc_update_tree(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
                     const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value,
                     uint8_t* terminal, const double* cur_xy, int path_changed, int variant, const double* cost_below);
+int orc_sample_viewpoints(const int64_t* times_ns, int32_t npts, double sampling_time, int32_t* out_idx, int32_t cap);
+int orc_gain_batch_views(orc_ctx* c, const sipp_eval_params* p, int32_t n, const int32_t* view_off, const double* view_xy, const double* start_xy,
+                         double* gain, uint32_t* counts, uint8_t* terminal, int variant);
+int orc_update_tree_views(orc_ctx* c, const sipp_eval_params* p, const sipp_updater_params* u, int32_t n, const int32_t* parent,
+                          const double* end_xy, const double* start_xy, double* gain, const double* cost, double* value, uint8_t* terminal,
+                          const double* cur_xy, int path_changed, int variant, const double* cost_below, const int32_t* view_off, const double* view_xy);
 }
 
 using namespace active_3d_planning;
@@ -150,6 +156,31 @@ static void growTree(TrajectorySegment* root, int n, double width, double height
   }
 }
 
+// like growTree, but every segment is a polyline of `npts` points with increasing time stamps and a heading per point: what a sensor
+// model with sampling_time > 0 samples its viewpoints from
+static void growTreeSampled(TrajectorySegment* root, int n, int npts, double width, double height, std::mt19937& rng) {
+  std::vector<TrajectorySegment*> all{root};
+  std::uniform_real_distribution<double> ux(-0.2, width + 0.2), uy(-0.2, height + 0.2), ut(0.15, 0.6), uyaw(-3.1, 3.1);
+  for (int i = 1; i < n; ++i) {
+    TrajectorySegment* par = all[rng() % all.size()];
+    TrajectorySegment* s = par->spawnChild();
+    const Eigen::Vector3d a = par->trajectory.empty() ? Eigen::Vector3d(1.0, 1.0, 0.0) : par->trajectory.back().position_W;
+    const Eigen::Vector3d b(ux(rng), uy(rng), 0.0);
+    int64_t t = 0;
+    for (int k = 0; k < npts; ++k) {
+      EigenTrajectoryPoint p;
+      const double f = (double)k / (npts - 1);
+      p.position_W = Eigen::Vector3d(a[0] + f * (b[0] - a[0]), a[1] + f * (b[1] - a[1]), 0.0);
+      const double yaw = uyaw(rng);
+      p.orientation_W_B = Eigen::Quaterniond(std::cos(yaw / 2), 0.0, 0.0, std::sin(yaw / 2));
+      p.time_from_start_ns = t;
+      t += (int64_t)(ut(rng) * 1e9);
+      s->trajectory.push_back(p);
+    }
+    all.push_back(s);
+  }
+}
+
 static int testCpu() {
   // every type string of the GPU package is registered by static initialisers, like the reference modules
   initialize::sipp_gpu_package();
@@ -198,6 +229,40 @@ static int testCpu() {
   u.updater = SIPP_UPD_DIRECT; u.following = SIPP_FOLLOW_UPDATE_ALL_NON_TERMINAL;
   trajectory_evaluator::updaterMasks(u, t, cur, false, &dg, &mv);
   for (size_t i = 1; i < t.nodes.size(); ++i) CHECK((dg[i] != 0) == !t.terminal[i] && mv[i] == 1, "UpdateAllNonTerminal at %zu", i);
+
+  // viewpoint sampling (SensorModelPlanExp::sampleViewpoints, sensor_model_planexp.cpp:65-90) against the checker's statement of it,
+  // and the mounting translation rotated by the point's orientation
+  {
+    TrajectorySegment sroot;
+    std::mt19937 r2(9);
+    growTreeSampled(&sroot, 60, 7, 16.0, 12.0, r2);
+    trajectory_evaluator::FlatTree st;
+    for (double stime : {0.0, -1.0, 0.2, 0.5, 0.9, 1.5, 100.0}) {
+      trajectory_evaluator::ViewSampler vs;
+      vs.sampling_time = stime;
+      vs.mounting_translation = Eigen::Vector3d(0.25, -0.1, 0.3);
+      st.build(&sroot, &vs);
+      CHECK(st.view_off.size() == st.nodes.size() + 1 && st.view_off[0] == 0, "view_off shape");
+      for (size_t i = 0; i < st.nodes.size(); ++i) {
+        const auto& tr = st.nodes[i]->trajectory;
+        std::vector<int64_t> times;
+        for (const auto& p : tr) times.push_back(p.time_from_start_ns);
+        std::vector<int32_t> want(tr.size() + 1);
+        const int k = orc_sample_viewpoints(times.data(), (int32_t)times.size(), stime, want.data(), (int32_t)want.size());
+        std::vector<int> got;
+        vs.indices(tr, &got);
+        CHECK((int)got.size() == k && st.view_off[i + 1] - st.view_off[i] == k, "node %zu: %zu viewpoints, checker %d (sampling_time %g)", i, got.size(), k, stime);
+        for (int j = 0; j < k && j < (int)got.size(); ++j) {
+          CHECK(got[j] == want[j], "node %zu viewpoint %d: index %d vs %d", i, j, got[j], want[j]);
+          const auto& p = tr[got[j]];
+          const double yaw = 2.0 * std::atan2(p.orientation_W_B.z(), p.orientation_W_B.w());
+          const double ex = p.position_W[0] + std::cos(yaw) * 0.25 - std::sin(yaw) * -0.1, ey = p.position_W[1] + std::sin(yaw) * 0.25 + std::cos(yaw) * -0.1;
+          const double gx = st.view_xy[2 * (st.view_off[i] + j)], gy = st.view_xy[2 * (st.view_off[i] + j) + 1];
+          CHECK(std::fabs(gx - ex) < 1e-12 && std::fabs(gy - ey) < 1e-12, "node %zu viewpoint %d: (%.15g, %.15g) vs (%.15g, %.15g)", i, j, gx, gy, ex, ey);
+        }
+      }
+    }
+  }
 
   // without a CUDA device the map module reports the failure through printError / checkParamsValid: no CPU fallback
   FakePlanner planner;
@@ -413,6 +478,59 @@ static int testGpu() {
       for (int i = 1; i < N; ++i)
         if (t.parent[i] == 0) { if (best < 0 || sub[i] > bv) { best = k; bv = sub[i]; } ++k; }
       CHECK(gev->selectNextBest(&root) == best, "selectNextBest");
+    }
+    // sensor_model/sampling_time > 0 + a mounting translation (sensor_model_planexp.cpp:18-90): per-node computeGain and the batched
+    // root-first pass over a tree of sampled polylines, against the checker scoring the same viewpoints
+    {
+      Module::ParamMap sp = evalParams(cfg.type, cfg.updater, cfg.following);
+      sp["sensor_model/sampling_time"] = "0.7";
+      sp["sensor_model/mounting_translation_x"] = "0.2";
+      sp["sensor_model/mounting_translation_y"] = "-0.15";
+      auto sev_owner = ModuleFactoryRegistry::createModule<TrajectoryEvaluator>(&sp, planner, &err);
+      CHECK(sev_owner != nullptr, "evaluator with sampled viewpoints: %s", err.c_str());
+      auto* sev = dynamic_cast<trajectory_evaluator::GpuGainEvaluator*>(sev_owner.get());
+      TrajectorySegment sroot;
+      std::mt19937 r3(21);
+      growTreeSampled(&sroot, 300, 6, W * 0.0625, H * 0.0625, r3);
+      trajectory_evaluator::ViewSampler vs;
+      vs.sampling_time = 0.7;
+      vs.mounting_translation = Eigen::Vector3d(0.2, -0.15, 0.0);
+      trajectory_evaluator::FlatTree st;
+      st.build(&sroot, &vs);
+      const int SN = (int)st.nodes.size();
+      std::vector<double> sg(SN), scost(SN), sval(SN, 0.0);
+      std::vector<uint8_t> stt(SN);
+      orc_gain_batch_views(orc, &P, SN, st.view_off.data(), st.view_xy.data(), st.start_xy.data(), sg.data(), nullptr, stt.data(), 1);
+      int bad = 0, multi = 0;
+      for (int i = 1; i < SN && sev; ++i) {
+        multi += st.view_off[i + 1] - st.view_off[i] > 1;
+        CHECK(sev->computeGain(st.nodes[i]), "computeGain (sampled viewpoints)");
+        CHECK(sev->computeCost(st.nodes[i]), "computeCost");
+        scost[i] = st.nodes[i]->cost;
+        const double a = st.nodes[i]->gain, b = sg[i];
+        bad += !(a == b || std::fabs(a - b) <= 1e-5 * std::fabs(b)) || (st.nodes[i]->gain_terminal != (stt[i] != 0));
+      }
+      CHECK(bad == 0, "%d gains / terminal flags differ with sampled viewpoints", bad);
+      CHECK(multi > SN / 3, "only %d of %d segments have several viewpoints", multi, SN);
+      // the batched pass
+      planner.position = Eigen::Vector3d(4.0, 3.0, 0.0);
+      const double cur_xy[2] = {4.0, 3.0};
+      std::vector<double> g2(SN), v2(SN);
+      std::vector<uint8_t> t2(SN);
+      for (int i = 0; i < SN; ++i) { g2[i] = st.nodes[i]->gain; v2[i] = st.nodes[i]->value; t2[i] = st.nodes[i]->gain_terminal; }
+      const sipp_updater_params U = sev ? sev->updaterParams() : sipp_updater_params();
+      orc_update_tree_views(orc, &P, &U, SN, st.parent.data(), st.end_xy.data(), st.start_xy.data(), g2.data(), scost.data(), v2.data(), t2.data(), cur_xy,
+                            U.updater == SIPP_UPD_RRT_STAR ? 1 : 0, 1, nullptr, st.view_off.data(), st.view_xy.data());
+      if (sev) CHECK(sev->updateSegment(&sroot), "updateSegment(root) with sampled viewpoints");
+      int dg = 0, dv = 0, dt = 0;
+      for (int i = (U.updater == SIPP_UPD_RRT_STAR ? 1 : 0); i < SN; ++i) {
+        const double g = st.nodes[i]->gain, v = st.nodes[i]->value;
+        dg += !(g == g2[i] || std::fabs(g - g2[i]) <= 1e-5 * std::fabs(g2[i]));
+        dv += !(v == v2[i] || std::fabs(v - v2[i]) <= 1e-5 * std::fabs(v2[i]));
+        dt += (st.nodes[i]->gain_terminal != (t2[i] != 0));
+      }
+      CHECK(dg == 0 && dv == 0 && dt == 0, "sampled viewpoints pass: %d gains, %d values, %d terminal flags differ", dg, dv, dt);
+      std::printf("    sampled viewpoints (sampling_time 0.7 s, mounting translation): %d of %d segments viewed from several points, gains / pass match\n", multi, SN);
     }
     orc_destroy(orc);
     for (auto& e : planner.errors) std::printf("    planner error: %s\n", e.c_str());
