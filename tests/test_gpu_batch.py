@@ -123,6 +123,44 @@ def test_batch_cycle_serves_every_evaluator_family(kw):
     b.close()
 
 
+@pytest.mark.parametrize("w,h,m", [(150, 100, 3), (33, 70, 2), (257, 129, 1)])
+def test_batch_on_ragged_map_sizes(w, h, m):
+    """map sizes that are no multiple of the 32-cell tile (partial tiles on two sides), a batch of one, a map narrower than a footprint:
+    ingest / plan (from scratch, then incremental) / cycle through the batch against the same calls map by map"""
+    params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001)
+    rng = np.random.default_rng(w * 1000 + h)
+    labs, single, batched = [], [], []
+    for k in range(m):
+        lab = synth.make_labels(w, h, 3500 + k)
+        ids = sorted(set(np.unique(lab).tolist()) - {0})
+        desc = sipp.make_desc(w, h, w * synth.MPP, h * synth.MPP, (0.5, 0.5), (w * synth.MPP - 0.5, h * synth.MPP - 0.5), min(ids), max(ids), max(ids))
+        labs.append(lab)
+        single.append(sipp.Context(desc))
+        batched.append(sipp.Context(desc))
+    b = sipp.Batch(batched)
+    for cyc in range(3):
+        sz = 41
+        xs = [int(rng.integers(-10, w)) for _ in range(m)]
+        ys = [int(rng.integers(-10, h)) for _ in range(m)]
+        if cyc == 0:
+            xs, ys = [0] * m, [0] * m
+        ps = [episode.extract_patch(labs[k], xs[k], ys[k], sz, sz) for k in range(m)]
+        b.ingest(xs, ys, ps)
+        plans = b.plan()
+        T = 300
+        xy = [np.ascontiguousarray(rng.uniform([-0.3, -0.3], [w * synth.MPP + 0.3, h * synth.MPP + 0.3], (T, 2))) for _ in range(m)]
+        cost = [rng.uniform(0.5, 3.0, T) for _ in range(m)]
+        bi, bv, gains = b.cycle(params, xy, cost, want_gain=True)
+        for k in range(m):
+            single[k].map_update_patch(xs[k], ys[k], ps[k])
+            c, st, _, n = single[k].plan(path_cap=1)
+            assert plans[k] == (c, st, n), (cyc, k)
+            assert np.array_equal(single[k].field_download(), batched[k].field_download(), equal_nan=True), (cyc, k)
+            g, _, v, i, val = single[k].cycle(params, xy[k], cost[k])
+            assert np.array_equal(g, gains[k]) and i == bi[k] and val == bv[k], (cyc, k)
+    b.close()
+
+
 def test_batch_refuses_what_it_does_not_serve():
     lab, desc = make_map(3300, sipp.make_desc)
     a, c = sipp.Context(desc), sipp.Context(desc)

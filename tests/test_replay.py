@@ -81,6 +81,17 @@ def test_saved_map_loader_errors(R, tmp_path):
         load(R, p)
 
 
+def test_replay_reports_its_failures(R, tmp_path):
+    """a missing saved map (with a GPU) or a missing GPU (here) ends in an error code and a message, never in made-up results"""
+    _, _, desc = synth.world(96, 64, 11, 3, sipp.make_desc)
+    arr = (C.c_char_p * 1)(str(tmp_path / "nothing_here").encode())
+    cost, status = np.full(1, 123.0), np.zeros(1, np.int32)
+    err = C.create_string_buffer(512)
+    rc = R.sipp_replay_saved_maps(arr, 1, C.byref(desc), 0, 4, None, None, cost.ctypes.data, status.ctypes.data, err, 512)
+    assert rc != 0 and err.value and cost[0] == 123.0, (rc, err.value)
+    assert b"cannot open" in err.value or b"no CPU fallback" in err.value or b"CUDA" in err.value, err.value
+
+
 @pytest.mark.gpu
 def test_replay_plans_every_saved_map_like_the_oracle(R, tmp_path):
     from oracle import oracle as orc
