@@ -496,22 +496,31 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
           if (m) {
             fence_gpu();      // the lowered neighbour cells are visible before the neighbour can be told to look
             __syncwarp();
-            // neighbours: N S W E NW NE SW SE
+            // neighbours: N S W E NW NE SW SE. Lane k decides for neighbour k (idle -> queued: ours to enqueue; a running tile re-runs
+            // itself), then lane 0 counts all of the warp's new entries into CTL_PENDING and reserves their queue positions with ONE
+            // returning atomic — the same thread later releases this tile, so its additions and its subtraction are ordered without a fence
+            int nt = -1;
             if (lane < 8 && ((m >> lane) & 1)) {
-              const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-              const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-              const int ntx_ = tx + ddx[lane], nty_ = ty + ddy[lane];
-              if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
-                const int nt = nty_ * a.ntx + ntx_;
-                if (atomicOr(&a.flags[nt], ST_QUEUED) == 0) {     // idle -> queued: ours to enqueue (a running tile re-runs itself)
-                  atomicAdd(&a.ctl[CTL_PENDING], 1);
-                  const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
-                  int* slot = a.queue + (pos % (unsigned)a.cap);
-                  int spins = 0;
-                  while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);   // never expected: cap >= number of tiles
-                  st_volatile_i32(slot, nt);
-                  ++push_local;
-                }
+              const int ntx_ = tx + ((0xA8 >> lane) & 1) - ((0x54 >> lane) & 1);      // dx: 0 0 -1 1 -1 1 -1 1
+              const int nty_ = ty + ((0xC2 >> lane) & 1) - ((0x31 >> lane) & 1);      // dy: -1 1 0 0 -1 -1 1 1
+              if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) nt = nty_ * a.ntx + ntx_;
+            }
+            const bool enq = nt >= 0 && atomicOr(&a.flags[nt], ST_QUEUED) == 0;
+            const unsigned em = __ballot_sync(0xFFFFFFFFu, enq);
+            if (em) {
+              unsigned pos0 = 0;
+              if (lane == 0) {
+                const int k = __popc(em);
+                atomicAdd(&a.ctl[CTL_PENDING], k);
+                pos0 = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], k);
+              }
+              pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
+              if (enq) {
+                // the slot is free: at most ntiles <= cap entries are outstanding (a tile is queued at most once), so the entry that
+                // used this slot one lap ago was popped, and the slot reset, long ago
+                const unsigned pos = pos0 + (unsigned)__popc(em & ((1u << lane) - 1u));
+                st_volatile_i32(a.queue + (pos % (unsigned)a.cap), nt);
+                ++push_local;
               }
             }
             __syncwarp();
@@ -526,9 +535,12 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
       // ---- done with this run: idle again, unless one of our cells was lowered meanwhile
       int again = 0;
       if (lane == 0) {
-        fence_gpu();
+        // shared ownership: nothing to order here — this thread's own additions to CTL_PENDING precede its subtraction (same address, same
+        // thread), the border ring was fenced before the neighbours were told to look, and the interior stores only have to be
+        // complete when the kernel is (a warp that re-runs this tile meanwhile starts from older, higher values: still upper bounds,
+        // and the stores land as minima)
         if (!(a.mode & 2)) atomicSub(&a.ctl[CTL_PENDING], 1);
-        else if (atomicCAS(&a.flags[ti], ST_RUN, 0) != ST_RUN) {
+        else if (fence_gpu(), atomicCAS(&a.flags[ti], ST_RUN, 0) != ST_RUN) {
           atomicExch(&a.flags[ti], ST_RUN);      // take the request; everything lowered before this point is re-loaded below
           fence_gpu();
           again = 1;
@@ -1587,6 +1599,18 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
     cudaEventElapsedTime(&t12, ev[1], ev[2]);
     cudaEventElapsedTime(&t23, ev[2], ev[3]);
     fprintf(stderr, "[sipp] plan phases: init+relax %.3f ms, backtrack %.3f ms, mask %.3f ms\n", t01, t12, t23);
+#ifdef SIPP_RELAX_PROFILE
+    {      // -DSIPP_RELAX_PROFILE: the workers' clock64 accounts (k_relax: SIPP_TICK), summed over all warps
+      int ctl[32];
+      cudaMemcpy(ctl, ctx->d_relax_ctl, sizeof(ctl), cudaMemcpyDeviceToHost);
+      unsigned long long tp[6];
+      memcpy(tp, ctl + 16, sizeof(tp));
+      const double act = ctl[CTL_ACTIVATIONS] > 0 ? ctl[CTL_ACTIVATIONS] : 1;
+      fprintf(stderr, "[sipp] relax cycles per activation: pop+wait %.0f  load %.0f  sweeps %.0f  store+cross %.0f  push+release %.0f  (activations %d, sweeps %d; "
+              "warp-cycles in total %.3g)\n", tp[0] / act, tp[1] / act, tp[2] / act, tp[3] / act, tp[4] / act, ctl[CTL_ACTIVATIONS], ctl[CTL_SWEEPS],
+              (double)(tp[0] + tp[1] + tp[2] + tp[3] + tp[4]));
+    }
+#endif
     for (auto& e : ev) cudaEventDestroy(e);
   }
   return SIPP_OK;

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-J=gpurun_out/r2_j33
-( timeout 900 python -m pytest tests/test_gpu_batch.py tests/test_replay.py -m gpu -q --timeout 600 --timeout-method thread ) > ${J}_py.log 2>&1; tail -n 30 ${J}_py.log | cut -c1-300
+J=gpurun_out/r2_j36
+( timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread ) > ${J}_pytest.log 2>&1
+tail -n 6 ${J}_pytest.log | cut -c1-300
