@@ -447,7 +447,7 @@ int sipp_create(const sipp_map_desc* d, int device, sipp_ctx** out) {
   rc |= dev_alloc(ctx, &ctx->d_seed_list, ntiles + ntiles / 4 + 2);    // seed map bytes + seed list ints
   // d_tile_w (edge-weight cache of the per-tile relaxation kernel) is allocated by field_plan when SIPP_RELAX_KERNEL=0 selects that kernel
   rc |= dev_alloc(ctx, &ctx->d_tile_flags, ntiles);
-  rc |= dev_alloc(ctx, &ctx->d_tile_list, ntiles > 16384 ? ntiles : (size_t)16384);   // ring queue: >= tiles and >= resident warps
+  rc |= dev_alloc(ctx, &ctx->d_tile_list, 2 * (ntiles > 16384 ? ntiles : (size_t)16384));   // two ring queues (plain + re-activated tiles), each >= tiles and >= resident warps
   rc |= dev_alloc(ctx, &ctx->d_relax_ctl, 32);
   rc |= dev_alloc(ctx, &ctx->d_path_nodes, cap);
   rc |= dev_alloc(ctx, &ctx->d_path_xy, 2 * cap);
