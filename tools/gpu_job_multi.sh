@@ -1,11 +1,14 @@
-# usage: bash tools/gpu_job_multi.sh N
+# usage: bash tools/gpu_job_multi.sh N [what]     what: all (default) | config4
 N=$1
+WHAT=${2:-all}
 mkdir -p gpurun_out
 J=gpurun_out/r2_multi_n$N
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 "$@"; }
-( run bench.py --gpus $N --steps 200 --warmup 10 > ${J}_bench.json 2> ${J}_bench.err ); echo "bench rc $?"; tail -c 700 ${J}_bench.json
+if [ "$WHAT" = "all" ]; then
+  ( run bench.py --gpus $N --steps 200 --warmup 10 > ${J}_bench.json 2> ${J}_bench.err ); echo "bench rc $?"; tail -c 700 ${J}_bench.json
+fi
 ( SIPP_BENCH_WORKLOAD=config4 run bench.py --gpus $N --steps 100 --warmup 10 > ${J}_config4.json 2> ${J}_config4.err ); echo "config4 rc $?"; tail -c 500 ${J}_config4.json
-if [ "$N" = "8" ]; then
+if [ "$N" = "8" ] && [ "$WHAT" = "all" ]; then
   ( SIPP_BATCH_THREADS=2 run tools/ensemble_bench.py --maps 128 --cycles 16 --mode batch --batches 2 > ${J}_ens.jsonl 2> ${J}_ens.err ); echo "ens rc $?"
   python -c "
 import json
