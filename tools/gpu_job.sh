@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-J=gpurun_out/r2_j39
-for W in 4096 8192 640; do
-  ( SIPP_LIB_PATH=$PWD/scouting-ipp_b200/libsipp_prev.so timeout 400 python tools/relax_ab.py $W 0 ) > ${J}_prev$W.log 2>&1
-  ( AB_KEEP_REF=1 timeout 400 python tools/relax_ab.py $W 0 ) > ${J}_new$W.log 2>&1
-  grep -o "W [0-9]* \|plan median [0-9.]* ms (min [0-9.]*)\|same_field=[A-Za-z]*" ${J}_prev$W.log ${J}_new$W.log | tr '\n' ' '; echo
+J=gpurun_out/r2_j40
+for P in 0 1 0 1; do
+  ( SIPP_RELAX_PAPE_BATCH=$P SIPP_BATCH_THREADS=4 timeout 300 python tools/ensemble_bench.py --maps 128 --cycles 16 --mode batch --batches 4 ) > ${J}_ens_p$P.json 2> ${J}_ens_p$P.err
+  python -c "import json; d=json.loads(open('${J}_ens_p$P.json').read().strip().splitlines()[-1]); print('pape_batch $P:', round(d['value']), d['ms_per_map_cycle_in_ensemble'])" || tail -n 3 ${J}_ens_p$P.err
 done
