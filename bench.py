@@ -328,11 +328,12 @@ def main():
     # ---- follower cost-to-go + path + mask: once per planning cycle (replicated per GPU: the wavefront does not shard)
     ctx.set_incremental(False)          # "plan" below = from scratch; the incremental re-plan is timed at the end (rank 0)
     ctx.plan()
-    plan_ms = []
+    plan_ms, relax_ms = [], []
     for _ in range(3):
         t0 = time.perf_counter()
         pcost, pstatus, _, plen = ctx.plan()
         plan_ms.append((time.perf_counter() - t0) * 1e3)
+        relax_ms.append(ctx.plan_phases()[0])      # the relaxation kernel alone, CUDA events on the plan's stream
     pstats = ctx.plan_stats()
 
     T = T_PER_GPU
@@ -677,6 +678,12 @@ def main():
                              "step k+1, the last gather is timed in full")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "cycle": {"plan_ms": float(np.median(plan_ms)), "plan_cost": pcost, "plan_path_nodes": plen, "plan_stats": pstats,
+                  "relax_roofline": {"bound": "hbm", "kernel": "k_relax", "kernel_ms": float(np.median(relax_ms)),
+                                     "achieved": 10.0 * W * H / (float(np.median(relax_ms)) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": 10.0 * W * H / (float(np.median(relax_ms)) * 1e-3) / 1e9 / peak,
+                                     "algorithmic_bytes_per_launch": 10 * W * H,
+                                     "note": "10 B per cell settled (u16 code read + f64 written); the kernel is bound by its chain of dependent tile "
+                                             "activations, not by bytes (DESIGN.md 4.2)"},
                   "eval_ms": total_ms / args.steps, "ms_per_full_cycle": float(np.median(plan_ms)) + total_ms / args.steps,
                   "incremental": incremental,
                   "ms_per_cycle_incremental": incremental["patch_ingest_ms_median"] + incremental["replan_ms_median"] + total_ms / args.steps,
