@@ -1401,6 +1401,7 @@ struct sipp_batch {
   uint8_t *h_cyc, *d_cyc;  size_t cyc_bytes;     // cycle: m view blocks + m gain blocks + candidates (xy, cost)
   uint8_t *d_res;  size_t res_bytes;  // cycle scratch: gain, value, terminal per candidate; best records at the front
   BestRec* h_best;                    // m records
+  int* d_roam;  int roam_cap;  bool roam_dirty;  int roam_share;     // shared relaxation queue (32 control ints, then roam_cap slots); cap 0 = off
   int64_t launches;
   char err[320];
 };
@@ -1444,7 +1445,7 @@ void sipp_batch_destroy(sipp_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
   void* hp[] = {b->h_plan, b->h_seed, b->h_out, b->h_ing, b->h_cyc, b->h_best};
-  void* dp[] = {b->d_plan, b->d_seed, b->d_out, b->d_ing, b->d_cyc, b->d_res};
+  void* dp[] = {b->d_plan, b->d_seed, b->d_out, b->d_ing, b->d_cyc, b->d_res, b->d_roam};
   for (void* p : hp) if (p) cudaFreeHost(p);
   for (void* p : dp) if (p) cudaFree(p);
   delete b;
@@ -1486,6 +1487,12 @@ int sipp_batch_create(sipp_ctx* const* ctxs, int32_t m, sipp_batch** out) {
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_out), sizeof(int) * 40 * m);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->d_out), sizeof(int) * 40 * m);
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_best), sizeof(BestRec) * m);
+  // one relaxation work queue for all maps (SIPP_BATCH_ROAM=0: every map's relaxation on worker CTAs of its own); SIPP_BATCH_SHARE = how
+  // many batches the caller runs side by side on this GPU (each takes that fraction of the SMs for its persistent workers)
+  b->roam_cap = (getenv("SIPP_BATCH_ROAM") && atoi(getenv("SIPP_BATCH_ROAM")) == 0) ? 0 : (int)field_roam_queue_ints(ntiles, m);
+  b->roam_share = getenv("SIPP_BATCH_SHARE") ? atoi(getenv("SIPP_BATCH_SHARE")) : 1;
+  b->roam_dirty = true;
+  if (e == cudaSuccess && b->roam_cap > 0) e = cudaMalloc(reinterpret_cast<void**>(&b->d_roam), sizeof(int) * (32 + (size_t)b->roam_cap));
   if (e != cudaSuccess) return fail(batch_fail(b, SIPP_ERR_CUDA, "batch staging: %s", cudaGetErrorString(e)));
   // helper threads for the per-map host loops: SIPP_BATCH_THREADS (total, including the caller), default 4
   int threads = getenv("SIPP_BATCH_THREADS") ? atoi(getenv("SIPP_BATCH_THREADS")) : 4;
@@ -1530,7 +1537,15 @@ static int batch_ingest_enqueue(sipp_batch* b, const int32_t* x0, const int32_t*
 static int batch_plan_enqueue(sipp_batch* b) {
   int n = 0;
   const std::function<void(int, const std::function<void(int)>&)> runner = [b](int count, const std::function<void(int)>& f) { b->pool.run(count, f); };
-  int rc = field_plan_batch(b->ctx.data(), b->m, b->h_plan, b->d_plan, b->h_seed, b->d_seed, b->seed_stride, b->d_out, b->stream, &n, &runner);
+  const bool roam = b->roam_cap > 0;
+  if (roam && b->roam_dirty) {
+    const int rr = field_roam_reset(b->ctx[0], b->d_roam + 32, b->roam_cap, b->d_roam, b->stream);
+    if (rr != SIPP_OK) return batch_err(b, rr, b->ctx[0]);
+    b->roam_dirty = false;
+    b->launches += 1;
+  }
+  int rc = field_plan_batch(b->ctx.data(), b->m, b->h_plan, b->d_plan, b->h_seed, b->d_seed, b->seed_stride, b->d_out, b->stream, &n, &runner,
+                            roam ? b->d_roam + 32 : nullptr, b->roam_cap, roam ? b->d_roam : nullptr, b->roam_share);
   if (rc != SIPP_OK) {
     for (sipp_ctx* c : b->ctx) c->warm_valid = false;
     return batch_err(b, rc, b->ctx[0]);
@@ -1550,6 +1565,7 @@ static int batch_plan_collect(sipp_batch* b, double* cost, int32_t* status, int3
     int32_t st = 0;
     const int rc = plan_collect(b->ctx[i], b->h_out + 40 * i, b->h_out + 40 * i + 16, &c, &st, &len, &found);
     if (rc != SIPP_OK && first_rc == SIPP_OK) first_rc = batch_err(b, rc, b->ctx[i]);
+    if (rc != SIPP_OK) b->roam_dirty = true;      // a watchdog abort leaves entries in the shared queue
     if (cost) cost[i * stride] = c;
     if (status) status[i * stride] = st;
     if (path_len) path_len[i * stride] = found ? len : 0;

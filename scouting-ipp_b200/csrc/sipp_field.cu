@@ -324,11 +324,26 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 //  (3) the kernel ends when the number of queued + running tiles drops to zero, i.e. at a global fixed point, which is unique.
 constexpr int ST_QUEUED = 1, ST_RUN = 2, ST_VISITED = 4;
 
-__device__ __forceinline__ void relax_body(const RelaxArgs& a) {
+// Batched form (ROAM): ONE work queue for all maps of a batch. An entry is (map << kRoamShift) | tile; a worker takes whatever
+// comes next and reads that map's argument block, so the workers go where the work is — a map with a long re-plan gets all the
+// warps the others no longer need, instead of a fixed share of CTAs that hold their SMs until their own map is drained. Tile
+// flags, statistics and the field stay per map; HEAD / TAIL / PENDING / ABORT are the batch's (pending == 0: every map is at its
+// fixed point). k_roam_collect moves what the per-map seeding kernels queued into it; k_gather_plan_out rewinds its counters.
+constexpr int kRoamShift = 20;
+struct RoamQ {
+  int* queue; int cap; int* ctl;
+  const char* args; size_t stride;     // map y's RelaxArgs at args + y * stride
+};
+
+template <bool ROAM>
+__device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& rq) {
   extern __shared__ __align__(16) uint8_t relax_smem[];
   __shared__ __align__(8) uint64_t s_bar[kRelaxWarps];
 
-  const FieldGeom& g = a.g;
+  int* const q_queue = ROAM ? rq.queue : a0.queue;
+  int* const q_ctl = ROAM ? rq.ctl : a0.ctl;
+  const int q_cap = ROAM ? rq.cap : a0.cap;
+  const int pape = ROAM ? 0 : a0.pape;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TileSmem& t = reinterpret_cast<TileSmem*>(relax_smem)[warp];
   const uint32_t bar = smem_addr(&s_bar[warp]);
@@ -350,9 +365,9 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
     int ti = -2;
     if (lane == 0) {
       // two-ring form: the ring of re-activated tiles first when it holds entries (a snapshot: a ticket taken in vain just waits there)
-      const bool ring1 = a.pape && (int)((unsigned)ld_volatile_i32(&a.ctl[CTL_TAIL1]) - (unsigned)ld_volatile_i32(&a.ctl[CTL_HEAD1])) > 0;
-      const unsigned ticket = (unsigned)atomicAdd(&a.ctl[ring1 ? CTL_HEAD1 : CTL_HEAD], 1);
-      int* slot = a.queue + (ring1 ? a.cap : 0) + (ticket % (unsigned)a.cap);
+      const bool ring1 = pape && (int)((unsigned)ld_volatile_i32(&q_ctl[CTL_TAIL1]) - (unsigned)ld_volatile_i32(&q_ctl[CTL_HEAD1])) > 0;
+      const unsigned ticket = (unsigned)atomicAdd(&q_ctl[ring1 ? CTL_HEAD1 : CTL_HEAD], 1);
+      int* slot = q_queue + (ring1 ? q_cap : 0) + (ticket % (unsigned)q_cap);
       int spins = 0;
       for (;;) {
         const int v = ld_volatile_i32(slot);
@@ -361,21 +376,28 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
           ti = v;
           break;
         }
-        if (ld_volatile_i32(&a.ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) break;
-        if (++spins > a.spin_limit) {
-          atomicExch(&a.ctl[CTL_ABORT], 1);
+        if (ld_volatile_i32(&q_ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&q_ctl[CTL_ABORT]) != 0) break;
+        if (++spins > a0.spin_limit) {
+          atomicExch(&q_ctl[CTL_ABORT], 1);
           break;
         }
         __nanosleep(64);
       }
       if (ti >= 0) {
-        atomicExch(&a.flags[ti], (a.mode & 2) ? ST_RUN : (a.pape ? ST_VISITED : 0));   // queued -> running; a lowering from here on sets QUEUED again
+        const RelaxArgs& am = ROAM ? *reinterpret_cast<const RelaxArgs*>(rq.args + (size_t)(ti >> kRoamShift) * rq.stride) : a0;
+        const int tm = ROAM ? (ti & ((1 << kRoamShift) - 1)) : ti;
+        atomicExch(&am.flags[tm], (a0.mode & 2) ? ST_RUN : (pape ? ST_VISITED : 0));   // queued -> running; a lowering from here on sets QUEUED again
         fence_gpu();
       }
     }
     ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
     if (ti < 0) break;
     SIPP_TICK(0)
+    const int tag = ROAM ? (ti >> kRoamShift) << kRoamShift : 0;      // this entry's map, as it goes into the entries pushed below
+    if (ROAM) ti &= (1 << kRoamShift) - 1;
+    const RelaxArgs& a = ROAM ? *reinterpret_cast<const RelaxArgs*>(rq.args + (size_t)(tag >> kRoamShift) * rq.stride) : a0;
+    const FieldGeom& g = a.g;
+    const int act0 = act_local, sweeps0 = sweeps_local, push0 = push_local;
 
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
@@ -516,12 +538,12 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
               // served first, so that the correction overtakes the front instead of trailing it. Only when there is a backlog: a ring
               // with waiting workers takes the entry whatever its kind.
               unsigned m1 = 0;
-              if (a.pape) {
+              if (pape) {
                 m1 = __ballot_sync(0xFFFFFFFFu, enq && (oldf & ST_VISITED));
                 int w0 = 0, w1 = 0;
                 if (lane == 0) {
-                  w0 = (int)((unsigned)ld_volatile_i32(&a.ctl[CTL_HEAD]) - (unsigned)ld_volatile_i32(&a.ctl[CTL_TAIL]));
-                  w1 = (int)((unsigned)ld_volatile_i32(&a.ctl[CTL_HEAD1]) - (unsigned)ld_volatile_i32(&a.ctl[CTL_TAIL1]));
+                  w0 = (int)((unsigned)ld_volatile_i32(&q_ctl[CTL_HEAD]) - (unsigned)ld_volatile_i32(&q_ctl[CTL_TAIL]));
+                  w1 = (int)((unsigned)ld_volatile_i32(&q_ctl[CTL_HEAD1]) - (unsigned)ld_volatile_i32(&q_ctl[CTL_TAIL1]));
                 }
                 w0 = __shfl_sync(0xFFFFFFFFu, w0, 0);
                 w1 = __shfl_sync(0xFFFFFFFFu, w1, 0);
@@ -531,9 +553,9 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
               const unsigned m0 = em & ~m1;
               unsigned pos0 = 0, pos1 = 0;
               if (lane == 0) {
-                atomicAdd(&a.ctl[CTL_PENDING], __popc(em));
-                if (m0) pos0 = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], __popc(m0));
-                if (m1) pos1 = (unsigned)atomicAdd(&a.ctl[CTL_TAIL1], __popc(m1));
+                atomicAdd(&q_ctl[CTL_PENDING], __popc(em));
+                if (m0) pos0 = (unsigned)atomicAdd(&q_ctl[CTL_TAIL], __popc(m0));
+                if (m1) pos1 = (unsigned)atomicAdd(&q_ctl[CTL_TAIL1], __popc(m1));
               }
               pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
               pos1 = __shfl_sync(0xFFFFFFFFu, pos1, 0);
@@ -543,7 +565,7 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
                 const bool r1 = (m1 >> lane) & 1;
                 const unsigned mm = r1 ? m1 : m0;
                 const unsigned pos = (r1 ? pos1 : pos0) + (unsigned)__popc(mm & ((1u << lane) - 1u));
-                st_volatile_i32(a.queue + (r1 ? a.cap : 0) + (pos % (unsigned)a.cap), nt);
+                st_volatile_i32(q_queue + (r1 ? q_cap : 0) + (pos % (unsigned)q_cap), nt | tag);
                 ++push_local;
               }
             }
@@ -563,31 +585,41 @@ __device__ __forceinline__ void relax_body(const RelaxArgs& a) {
         // thread), the border ring was fenced before the neighbours were told to look, and the interior stores only have to be
         // complete when the kernel is (a warp that re-runs this tile meanwhile starts from older, higher values: still upper bounds,
         // and the stores land as minima)
-        if (!(a.mode & 2)) atomicSub(&a.ctl[CTL_PENDING], 1);
+        if (!(a.mode & 2)) atomicSub(&q_ctl[CTL_PENDING], 1);
         else if (fence_gpu(), atomicCAS(&a.flags[ti], ST_RUN, 0) != ST_RUN) {
           atomicExch(&a.flags[ti], ST_RUN);      // take the request; everything lowered before this point is re-loaded below
           fence_gpu();
           again = 1;
         } else {
-          atomicSub(&a.ctl[CTL_PENDING], 1);     // after our pushes were counted: pending reaches 0 only at the global fixed point
+          atomicSub(&q_ctl[CTL_PENDING], 1);     // after our pushes were counted: pending reaches 0 only at the global fixed point
         }
       }
       again = __shfl_sync(0xFFFFFFFFu, again, 0);
       SIPP_TICK(4)
       if (!again) break;
     }
+    if (ROAM) {      // statistics go to the map the tile belongs to
+      const int pushed = __reduce_add_sync(0xFFFFFFFFu, push_local - push0);
+      if (lane == 0) {
+        if (pushed) atomicAdd(&a.ctl[CTL_PUSHES], pushed);
+        atomicAdd(&a.ctl[CTL_ACTIVATIONS], act_local - act0);
+        atomicAdd(&a.ctl[CTL_SWEEPS], sweeps_local - sweeps0);
+      }
+    }
   }
+  if (ROAM) return;
 #ifdef SIPP_RELAX_PROFILE
   if (lane == 0)
-    for (int i = 0; i < 6; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + 16) + i, (unsigned long long)tp[i]);
+    for (int i = 0; i < 6; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a0.ctl + 16) + i, (unsigned long long)tp[i]);
 #endif
   // statistics
-  atomicAdd(&a.ctl[CTL_PUSHES], push_local);
+  atomicAdd(&a0.ctl[CTL_PUSHES], push_local);
   if (lane == 0) {
-    atomicAdd(&a.ctl[CTL_ACTIVATIONS], act_local);
-    atomicAdd(&a.ctl[CTL_SWEEPS], sweeps_local);
+    atomicAdd(&a0.ctl[CTL_ACTIVATIONS], act_local);
+    atomicAdd(&a0.ctl[CTL_SWEEPS], sweeps_local);
   }
 }
+__device__ __forceinline__ void relax_body(const RelaxArgs& a) { relax_body_t<false>(a, RoamQ{}); }
 
 // Plan from scratch, first kernel: field <- +inf, empty work queue, zeroed control block and counters; the ingest marks of an abandoned
 // warm start are cleared as well (mark16 != nullptr)
@@ -1274,11 +1306,52 @@ SIPP_BATCH_KERNEL(k_path_finish_b, , rs, true, path_finish_body)
 #undef SIPP_BATCH_KERNEL
 
 // results of a batched plan: every map's plan_out[0..9] and relaxation control block [0..23] gathered into one array (one copy back)
-__global__ void k_gather_plan_out(const PlanArgsAll* __restrict__ all, int* __restrict__ out) {
+__global__ void k_gather_plan_out(const PlanArgsAll* __restrict__ all, int* __restrict__ out, int* roam_ctl) {
   const PlanArgsAll& m = all[blockIdx.x];
   const int t = threadIdx.x;
   if (t < 10) out[blockIdx.x * 40 + t] = m.pa.out[t];
-  else if (t >= 16 && t < 40) out[blockIdx.x * 40 + t] = m.ra.ctl[t - 16];
+  else if (t >= 16 && t < 40) {
+    int v = m.ra.ctl[t - 16];
+    if (roam_ctl && t - 16 == CTL_ABORT && v == 0) v = roam_ctl[CTL_ABORT];      // the shared queue's watchdog fails every map of the batch
+    out[blockIdx.x * 40 + t] = v;
+  }
+  // the workers left with one unserved ticket each: rewind the shared queue's counters for the next plan (every slot is empty again
+  // and pending is zero after a run that was not aborted; an aborted one is reset by the host)
+  if (roam_ctl && blockIdx.x == 0 && t == 63 && roam_ctl[CTL_ABORT] == 0) {
+    roam_ctl[CTL_HEAD] = 0;
+    roam_ctl[CTL_TAIL] = 0;
+  }
+}
+
+// shared work queue of a batch (RoamQ): block y moves what map y's seeding kernels queued — entries [0, TAIL) of its own queue,
+// HEAD is 0 at this point in both plan forms — into the batch's queue, tagged with the map
+__global__ void k_roam_collect(const PlanArgsAll* __restrict__ all, RoamQ rq) {
+  const RelaxArgs& a = all[blockIdx.x].ra;
+  __shared__ unsigned base;
+  const int n = ld_volatile_i32(&a.ctl[CTL_TAIL]);
+  if (n <= 0) return;
+  if (threadIdx.x == 0) {
+    base = (unsigned)atomicAdd(&rq.ctl[CTL_TAIL], n);
+    atomicAdd(&rq.ctl[CTL_PENDING], n);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {      // handed over: a later plan that seeds nothing must not find this count again
+    st_volatile_i32(&a.ctl[CTL_TAIL], 0);
+    st_volatile_i32(&a.ctl[CTL_PENDING], 0);
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int v = a.queue[i];
+    a.queue[i] = -1;
+    rq.queue[(base + (unsigned)i) % (unsigned)rq.cap] = v | ((int)blockIdx.x << kRoamShift);
+  }
+}
+__global__ void __launch_bounds__(kRelaxWarps * 32) k_relax_roam(const PlanArgsAll* __restrict__ all, RoamQ rq) {
+  relax_body_t<true>(all[0].ra, rq);
+}
+__global__ void k_roam_reset(RoamQ rq) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = i0; i < rq.cap; i += gridDim.x * blockDim.x) rq.queue[i] = -1;
+  if (i0 < 32) rq.ctl[i0] = 0;
 }
 
 }  // namespace
@@ -1314,6 +1387,7 @@ int device_setup(sipp_ctx* ctx, DevInfo* out) {
     SIPP_CUDA_CHECK(ctx, cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
@@ -1652,8 +1726,23 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s) {
 // least as large). Returns after enqueueing on `s` (the caller synchronises and reads d_out).
 size_t field_plan_batch_args_bytes() { return sizeof(PlanArgsAll); }
 
+// roam_queue / roam_cap / roam_ctl: the batch's shared relaxation queue (field_roam_*), nullptr = every map's relaxation on CTAs of its own
+size_t field_roam_queue_ints(int ntiles, int m) {
+  if (m >= (1 << (31 - kRoamShift)) || ntiles >= (1 << kRoamShift)) return 0;      // the entry's map / tile fields
+  size_t cap = 1024;
+  while (cap < (size_t)ntiles * m) cap <<= 1;      // a tile is queued at most once: never more entries than tiles
+  return cap;
+}
+int field_roam_reset(sipp_ctx* c0, int* roam_queue, int roam_cap, int* roam_ctl, cudaStream_t s) {
+  RoamQ rq{roam_queue, roam_cap, roam_ctl, nullptr, 0};
+  k_roam_reset<<<64, 256, 0, s>>>(rq);
+  SIPP_CUDA_CHECK(c0, cudaGetLastError());
+  return SIPP_OK;
+}
+
 int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, uint8_t* h_seed, uint8_t* d_seed, size_t seed_stride, int* d_out,
-                     cudaStream_t s, int* launches, const std::function<void(int, const std::function<void(int)>&)>* runner) {
+                     cudaStream_t s, int* launches, const std::function<void(int, const std::function<void(int)>&)>* runner,
+                     int* roam_queue, int roam_cap, int* roam_ctl, int roam_share) {
   if (m <= 0) return SIPP_OK;
   sipp_ctx* c0 = ctxs[0];
   DevInfo dev;
@@ -1661,7 +1750,7 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
   if (rc != SIPP_OK) return rc;
   PlanArgsAll* A = reinterpret_cast<PlanArgsAll*>(h_args);
   const int ntiles = c0->n_tiles_x * c0->n_tiles_y;
-  int any_init = 0, any_inc = 0, any_inval = 0, any_weights_all = 0, max_nl = 0, any_check = 0, max_relax = 1, max_inval = 1;
+  int any_init = 0, any_inc = 0, any_inval = 0, any_weights_all = 0, max_nl = 0, any_check = 0, max_relax = 1, max_inval = 1, sum_relax = 0;
   for (int i = 0; i < m; ++i) {
     sipp_ctx* ctx = ctxs[i];
     if (!ctx->d_tile_w) {
@@ -1691,6 +1780,7 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
       else if (A[i].wa.n_items > max_nl) max_nl = A[i].wa.n_items;
     }
     if (A[i].relax_grid > max_relax) max_relax = A[i].relax_grid;
+    sum_relax += A[i].relax_grid;
     if (A[i].inval_grid > max_inval) max_inval = A[i].inval_grid;
   }
   SIPP_CUDA_CHECK(c0, cudaMemcpyAsync(d_args, h_args, (size_t)m * sizeof(PlanArgsAll), cudaMemcpyHostToDevice, s));
@@ -1711,13 +1801,23 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
     k_seed_relax_b<<<dim3((ntiles + 255) / 256, M), 256, 0, s>>>(dA);
     n += 2;
   }
-  k_relax_b<<<dim3(max_relax, M), kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA);
+  if (roam_queue) {
+    RoamQ rq{roam_queue, roam_cap, roam_ctl, reinterpret_cast<const char*>(d_args) + offsetof(PlanArgsAll, ra), sizeof(PlanArgsAll)};
+    int grid = dev.num_sms * dev.occ / (roam_share > 1 ? roam_share : 1);      // batches that run side by side split the SMs
+    if (grid > sum_relax) grid = sum_relax;
+    if (grid < 1) grid = 1;
+    k_roam_collect<<<M, 256, 0, s>>>(dA, rq);
+    k_relax_roam<<<grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA, rq);
+    n += 1;
+  } else {
+    k_relax_b<<<dim3(max_relax, M), kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA);
+  }
   if (any_check) { k_path_check_b<<<dim3(4, M), 256, 0, s>>>(dA); n += 1; }
   k_pred_b<<<dim3(ntiles, M), kPredThreads, 0, s>>>(dA);
   k_backtrack_b<<<dim3(1, M), kBackThreads, PW * PW, s>>>(dA);
   k_mask_clear_b<<<dim3(32, M), 256, 0, s>>>(dA);
   k_path_finish_b<<<dim3(4, M), 256, 0, s>>>(dA);
-  k_gather_plan_out<<<M, 64, 0, s>>>(dA, d_out);
+  k_gather_plan_out<<<M, 64, 0, s>>>(dA, d_out, roam_queue ? roam_ctl : nullptr);
   n += 6;
   SIPP_CUDA_CHECK(c0, cudaGetLastError());
   if (launches) *launches = n;

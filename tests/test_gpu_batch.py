@@ -20,8 +20,11 @@ def make_map(seed, mk):
     return lab, desc
 
 
-def test_batch_steps_match_independent_contexts():
-    """ingest / plan / cycle through the batch against the same calls made map by map: from scratch, then incrementally"""
+@pytest.mark.parametrize("roam", ["1", "0"])
+def test_batch_steps_match_independent_contexts(roam, monkeypatch):
+    """ingest / plan / cycle through the batch against the same calls made map by map: from scratch, then incrementally; with the
+    batch's shared relaxation queue (the default) and with per-map relaxation workers"""
+    monkeypatch.setenv("SIPP_BATCH_ROAM", roam)
     m, T = 5, 777
     params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001)
     labs, single, batched = [], [], []
@@ -56,6 +59,8 @@ def test_batch_steps_match_independent_contexts():
             assert plans[k] == (c, st, n), (cyc, k, plans[k], (c, st, n))
             assert single[k].plan_info()["incremental"] == batched[k].plan_info()["incremental"] == (cyc > 0)       # same start mode: scratch, then incremental
             assert np.array_equal(single[k].field_download(), batched[k].field_download()), (cyc, k)
+            if cyc == 0:      # the relaxation statistics stay per map
+                assert batched[k].plan_stats()["tile_activations"] >= (W // 32) * (H // 32) and batched[k].plan_stats()["aborted"] == 0
             ms, mb = single[k].map_download(), batched[k].map_download()
             for a_, b_ in zip(ms, mb):
                 assert np.array_equal(a_, b_), (cyc, k)
