@@ -1,6 +1,7 @@
 // C ABI of libsipp.so (include/sipp.h): context, host-side sequential bookkeeping, staging and launches.
 // There is no CPU compute path in here: every result comes from the kernels in sipp_{map,gain,field,select}.cu.
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1401,7 +1402,7 @@ struct sipp_batch {
   uint8_t *h_cyc, *d_cyc;  size_t cyc_bytes;     // cycle: m view blocks + m gain blocks + candidates (xy, cost)
   uint8_t *d_res;  size_t res_bytes;  // cycle scratch: gain, value, terminal per candidate; best records at the front
   BestRec* h_best;                    // m records
-  int* d_roam;  int roam_cap;  bool roam_dirty;  int roam_share;     // shared relaxation queue (32 control ints, then roam_cap slots); cap 0 = off
+  int* d_roam;  int roam_cap;  bool roam_dirty;  int roam_share, roam_kind;     // shared relaxation queue (32 control ints, then roam_cap slots); cap 0 = off
   int64_t launches;
   char err[320];
 };
@@ -1489,7 +1490,9 @@ int sipp_batch_create(sipp_ctx* const* ctxs, int32_t m, sipp_batch** out) {
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_best), sizeof(BestRec) * m);
   // one relaxation work queue for all maps (SIPP_BATCH_ROAM=0: every map's relaxation on worker CTAs of its own); SIPP_BATCH_SHARE = how
   // many batches the caller runs side by side on this GPU (each takes that fraction of the SMs for its persistent workers)
-  b->roam_cap = (getenv("SIPP_BATCH_ROAM") && atoi(getenv("SIPP_BATCH_ROAM")) == 0) ? 0 : (int)field_roam_queue_ints(ntiles, m);
+  // SIPP_BATCH_ROAM: 0 = off, 1 = workers with the staged weight copy (5 warps per SM), 2 = weights read from global memory (16 warps per SM)
+  b->roam_kind = getenv("SIPP_BATCH_ROAM") ? atoi(getenv("SIPP_BATCH_ROAM")) : 2;
+  b->roam_cap = b->roam_kind == 0 ? 0 : (int)field_roam_queue_ints(ntiles, m);
   b->roam_share = getenv("SIPP_BATCH_SHARE") ? atoi(getenv("SIPP_BATCH_SHARE")) : 1;
   b->roam_dirty = true;
   if (e == cudaSuccess && b->roam_cap > 0) e = cudaMalloc(reinterpret_cast<void**>(&b->d_roam), sizeof(int) * (32 + (size_t)b->roam_cap));
@@ -1545,7 +1548,7 @@ static int batch_plan_enqueue(sipp_batch* b) {
     b->launches += 1;
   }
   int rc = field_plan_batch(b->ctx.data(), b->m, b->h_plan, b->d_plan, b->h_seed, b->d_seed, b->seed_stride, b->d_out, b->stream, &n, &runner,
-                            roam ? b->d_roam + 32 : nullptr, b->roam_cap, roam ? b->d_roam : nullptr, b->roam_share);
+                            roam ? b->d_roam + 32 : nullptr, b->roam_cap, roam ? b->d_roam : nullptr, b->roam_share, b->roam_kind);
   if (rc != SIPP_OK) {
     for (sipp_ctx* c : b->ctx) c->warm_valid = false;
     return batch_err(b, rc, b->ctx[0]);
@@ -1717,7 +1720,18 @@ int sipp_batch_episode_run(sipp_batch* b, const int32_t* const* truth, const sip
     if ((rc = batch_ingest_enqueue(b, x0.data(), y0.data(), rows, cols, pp.data())) != SIPP_OK) return rc;
     SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
   }
+  // SIPP_BATCH_TIMING=1: where a batch-cycle's wall time goes (host preparation per step, the wait for the stream) and how long the
+  // stream was busy (events around the enqueued work), printed once per episode
+  const bool timing = getenv("SIPP_BATCH_TIMING") && atoi(getenv("SIPP_BATCH_TIMING")) != 0;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};      // cut, ingest, plan, cycle (host, enqueue included), wait, collect, stream busy (ms)
+  cudaEvent_t tev[2] = {nullptr, nullptr};
+  if (timing) { cudaEventCreate(&tev[0]); cudaEventCreate(&tev[1]); }
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   for (int c = 0; c < cycles; ++c) {
+    auto tp = now();
+    auto lap = [&](int i) { if (timing) { acc[i] += ms_since(tp); tp = now(); } };
+    if (timing) cudaEventRecord(tev[0], b->stream);
     for (int k = 0; k < m; ++k) {
       const sipp_ctx* ctx = b->ctx[k];
       const int ix = (int)(px[k] * (long)W / ctx->desc.width), iy = (int)(py[k] * (long)H / ctx->desc.height);   // sipp_patch_origin
@@ -1727,10 +1741,16 @@ int sipp_batch_episode_run(sipp_batch* b, const int32_t* const* truth, const sip
       cc[k] = cand_cost[k] + (size_t)c * n;
     }
     cut(fov, fov);
+    lap(0);
     if ((rc = batch_ingest_enqueue(b, x0.data(), y0.data(), fov, fov, pp.data())) != SIPP_OK) return rc;
+    lap(1);
     if ((rc = batch_plan_enqueue(b)) != SIPP_OK) return rc;
+    lap(2);
     if ((rc = batch_cycle_enqueue(b, params, n, xy.data(), cc.data())) != SIPP_OK) return rc;
+    if (timing) cudaEventRecord(tev[1], b->stream);
+    lap(3);
     SIPP_BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+    lap(4);
     if ((rc = batch_plan_collect(b, path_cost ? path_cost + c : nullptr, plan_status ? plan_status + c : nullptr, path_len ? path_len + c : nullptr,
                                  (size_t)cycles)) != SIPP_OK)
       return rc;
@@ -1740,6 +1760,17 @@ int sipp_batch_episode_run(sipp_batch* b, const int32_t* const* truth, const sip
       if (best_value) best_value[(size_t)k * cycles + c] = b->h_best[k].value;
       if (bi >= 0) { px[k] = xy[k][2 * bi]; py[k] = xy[k][2 * bi + 1]; }
     }
+    lap(5);
+    if (timing) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, tev[0], tev[1]) == cudaSuccess) acc[6] += t;
+    }
+  }
+  if (timing) {
+    const double k = cycles > 0 ? 1.0 / cycles : 0.0;
+    fprintf(stderr, "[sipp] batch of %d maps, ms per batch-cycle: host cut %.3f, ingest %.3f, plan %.3f, cycle %.3f, wait for the stream %.3f, collect %.3f; "
+            "first launch to last kernel on the stream %.3f\n", m, acc[0] * k, acc[1] * k, acc[2] * k, acc[3] * k, acc[4] * k, acc[5] * k, acc[6] * k);
+    cudaEventDestroy(tev[0]); cudaEventDestroy(tev[1]);
   }
   return SIPP_OK;
 }

@@ -17,6 +17,7 @@
 // queue, a warp iterates its tile in shared memory to the tile-local fixed point with Gauss-Seidel row sweeps, merges
 // the result with atomicMin and queues the neighbours whose halo it lowered. No grid barriers (see k_relax).
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <math_constants.h>
 
 #include <cmath>
@@ -98,6 +99,28 @@ struct TileSmem {
 };
 static_assert(sizeof(TileSmem) == (TP * TP + kTileWDoubles) * sizeof(double), "weight planes must be contiguous");
 static_assert((TP * TP * sizeof(double)) % 16 == 0 && (kTileWDoubles * sizeof(double)) % 16 == 0, "bulk copy needs 16-byte granularity");
+// The same worker without the staged copy of the weights: only d lives in shared memory (9 KB instead of 46 KB per warp, so three
+// times as many warps fit on an SM) and the sweeps read the weight planes straight from the cache block in global memory (read-only
+// while the relaxation runs: ld.global.nc). More latency per activation, more activations in flight: the form for a batch of
+// maps, where the workers are busy, not for one map, where the chain of dependent activations bounds the plan.
+struct TileD {
+  double d[TP][TP];
+};
+template <bool STAGED> struct WView;
+template <> struct WView<true> {
+  const TileSmem* t;
+  __device__ __forceinline__ double we(int r, int c) const { return t->we[r][c]; }
+  __device__ __forceinline__ double ws(int r, int c) const { return t->ws[r][c]; }
+  __device__ __forceinline__ double wse(int r, int c) const { return t->wse[r][c]; }
+  __device__ __forceinline__ double wsw(int r, int c) const { return t->wsw[r][c]; }
+};
+template <> struct WView<false> {
+  const double* w;
+  __device__ __forceinline__ double we(int r, int c) const { return __ldg(w + r * TP + c); }
+  __device__ __forceinline__ double ws(int r, int c) const { return __ldg(w + TP * TP + r * TP + c); }
+  __device__ __forceinline__ double wse(int r, int c) const { return __ldg(w + 2 * TP * TP + r * TP + c); }
+  __device__ __forceinline__ double wsw(int r, int c) const { return __ldg(w + 3 * TP * TP + r * TP + c); }
+};
 
 // weight of an edge of length `dist` between cells with half costs hca / hcb: dist * (hca + hcb), the reference's
 // (dist * (ca + cb)) / 2.0 (prm_star_planner.cpp:178-181); +inf for a missing edge (never NaN, also for zero costs)
@@ -111,8 +134,8 @@ __device__ __forceinline__ double edge_w(double dist, double hca, double hcb) {
 // Row r is relaxed against them (N, NW, NE) and against itself (W, E) in a shuffle loop that runs until no lane changes; a
 // row nothing changes in costs one iteration. All edge weights come from the per-tile planes. Returns (warp-uniform)
 // whether any cell was lowered; bit r-1 of `rows_changed` = this lane's cell in row r was lowered.
-template <int DIR>
-__device__ __forceinline__ bool sweep_rows(TileSmem& t, int lane, uint32_t& rows_changed) {
+template <int DIR, class Tile, class WV>
+__device__ __forceinline__ bool sweep_rows(Tile& t, const WV& w, int lane, uint32_t& rows_changed) {
   const int lx = lane + 1;
   bool chg = false;
   const int r_first = (DIR > 0) ? 0 : TP - 1;
@@ -121,10 +144,10 @@ __device__ __forceinline__ bool sweep_rows(TileSmem& t, int lane, uint32_t& rows
   for (int i = 0; i < TS; ++i) {
     const int r = (DIR > 0) ? (1 + i) : (TS - i);
     // weights of the edges to the previous row's three cells and to the row neighbours
-    const double wn = (DIR > 0) ? t.ws[r - 1][lx] : t.ws[r][lx];
-    const double wnl = (DIR > 0) ? t.wse[r - 1][lx - 1] : t.wsw[r][lx];
-    const double wnr = (DIR > 0) ? t.wsw[r - 1][lx + 1] : t.wse[r][lx];
-    const double wl = t.we[r][lx - 1], wr = t.we[r][lx];
+    const double wn = (DIR > 0) ? w.ws(r - 1, lx) : w.ws(r, lx);
+    const double wnl = (DIR > 0) ? w.wse(r - 1, lx - 1) : w.wsw(r, lx);
+    const double wnr = (DIR > 0) ? w.wsw(r - 1, lx + 1) : w.wse(r, lx);
+    const double wl = w.we(r, lx - 1), wr = w.we(r, lx);
     const double hl = t.d[r][0], hr = t.d[r][TP - 1];      // left / right halo of this row (constant during the sweep)
     double d = t.d[r][lx];
     const double d0 = d;
@@ -158,16 +181,16 @@ __device__ __forceinline__ bool sweep_rows(TileSmem& t, int lane, uint32_t& rows
 // iff no cell can be lowered from the three cells of the row a DIR sweep would come from — exactly the first thing such a sweep
 // tests for every row, here without the in-row shuffle loop and without any dependence between rows (the loads and adds of all
 // rows overlap). One sweep + this test replaces the "confirming" second sweep of a run whose front came from one side.
-template <int DIR>
-__device__ __forceinline__ bool sweep_needed(const TileSmem& t, int lane) {
+template <int DIR, class Tile, class WV>
+__device__ __forceinline__ bool sweep_needed(const Tile& t, const WV& w, int lane) {
   const int lx = lane + 1;
   bool need = false;
 #pragma unroll 8
   for (int r = 1; r <= TS; ++r) {
     const int p = r - DIR;                                  // the row a DIR sweep relaxes row r against
-    const double wn = (DIR > 0) ? t.ws[r - 1][lx] : t.ws[r][lx];
-    const double wnl = (DIR > 0) ? t.wse[r - 1][lx - 1] : t.wsw[r][lx];
-    const double wnr = (DIR > 0) ? t.wsw[r - 1][lx + 1] : t.wse[r][lx];
+    const double wn = (DIR > 0) ? w.ws(r - 1, lx) : w.ws(r, lx);
+    const double wnl = (DIR > 0) ? w.wse(r - 1, lx - 1) : w.wsw(r, lx);
+    const double wnr = (DIR > 0) ? w.wsw(r - 1, lx + 1) : w.wse(r, lx);
     double ca = __dadd_rn(t.d[p][lx], wn);
     { const double c1 = __dadd_rn(t.d[p][lx - 1], wnl), c2 = __dadd_rn(t.d[p][lx + 1], wnr); const double c3 = c1 < c2 ? c1 : c2; ca = c3 < ca ? c3 : ca; }
     need |= ca < t.d[r][lx];
@@ -178,7 +201,8 @@ __device__ __forceinline__ bool sweep_needed(const TileSmem& t, int lane) {
 // Loads d of the 34x34 window whose interior starts at (x0, y0) into shared memory. Loads are issued in batches (plain
 // L2-coherent ld.global.cg: other warps update the field with L2 atomics while k_relax runs, so L1 is bypassed; an aligned
 // 8-byte load cannot tear) so that their latencies overlap instead of serialising on the stores.
-__device__ __forceinline__ void load_d(TileSmem& t, const FieldGeom& g, const double* field, int x0, int y0, int lane) {
+template <class Tile>
+__device__ __forceinline__ void load_d(Tile& t, const FieldGeom& g, const double* field, int x0, int y0, int lane) {
   const int gx = x0 + lane;                  // interior column of this lane (tile column lane + 1)
   const bool colin = gx >= 0 && gx < g.W;
   double hv[3];
@@ -212,7 +236,8 @@ __device__ __forceinline__ void load_d(TileSmem& t, const FieldGeom& g, const do
 // Re-run of a tile by the warp that already holds it (exclusive ownership): only the border ring (rows / columns 1 and 32,
 // other tiles push into it) and the halo (rows / columns 0 and 33) can have changed. Loads them, keeps the lower of (held,
 // loaded) — they can only differ by a push — and returns the set of tile rows (0..33) that received a lower value.
-__device__ __forceinline__ uint64_t reload_ring(TileSmem& t, const FieldGeom& g, const double* field, int x0, int y0, int lane) {
+template <class Tile>
+__device__ __forceinline__ uint64_t reload_ring(Tile& t, const FieldGeom& g, const double* field, int x0, int y0, int lane) {
   const int rows4[4] = {0, 1, TS, TP - 1};
   double rv[4], cv[4], kv = CUDART_INF;
   const int gxc = x0 + lane, gyr = y0 + lane;          // this lane's interior column (tile col lane+1) / row (tile row lane+1)
@@ -335,22 +360,25 @@ struct RoamQ {
   const char* args; size_t stride;     // map y's RelaxArgs at args + y * stride
 };
 
-template <bool ROAM>
+template <bool ROAM, bool STAGED>
 __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& rq) {
   extern __shared__ __align__(16) uint8_t relax_smem[];
-  __shared__ __align__(8) uint64_t s_bar[kRelaxWarps];
+  __shared__ __align__(8) uint64_t s_bar[kRelaxWarps];      // STAGED only (kRelaxWarps warps per CTA)
+  using Tile = typename std::conditional<STAGED, TileSmem, TileD>::type;
 
   int* const q_queue = ROAM ? rq.queue : a0.queue;
   int* const q_ctl = ROAM ? rq.ctl : a0.ctl;
   const int q_cap = ROAM ? rq.cap : a0.cap;
   const int pape = ROAM ? 0 : a0.pape;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  TileSmem& t = reinterpret_cast<TileSmem*>(relax_smem)[warp];
-  const uint32_t bar = smem_addr(&s_bar[warp]);
-  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  uint32_t bar_parity = 0;
+  Tile& t = reinterpret_cast<Tile*>(relax_smem)[warp];
+  uint32_t bar = 0, bar_parity = 0;
+  if constexpr (STAGED) {
+    bar = smem_addr(&s_bar[warp]);
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  }
 
   int sweeps_local = 0, act_local = 0, push_local = 0;
 #ifdef SIPP_RELAX_PROFILE
@@ -405,13 +433,19 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
     // the tile's weight block: one bulk async copy global -> shared, completion on this warp's mbarrier; it overlaps with the
     // loads of d below
     __syncwarp();           // everyone is done reading the previous tile's planes
-    if (lane == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kTileWDoubles * sizeof(double))) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(&t.we[0][0])),
-                   "l"(a.tile_w + (size_t)ti * kTileWDoubles), "r"((uint32_t)(kTileWDoubles * sizeof(double))), "r"(bar)
-                   : "memory");
+    WView<STAGED> wv;
+    bool weights_pending = STAGED;
+    if constexpr (STAGED) {
+      wv.t = &t;
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kTileWDoubles * sizeof(double))) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(&t.we[0][0])),
+                     "l"(a.tile_w + (size_t)ti * kTileWDoubles), "r"((uint32_t)(kTileWDoubles * sizeof(double))), "r"(bar)
+                     : "memory");
+      }
+    } else {
+      wv.w = a.tile_w + (size_t)ti * kTileWDoubles;
     }
-    bool weights_pending = true;
 
     bool first_run = true;
     for (;;) {   // runs of this tile: again whenever somebody lowered one of its cells while it was running
@@ -437,7 +471,7 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
       bool published = false, any_change = false;
       for (int it = 0;; ++it) {
         uint32_t rows_changed = 0;
-        const bool c = (it & 1) ? sweep_rows<-1>(t, lane, rows_changed) : sweep_rows<+1>(t, lane, rows_changed);
+        const bool c = (it & 1) ? sweep_rows<-1>(t, wv, lane, rows_changed) : sweep_rows<+1>(t, wv, lane, rows_changed);
         ++sweeps_local;
         SIPP_TICK(2)
         const bool last = !c && it >= 1;
@@ -487,32 +521,32 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
             // top halo row (0, lx) from interior row 1; bottom halo row (TP-1, lx) from interior row TS
             {
               double cl = CUDART_INF, cr = CUDART_INF;
-              if (lx > 1) cl = __dadd_rn(t.d[1][lx - 1], t.wsw[0][lx]);
-              if (lx < TS) cr = __dadd_rn(t.d[1][lx + 1], t.wse[0][lx]);
-              if (offer(0, lx, min3(__dadd_rn(t.d[1][lx], t.ws[0][lx]), cl, cr))) m |= 1;
+              if (lx > 1) cl = __dadd_rn(t.d[1][lx - 1], wv.wsw(0, lx));
+              if (lx < TS) cr = __dadd_rn(t.d[1][lx + 1], wv.wse(0, lx));
+              if (offer(0, lx, min3(__dadd_rn(t.d[1][lx], wv.ws(0, lx)), cl, cr))) m |= 1;
               cl = CUDART_INF; cr = CUDART_INF;
-              if (lx > 1) cl = __dadd_rn(t.d[TS][lx - 1], t.wse[TS][lx - 1]);
-              if (lx < TS) cr = __dadd_rn(t.d[TS][lx + 1], t.wsw[TS][lx + 1]);
-              if (offer(TP - 1, lx, min3(__dadd_rn(t.d[TS][lx], t.ws[TS][lx]), cl, cr))) m |= 2;
+              if (lx > 1) cl = __dadd_rn(t.d[TS][lx - 1], wv.wse(TS, lx - 1));
+              if (lx < TS) cr = __dadd_rn(t.d[TS][lx + 1], wv.wsw(TS, lx + 1));
+              if (offer(TP - 1, lx, min3(__dadd_rn(t.d[TS][lx], wv.ws(TS, lx)), cl, cr))) m |= 2;
             }
             // left halo column (ly, 0) from interior column 1; right halo column (ly, TP-1) from interior column TS
             {
               double cu = CUDART_INF, cd = CUDART_INF;
-              if (ly > 1) cu = __dadd_rn(t.d[ly - 1][1], t.wsw[ly - 1][1]);
-              if (ly < TS) cd = __dadd_rn(t.d[ly + 1][1], t.wse[ly][0]);
-              if (offer(ly, 0, min3(__dadd_rn(t.d[ly][1], t.we[ly][0]), cu, cd))) m |= 4;
+              if (ly > 1) cu = __dadd_rn(t.d[ly - 1][1], wv.wsw(ly - 1, 1));
+              if (ly < TS) cd = __dadd_rn(t.d[ly + 1][1], wv.wse(ly, 0));
+              if (offer(ly, 0, min3(__dadd_rn(t.d[ly][1], wv.we(ly, 0)), cu, cd))) m |= 4;
               cu = CUDART_INF; cd = CUDART_INF;
-              if (ly > 1) cu = __dadd_rn(t.d[ly - 1][TS], t.wse[ly - 1][TS]);
-              if (ly < TS) cd = __dadd_rn(t.d[ly + 1][TS], t.wsw[ly][TP - 1]);
-              if (offer(ly, TP - 1, min3(__dadd_rn(t.d[ly][TS], t.we[ly][TS]), cu, cd))) m |= 8;
+              if (ly > 1) cu = __dadd_rn(t.d[ly - 1][TS], wv.wse(ly - 1, TS));
+              if (ly < TS) cd = __dadd_rn(t.d[ly + 1][TS], wv.wsw(ly, TP - 1));
+              if (offer(ly, TP - 1, min3(__dadd_rn(t.d[ly][TS], wv.we(ly, TS)), cu, cd))) m |= 8;
             }
             if (lane < 4) {                        // corners: NW NE SW SE from the diagonal interior cell
               double cand;
               int hy, hx;
-              if (lane == 0) { hy = 0; hx = 0; cand = __dadd_rn(t.d[1][1], t.wse[0][0]); }
-              else if (lane == 1) { hy = 0; hx = TP - 1; cand = __dadd_rn(t.d[1][TS], t.wsw[0][TP - 1]); }
-              else if (lane == 2) { hy = TP - 1; hx = 0; cand = __dadd_rn(t.d[TS][1], t.wsw[TS][1]); }
-              else { hy = TP - 1; hx = TP - 1; cand = __dadd_rn(t.d[TS][TS], t.wse[TS][TS]); }
+              if (lane == 0) { hy = 0; hx = 0; cand = __dadd_rn(t.d[1][1], wv.wse(0, 0)); }
+              else if (lane == 1) { hy = 0; hx = TP - 1; cand = __dadd_rn(t.d[1][TS], wv.wsw(0, TP - 1)); }
+              else if (lane == 2) { hy = TP - 1; hx = 0; cand = __dadd_rn(t.d[TS][1], wv.wsw(TS, 1)); }
+              else { hy = TP - 1; hx = TP - 1; cand = __dadd_rn(t.d[TS][TS], wv.wse(TS, TS)); }
               if (offer(hy, hx, cand)) m |= 16 << lane;
             }
           }
@@ -576,7 +610,7 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
         }
         if (last) break;
         // the opposite sweep only if it has something to do (tested on the halo as the publish above left it)
-        if (a.check && !((it & 1) ? sweep_needed<+1>(t, lane) : sweep_needed<-1>(t, lane))) break;
+        if (a.check && !((it & 1) ? sweep_needed<+1>(t, wv, lane) : sweep_needed<-1>(t, wv, lane))) break;
       }
       // ---- done with this run: idle again, unless one of our cells was lowered meanwhile
       int again = 0;
@@ -619,7 +653,7 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
     atomicAdd(&a0.ctl[CTL_SWEEPS], sweeps_local);
   }
 }
-__device__ __forceinline__ void relax_body(const RelaxArgs& a) { relax_body_t<false>(a, RoamQ{}); }
+__device__ __forceinline__ void relax_body(const RelaxArgs& a) { relax_body_t<false, true>(a, RoamQ{}); }
 
 // Plan from scratch, first kernel: field <- +inf, empty work queue, zeroed control block and counters; the ingest marks of an abandoned
 // warm start are cleared as well (mark16 != nullptr)
@@ -1346,7 +1380,11 @@ __global__ void k_roam_collect(const PlanArgsAll* __restrict__ all, RoamQ rq) {
   }
 }
 __global__ void __launch_bounds__(kRelaxWarps * 32) k_relax_roam(const PlanArgsAll* __restrict__ all, RoamQ rq) {
-  relax_body_t<true>(all[0].ra, rq);
+  relax_body_t<true, true>(all[0].ra, rq);
+}
+constexpr int kRoamWarps = 16;      // weights read from global memory: 16 x 9 KB of shared memory per CTA
+__global__ void __launch_bounds__(kRoamWarps * 32) k_relax_roam_g(const PlanArgsAll* __restrict__ all, RoamQ rq) {
+  relax_body_t<true, false>(all[0].ra, rq);
 }
 __global__ void k_roam_reset(RoamQ rq) {
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1388,6 +1426,7 @@ int device_setup(sipp_ctx* ctx, DevInfo* out) {
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRoamWarps * sizeof(TileD))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
@@ -1742,7 +1781,7 @@ int field_roam_reset(sipp_ctx* c0, int* roam_queue, int roam_cap, int* roam_ctl,
 
 int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, uint8_t* h_seed, uint8_t* d_seed, size_t seed_stride, int* d_out,
                      cudaStream_t s, int* launches, const std::function<void(int, const std::function<void(int)>&)>* runner,
-                     int* roam_queue, int roam_cap, int* roam_ctl, int roam_share) {
+                     int* roam_queue, int roam_cap, int* roam_ctl, int roam_share, int roam_kind) {
   if (m <= 0) return SIPP_OK;
   sipp_ctx* c0 = ctxs[0];
   DevInfo dev;
@@ -1807,7 +1846,15 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
     if (grid > sum_relax) grid = sum_relax;
     if (grid < 1) grid = 1;
     k_roam_collect<<<M, 256, 0, s>>>(dA, rq);
-    k_relax_roam<<<grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA, rq);
+    if (roam_kind == 2) {      // weights from global memory, kRoamWarps warps per CTA (one CTA per SM)
+      int grid_g = dev.num_sms / (roam_share > 1 ? roam_share : 1);
+      const int want_g = (sum_relax * kRelaxWarps + kRoamWarps - 1) / kRoamWarps;
+      if (grid_g > want_g) grid_g = want_g;
+      if (grid_g < 1) grid_g = 1;
+      k_relax_roam_g<<<grid_g, kRoamWarps * 32, kRoamWarps * sizeof(TileD), s>>>(dA, rq);
+    } else {
+      k_relax_roam<<<grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA, rq);
+    }
     n += 1;
   } else {
     k_relax_b<<<dim3(max_relax, M), kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA);

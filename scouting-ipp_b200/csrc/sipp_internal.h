@@ -262,7 +262,7 @@ int field_plan(sipp_ctx* ctx, cudaStream_t s);
 size_t field_plan_batch_args_bytes();
 int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, uint8_t* h_seed, uint8_t* d_seed, size_t seed_stride, int* d_out,
                      cudaStream_t s, int* launches, const std::function<void(int, const std::function<void(int)>&)>* runner,
-                     int* roam_queue, int roam_cap, int* roam_ctl, int roam_share);
+                     int* roam_queue, int roam_cap, int* roam_ctl, int roam_share, int roam_kind);
 // the shared relaxation queue of a batch: capacity in ints for m maps of ntiles tiles (0: not representable, use per-map workers); reset
 // (all slots empty, counters zero) before the first plan and after a watchdog abort
 size_t field_roam_queue_ints(int ntiles, int m);

@@ -20,10 +20,10 @@ def make_map(seed, mk):
     return lab, desc
 
 
-@pytest.mark.parametrize("roam", ["1", "0"])
+@pytest.mark.parametrize("roam", ["2", "1", "0"])
 def test_batch_steps_match_independent_contexts(roam, monkeypatch):
     """ingest / plan / cycle through the batch against the same calls made map by map: from scratch, then incrementally; with the
-    batch's shared relaxation queue (the default) and with per-map relaxation workers"""
+    batch's shared relaxation queue (2: weights read from global memory, the default; 1: staged in shared memory) and with per-map relaxation workers (0)"""
     monkeypatch.setenv("SIPP_BATCH_ROAM", roam)
     m, T = 5, 777
     params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001)
