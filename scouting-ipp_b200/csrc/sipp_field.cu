@@ -358,6 +358,7 @@ constexpr int kRoamShift = 20;
 struct RoamQ {
   int* queue; int cap; int* ctl;
   const char* args; size_t stride;     // map y's RelaxArgs at args + y * stride
+  int spin_limit;                      // the watchdog's (map 0's argument block may be one that does not run this step)
 };
 
 template <bool ROAM, bool STAGED>
@@ -405,7 +406,7 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
           break;
         }
         if (ld_volatile_i32(&q_ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&q_ctl[CTL_ABORT]) != 0) break;
-        if (++spins > a0.spin_limit) {
+        if (++spins > (ROAM ? rq.spin_limit : a0.spin_limit)) {
           atomicExch(&q_ctl[CTL_ABORT], 1);
           break;
         }
@@ -414,7 +415,7 @@ __device__ __forceinline__ void relax_body_t(const RelaxArgs& a0, const RoamQ& r
       if (ti >= 0) {
         const RelaxArgs& am = ROAM ? *reinterpret_cast<const RelaxArgs*>(rq.args + (size_t)(ti >> kRoamShift) * rq.stride) : a0;
         const int tm = ROAM ? (ti & ((1 << kRoamShift) - 1)) : ti;
-        atomicExch(&am.flags[tm], (a0.mode & 2) ? ST_RUN : (pape ? ST_VISITED : 0));   // queued -> running; a lowering from here on sets QUEUED again
+        atomicExch(&am.flags[tm], (am.mode & 2) ? ST_RUN : (pape ? ST_VISITED : 0));   // queued -> running; a lowering from here on sets QUEUED again
         fence_gpu();
       }
     }
@@ -723,8 +724,13 @@ struct InvalArgs {
 };
 enum { CTL_MARKED = 7, CTL_EXITED = 8 };
 
-__device__ __forceinline__ void inval_body(const InvalArgs& a) {
+// ROAM: the batch's shared queue (see relax_body_t) — entries carry their map, rq.args + map * rq.stride is that map's InvalArgs
+template <bool ROAM>
+__device__ __forceinline__ void inval_body_t(const InvalArgs& a0, const RoamQ& rq) {
   __shared__ InvalSmem sm[kInvalWarps];
+  int* const q_queue = ROAM ? rq.queue : a0.queue;
+  int* const q_ctl = ROAM ? rq.ctl : a0.ctl;
+  const int q_cap = ROAM ? rq.cap : a0.cap;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   InvalSmem& t = sm[warp];
   const int NDX[8] = {-1, -1, -1, 0, 0, 1, 1, 1};   // k_pred's neighbour order
@@ -733,23 +739,28 @@ __device__ __forceinline__ void inval_body(const InvalArgs& a) {
   for (;;) {
     int ti = -2;
     if (lane == 0) {
-      const unsigned ticket = (unsigned)atomicAdd(&a.ctl[CTL_HEAD], 1);
-      int* slot = a.queue + (ticket % (unsigned)a.cap);
+      const unsigned ticket = (unsigned)atomicAdd(&q_ctl[CTL_HEAD], 1);
+      int* slot = q_queue + (ticket % (unsigned)q_cap);
       int spins = 0;
       for (;;) {
         const int v = ld_volatile_i32(slot);
         if (v >= 0) { st_volatile_i32(slot, -1); ti = v; break; }
-        if (ld_volatile_i32(&a.ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&a.ctl[CTL_ABORT]) != 0) break;
-        if (++spins > a.spin_limit) { atomicExch(&a.ctl[CTL_ABORT], 1); break; }
+        if (ld_volatile_i32(&q_ctl[CTL_PENDING]) == 0 || ld_volatile_i32(&q_ctl[CTL_ABORT]) != 0) break;
+        if (++spins > (ROAM ? rq.spin_limit : a0.spin_limit)) { atomicExch(&q_ctl[CTL_ABORT], 1); break; }
         __nanosleep(64);
       }
       if (ti >= 0) {
-        atomicExch(&a.flags[ti], 0);      // queued -> running: a mark arriving from now on queues the tile again
+        const InvalArgs& am = ROAM ? *reinterpret_cast<const InvalArgs*>(rq.args + (size_t)(ti >> kRoamShift) * rq.stride) : a0;
+        atomicExch(&am.flags[ROAM ? (ti & ((1 << kRoamShift) - 1)) : ti], 0);      // queued -> running: a mark arriving from now on queues the tile again
         fence_gpu();
       }
     }
     ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
     if (ti < 0) break;
+    const int tag = ROAM ? (ti >> kRoamShift) << kRoamShift : 0;
+    if (ROAM) ti &= (1 << kRoamShift) - 1;
+    const InvalArgs& a = ROAM ? *reinterpret_cast<const InvalArgs*>(rq.args + (size_t)(tag >> kRoamShift) * rq.stride) : a0;
+    const int marked0 = marked_local;
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
     // ---- load: lane = tile column (+ the two halo columns by lanes 0 / 1), all rows. Every load is issued before the first
@@ -858,21 +869,39 @@ __device__ __forceinline__ void inval_body(const InvalArgs& a) {
       if (ntx_ >= 0 && ntx_ < a.ntx && nty_ >= 0 && nty_ < a.nty) {
         const int nt = nty_ * a.ntx + ntx_;
         if (atomicOr(&a.flags[nt], ST_QUEUED) == 0) {
-          atomicAdd(&a.ctl[CTL_PENDING], 1);
-          const unsigned pos = (unsigned)atomicAdd(&a.ctl[CTL_TAIL], 1);
-          int* slot = a.queue + (pos % (unsigned)a.cap);
+          atomicAdd(&q_ctl[CTL_PENDING], 1);
+          const unsigned pos = (unsigned)atomicAdd(&q_ctl[CTL_TAIL], 1);
+          int* slot = q_queue + (pos % (unsigned)q_cap);
           int spins = 0;
           while (ld_volatile_i32(slot) != -1 && ++spins < a.spin_limit) __nanosleep(32);
-          st_volatile_i32(slot, nt);
+          st_volatile_i32(slot, nt | tag);
         }
       }
     }
     __syncwarp();
+    if (ROAM) {      // the count of invalidated cells goes to the tile's map
+      const int marked = __reduce_add_sync(0xFFFFFFFFu, marked_local - marked0);
+      if (lane == 0 && marked) atomicAdd(&a.plan_out[5], marked);
+    }
     if (lane == 0) {
       fence_gpu();
-      atomicSub(&a.ctl[CTL_PENDING], 1);
+      atomicSub(&q_ctl[CTL_PENDING], 1);
     }
   }
+  if (ROAM) {      // the last warp to leave rewinds the shared queue (every slot is empty again, the workers' unserved tickets are forgotten)
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      const int total = (int)gridDim.x * kInvalWarps;
+      if (atomicAdd(&q_ctl[CTL_EXITED], 1) == total - 1) {
+        st_volatile_i32(&q_ctl[CTL_HEAD], 0);
+        st_volatile_i32(&q_ctl[CTL_TAIL], 0);
+        st_volatile_i32(&q_ctl[CTL_EXITED], 0);
+      }
+    }
+    return;
+  }
+  const InvalArgs& a = a0;
   if (marked_local) atomicAdd(&a.ctl[CTL_MARKED], marked_local);
   // the last warp to leave hands the queue over to the relaxation: every slot is back to -1 and every flag to 0 (whatever was
   // pushed has been popped), only the counters have to be rewound — no separate reset kernel between the two phases
@@ -889,6 +918,7 @@ __device__ __forceinline__ void inval_body(const InvalArgs& a) {
     }
   }
 }
+__device__ __forceinline__ void inval_body(const InvalArgs& a) { inval_body_t<false>(a, RoamQ{}); }
 
 // First kernel of an incremental plan: resets the work queue and seeds it with the tiles the patches touched. `list` (nl tile
 // ids, the queue order) and `seedmap` (one byte per tile, the same set) come from the host in one copy; seedmap == nullptr: none.
@@ -1359,7 +1389,8 @@ __global__ void k_gather_plan_out(const PlanArgsAll* __restrict__ all, int* __re
 
 // shared work queue of a batch (RoamQ): block y moves what map y's seeding kernels queued — entries [0, TAIL) of its own queue,
 // HEAD is 0 at this point in both plan forms — into the batch's queue, tagged with the map
-__global__ void k_roam_collect(const PlanArgsAll* __restrict__ all, RoamQ rq) {
+__global__ void k_roam_collect(const PlanArgsAll* __restrict__ all, RoamQ rq, int inval_only) {
+  if (inval_only && !all[blockIdx.x].on_inval) return;      // before the invalidation: only the maps that run it (a map that starts over holds its start tile)
   const RelaxArgs& a = all[blockIdx.x].ra;
   __shared__ unsigned base;
   const int n = ld_volatile_i32(&a.ctl[CTL_TAIL]);
@@ -1382,8 +1413,12 @@ __global__ void k_roam_collect(const PlanArgsAll* __restrict__ all, RoamQ rq) {
 __global__ void __launch_bounds__(kRelaxWarps * 32) k_relax_roam(const PlanArgsAll* __restrict__ all, RoamQ rq) {
   relax_body_t<true, true>(all[0].ra, rq);
 }
-constexpr int kRoamWarps = 16;      // weights read from global memory: 16 x 9 KB of shared memory per CTA
-__global__ void __launch_bounds__(kRoamWarps * 32) k_relax_roam_g(const PlanArgsAll* __restrict__ all, RoamQ rq) {
+__global__ void __launch_bounds__(kInvalWarps * 32) k_inval_roam(const PlanArgsAll* __restrict__ all, RoamQ rq) {
+  inval_body_t<true>(all[0].ia, rq);
+}
+// weights read from global memory: WARPS x 9 KB of shared memory per CTA, one CTA per SM (24 warps: 80 registers per thread, no spills)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_relax_roam_g(const PlanArgsAll* __restrict__ all, RoamQ rq) {
   relax_body_t<true, false>(all[0].ra, rq);
 }
 __global__ void k_roam_reset(RoamQ rq) {
@@ -1426,7 +1461,9 @@ int device_setup(sipp_ctx* ctx, DevInfo* out) {
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRelaxWarps * sizeof(TileSmem))));
-    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRoamWarps * sizeof(TileD))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam_g<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(TileD))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam_g<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(20 * sizeof(TileD))));
+    SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_roam_g<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(24 * sizeof(TileD))));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem)));
     SIPP_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, PW * PW));
@@ -1773,7 +1810,7 @@ size_t field_roam_queue_ints(int ntiles, int m) {
   return cap;
 }
 int field_roam_reset(sipp_ctx* c0, int* roam_queue, int roam_cap, int* roam_ctl, cudaStream_t s) {
-  RoamQ rq{roam_queue, roam_cap, roam_ctl, nullptr, 0};
+  RoamQ rq{roam_queue, roam_cap, roam_ctl, nullptr, 0, 0};
   k_roam_reset<<<64, 256, 0, s>>>(rq);
   SIPP_CUDA_CHECK(c0, cudaGetLastError());
   return SIPP_OK;
@@ -1789,7 +1826,7 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
   if (rc != SIPP_OK) return rc;
   PlanArgsAll* A = reinterpret_cast<PlanArgsAll*>(h_args);
   const int ntiles = c0->n_tiles_x * c0->n_tiles_y;
-  int any_init = 0, any_inc = 0, any_inval = 0, any_weights_all = 0, max_nl = 0, any_check = 0, max_relax = 1, max_inval = 1, sum_relax = 0;
+  int any_init = 0, any_inc = 0, any_inval = 0, any_weights_all = 0, max_nl = 0, any_check = 0, max_relax = 1, max_inval = 1, sum_relax = 0, sum_inval = 0;
   for (int i = 0; i < m; ++i) {
     sipp_ctx* ctx = ctxs[i];
     if (!ctx->d_tile_w) {
@@ -1821,6 +1858,7 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
     if (A[i].relax_grid > max_relax) max_relax = A[i].relax_grid;
     sum_relax += A[i].relax_grid;
     if (A[i].inval_grid > max_inval) max_inval = A[i].inval_grid;
+    if (A[i].on_inval) sum_inval += A[i].inval_grid;
   }
   SIPP_CUDA_CHECK(c0, cudaMemcpyAsync(d_args, h_args, (size_t)m * sizeof(PlanArgsAll), cudaMemcpyHostToDevice, s));
   if (any_inval) SIPP_CUDA_CHECK(c0, cudaMemcpyAsync(d_seed, h_seed, (size_t)m * seed_stride, cudaMemcpyHostToDevice, s));
@@ -1835,23 +1873,36 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
   if (any_inc) { k_inc_begin_b<<<dim3(16, M), 256, 0, s>>>(dA); n += 1; }
   const int wgrid = any_weights_all ? ntiles : max_nl;
   if (wgrid > 0) { k_weights_b<<<dim3(wgrid, M), kWeightThreads, 0, s>>>(dA); n += 1; }
-  if (any_inval) {
+  if (any_inval && roam_queue) {
+    RoamQ rq{roam_queue, roam_cap, roam_ctl, reinterpret_cast<const char*>(d_args) + offsetof(PlanArgsAll, ia), sizeof(PlanArgsAll), kSpinLimit};
+    int grid = 4 * dev.num_sms / (roam_share > 1 ? roam_share : 1);      // small CTAs (18 KB of shared memory): several per SM
+    if (grid > sum_inval) grid = sum_inval;
+    if (grid < 1) grid = 1;
+    k_roam_collect<<<M, 256, 0, s>>>(dA, rq, 1);
+    k_inval_roam<<<grid, kInvalWarps * 32, 0, s>>>(dA, rq);
+    k_seed_relax_b<<<dim3((ntiles + 255) / 256, M), 256, 0, s>>>(dA);
+    n += 3;
+  } else if (any_inval) {
     k_inval_b<<<dim3(max_inval, M), kInvalWarps * 32, 0, s>>>(dA);
     k_seed_relax_b<<<dim3((ntiles + 255) / 256, M), 256, 0, s>>>(dA);
     n += 2;
   }
   if (roam_queue) {
-    RoamQ rq{roam_queue, roam_cap, roam_ctl, reinterpret_cast<const char*>(d_args) + offsetof(PlanArgsAll, ra), sizeof(PlanArgsAll)};
+    RoamQ rq{roam_queue, roam_cap, roam_ctl, reinterpret_cast<const char*>(d_args) + offsetof(PlanArgsAll, ra), sizeof(PlanArgsAll), kSpinLimit};
     int grid = dev.num_sms * dev.occ / (roam_share > 1 ? roam_share : 1);      // batches that run side by side split the SMs
     if (grid > sum_relax) grid = sum_relax;
     if (grid < 1) grid = 1;
-    k_roam_collect<<<M, 256, 0, s>>>(dA, rq);
-    if (roam_kind == 2) {      // weights from global memory, kRoamWarps warps per CTA (one CTA per SM)
+    k_roam_collect<<<M, 256, 0, s>>>(dA, rq, 0);
+    if (roam_kind == 2) {      // weights from global memory, one CTA of 16 / 20 / 24 warps per SM (SIPP_ROAM_WARPS)
+      static const int warps_env = getenv("SIPP_ROAM_WARPS") ? atoi(getenv("SIPP_ROAM_WARPS")) : 20;
+      const int warps = warps_env >= 24 ? 24 : warps_env >= 20 ? 20 : 16;
       int grid_g = dev.num_sms / (roam_share > 1 ? roam_share : 1);
-      const int want_g = (sum_relax * kRelaxWarps + kRoamWarps - 1) / kRoamWarps;
+      const int want_g = (sum_relax * kRelaxWarps + warps - 1) / warps;
       if (grid_g > want_g) grid_g = want_g;
       if (grid_g < 1) grid_g = 1;
-      k_relax_roam_g<<<grid_g, kRoamWarps * 32, kRoamWarps * sizeof(TileD), s>>>(dA, rq);
+      if (warps == 24) k_relax_roam_g<24><<<grid_g, 24 * 32, 24 * sizeof(TileD), s>>>(dA, rq);
+      else if (warps == 20) k_relax_roam_g<20><<<grid_g, 20 * 32, 20 * sizeof(TileD), s>>>(dA, rq);
+      else k_relax_roam_g<16><<<grid_g, 16 * 32, 16 * sizeof(TileD), s>>>(dA, rq);
     } else {
       k_relax_roam<<<grid, kRelaxWarps * 32, kRelaxWarps * sizeof(TileSmem), s>>>(dA, rq);
     }
