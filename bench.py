@@ -307,7 +307,6 @@ def ensemble_workload(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     EW, EH, ET, maps, nb = 640, 480, 1024, int(os.environ.get("SIPP_BENCH_ENSEMBLE_MAPS", "128")), 2
     cycles = 40 if args.steps == 200 else max(1, args.steps)          # run_experiment.sh scale unless --steps says otherwise
-    os.environ.setdefault("SIPP_BATCH_SHARE", str(nb))
     params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001)
     worlds = []
     for sd in [2000 + i for i in range(maps * world)][rank::world]:
@@ -318,6 +317,8 @@ def ensemble_workload(args):
     cands = {sd: episode.episode_candidates(EW, EH, sd, cycles, ET) for sd, _, _ in worlds}
     groups = [worlds[k::nb] for k in range(nb)]
     batches = [sipp.Batch([w[2] for w in g]) for g in groups]
+    for b in batches:
+        b.set_sharing(nb)
 
     def run_group(k, ncyc=None):
         g = groups[k]

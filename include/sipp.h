@@ -372,6 +372,9 @@ int sipp_batch_create(sipp_ctx* const* ctxs, int32_t m, sipp_batch** out);   /* 
 void sipp_batch_destroy(sipp_batch* batch);                                   /* the contexts stay alive */
 const char* sipp_batch_last_error(const sipp_batch* batch);
 int64_t sipp_batch_launch_count(const sipp_batch* batch);
+/* How many batches the caller drives side by side on this GPU (default 1, or SIPP_BATCH_SHARE): the batch's persistent relaxation /
+ * invalidation workers then take 1/n of the SMs, so that the chain-bound phases of one batch run beside the busy phases of another. */
+int sipp_batch_set_sharing(sipp_batch* batch, int32_t batches_on_this_gpu);
 /* sipp_map_update_patch for every map: map i ingests the rows x cols patch labels[i] at (x0[i], y0[i]) */
 int sipp_batch_ingest(sipp_batch* batch, const int32_t* x0, const int32_t* y0, int32_t rows, int32_t cols, const int32_t* const* labels);
 /* sipp_plan for every map (from scratch or incremental, decided per map): cost / status / path_len are m entries (any may be NULL) */

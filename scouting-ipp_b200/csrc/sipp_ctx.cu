@@ -1510,6 +1510,13 @@ int sipp_batch_create(sipp_ctx* const* ctxs, int32_t m, sipp_batch** out) {
   std::lock_guard<std::mutex> lock__((b)->mu);                                                                    \
   if (cudaSetDevice((b)->device) != cudaSuccess) return batch_fail((b), SIPP_ERR_CUDA, "cudaSetDevice failed")
 
+int sipp_batch_set_sharing(sipp_batch* b, int32_t batches_on_this_gpu) {
+  SIPP_BATCH_ENTER(b);
+  if (batches_on_this_gpu < 1 || batches_on_this_gpu > 64) return batch_fail(b, SIPP_ERR_INVALID_ARG, "batches_on_this_gpu %d out of range [1, 64]", batches_on_this_gpu);
+  b->roam_share = batches_on_this_gpu;
+  return SIPP_OK;
+}
+
 // ---- steps: enqueue on the batch stream; nothing here synchronises ------------------------------------------------------------
 // patches: labels + (size_t)i * label_stride = the rows x cols patch of map i (host memory)
 static int batch_ingest_enqueue(sipp_batch* b, const int32_t* x0, const int32_t* y0, int rows, int cols, const int32_t* const* labels) {

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "sipp_peer_export", "sipp_peer_attach", "sipp_peer_detach", "sipp_peer_status", "sipp_cycle_shard_dev", "sipp_cycle_shard",
     "sipp_peer_exchange_dev", "sipp_cycle_shard_pipelined_dev", "sipp_peer_flush_dev", "sipp_episode_run", "sipp_cost_integral", "sipp_set_incremental", "sipp_plan_info",
     "sipp_path_download", "sipp_truth_upload", "sipp_travel_cost", "sipp_plan_phases",
-    "sipp_batch_create", "sipp_batch_destroy", "sipp_batch_last_error", "sipp_batch_launch_count", "sipp_batch_ingest", "sipp_batch_plan",
+    "sipp_batch_create", "sipp_batch_destroy", "sipp_batch_last_error", "sipp_batch_launch_count", "sipp_batch_set_sharing", "sipp_batch_ingest", "sipp_batch_plan",
     "sipp_batch_cycle", "sipp_batch_episode_run", "sipp_gain_batch_views", "sipp_update_tree_views",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 128
@@ -225,6 +225,7 @@ def lib():
         L.sipp_batch_last_error.restype = C.c_char_p
         L.sipp_batch_launch_count.argtypes = [vp]
         L.sipp_batch_launch_count.restype = C.c_int64
+        L.sipp_batch_set_sharing.argtypes = [vp, C.c_int32]
         L.sipp_batch_ingest.argtypes = [vp, vp, vp, i32, i32, vp]
         L.sipp_batch_plan.argtypes = [vp, vp, vp, vp]
         L.sipp_batch_cycle.argtypes = [vp, C.POINTER(EvalParams), i32, vp, vp, vp, vp, vp]
@@ -585,6 +586,10 @@ class Batch:
 
     def launch_count(self):
         return int(self._L.sipp_batch_launch_count(self._h))
+
+    def set_sharing(self, batches_on_this_gpu):
+        """how many batches run side by side on this GPU: the persistent workers of this one take that fraction of the SMs"""
+        self._check(self._L.sipp_batch_set_sharing(self._h, int(batches_on_this_gpu)))
 
     def ingest(self, x0, y0, patches):
         """patches: m arrays [rows][cols] int32 (one shape)"""

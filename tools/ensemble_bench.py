@@ -52,6 +52,9 @@ def main():
         nb = max(1, min(args.batches, len(worlds) // 8 or 1))
         groups = [worlds[k::nb] for k in range(nb)]
         batches = [sipp.Batch([w[2] for w in g]) for g in groups]
+        if not os.environ.get("SIPP_BATCH_SHARE"):
+            for b in batches:
+                b.set_sharing(nb)
 
         def run_group(k, ncyc=None):
             g = groups[k]

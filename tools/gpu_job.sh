@@ -1,14 +1,7 @@
 mkdir -p gpurun_out
-J=gpurun_out/r2_j53
-run() { # warps maps batches share threads
-SIPP_ROAM_WARPS=$1 SIPP_BATCH_TIMING=1 SIPP_BATCH_SHARE=$4 SIPP_BATCH_THREADS=$5 timeout 300 python tools/ensemble_bench.py --mode batch --maps $2 --cycles 16 --batches $3 > ${J}_ens_w$1_m$2_b$3_s$4.json 2> ${J}_ens_w$1_m$2_b$3_s$4.err
-echo "warps=$1 maps=$2 batches=$3 share=$4 threads=$5: $(python -c "import json,sys; d=json.loads(open('${J}_ens_w$1_m$2_b$3_s$4.json').read().strip().splitlines()[-1]); print(d['value'])" 2>&1 | tail -n 1)"
-grep "batch of" ${J}_ens_w$1_m$2_b$3_s$4.err | tail -n 1 | cut -c150-300
-}
-run 16 512 2 2 8
-run 20 512 2 2 8
-run 24 512 2 2 8
-run 16 512 1 1 8
-run 24 512 1 1 8
-run 24 128 2 2 8
-run 16 128 2 2 8
+J=gpurun_out/r2_j54
+timeout 1500 python -m pytest tests -m gpu -x -q > ${J}_tests.log 2>&1; echo "tests rc $?"; tail -n 3 ${J}_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${J}_smoke.log 2>&1; echo "smoke rc $?"; tail -n 1 ${J}_smoke.log
+timeout 600 python bench.py > ${J}_bench_n1.json 2> ${J}_bench_n1.err; echo "bench rc $?"; cut -c1-300 ${J}_bench_n1.json
+SIPP_BATCH_THREADS=8 timeout 600 python bench.py --workload ensemble > ${J}_ensemble_n1.json 2> ${J}_ensemble_n1.err; echo "rc $?"; cut -c1-260 ${J}_ensemble_n1.json
+SIPP_BENCH_ENSEMBLE_MAPS=1024 SIPP_BATCH_THREADS=8 timeout 600 python bench.py --workload ensemble > ${J}_ensemble_n1_m1024.json 2> ${J}_ensemble_n1_m1024.err; echo "rc $?"; cut -c1-260 ${J}_ensemble_n1_m1024.json
