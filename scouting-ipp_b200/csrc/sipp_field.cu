@@ -704,12 +704,8 @@ __device__ __forceinline__ void field_seed_body(const FieldSeedArgs& a) {
 //  (2) the relaxation restarts from the tiles the patches touched (lower weights) and the tiles in and around the invalidated
 //      region; from upper bounds it converges to the same least fixed point as from +inf (the operator is monotone, also in
 //      rounded arithmetic), so the field has the bits of a from-scratch plan — tests compare the two.
-// k_inval is a persistent tile work-queue kernel like k_relax, one warp per 32x32 tile, bytes instead of doubles.
+// k_inval is a persistent tile work-queue kernel like k_relax, one warp per 32x32 tile; the tile is held as bit masks in registers.
 constexpr int kInvalWarps = 8;
-struct InvalSmem {
-  uint8_t m[TP][TP + 2];    // marks incl. halo (row pitch 36)
-  uint8_t p[TS][TS];        // predecessor directions
-};
 struct InvalArgs {
   int W, H, ntx, nty;
   uint8_t* mark;            // [H][pitch]
@@ -727,14 +723,10 @@ enum { CTL_MARKED = 7, CTL_EXITED = 8 };
 // ROAM: the batch's shared queue (see relax_body_t) — entries carry their map, rq.args + map * rq.stride is that map's InvalArgs
 template <bool ROAM>
 __device__ __forceinline__ void inval_body_t(const InvalArgs& a0, const RoamQ& rq) {
-  __shared__ InvalSmem sm[kInvalWarps];
   int* const q_queue = ROAM ? rq.queue : a0.queue;
   int* const q_ctl = ROAM ? rq.ctl : a0.ctl;
   const int q_cap = ROAM ? rq.cap : a0.cap;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  InvalSmem& t = sm[warp];
-  const int NDX[8] = {-1, -1, -1, 0, 0, 1, 1, 1};   // k_pred's neighbour order
-  const int NDY[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  const int lane = threadIdx.x & 31;
   int marked_local = 0;
   for (;;) {
     int ti = -2;
@@ -763,8 +755,12 @@ __device__ __forceinline__ void inval_body_t(const InvalArgs& a0, const RoamQ& r
     const int marked0 = marked_local;
     const int tx = ti % a.ntx, ty = ti / a.ntx;
     const int x0 = tx * TS, y0 = ty * TS;
-    // ---- load: lane = tile column (+ the two halo columns by lanes 0 / 1), all rows. Every load is issued before the first
-    // store (registers), so their latencies overlap instead of queueing behind the shared-memory stores
+    // ---- load: lane = tile column (+ the two halo columns by lanes 0 / 1), all rows, every load issued before the first use. The
+    // tile then lives in registers as bit masks over the rows of this lane's column: Mi = marked cells (bit r = tile row r), tb = the
+    // column's cells in the halo rows (bit 0: row -1, bit 1: row 32), P[k] = cells whose canonical predecessor is neighbour k.
+    uint32_t Mi = 0, fresh = 0, tb = 0;      // fresh: cells carrying an unpublished ingest mark (value 1)
+    uint32_t P[8];
+    uint32_t HLi, HLtb, HRi, HRtb;           // the west / east halo columns, same encoding
     {
       const int gx = x0 + lane;
       const bool colin = gx < a.W;
@@ -783,51 +779,56 @@ __device__ __forceinline__ void inval_body_t(const InvalArgs& a0, const RoamQ& r
         const int gy = y0 + r;
         pv[r] = (gy < a.H && colin) ? a.pred[(size_t)gy * a.pitch + gx] : (uint8_t)255;
       }
+      uint32_t Hi = 0, Htb = 0;
+      tb = (mv[0] != 0 ? 1u : 0u) | (mv[TP - 1] != 0 ? 2u : 0u);
+      Htb = (hv[0] != 0 ? 1u : 0u) | (hv[TP - 1] != 0 ? 2u : 0u);
 #pragma unroll
-      for (int r = 0; r < TP; ++r) {
-        t.m[r][lane + 1] = mv[r];
-        if (lane < 2) t.m[r][lane ? TP - 1 : 0] = hv[r];
+      for (int r = 0; r < TS; ++r) {
+        Mi |= (mv[r + 1] != 0 ? 1u : 0u) << r;
+        fresh |= (mv[r + 1] == 1 ? 1u : 0u) << r;
+        Hi |= (hv[r + 1] != 0 ? 1u : 0u) << r;
+      }
+      uint32_t b0 = 0, b1 = 0, b2 = 0, bv = 0;      // bit planes of the predecessor index, bv: the cell has one
+#pragma unroll
+      for (int r = 0; r < TS; ++r) {
+        const uint32_t pp = pv[r];
+        bv |= (pp < 8u ? 1u : 0u) << r;
+        b0 |= (pp & 1u) << r;
+        b1 |= ((pp >> 1) & 1u) << r;
+        b2 |= ((pp >> 2) & 1u) << r;
       }
 #pragma unroll
-      for (int r = 0; r < TS; ++r) t.p[r][lane] = pv[r];
+      for (int k = 0; k < 8; ++k) P[k] = bv & ((k & 1) ? b0 : ~b0) & ((k & 2) ? b1 : ~b1) & ((k & 4) ? b2 : ~b2);
+      HLi = __shfl_sync(0xFFFFFFFFu, Hi, 0); HLtb = __shfl_sync(0xFFFFFFFFu, Htb, 0);
+      HRi = __shfl_sync(0xFFFFFFFFu, Hi, 1); HRtb = __shfl_sync(0xFFFFFFFFu, Htb, 1);
     }
-    __syncwarp();
-    // ---- propagate to the tile-local fixed point: a cell is marked when its predecessor is. Alternating down / up sweeps; inside a
-    // row the W / E dependencies are iterated with shuffles until nothing changes.
-    uint32_t newly[2] = {0u, 0u};          // bit r (of word r >> 5... TS == 32: one word) : this lane's cell in row r was marked here
-    uint32_t fresh = 0;                    // rows where this lane's cell carries an unpublished ingest mark (value 1)
-    for (int r = 0; r < TS; ++r) if (t.m[r + 1][lane + 1] == 1) fresh |= 1u << r;
-    for (int it = 0;; ++it) {
-      bool chg = false;
-      for (int i = 0; i < TS; ++i) {
-        const int r = (it & 1) ? (TS - 1 - i) : i;
-        int mk = t.m[r + 1][lane + 1] != 0;
-        const int p = t.p[r][lane];
-        int dx = 0, dy = 0;
-        if (p < 8) { dx = NDX[p]; dy = NDY[p]; }
-        if (!mk && p < 8 && dy != 0 && t.m[r + 1 + dy][lane + 1 + dx] != 0) mk = 1;     // predecessor in the row above / below
-        // predecessor in this row: W / E chains
-        const int hl = t.m[r + 1][0] != 0, hr = t.m[r + 1][TP - 1] != 0;
-        bool again;
-        int mk0 = t.m[r + 1][lane + 1] != 0;
-        do {
-          int ml = __shfl_up_sync(0xFFFFFFFFu, mk, 1), mr = __shfl_down_sync(0xFFFFFFFFu, mk, 1);
-          if (lane == 0) ml = hl;
-          if (lane == 31) mr = hr;
-          again = !mk && p < 8 && dy == 0 && ((dx < 0 && ml) || (dx > 0 && mr));
-          if (again) mk = 1;
-        } while (__any_sync(0xFFFFFFFFu, again));
-        if (mk && !mk0) {
-          t.m[r + 1][lane + 1] = 2;
-          newly[0] |= 1u << r;
-          chg = true;
-        }
-        __syncwarp();
+    // ---- propagate to the tile-local fixed point: a cell is marked when its predecessor is (k_pred's neighbour order: k = 0..7 =
+    // (dx, dy) = (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)). Each round takes the neighbour columns' masks with one shuffle
+    // each, ORs in the cells whose predecessor in those columns is marked, then closes the lane's own column (N / S chains) in registers;
+    // rounds repeat until no lane changes. The halo (rows -1 / 32, columns -1 / 32) is input only.
+    uint32_t tbl = __shfl_up_sync(0xFFFFFFFFu, tb, 1), tbr = __shfl_down_sync(0xFFFFFFFFu, tb, 1);
+    if (lane == 0) tbl = HLtb;
+    if (lane == 31) tbr = HRtb;
+    const uint32_t M0 = Mi;
+    auto up = [](uint32_t m, uint32_t halo) { return (m << 1) | (halo & 1u); };            // the column's value one row above each row
+    auto dn = [](uint32_t m, uint32_t halo) { return (m >> 1) | ((halo >> 1) << 31); };    // one row below
+    for (;;) {
+      uint32_t L = __shfl_up_sync(0xFFFFFFFFu, Mi, 1), R = __shfl_down_sync(0xFFFFFFFFu, Mi, 1);
+      if (lane == 0) L = HLi;
+      if (lane == 31) R = HRi;
+      uint32_t Mn = Mi | (P[0] & up(L, tbl)) | (P[1] & L) | (P[2] & dn(L, tbl)) | (P[5] & up(R, tbr)) | (P[6] & R) | (P[7] & dn(R, tbr));
+      for (;;) {
+        const uint32_t v = ((P[3] & up(Mn, tb)) | (P[4] & dn(Mn, tb))) & ~Mn;
+        if (!v) break;
+        Mn |= v;
       }
-      if (!__any_sync(0xFFFFFFFFu, chg) && it >= 1) break;
+      const bool chg = Mn != Mi;
+      Mi = Mn;
+      if (!__any_sync(0xFFFFFFFFu, chg)) break;
     }
+    const uint32_t newly = Mi & ~M0;          // bit r: this lane's cell in row r was marked here
     // ---- publish: marks (value 2) and d = +inf for every cell marked here or carrying a fresh ingest mark
-    const uint32_t pub = newly[0] | fresh;
+    const uint32_t pub = newly | fresh;
     {
       const int gx = x0 + lane;
       uint32_t rc = pub;
@@ -841,9 +842,7 @@ __device__ __forceinline__ void inval_body_t(const InvalArgs& a0, const RoamQ& r
       }
     }
     const uint32_t any_pub = __reduce_or_sync(0xFFFFFFFFu, pub);
-    uint32_t any_mark = 0;
-    for (int r = 0; r < TS; ++r) if (t.m[r + 1][lane + 1] != 0) any_mark |= 1u << r;
-    any_mark = __reduce_or_sync(0xFFFFFFFFu, any_mark);
+    const uint32_t any_mark = __reduce_or_sync(0xFFFFFFFFu, Mi);
     if (lane == 0 && any_mark) a.tile_seed[ti] = 1;
     // neighbours whose cells may hang off a cell published here: the side / corner of the border ring it lies on
     int m = 0;   // N S W E NW NE SW SE
