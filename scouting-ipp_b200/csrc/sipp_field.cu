@@ -108,6 +108,7 @@ struct TileD {
 };
 template <bool STAGED> struct WView;
 template <> struct WView<true> {
+  static constexpr int kAhead = 0;      // rows whose weights a sweep requests ahead of the row it works on: none (shared memory)
   const TileSmem* t;
   __device__ __forceinline__ double we(int r, int c) const { return t->we[r][c]; }
   __device__ __forceinline__ double ws(int r, int c) const { return t->ws[r][c]; }
@@ -115,6 +116,7 @@ template <> struct WView<true> {
   __device__ __forceinline__ double wsw(int r, int c) const { return t->wsw[r][c]; }
 };
 template <> struct WView<false> {
+  static constexpr int kAhead = 2;      // two rows ahead: an L2 round trip is longer than one row's in-row loop
   const double* w;
   __device__ __forceinline__ double we(int r, int c) const { return __ldg(w + r * TP + c); }
   __device__ __forceinline__ double ws(int r, int c) const { return __ldg(w + TP * TP + r * TP + c); }
@@ -140,14 +142,35 @@ __device__ __forceinline__ bool sweep_rows(Tile& t, const WV& w, int lane, uint3
   bool chg = false;
   const int r_first = (DIR > 0) ? 0 : TP - 1;
   double pl = t.d[r_first][lx - 1], pc = t.d[r_first][lx], pr = t.d[r_first][lx + 1];
+  // weights of the edges to the previous row's three cells and to the row neighbours, for the i-th row of the sweep
+  struct W5 { double wn, wnl, wnr, wl, wr; };
+  auto fetch = [&](int i) -> W5 {
+    const int r = (DIR > 0) ? (1 + i) : (TS - i);
+    W5 q;
+    q.wn = (DIR > 0) ? w.ws(r - 1, lx) : w.ws(r, lx);
+    q.wnl = (DIR > 0) ? w.wse(r - 1, lx - 1) : w.wsw(r, lx);
+    q.wnr = (DIR > 0) ? w.wsw(r - 1, lx + 1) : w.wse(r, lx);
+    q.wl = w.we(r, lx - 1);
+    q.wr = w.we(r, lx);
+    return q;
+  };
+  constexpr int AH = WV::kAhead;
+  W5 ahead[AH > 0 ? AH : 1];
+#pragma unroll
+  for (int k = 0; k < AH; ++k) ahead[k] = fetch(k);
 #pragma unroll 4
   for (int i = 0; i < TS; ++i) {
     const int r = (DIR > 0) ? (1 + i) : (TS - i);
-    // weights of the edges to the previous row's three cells and to the row neighbours
-    const double wn = (DIR > 0) ? w.ws(r - 1, lx) : w.ws(r, lx);
-    const double wnl = (DIR > 0) ? w.wse(r - 1, lx - 1) : w.wsw(r, lx);
-    const double wnr = (DIR > 0) ? w.wsw(r - 1, lx + 1) : w.wse(r, lx);
-    const double wl = w.we(r, lx - 1), wr = w.we(r, lx);
+    W5 cur;
+    if constexpr (AH == 0) {
+      cur = fetch(i);
+    } else {      // the loads of row i + AH are in flight while rows i .. i + AH - 1 run their in-row loops
+      cur = ahead[0];
+#pragma unroll
+      for (int k = 0; k + 1 < AH; ++k) ahead[k] = ahead[k + 1];
+      if (i + AH < TS) ahead[AH - 1] = fetch(i + AH);
+    }
+    const double wn = cur.wn, wnl = cur.wnl, wnr = cur.wnr, wl = cur.wl, wr = cur.wr;
     const double hl = t.d[r][0], hr = t.d[r][TP - 1];      // left / right halo of this row (constant during the sweep)
     double d = t.d[r][lx];
     const double d0 = d;
