@@ -1878,7 +1878,9 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
       else if (A[i].wa.n_items > max_nl) max_nl = A[i].wa.n_items;
     }
     if (A[i].relax_grid > max_relax) max_relax = A[i].relax_grid;
-    sum_relax += A[i].relax_grid;
+    // shared queue: the workers are not tied to a map, so the grid follows the batch's tiles (one warp per ~3 tiles, as for a single
+    // map), not the per-map shares above — idle workers only wait on their tickets
+    sum_relax += roam_queue ? (ntiles + 15) / 16 : A[i].relax_grid;
     if (A[i].inval_grid > max_inval) max_inval = A[i].inval_grid;
     if (A[i].on_inval) sum_inval += A[i].inval_grid;
   }
