@@ -288,7 +288,7 @@ def ensemble_workload(args):
     """SIPP_BENCH_WORKLOAD=ensemble / --workload ensemble (BASELINE config 5, not the default line): 128 independent 640x480 maps per GPU,
     each running an episode of planning cycles {ingest the 65x65 patch at the scout, re-plan the follower path incrementally, score 1024
     candidate views, select, move}; the maps advance together through sipp_batch_episode_run (every kernel launched once per batch,
-    one relaxation work queue for the batch), two batches side by side per GPU. Maps shard over the GPUs with no data-path
+    one relaxation work queue for the batch), two batches side by side per GPU (SIPP_BENCH_ENSEMBLE_BATCHES). Maps shard over the GPUs with no data-path
     communication (weak scaling). A step = one planning cycle of every map; host wall clock between device synchronisations, max over
     ranks — the loop is host-driven (one synchronisation per batch-cycle), so this IS the end-to-end number."""
     from concurrent.futures import ThreadPoolExecutor
@@ -305,7 +305,7 @@ def ensemble_workload(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    EW, EH, ET, maps, nb = 640, 480, 1024, int(os.environ.get("SIPP_BENCH_ENSEMBLE_MAPS", "128")), 2
+    EW, EH, ET, maps, nb = 640, 480, 1024, int(os.environ.get("SIPP_BENCH_ENSEMBLE_MAPS", "128")), int(os.environ.get("SIPP_BENCH_ENSEMBLE_BATCHES", "2"))
     cycles = 40 if args.steps == 200 else max(1, args.steps)          # run_experiment.sh scale unless --steps says otherwise
     params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001)
     worlds = []
