@@ -1438,7 +1438,7 @@ __global__ void __launch_bounds__(kRelaxWarps * 32) k_relax_roam(const PlanArgsA
 __global__ void __launch_bounds__(kInvalWarps * 32) k_inval_roam(const PlanArgsAll* __restrict__ all, RoamQ rq) {
   inval_body_t<true>(all[0].ia, rq);
 }
-// weights read from global memory: WARPS x 9 KB of shared memory per CTA, one CTA per SM (24 warps: 80 registers per thread, no spills)
+// weights read from global memory: WARPS x 9 KB of shared memory per CTA, one CTA per SM (16 / 20 / 24 warps: 100 / 90 / 80 registers per thread)
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_relax_roam_g(const PlanArgsAll* __restrict__ all, RoamQ rq) {
   relax_body_t<true, false>(all[0].ra, rq);
@@ -1899,7 +1899,7 @@ int field_plan_batch(sipp_ctx* const* ctxs, int m, void* h_args, void* d_args, u
   if (wgrid > 0) { k_weights_b<<<dim3(wgrid, M), kWeightThreads, 0, s>>>(dA); n += 1; }
   if (any_inval && roam_queue) {
     RoamQ rq{roam_queue, roam_cap, roam_ctl, reinterpret_cast<const char*>(d_args) + offsetof(PlanArgsAll, ia), sizeof(PlanArgsAll), kSpinLimit};
-    int grid = 4 * dev.num_sms / (roam_share > 1 ? roam_share : 1);      // small CTAs (18 KB of shared memory): several per SM
+    int grid = 4 * dev.num_sms / (roam_share > 1 ? roam_share : 1);      // small CTAs (no shared memory): several per SM
     if (grid > sum_inval) grid = sum_inval;
     if (grid < 1) grid = 1;
     k_roam_collect<<<M, 256, 0, s>>>(dA, rq, 1);
