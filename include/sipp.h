@@ -361,7 +361,9 @@ int sipp_update_tree_views(sipp_ctx* ctx, const sipp_eval_params* params, const 
  * one synchronisation per map-cycle — instead of m contexts x ~20 stream operations fed by m host threads. The contexts keep all
  * state (sipp_map_download, sipp_field_download, sipp_path_download ... work between batch calls); they must be idle when a batch
  * call starts and must not be driven from other threads while it runs. Results are bit-identical to the same calls made map by
- * map (tests/test_gpu_batch.py).
+ * map (tests/test_gpu_batch.py). The two persistent kernels of a re-plan (invalidation, relaxation) run on ONE work queue per batch:
+ * their workers take tiles of whichever map has work, so a batch-cycle lasts as long as the batch's total work, not as its slowest
+ * map (a watchdog abort of that queue fails every map of the step with SIPP_ERR_CUDA).
  * Limits: maps without compute_closest_observed; sipp_batch_cycle serves every evaluator except ExpandLowCostArea (its
  * closest-observed planes) and RRTStarEvaluator's binary + discount mode (per-candidate start points) and refuses those two.
  * Replaces, for evaluation runs over many maps, the one-planner-process-per-saved-map loop of data_analysis/evaluation.py:39-62,
