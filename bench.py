@@ -309,7 +309,8 @@ def ensemble_workload(args):
     cycles = 40 if args.steps == 200 else max(1, args.steps)          # run_experiment.sh scale unless --steps says otherwise
     params = sipp.make_params(sipp.EVAL_RRT_STAR, half_fov=32, non_path_voxel_gain=0.001)
     worlds = []
-    for sd in [2000 + i for i in range(maps * world)][rank::world]:
+    from sipp import shard
+    for sd in shard.ensemble_shard([2000 + i for i in range(maps * world)], rank, world):
         lab = synth.make_labels(EW, EH, sd)
         ids_ = sorted(set(np.unique(lab).tolist()) - {0})
         desc = sipp.make_desc(EW, EH, EW * synth.MPP, EH * synth.MPP, (0.5, 0.5), (EW * synth.MPP - 0.5, EH * synth.MPP - 0.5), min(ids_), max(ids_), max(ids_))
@@ -339,12 +340,8 @@ def ensemble_workload(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         clocks = sampler.result()
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt_max = float(t.item())
+    value, dt_max = shard.job_throughput(maps * cycles, dt, world)      # all ranks' map-cycles over the slowest rank's time
     launches = sum(b.launch_count() for b in batches) - l0
-    value = maps * world * cycles / dt_max
     h2d = maps * (65 * 65 * 4 + ET * 24)        # per cycle and GPU: every map's patch + candidates (argument blocks not counted)
     d2h = maps * (40 * 4 + 16)                  # plan words + the winner record
     line = {"metric": "ensemble map-cycles/s (640x480 maps, 1024 candidates per cycle)", "value": value, "unit": "map-cycles/s", "n_gpus": world,

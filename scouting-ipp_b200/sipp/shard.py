@@ -40,3 +40,19 @@ def gather_best(local_rec, world, group=None, out=None):
     cand = torch.where(valid & (vals == best), idx, torch.full_like(idx, torch.iinfo(torch.int64).max))
     j = torch.argmin(cand)
     return recs.index_select(0, j.view(1)).view(2)
+
+
+def ensemble_shard(items, rank, world):
+    """Maps of an ensemble owned by `rank`: every world-th one starting at `rank` (maps are independent — no data-path
+    communication; only the timing is reduced over the ranks)."""
+    return list(items)[int(rank)::int(world)]
+
+
+def job_throughput(units_per_rank, seconds_local, world, group=None):
+    """Whole-job rate of a sharded run: all ranks' units over the slowest rank's time (all_reduce MAX of the local time)."""
+    t = torch.tensor([float(seconds_local)], dtype=torch.float64)
+    if world > 1:
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(units_per_rank) * world / float(t.item()), float(t.item())

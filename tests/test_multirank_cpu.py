@@ -83,3 +83,37 @@ def test_gather_best_tie_and_nan_rules():
     vals = recs[:, 0].view(torch.float64)
     assert vals[0] == 3.0 and torch.isnan(vals[1])
     assert int(recs[2][1]) == 7
+
+
+def _ensemble_worker(rank, world, port, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scouting-ipp_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seeds = [2000 + i for i in range(5 * world)]
+    mine = shard.ensemble_shard(seeds, rank, world)
+    value, t = shard.job_throughput(len(mine) * 40, 1.0 + rank, world)        # rank r "took" 1 + r seconds
+    ret[rank] = (mine, value, t)
+    dist.destroy_process_group()
+
+
+def test_ensemble_shards_are_a_partition_and_the_slowest_rank_sets_the_rate():
+    """bench.py --workload ensemble: maps r::world per rank, whole-job rate = all map-cycles / max over ranks of the time"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    ps = [mp.Process(target=_ensemble_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    all_maps = sorted(ret[0][0] + ret[1][0])
+    assert all_maps == [2000 + i for i in range(10)] and not set(ret[0][0]) & set(ret[1][0])
+    for r in range(world):
+        assert ret[r][2] == 2.0 and ret[r][1] == 5 * 40 * 2 / 2.0
+    assert shard.ensemble_shard(range(7), 0, 1) == list(range(7))
+    assert shard.job_throughput(100, 4.0, 1) == (25.0, 4.0)
